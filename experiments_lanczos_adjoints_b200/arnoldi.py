@@ -1,0 +1,169 @@
+"""Arnoldi / Hessenberg factorisation with CGS2 re-orthogonalisation and its adjoint.
+
+Host-side mirror of `/root/reference/src/matfree_extensions/arnoldi.py`: same factory
+signature, same outputs `(Q (n,K), H (K,K), r (n,), c ())`, same error behaviour.  The two
+loops (`_forward`, `arnoldi.py:57-101`; `_adjoint`, `arnoldi.py:104-220`) run in
+`bl_arnoldi_forward` / `bl_arnoldi_adjoint` of libb200lanczos.so.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from experiments_lanczos_adjoints_b200 import _lib
+from experiments_lanczos_adjoints_b200 import device as dev
+from experiments_lanczos_adjoints_b200.operators import Operator
+
+
+def _require_operator(matvec):
+    if not isinstance(matvec, Operator):
+        raise TypeError(
+            "matvec must be an operator object from experiments_lanczos_adjoints_b200.operators "
+            "(SparseOperator, DenseOperator, GramOperator, WaveStencilOperator, CallbackOperator); "
+            "plain Python callables cannot be traced onto the device without JAX."
+        )
+
+
+def _run(op, name, *args):
+    """C-ABI call that re-raises an exception thrown inside a user callback."""
+    try:
+        _lib.call(name, *args)
+    except _lib.BLError:
+        err, op._error = getattr(op, "_error", None), None
+        if err is not None:
+            raise err
+        raise
+
+
+def _ptr(a):
+    return a.ptr if a is not None else None
+
+
+class _Workspace:
+    """Per-(n, K, dtype) scratch, reused across calls of one algorithm object."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes):
+        buf = self._bufs.get(key)
+        if buf is None or buf.size * 4 < nbytes:
+            buf = dev.DeviceArray(((nbytes + 3) // 4,), np.float32)  # raw bytes
+            self._bufs[key] = buf
+        return buf
+
+
+def _cotangent_basis(x, K, n, dtype, transposed_input):
+    """Bring a `(n, K)` (reference layout) or `(K, n)` cotangent into basis layout."""
+    if x is None:
+        return None
+    if isinstance(x, dev.DeviceArray):
+        if x.ndim != 2:
+            raise ValueError("basis cotangent must be 2-D")
+        stored_kn = x._shape == (K, n)
+        if stored_kn and x.dtype == np.dtype(dtype) and (x.ld * x.dtype.itemsize) % 16 == 0 and (
+            x.is_transposed == transposed_input
+        ):
+            return x  # already K rows of length n in device memory
+        x = x.numpy()
+    mat = np.asarray(x, dtype=dtype)
+    if transposed_input:
+        mat = mat.T  # (n, K) -> (K, n)
+    if mat.shape != (K, n):
+        raise ValueError(f"basis cotangent has shape {np.shape(x)}, expected {(n, K) if transposed_input else (K, n)}")
+    if not mat.any():
+        return None
+    return dev.basis_from_host(mat, dtype)
+
+
+def _cotangent_vec(x, n, dtype):
+    if x is None:
+        return None
+    if isinstance(x, dev.DeviceArray):
+        return dev.asarray(x, dtype=dtype)
+    arr = np.asarray(x, dtype=dtype).reshape(-1)
+    if arr.size != n:
+        raise ValueError(f"cotangent has {arr.size} elements, expected {n}")
+    if not arr.any():
+        return None
+    return dev.asarray(arr)
+
+
+class HessenbergEstimate:
+    """What `arnoldi.hessenberg(...)` returns: `estimate(v, *params) -> (Q, H, r, c)`,
+    plus `.vjp(v, *params) -> (outputs, pullback)` standing in for `jax.vjp` on the
+    reference's `custom_vjp` pair (`arnoldi.py:29-53`)."""
+
+    def __init__(self, op, krylov_depth, *, reortho, custom_vjp, reortho_vjp):
+        self.op, self.K = op, krylov_depth
+        self.reortho, self.custom_vjp, self.reortho_vjp = reortho, custom_vjp, reortho_vjp
+        self._ws = _Workspace()
+
+    # arnoldi.py:26 — `reortho_` is always `reortho_vjp`; only "none" switches the 2nd pass off
+    @property
+    def _second_pass(self) -> bool:
+        return self.reortho_vjp != "none"
+
+    def _forward(self, v, params, stream):
+        op, K = self.op, self.K
+        v = dev.asarray(v)
+        if v.ndim != 1:
+            raise ValueError("v must be a flat vector")
+        n, dtype = v.shape[0], v.dtype
+        if not isinstance(K, (int, np.integer)) or K < 1 or K > n:  # arnoldi.py:58-60
+            raise ValueError(f"Parameter depth {K} is outside the expected range")
+        if n != op.n:
+            raise ValueError(f"operator acts on vectors of length {op.n}, got {n}")
+        bound = op.bind(params, dtype, stream)
+        ld = dev.basis_ld(n, dtype)
+        Q = dev.DeviceArray((K, n), dtype, ld=ld)
+        H = dev.DeviceArray((K, K), dtype)
+        r = dev.DeviceArray((n,), dtype)
+        c = dev.DeviceArray((), dtype)
+        nbytes = _lib.load().bl_arnoldi_workspace_bytes(n, K, dev.dtype_code(dtype))
+        ws = self._ws.get(("arnoldi", n, K, dtype.str), nbytes)
+        _run(op, "bl_arnoldi_forward", op._handle, dev.dtype_code(dtype), n, K, int(self._second_pass),
+             v.ptr, Q.ptr, ld, H.ptr, r.ptr, c.ptr, ws.ptr, nbytes, stream.ptr)  # fmt: skip
+        return (Q, H, r, c), (n, dtype, ld, nbytes, ws, bound)
+
+    def __call__(self, v, *params, stream=None):
+        (Q, H, r, c), _ = self._forward(v, params, stream or dev.default_stream())
+        return Q.T, H, r, c  # Q shown as (n, K) like the reference
+
+    def vjp(self, v, *params, stream=None):
+        if not self.custom_vjp:
+            raise NotImplementedError(
+                "custom_vjp=False asks for autodiff through the loop (arnoldi.py:51-53); this build "
+                "has no tracing autodiff — differentiate with custom_vjp=True (the adjoint sweep)."
+            )
+        stream = stream or dev.default_stream()
+        (Q, H, r, c), (n, dtype, ld, nbytes, ws, bound) = self._forward(v, params, stream)
+        op, K = self.op, self.K
+
+        def pullback(cotangents):
+            dQ, dH, dr, dc = cotangents
+            dQb = _cotangent_basis(dQ, K, n, dtype, transposed_input=True)
+            dHd = dev.asarray(np.zeros((K, K), dtype) if dH is None else dH, dtype=dtype)
+            drd = _cotangent_vec(dr, n, dtype)
+            dcd = None if dc is None else dev.asarray(np.asarray(dc, dtype=dtype).reshape(1))
+            op.bind(bound, dtype, stream)  # same parameter values as the forward pass
+            op.grad_zero(dtype, stream)
+            dv = dev.DeviceArray((n,), dtype)
+            Lam = dev.DeviceArray((K, n), dtype, ld=ld)
+            _run(op, "bl_arnoldi_adjoint", op._handle, dev.dtype_code(dtype), n, K,
+                 int(self.reortho == "full"), Q.ptr, ld, H.ptr, r.ptr, c.ptr, _ptr(dQb), dHd.ptr,
+                 _ptr(drd), _ptr(dcd), dv.ptr, Lam.ptr, ws.ptr, nbytes, stream.ptr)  # fmt: skip
+            grads = op.grad_export(dtype, stream=stream)
+            return (dv, *grads)
+
+        return (Q.T, H, r, c), pullback
+
+
+def hessenberg(matvec, krylov_depth, /, *, reortho: str, custom_vjp: bool = True, reortho_vjp: str = "match"):
+    """Drop-in for `arnoldi.hessenberg` (`/root/reference/src/matfree_extensions/arnoldi.py:7-54`)."""
+    reortho_expected = ["none", "full"]
+    if not isinstance(reortho, str) or reortho not in reortho_expected:  # arnoldi.py:16-19
+        msg = f"Unexpected input for {reortho}: either of {reortho_expected} expected."
+        raise TypeError(msg)
+    _require_operator(matvec)
+    return HessenbergEstimate(matvec, krylov_depth, reortho=reortho, custom_vjp=custom_vjp, reortho_vjp=reortho_vjp)

@@ -1,0 +1,706 @@
+// Host-side drivers of the Krylov loops: they only enqueue kernels on the caller's stream.
+//   bl_arnoldi_forward  <- arnoldi._forward / _forward_step   (arnoldi.py:57-101)
+//   bl_arnoldi_adjoint  <- arnoldi._adjoint / _adjoint_step   (arnoldi.py:104-220)
+//   bl_lanczos3_*       <- lanczos._forward / _adjoint        (lanczos.py:215-335)
+#include <algorithm>
+
+#include "krylov_kernels.cuh"
+#include "operators.cuh"
+
+namespace bl {
+namespace {
+
+struct Grid {
+  int dots = 1, combine = 1;
+};
+
+// Upper bounds the workspace is sized for (148 SMs on B200: 2 / 16 blocks per SM).
+constexpr int kMaxDotsGrid = 296;
+constexpr int kMaxCombineGrid = 2368;
+
+int64_t gram_parts_for(int64_t n, int64_t K) {
+  return std::max<int64_t>(1, std::min<int64_t>(kMaxDotsGrid, std::min<int64_t>((n + 1023) / 1024, (4 << 20) / (K * K) + 1)));
+}
+
+template <typename T>
+Grid pick_grid(int64_t n) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t groups = (n + VN - 1) / VN;
+  Grid g;
+  const int sms = sm_count();
+  g.dots = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(2 * sms, kMaxDotsGrid), (groups + 255) / 256));
+  g.combine = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(16 * sms, kMaxCombineGrid), (groups + kCombineThreads - 1) / kCombineThreads));
+  return g;
+}
+
+// Carves the caller's workspace.
+struct Workspace {
+  unsigned char* base;
+  size_t size, used = 0;
+  Workspace(void* p, size_t bytes) : base(static_cast<unsigned char*>(p)), size(bytes) {}
+  void* take(size_t bytes) {
+    used = align_up(used, 256);
+    void* p = base + used;
+    used += bytes;
+    return p;
+  }
+  bool ok() const { return used <= size; }
+};
+
+struct Common {
+  unsigned int* counters;  // [0] dots, [1] combine
+  double* scal;
+  double* red;
+  double* coefA;
+  double* coefB;
+  double* coefC;
+  double* partials_dots;
+  double* partials_comb;
+};
+
+size_t common_bytes(int64_t n, int64_t K) {
+  size_t b = 0;
+  b += 256;                                   // counters
+  b += align_up(S_COUNT * 8, 256);            // scal
+  b += 4 * align_up((K + 2) * 8, 256);        // red, coefA, coefB, coefC
+  b += align_up((size_t)(K + 2) * kMaxDotsGrid * 8, 256);  // partials_dots
+  b += align_up((size_t)kMaxCombineGrid * 8, 256);         // partials_comb
+  (void)n;
+  return b + 8 * 256;
+}
+
+void carve_common(Workspace& w, int64_t K, Common& c) {
+  c.counters = static_cast<unsigned int*>(w.take(256));
+  c.scal = static_cast<double*>(w.take(S_COUNT * 8));
+  c.red = static_cast<double*>(w.take((K + 2) * 8));
+  c.coefA = static_cast<double*>(w.take((K + 2) * 8));
+  c.coefB = static_cast<double*>(w.take((K + 2) * 8));
+  c.coefC = static_cast<double*>(w.take((K + 2) * 8));
+  c.partials_dots = static_cast<double*>(w.take((size_t)(K + 2) * kMaxDotsGrid * 8));
+  c.partials_comb = static_cast<double*>(w.take((size_t)kMaxCombineGrid * 8));
+}
+
+template <typename T>
+int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_t n, Epi epi, cudaStream_t s) {
+  epi.red = c.red;
+  epi.scal = c.scal;
+  k_dots<T><<<g.dots, kDotsThreads, 0, s>>>(blk, x, n, c.partials_dots, c.counters + 0, epi);
+  BL_LAUNCHED();
+  return BL_OK;
+}
+
+template <typename T>
+int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cudaStream_t s) {
+  a.partials = c.partials_comb;
+  a.counter = c.counters + 1;
+  a.epi.red = c.red;
+  a.epi.scal = c.scal;
+  const size_t smem = (size_t)(a.blk[0].nrows + a.blk[1].nrows + 1) * sizeof(T);
+  if (norm)
+    k_combine<T, true><<<g.combine, kCombineThreads, smem, s>>>(a);
+  else
+    k_combine<T, false><<<g.combine, kCombineThreads, smem, s>>>(a);
+  BL_LAUNCHED();
+  return BL_OK;
+}
+
+template <typename T>
+int launch_scale_copy(int64_t n, const T* x, double mul, const double* div_ptr, T* out, int64_t n_pad, cudaStream_t s) {
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(16 * sm_count(), (n_pad + 255) / 256));
+  k_scale_copy<T><<<blocks, 256, 0, s>>>(n, x, mul, div_ptr, out, n_pad);
+  BL_LAUNCHED();
+  return BL_OK;
+}
+
+RowBlock rows(const void* base, int64_t ld, int row0, int nrows, const double* coef = nullptr,
+              double sign = 1.0, int coef0 = 0) {
+  RowBlock b;
+  b.base = base;
+  b.ld = ld;
+  b.row0 = row0;
+  b.nrows = nrows;
+  b.coef = coef;
+  b.sign = sign;
+  b.coef0 = coef0;
+  return b;
+}
+
+VecTerm term(const void* ptr, double imm = 1.0, const double* coef_ptr = nullptr) {
+  VecTerm t;
+  t.ptr = ptr;
+  t.coef_imm = imm;
+  t.coef_ptr = coef_ptr;
+  return t;
+}
+
+int check_basis(int dtype, int64_t n, int64_t K, int64_t ld, const void* Q) {
+  BL_REQUIRE(dtype == BL_F32 || dtype == BL_F64, "dtype must be BL_F32 or BL_F64");
+  BL_REQUIRE(n >= 1, "n must be positive");
+  if (K < 1 || K > n) {
+    set_error("Parameter depth " + std::to_string(K) + " is outside the expected range");
+    return BL_EDEPTH;
+  }
+  BL_REQUIRE(ld >= n && (ld * dtype_size(dtype)) % 16 == 0, "ld must be >= n and a multiple of 16 bytes");
+  BL_REQUIRE(reinterpret_cast<uintptr_t>(Q) % 16 == 0, "basis pointer must be 16-byte aligned");
+  return BL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename T>
+int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool second_pass, const T* v, T* Q,
+                      int64_t ld, T* H, T* r, T* c_out, void* workspace, size_t wbytes, cudaStream_t s) {
+  Workspace w(workspace, wbytes);
+  Common c;
+  carve_common(w, K, c);
+  BL_REQUIRE(w.ok(), "workspace too small (bl_arnoldi_workspace_bytes)");
+  const Grid g = pick_grid<T>(n);
+
+  BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
+  BL_CUDA(cudaMemsetAsync(H, 0, (size_t)K * K * sizeof(T), s));
+  BL_CUDA(cudaMemcpyAsync(r, v, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+
+  {  // initlength = sqrt(v . v); c = 1/initlength                              arnoldi.py:66,75
+    Epi e;
+    e.mode = EPI_INIT_NORM;
+    e.m = 1;
+    e.out_t = c_out;
+    BL_CHECK(launch_dots<T>(g, c, rows(r, n, 0, 1), r, n, e, s));
+  }
+  for (int i = 0; i < K; ++i) {
+    T* qi = Q + (int64_t)i * ld;
+    // v /= length; Q[:, i] = v                                                 arnoldi.py:80-81
+    BL_CHECK(launch_scale_copy<T>(n, r, 1.0, c.scal + S_LEN, qi, ld, s));
+    // v = matvec(v, *params)                                                   arnoldi.py:84
+    BL_CHECK(op->matvec(dtype, qi, r, s));
+    const int m = i + 1;
+    {  // h = Q^H v (active columns only)                                       arnoldi.py:87
+      Epi e;
+      e.mode = EPI_FWD_A;
+      e.i = i;
+      e.K = K;
+      e.m = m;
+      e.H = H;
+      e.coef = c.coefA;
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, m), r, n, e, s));
+    }
+    {  // v = v - Q h                                                           arnoldi.py:88
+      CombineArgs a;
+      a.n = n;
+      a.out = r;
+      a.nvec = 1;
+      a.vec[0] = term(r);
+      a.blk[0] = rows(Q, ld, 0, m, c.coefA, -1.0);
+      a.epi.mode = EPI_FWD_NORM;
+      a.epi.i = i;
+      a.epi.K = K;
+      a.epi.H = H;
+      BL_CHECK(launch_combine<T>(g, c, a, !second_pass, s));
+    }
+    if (second_pass) {  // v = v - Q (Q^H v); h is not updated                  arnoldi.py:91-92
+      Epi e;
+      e.mode = EPI_FWD_B;
+      e.m = m;
+      e.coef = c.coefB;
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, m), r, n, e, s));
+      CombineArgs a;
+      a.n = n;
+      a.out = r;
+      a.nvec = 1;
+      a.vec[0] = term(r);
+      a.blk[0] = rows(Q, ld, 0, m, c.coefB, -1.0);
+      a.epi.mode = EPI_FWD_NORM;  // length = sqrt(v . v); h[i+1] = length       arnoldi.py:95-98
+      a.epi.i = i;
+      a.epi.K = K;
+      a.epi.H = H;
+      BL_CHECK(launch_combine<T>(g, c, a, true, s));
+    }
+  }
+  return BL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename T>
+int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reortho_full, const T* Q,
+                      int64_t ld, const T* H, const T* r, const T* c_in, const T* dQ, const T* dH,
+                      const T* dr, const T* dc, T* dv, T* Lambda, void* workspace, size_t wbytes,
+                      cudaStream_t s) {
+  Workspace w(workspace, wbytes);
+  Common c;
+  carve_common(w, K, c);
+  double* eta = static_cast<double*>(w.take((size_t)K * 8));
+  double* Gamma = static_cast<double*>(w.take((size_t)K * K * 8));
+  double* PiGamma = static_cast<double*>(w.take((size_t)K * K * 8));
+  double* Gmat = static_cast<double*>(w.take((size_t)K * K * 8));
+  const int gram_parts = (int)gram_parts_for(n, K);
+  double* gram_partial = static_cast<double*>(w.take((size_t)gram_parts * K * K * 8));
+  T* z = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  T* lam = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  BL_REQUIRE(w.ok(), "workspace too small (bl_arnoldi_workspace_bytes)");
+  const Grid g = pick_grid<T>(n);
+
+  BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
+  BL_CUDA(cudaMemsetAsync(Gamma, 0, (size_t)K * K * 8, s));
+
+  // eta = dH e_K - Q^T dr ; lambda_K = dr + Q eta                             arnoldi.py:119-120
+  {
+    Epi e;
+    e.mode = EPI_ADJ_ETA;
+    e.K = K;
+    e.dH = dH;
+    e.eta = eta;
+    e.coef = c.coefA;
+    if (dr) {
+      e.m = K;
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, K), dr, n, e, s));
+    } else {
+      e.m = 0;
+      e.red = c.red;
+      e.scal = c.scal;
+      k_epilogue_only<T><<<1, 256, 0, s>>>(e);
+      BL_LAUNCHED();
+    }
+    CombineArgs a;
+    a.n = n;
+    a.out = lam;
+    if (dr) {
+      a.nvec = 1;
+      a.vec[0] = term(dr);
+    }
+    a.blk[0] = rows(Q, ld, 0, K, c.coefA, 1.0);
+    BL_CHECK(launch_combine<T>(g, c, a, false, s));
+  }
+  // Pi_gamma = -dc c e1 e1^T + H dH^T - dQ^T Q                                arnoldi.py:127
+  if (dQ) {
+    constexpr int TK = 16;
+    const size_t smem = 2 * (size_t)K * (TK + 1) * sizeof(T);
+    BL_REQUIRE(K <= 128, "dense dQ cotangent supported up to krylov depth 128");
+    BL_CUDA(cudaFuncSetAttribute(k_gram_partial<T, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gram_partial<T, TK><<<gram_parts, 256, smem, s>>>(K, n, dQ, Q, ld, gram_partial);
+    BL_LAUNCHED();
+    k_gram_reduce<<<(K * K + 255) / 256, 256, 0, s>>>(K * K, gram_parts, gram_partial, Gmat);
+    BL_LAUNCHED();
+  }
+  {
+    dim3 grid(K, (K + 127) / 128);
+    k_pi_gamma<T><<<grid, 128, 0, s>>>(K, H, dH, dc, c_in, dQ ? Gmat : nullptr, PiGamma);
+    BL_LAUNCHED();
+  }
+
+  for (int idx = K - 1; idx >= 0; --idx) {
+    T* Lrow = Lambda + (int64_t)idx * ld;
+    if (reortho_full) {
+      // lambda -= P^T (P lambda) - P^T p, rows <= idx+1 of P = Q^T              arnoldi.py:201-204
+      const int mact = std::min(idx + 2, K);
+      Epi e;
+      e.mode = EPI_ADJ_REPROJ;
+      e.i = idx;
+      e.K = K;
+      e.m = mact;
+      e.dH = dH;
+      e.coef = c.coefA;
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, mact), lam, n, e, s));
+      CombineArgs a;
+      a.n = n;
+      a.out = Lrow;  // Lambda[:, idx] = lambda                                   arnoldi.py:216
+      a.nvec = 1;
+      a.vec[0] = term(lam);
+      a.blk[0] = rows(Q, ld, 0, mact, c.coefA, 1.0);
+      BL_CHECK(launch_combine<T>(g, c, a, false, s));
+    } else {
+      BL_CHECK(launch_scale_copy<T>(n, lam, 1.0, nullptr, Lrow, n, s));
+    }
+    // (A^T lambda, dparams += ...) = vjp of matvec at (q_idx, params)            arnoldi.py:207-209
+    BL_CHECK(op->vjp(dtype, Q + (int64_t)idx * ld, Lrow, z, s));
+    {  // Gamma[idx, :] and the coefficients of the back-substitution             arnoldi.py:212-218
+      Epi e;
+      e.mode = EPI_ADJ_GAMMA;
+      e.i = idx;
+      e.K = K;
+      e.m = idx + 1;
+      e.Hc = H;
+      e.Gamma = Gamma;
+      e.PiGamma = PiGamma;
+      e.eta = eta;
+      e.coef = c.coefB;
+      e.coef2 = c.coefC;
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, idx + 1), z, n, e, s));
+    }
+    {  // lambda = (Pi_xi[idx] + Q gamma_row - alpha lambda + A^T lambda - Lambda beta_plus) / beta_minus
+      CombineArgs a;
+      a.n = n;
+      a.out = lam;
+      int nv = 0;
+      if (dQ) a.vec[nv++] = term(dQ + (int64_t)idx * ld);
+      a.vec[nv++] = term(r, 1.0, c.scal + S_ETA_IDX);
+      a.vec[nv++] = term(Lrow, 1.0, c.scal + S_NEG_ALPHA);
+      a.vec[nv++] = term(z);
+      a.nvec = nv;
+      a.blk[0] = rows(Q, ld, 0, K, c.coefB, 1.0);
+      a.blk[1] = rows(Lambda, ld, idx + 1, K - idx - 1, c.coefC, 1.0, idx + 1);
+      a.out_div_ptr = c.scal + S_BETA_MINUS;
+      BL_CHECK(launch_combine<T>(g, c, a, false, s));
+    }
+  }
+  // dv = lambda * c                                                              arnoldi.py:166
+  k_load_scalar<T><<<1, 1, 0, s>>>(c_in, c.scal + S_C);
+  BL_LAUNCHED();
+  {
+    CombineArgs a;
+    a.n = n;
+    a.out = dv;
+    a.nvec = 1;
+    a.vec[0] = term(lam, 1.0, c.scal + S_C);
+    BL_CHECK(launch_combine<T>(g, c, a, false, s));
+  }
+  return BL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename T>
+int lanczos3_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, const T* v, T* xs, int64_t ld,
+                       T* alphas, T* betas, void* workspace, size_t wbytes, cudaStream_t s) {
+  Workspace w(workspace, wbytes);
+  Common c;
+  carve_common(w, K, c);
+  T* wv = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  BL_REQUIRE(w.ok(), "workspace too small (bl_lanczos3_workspace_bytes)");
+  const Grid g = pick_grid<T>(n);
+  BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
+  {  // v0 = vec / ||vec||                                                        lanczos.py:222
+    Epi e;
+    e.mode = EPI_INIT_NORM;
+    e.m = 1;
+    BL_CHECK(launch_dots<T>(g, c, rows(v, n, 0, 1), v, n, e, s));
+    BL_CHECK(launch_scale_copy<T>(n, v, 1.0, c.scal + S_LEN, xs, ld, s));
+  }
+  for (int i = 0; i < K; ++i) {
+    const T* xi = xs + (int64_t)i * ld;
+    BL_CHECK(op->matvec(dtype, xi, wv, s));
+    {  // a = x . (A x)                                                           lanczos.py:256,280
+      Epi e;
+      e.mode = EPI_L3_ALPHA;
+      e.i = i;
+      e.m = 1;
+      e.out_t = alphas;
+      e.coef = c.coefA;
+      BL_CHECK(launch_dots<T>(g, c, rows(xs, ld, i, 1), wv, n, e, s));
+    }
+    {  // r = A x - a x - b x_prev ; b = ||r||                                    lanczos.py:281-283
+      CombineArgs a;
+      a.n = n;
+      a.out = wv;
+      a.nvec = 1;
+      a.vec[0] = term(wv);
+      a.blk[0] = i == 0 ? rows(xs, ld, 0, 1, c.coefA, 1.0) : rows(xs, ld, i - 1, 2, c.coefA, 1.0);
+      a.epi.mode = EPI_L3_BETA;
+      a.epi.i = i;
+      a.epi.out_t = betas;
+      BL_CHECK(launch_combine<T>(g, c, a, true, s));
+    }
+    // x_next = r / b                                                              lanczos.py:284
+    BL_CHECK(launch_scale_copy<T>(n, wv, 1.0, c.scal + S_LEN, xs + (int64_t)(i + 1) * ld, ld, s));
+  }
+  return BL_OK;
+}
+
+template <typename T>
+int lanczos3_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, const T* xs, int64_t ld,
+                       const T* alphas, const T* betas, const T* dxs, const T* dalphas, const T* dbetas,
+                       const T* vnorm, T* dv, void* workspace, size_t wbytes, cudaStream_t s) {
+  Workspace w(workspace, wbytes);
+  Common c;
+  carve_common(w, K, c);
+  T* xi = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  T* lamA = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  T* lamB = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  T* wv = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  BL_REQUIRE(w.ok(), "workspace too small (bl_lanczos3_workspace_bytes)");
+  const Grid g = pick_grid<T>(n);
+  BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
+  // init: xi = -dxs[K], lambda_plus = 0                                          lanczos.py:303
+  if (dxs)
+    BL_CHECK(launch_scale_copy<T>(n, dxs + (int64_t)K * ld, -1.0, nullptr, xi, n, s));
+  else
+    BL_CUDA(cudaMemsetAsync(xi, 0, (size_t)n * sizeof(T), s));
+  T* lam_plus = lamA;
+  T* lam = lamB;
+  BL_CUDA(cudaMemsetAsync(lam_plus, 0, (size_t)n * sizeof(T), s));
+  for (int k = K - 1; k >= 0; --k) {
+    {  // lambda_plus . x_k
+      Epi e;
+      e.mode = EPI_L3_ADJ_DOT;
+      e.m = 1;
+      e.slot = S_DOT0;
+      BL_CHECK(launch_dots<T>(g, c, rows(xs, ld, k, 1), lam_plus, n, e, s));
+    }
+    {  // x_k . xi, x_{k+1} . xi -> mu, nu                                        lanczos.py:322-324
+      Epi e;
+      e.mode = EPI_L3_ADJ_MUNU;
+      e.i = k;
+      e.m = 2;
+      e.in_t = dalphas;
+      e.in_t2 = dbetas;
+      e.in_t3 = alphas;
+      e.in_t4 = betas;
+      e.coef = c.coefA;
+      e.coef2 = c.coefB;
+      BL_CHECK(launch_dots<T>(g, c, rows(xs, ld, k, 2), xi, n, e, s));
+    }
+    {  // lambda = -xi/b + mu x_{k+1} + nu x_k                                    lanczos.py:325
+      CombineArgs a;
+      a.n = n;
+      a.out = lam;
+      a.nvec = 1;
+      a.vec[0] = term(xi, 1.0, c.scal + S_INV_B);
+      a.blk[0] = rows(xs, ld, k, 2, c.coefA, 1.0);
+      BL_CHECK(launch_combine<T>(g, c, a, false, s));
+    }
+    // A lambda and dparams += d<x_k, A(lambda)>/dparams                          lanczos.py:328-329
+    BL_CHECK(op->matvec(dtype, lam, wv, s));
+    BL_CHECK(op->vjp(dtype, lam, xs + (int64_t)k * ld, nullptr, s));
+    {  // xi = -dx_k - A lambda + a lambda + b lambda_plus - b nu x_{k+1}         lanczos.py:332
+      CombineArgs a;
+      a.n = n;
+      a.out = xi;
+      int nv = 0;
+      if (dxs) a.vec[nv++] = term(dxs + (int64_t)k * ld, -1.0);
+      a.vec[nv++] = term(wv, -1.0);
+      a.vec[nv++] = term(lam, 1.0, c.scal + S_A);
+      a.vec[nv++] = term(lam_plus, 1.0, c.scal + S_B);
+      a.nvec = nv;
+      a.blk[0] = rows(xs, ld, k, 2, c.coefB, 1.0);
+      BL_CHECK(launch_combine<T>(g, c, a, false, s));
+    }
+    std::swap(lam, lam_plus);
+  }
+  {  // grad_initvec = ((xi . x0) x0 - xi) / ||v||   (xi is what the reference calls lambda_1)  :311
+    Epi e;
+    e.mode = EPI_L3_ADJ_FINAL;
+    e.m = 1;
+    e.in_t = vnorm;
+    e.coef = c.coefA;
+    BL_CHECK(launch_dots<T>(g, c, rows(xs, ld, 0, 1), xi, n, e, s));
+    CombineArgs a;
+    a.n = n;
+    a.out = dv;
+    a.nvec = 1;
+    a.vec[0] = term(xi, 1.0, c.scal + S_TMP0);
+    a.blk[0] = rows(xs, ld, 0, 1, c.coefA, 1.0);
+    BL_CHECK(launch_combine<T>(g, c, a, false, s));
+  }
+  return BL_OK;
+}
+
+}  // namespace
+}  // namespace bl
+
+using namespace bl;
+
+extern "C" {
+
+size_t bl_arnoldi_workspace_bytes(int64_t n, int64_t K, int dtype) {
+  const size_t ld = align_up((size_t)n, 64);
+  size_t b = common_bytes(n, K);
+  b += align_up((size_t)K * 8, 256);
+  b += 3 * align_up((size_t)K * K * 8, 256);
+  const int64_t gram_parts = gram_parts_for(n, K);
+  b += align_up((size_t)gram_parts * K * K * 8, 256);
+  b += 2 * align_up((ld + 64) * dtype_size(dtype), 256);
+  return b + 16 * 256;
+}
+
+int bl_arnoldi_forward(bl_operator_t* op, int dtype, int64_t n, int64_t K, int second_pass, const void* v,
+                       void* Q, int64_t ld, void* H, void* r, void* c, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  BL_REQUIRE(op && v && Q && H && r && c && workspace, "NULL argument");
+  BL_CHECK(check_basis(dtype, n, K, ld, Q));
+  BL_REQUIRE(op->n == n, "operator size does not match n");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    return arnoldi_forward_t<float>(op, dtype, n, (int)K, second_pass != 0, (const float*)v, (float*)Q, ld,
+                                    (float*)H, (float*)r, (float*)c, workspace, workspace_bytes, s);
+  return arnoldi_forward_t<double>(op, dtype, n, (int)K, second_pass != 0, (const double*)v, (double*)Q, ld,
+                                   (double*)H, (double*)r, (double*)c, workspace, workspace_bytes, s);
+}
+
+int bl_arnoldi_adjoint(bl_operator_t* op, int dtype, int64_t n, int64_t K, int reortho_full, const void* Q,
+                       int64_t ld, const void* H, const void* r, const void* c, const void* dQ,
+                       const void* dH, const void* dr, const void* dc, void* dv, void* Lambda,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  BL_REQUIRE(op && Q && H && r && c && dH && dv && Lambda && workspace, "NULL argument");
+  BL_CHECK(check_basis(dtype, n, K, ld, Q));
+  BL_REQUIRE(reinterpret_cast<uintptr_t>(Lambda) % 16 == 0, "Lambda must be 16-byte aligned");
+  BL_REQUIRE(dQ == nullptr || reinterpret_cast<uintptr_t>(dQ) % 16 == 0, "dQ must be 16-byte aligned");
+  BL_REQUIRE(op->n == n, "operator size does not match n");
+  BL_REQUIRE(ld <= (int64_t)align_up((size_t)n, 64), "ld must be at most n rounded up to 64");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    return arnoldi_adjoint_t<float>(op, dtype, n, (int)K, reortho_full != 0, (const float*)Q, ld, (const float*)H,
+                                    (const float*)r, (const float*)c, (const float*)dQ, (const float*)dH,
+                                    (const float*)dr, (const float*)dc, (float*)dv, (float*)Lambda, workspace,
+                                    workspace_bytes, s);
+  return arnoldi_adjoint_t<double>(op, dtype, n, (int)K, reortho_full != 0, (const double*)Q, ld, (const double*)H,
+                                   (const double*)r, (const double*)c, (const double*)dQ, (const double*)dH,
+                                   (const double*)dr, (const double*)dc, (double*)dv, (double*)Lambda, workspace,
+                                   workspace_bytes, s);
+}
+
+size_t bl_lanczos3_workspace_bytes(int64_t n, int64_t K, int dtype) {
+  const size_t ld = align_up((size_t)n, 64);
+  return common_bytes(n, K) + 4 * align_up((ld + 64) * dtype_size(dtype), 256) + 16 * 256;
+}
+
+int bl_lanczos3_forward(bl_operator_t* op, int dtype, int64_t n, int64_t K, const void* v, void* xs,
+                        int64_t ld, void* alphas, void* betas, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  BL_REQUIRE(op && v && xs && alphas && betas && workspace, "NULL argument");
+  BL_CHECK(check_basis(dtype, n, K, ld, xs));
+  BL_REQUIRE(ld <= (int64_t)align_up((size_t)n, 64), "ld must be at most n rounded up to 64");
+  BL_REQUIRE(op->n == n, "operator size does not match n");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    return lanczos3_forward_t<float>(op, dtype, n, (int)K, (const float*)v, (float*)xs, ld, (float*)alphas,
+                                     (float*)betas, workspace, workspace_bytes, s);
+  return lanczos3_forward_t<double>(op, dtype, n, (int)K, (const double*)v, (double*)xs, ld, (double*)alphas,
+                                    (double*)betas, workspace, workspace_bytes, s);
+}
+
+int bl_lanczos3_adjoint(bl_operator_t* op, int dtype, int64_t n, int64_t K, const void* xs, int64_t ld,
+                        const void* alphas, const void* betas, const void* dxs, const void* dalphas,
+                        const void* dbetas, const void* vnorm, void* dv, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  BL_REQUIRE(op && xs && alphas && betas && dalphas && dbetas && vnorm && dv && workspace, "NULL argument");
+  BL_CHECK(check_basis(dtype, n, K, ld, xs));
+  BL_REQUIRE(ld <= (int64_t)align_up((size_t)n, 64), "ld must be at most n rounded up to 64");
+  BL_REQUIRE(op->n == n, "operator size does not match n");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    return lanczos3_adjoint_t<float>(op, dtype, n, (int)K, (const float*)xs, ld, (const float*)alphas,
+                                     (const float*)betas, (const float*)dxs, (const float*)dalphas,
+                                     (const float*)dbetas, (const float*)vnorm, (float*)dv, workspace,
+                                     workspace_bytes, s);
+  return lanczos3_adjoint_t<double>(op, dtype, n, (int)K, (const double*)xs, ld, (const double*)alphas,
+                                    (const double*)betas, (const double*)dxs, (const double*)dalphas,
+                                    (const double*)dbetas, (const double*)vnorm, (double*)dv, workspace,
+                                    workspace_bytes, s);
+}
+
+// ---- small vector helpers ---------------------------------------------------------------
+size_t bl_vec_workspace_bytes(void) { return common_bytes(0, 1024) + 16 * 256; }
+
+}  // extern "C"
+
+namespace bl {
+namespace {
+template <typename T>
+int rows_dot_t(int64_t n, int nrows, const T* M, int64_t ld, const T* x, T* out, void* workspace, size_t wbytes,
+               cudaStream_t s) {
+  Workspace w(workspace, wbytes);
+  Common c;
+  carve_common(w, std::max(nrows, 1), c);
+  BL_REQUIRE(w.ok(), "workspace too small (bl_vec_workspace_bytes)");
+  BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
+  Epi e;
+  e.mode = EPI_STORE;
+  e.m = nrows;
+  e.out_t = out;
+  return launch_dots<T>(pick_grid<T>(n), c, rows(M, ld, 0, nrows), x, n, e, s);
+}
+
+template <typename T>
+int rows_combine_t(int64_t n, int nrows, const T* M, int64_t ld, const double* coef_host, bool accumulate, T* out,
+                   void* workspace, size_t wbytes, cudaStream_t s) {
+  Workspace w(workspace, wbytes);
+  Common c;
+  carve_common(w, std::max(nrows, 1), c);
+  BL_REQUIRE(w.ok(), "workspace too small (bl_vec_workspace_bytes)");
+  BL_CUDA(cudaMemcpyAsync(c.coefA, coef_host, (size_t)nrows * 8, cudaMemcpyHostToDevice, s));
+  CombineArgs a;
+  a.n = n;
+  a.out = out;
+  if (accumulate) {
+    a.nvec = 1;
+    a.vec[0] = term(out);
+  }
+  a.blk[0] = rows(M, ld, 0, nrows, c.coefA, 1.0);
+  return launch_combine<T>(pick_grid<T>(n), c, a, false, s);
+}
+
+template <typename T>
+__global__ void k_transpose(int64_t rows_, int64_t cols, const T* __restrict__ src, int64_t ld_src,
+                            T* __restrict__ dst, int64_t ld_dst) {
+  __shared__ T tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int64_t r = r0 + dy, cidx = c0 + threadIdx.x;
+    if (r < rows_ && cidx < cols) tile[dy][threadIdx.x] = src[r * ld_src + cidx];
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int64_t cidx = c0 + dy, r = r0 + threadIdx.x;
+    if (r < rows_ && cidx < cols) dst[cidx * ld_dst + r] = tile[threadIdx.x][dy];
+  }
+}
+}  // namespace
+}  // namespace bl
+
+extern "C" {
+
+int bl_rows_dot(int dtype, int64_t n, int64_t nrows, const void* M, int64_t ld, const void* x, void* out,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  BL_REQUIRE(M && x && out && workspace && n >= 1 && nrows >= 1 && nrows <= 1024, "bad rows_dot arguments");
+  BL_REQUIRE((ld * dtype_size(dtype)) % 16 == 0 || nrows == 1, "ld must be a multiple of 16 bytes");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    return rows_dot_t<float>(n, (int)nrows, (const float*)M, ld, (const float*)x, (float*)out, workspace, workspace_bytes, s);
+  return rows_dot_t<double>(n, (int)nrows, (const double*)M, ld, (const double*)x, (double*)out, workspace, workspace_bytes, s);
+}
+
+int bl_vec_dot(int dtype, int64_t n, const void* x, const void* y, void* out, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  return bl_rows_dot(dtype, n, 1, x, n, y, out, workspace, workspace_bytes, stream);
+}
+
+int bl_rows_combine(int dtype, int64_t n, int64_t nrows, const void* M, int64_t ld, const double* coef_host,
+                    int accumulate, void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  BL_REQUIRE(M && coef_host && out && workspace && n >= 1 && nrows >= 1 && nrows <= 1024, "bad rows_combine arguments");
+  BL_REQUIRE((ld * dtype_size(dtype)) % 16 == 0 || nrows == 1, "ld must be a multiple of 16 bytes");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    return rows_combine_t<float>(n, (int)nrows, (const float*)M, ld, coef_host, accumulate != 0, (float*)out, workspace, workspace_bytes, s);
+  return rows_combine_t<double>(n, (int)nrows, (const double*)M, ld, coef_host, accumulate != 0, (double*)out, workspace, workspace_bytes, s);
+}
+
+int bl_vec_axpby(int dtype, int64_t n, double a, const void* x, double b, const void* y, void* out, void* stream) {
+  BL_REQUIRE(x && out && n >= 1, "bad axpby arguments");
+  BL_REQUIRE(b == 0.0 || y != nullptr, "y is NULL with b != 0");
+  cudaStream_t s = as_stream(stream);
+  // reuse combine without coefficient rows; no workspace needed (no reduction)
+  Common c{};
+  CombineArgs args;
+  args.n = n;
+  args.out = out;
+  args.nvec = 1;
+  args.vec[0] = term(x, a);
+  if (b != 0.0) {
+    args.nvec = 2;
+    args.vec[1] = term(y, b);
+  }
+  if (dtype == BL_F32) return launch_combine<float>(pick_grid<float>(n), c, args, false, s);
+  return launch_combine<double>(pick_grid<double>(n), c, args, false, s);
+}
+
+int bl_transpose(int dtype, int64_t rows_, int64_t cols, const void* src, int64_t ld_src, void* dst,
+                 int64_t ld_dst, void* stream) {
+  BL_REQUIRE(src && dst && rows_ >= 1 && cols >= 1 && ld_src >= cols && ld_dst >= rows_, "bad transpose arguments");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows_ + 31) / 32)), block(32, 8);
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    k_transpose<float><<<grid, block, 0, s>>>(rows_, cols, (const float*)src, ld_src, (float*)dst, ld_dst);
+  else
+    k_transpose<double><<<grid, block, 0, s>>>(rows_, cols, (const double*)src, ld_src, (double*)dst, ld_dst);
+  BL_LAUNCHED();
+  return BL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// Operator interface behind bl_operator_t: the reference's user-supplied `matvec(v, *params)`
+// and the pullback `jax.vjp` gives the adjoint sweep (arnoldi.py:207-209).
+#pragma once
+
+#include "common.cuh"
+
+struct bl_operator {
+  int64_t n = 0;  // square operators: length of x and y
+  virtual ~bl_operator() {}
+  virtual int num_params() const = 0;
+  virtual int64_t param_size(int index) const = 0;
+  virtual int set_params(int dtype, const void* const* params, int num, cudaStream_t s) = 0;
+  virtual int matvec(int dtype, const void* x, void* y, cudaStream_t s) = 0;
+  // z = A^T lam (skipped when z == nullptr); grad += d<lam, A(q)>/dparams
+  virtual int vjp(int dtype, const void* q, const void* lam, void* z, cudaStream_t s) = 0;
+  virtual int grad_zero(int dtype, cudaStream_t s) = 0;
+  virtual int grad_export(int dtype, void* const* grads, int num, cudaStream_t s) = 0;
+};
+
+namespace bl {
+
+// Small RAII device buffer used by operators for their own (long-lived) storage.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  int ensure(size_t want) {
+    if (want <= bytes) return BL_OK;
+    release();
+    if (cudaMalloc(&p, want ? want : 1) != cudaSuccess) {
+      set_error("cudaMalloc failed in operator storage");
+      p = nullptr;
+      return BL_ENOMEM;
+    }
+    bytes = want;
+    return BL_OK;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace bl

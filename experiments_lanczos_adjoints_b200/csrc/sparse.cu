@@ -1,0 +1,366 @@
+// Sparse COO/BCOO operand -> SELL-32 SpMV, transposed SpMV and parameter cotangent.
+//
+// Reference behaviour replaced: `BCOO((params, M.indices), shape) @ x` and its `jax.vjp`
+// (/root/reference/experiments/benchmarks/wall_times_vjp_through_lanczos_arnoldi/suite_sparse/benchmark.py:61-68,
+//  /root/reference/src/matfree_extensions/util/exp_util.py:35-42).
+//
+// Layout in HBM (per operator, built once on the host):
+//   SELL-32 ("sliced ELLPACK", slice height 32 = one warp, no row sorting) of A and of A^T:
+//     slice_ptr[s]            int64   first slot of slice s
+//     col[slot]               int32   column (A) / row (A^T) index; padding repeats a valid index
+//     src[slot]               int32   COO position whose parameter lives in this slot, -1 = padding
+//     val[slot]               T       gathered from the parameter vector by set_params
+//   slot(row r, k-th entry) = slice_ptr[r/32] + k*32 + r%32  -> a warp reads 128 contiguous
+//   bytes of `val` and of `col` per k: fully coalesced.
+//   grad[slot] (T) accumulates lam[r]*q[col] in the same layout; grad_export scatters to COO order.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "operators.cuh"
+
+namespace bl {
+
+namespace {
+
+constexpr int kSlice = 32;
+
+struct SellHost {
+  std::vector<int64_t> slice_ptr;    // nslices + 1
+  std::vector<int32_t> col;          // nslots
+  std::vector<int32_t> src;          // nslots
+  std::vector<int64_t> slot_of_csr;  // nnz
+  int64_t nslots = 0;
+};
+
+struct CsrHost {
+  std::vector<int32_t> row_ptr, col_idx, perm;
+};
+
+// Stable sort of COO entries by (row, col): counting sort on the row, stable sort on the
+// column inside each row.  Same result as np.lexsort((col, row)) (oracle/operators.py).
+CsrHost coo_to_csr(int64_t nrows, int64_t nnz, const int32_t* row, const int32_t* col) {
+  CsrHost c;
+  c.row_ptr.assign(nrows + 1, 0);
+  for (int64_t e = 0; e < nnz; ++e) c.row_ptr[row[e] + 1]++;
+  for (int64_t r = 0; r < nrows; ++r) c.row_ptr[r + 1] += c.row_ptr[r];
+  c.perm.resize(nnz);
+  std::vector<int32_t> fill(c.row_ptr.begin(), c.row_ptr.end() - 1);
+  for (int64_t e = 0; e < nnz; ++e) c.perm[fill[row[e]]++] = (int32_t)e;
+  for (int64_t r = 0; r < nrows; ++r)
+    std::stable_sort(c.perm.begin() + c.row_ptr[r], c.perm.begin() + c.row_ptr[r + 1],
+                     [&](int32_t a, int32_t b) { return col[a] < col[b]; });
+  c.col_idx.resize(nnz);
+  for (int64_t k = 0; k < nnz; ++k) c.col_idx[k] = col[c.perm[k]];
+  return c;
+}
+
+SellHost csr_to_sell(int64_t nrows, const CsrHost& c) {
+  SellHost s;
+  const int64_t nslices = (nrows + kSlice - 1) / kSlice;
+  s.slice_ptr.assign(nslices + 1, 0);
+  for (int64_t sl = 0; sl < nslices; ++sl) {
+    int64_t w = 0;
+    for (int64_t r = sl * kSlice; r < std::min<int64_t>(nrows, (sl + 1) * kSlice); ++r)
+      w = std::max<int64_t>(w, c.row_ptr[r + 1] - c.row_ptr[r]);
+    s.slice_ptr[sl + 1] = s.slice_ptr[sl] + w * kSlice;
+  }
+  s.nslots = s.slice_ptr[nslices];
+  s.col.assign(s.nslots, 0);
+  s.src.assign(s.nslots, -1);
+  s.slot_of_csr.resize(c.col_idx.size());
+  for (int64_t r = 0; r < nrows; ++r) {
+    const int64_t sl = r / kSlice, lane = r % kSlice;
+    const int64_t w = (s.slice_ptr[sl + 1] - s.slice_ptr[sl]) / kSlice;
+    const int64_t len = c.row_ptr[r + 1] - c.row_ptr[r];
+    int32_t padcol = len > 0 ? c.col_idx[c.row_ptr[r]] : 0;
+    for (int64_t k = 0; k < w; ++k) {
+      const int64_t slot = s.slice_ptr[sl] + k * kSlice + lane;
+      if (k < len) {
+        s.col[slot] = c.col_idx[c.row_ptr[r] + k];
+        s.src[slot] = c.perm[c.row_ptr[r] + k];
+        s.slot_of_csr[c.row_ptr[r] + k] = slot;
+      } else {
+        s.col[slot] = padcol;
+      }
+    }
+  }
+  return s;
+}
+
+// ---- kernels ----
+template <typename T>
+__global__ void k_gather_values(int64_t nslots, const int32_t* __restrict__ src,
+                                const T* __restrict__ params, T* __restrict__ val) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslots;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t s = src[i];
+    val[i] = s >= 0 ? params[s] : T(0);
+  }
+}
+
+template <typename T>
+__global__ void k_scatter_grad(int64_t nslots, const int32_t* __restrict__ src,
+                               const T* __restrict__ grad, T* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslots;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t s = src[i];
+    if (s >= 0) out[s] = grad[i];
+  }
+}
+
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_t(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream_t(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+// y[r] = sum_k val[slot] * x[col[slot]]; one warp per slice, lane = row within the slice.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_sell_spmv(int64_t nrows, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+            const T* __restrict__ val, const T* __restrict__ x, T* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = slice * kSlice + lane;
+  if (slice * kSlice >= nrows) return;
+  const int64_t s0 = slice_ptr[slice], s1 = slice_ptr[slice + 1];
+  T acc0 = T(0), acc1 = T(0);
+  int64_t p = s0 + lane;
+  for (; p + kSlice < s1; p += 2 * kSlice) {
+    const int c0 = ld_stream_i32(col + p), c1 = ld_stream_i32(col + p + kSlice);
+    const T v0 = ld_stream_t(val + p), v1 = ld_stream_t(val + p + kSlice);
+    acc0 = fma(v0, __ldg(x + c0), acc0);
+    acc1 = fma(v1, __ldg(x + c1), acc1);
+  }
+  if (p < s1) acc0 = fma(ld_stream_t(val + p), __ldg(x + ld_stream_i32(col + p)), acc0);
+  if (r < nrows) y[r] = acc0 + acc1;
+}
+
+// Adjoint of the sparse matvec in one launch:
+//   z[r]       = sum_k valT[slot] * lam[colT[slot]]      (A^T lam, via SELL of A^T; optional)
+//   grad[slot] += lam[r] * q[col[slot]]                   (d<lam, A q>/dparams, SELL of A)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_sell_vjp(int64_t nrows, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+           T* __restrict__ grad, const int64_t* __restrict__ slice_ptr_t,
+           const int32_t* __restrict__ col_t, const T* __restrict__ val_t, const T* __restrict__ q,
+           const T* __restrict__ lam, T* __restrict__ z) {
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = slice * kSlice + lane;
+  if (slice * kSlice >= nrows) return;
+  if (z != nullptr) {
+    const int64_t s0 = slice_ptr_t[slice], s1 = slice_ptr_t[slice + 1];
+    T acc0 = T(0), acc1 = T(0);
+    int64_t p = s0 + lane;
+    for (; p + kSlice < s1; p += 2 * kSlice) {
+      const int c0 = ld_stream_i32(col_t + p), c1 = ld_stream_i32(col_t + p + kSlice);
+      const T v0 = ld_stream_t(val_t + p), v1 = ld_stream_t(val_t + p + kSlice);
+      acc0 = fma(v0, __ldg(lam + c0), acc0);
+      acc1 = fma(v1, __ldg(lam + c1), acc1);
+    }
+    if (p < s1) acc0 = fma(ld_stream_t(val_t + p), __ldg(lam + ld_stream_i32(col_t + p)), acc0);
+    if (r < nrows) z[r] = acc0 + acc1;
+  }
+  {
+    const int64_t s0 = slice_ptr[slice], s1 = slice_ptr[slice + 1];
+    const T lr = r < nrows ? __ldg(lam + r) : T(0);
+    for (int64_t p = s0 + lane; p < s1; p += kSlice) {
+      const int c = ld_stream_i32(col + p);
+      grad[p] = fma(lr, __ldg(q + c), grad[p]);
+    }
+  }
+}
+
+struct SellDev {
+  DevBuf slice_ptr, col, src, val;
+  int64_t nslots = 0, nslices = 0;
+  int upload(const SellHost& h) {
+    nslots = h.nslots;
+    nslices = (int64_t)h.slice_ptr.size() - 1;
+    BL_CHECK(slice_ptr.ensure(h.slice_ptr.size() * sizeof(int64_t)));
+    BL_CHECK(col.ensure(std::max<size_t>(1, h.col.size()) * sizeof(int32_t)));
+    BL_CHECK(src.ensure(std::max<size_t>(1, h.src.size()) * sizeof(int32_t)));
+    BL_CUDA(cudaMemcpy(slice_ptr.p, h.slice_ptr.data(), h.slice_ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (!h.col.empty()) {
+      BL_CUDA(cudaMemcpy(col.p, h.col.data(), h.col.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      BL_CUDA(cudaMemcpy(src.p, h.src.data(), h.src.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    return BL_OK;
+  }
+};
+
+}  // namespace
+
+struct SparseOperator : bl_operator {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  CsrHost csr;                 // kept for the bit-exact export
+  SellHost sell_h, sell_t_h;   // idem
+  SellDev sell, sell_t;
+  DevBuf grad;
+  int bound_dtype = -1;
+
+  int num_params() const override { return 1; }
+  int64_t param_size(int) const override { return nnz; }
+
+  int build(const int32_t* row, const int32_t* col) {
+    csr = coo_to_csr(n_rows, nnz, row, col);
+    sell_h = csr_to_sell(n_rows, csr);
+    CsrHost csr_t = coo_to_csr(n_cols, nnz, col, row);
+    sell_t_h = csr_to_sell(n_cols, csr_t);
+    return BL_OK;  // pure host index work: testable without a GPU; upload happens on first bind
+  }
+
+  bool uploaded = false;
+  int ensure_uploaded() {
+    if (uploaded) return BL_OK;
+    BL_CHECK(sell.upload(sell_h));
+    BL_CHECK(sell_t.upload(sell_t_h));
+    uploaded = true;
+    return BL_OK;
+  }
+
+  template <typename T>
+  int set_params_t(const T* params, cudaStream_t s) {
+    BL_CHECK(sell.val.ensure(std::max<int64_t>(1, sell.nslots) * sizeof(T)));
+    BL_CHECK(sell_t.val.ensure(std::max<int64_t>(1, sell_t.nslots) * sizeof(T)));
+    BL_CHECK(grad.ensure(std::max<int64_t>(1, sell.nslots) * sizeof(T)));
+    const int blocks = 148 * 8;
+    if (sell.nslots > 0) {
+      k_gather_values<T><<<blocks, 256, 0, s>>>(sell.nslots, sell.src.as<int32_t>(), params, sell.val.as<T>());
+      BL_LAUNCHED();
+    }
+    if (sell_t.nslots > 0) {
+      k_gather_values<T><<<blocks, 256, 0, s>>>(sell_t.nslots, sell_t.src.as<int32_t>(), params, sell_t.val.as<T>());
+      BL_LAUNCHED();
+    }
+    return BL_OK;
+  }
+
+  int set_params(int dtype, const void* const* params, int num, cudaStream_t s) override {
+    BL_REQUIRE(num == 1 && params && params[0], "sparse operator takes one parameter (COO data)");
+    BL_CHECK(ensure_uploaded());
+    bound_dtype = dtype;
+    return dtype == BL_F32 ? set_params_t<float>(static_cast<const float*>(params[0]), s)
+                           : set_params_t<double>(static_cast<const double*>(params[0]), s);
+  }
+
+  template <typename T>
+  int matvec_t(const T* x, T* y, cudaStream_t s) {
+    const int64_t threads = sell.nslices * kSlice;
+    const int blocks = (int)((threads + 255) / 256);
+    if (blocks > 0) {
+      k_sell_spmv<T><<<blocks, 256, 0, s>>>(n_rows, sell.slice_ptr.as<int64_t>(), sell.col.as<int32_t>(),
+                                            sell.val.as<T>(), x, y);
+      BL_LAUNCHED();
+    }
+    return BL_OK;
+  }
+
+  int matvec(int dtype, const void* x, void* y, cudaStream_t s) override {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    return dtype == BL_F32 ? matvec_t<float>(static_cast<const float*>(x), static_cast<float*>(y), s)
+                           : matvec_t<double>(static_cast<const double*>(x), static_cast<double*>(y), s);
+  }
+
+  template <typename T>
+  int vjp_t(const T* q, const T* lam, T* z, cudaStream_t s) {
+    const int64_t rows = std::max(n_rows, n_cols);
+    const int64_t threads = ((rows + kSlice - 1) / kSlice) * kSlice;
+    const int blocks = (int)((threads + 255) / 256);
+    if (blocks > 0) {
+      k_sell_vjp<T><<<blocks, 256, 0, s>>>(rows, sell.slice_ptr.as<int64_t>(), sell.col.as<int32_t>(),
+                                           grad.as<T>(), sell_t.slice_ptr.as<int64_t>(),
+                                           sell_t.col.as<int32_t>(), sell_t.val.as<T>(), q, lam, z);
+      BL_LAUNCHED();
+    }
+    return BL_OK;
+  }
+
+  int vjp(int dtype, const void* q, const void* lam, void* z, cudaStream_t s) override {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    BL_REQUIRE(n_rows == n_cols, "vjp needs a square operator");
+    return dtype == BL_F32
+               ? vjp_t<float>(static_cast<const float*>(q), static_cast<const float*>(lam), static_cast<float*>(z), s)
+               : vjp_t<double>(static_cast<const double*>(q), static_cast<const double*>(lam), static_cast<double*>(z), s);
+  }
+
+  int grad_zero(int dtype, cudaStream_t s) override {
+    BL_CHECK(grad.ensure(std::max<int64_t>(1, sell.nslots) * dtype_size(dtype)));
+    BL_CUDA(cudaMemsetAsync(grad.p, 0, std::max<int64_t>(1, sell.nslots) * dtype_size(dtype), s));
+    return BL_OK;
+  }
+
+  int grad_export(int dtype, void* const* grads, int num, cudaStream_t s) override {
+    BL_REQUIRE(num == 1 && grads && grads[0], "sparse operator has one gradient buffer");
+    if (sell.nslots == 0) return BL_OK;
+    const int blocks = 148 * 8;
+    if (dtype == BL_F32)
+      k_scatter_grad<float><<<blocks, 256, 0, s>>>(sell.nslots, sell.src.as<int32_t>(), grad.as<float>(), static_cast<float*>(grads[0]));
+    else
+      k_scatter_grad<double><<<blocks, 256, 0, s>>>(sell.nslots, sell.src.as<int32_t>(), grad.as<double>(), static_cast<double*>(grads[0]));
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+};
+
+}  // namespace bl
+
+extern "C" {
+
+int bl_op_sparse_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* coo_row_host,
+                        const int32_t* coo_col_host, bl_operator_t** op) {
+  BL_REQUIRE(op != nullptr, "op is NULL");
+  BL_REQUIRE(n_rows > 0 && n_cols > 0 && nnz >= 0, "bad shape");
+  BL_REQUIRE(nnz == 0 || (coo_row_host && coo_col_host), "index arrays are NULL");
+  BL_REQUIRE(nnz < (int64_t)1 << 31, "nnz must fit int32");
+  for (int64_t e = 0; e < nnz; ++e) {
+    BL_REQUIRE(coo_row_host[e] >= 0 && coo_row_host[e] < n_rows, "row index out of range");
+    BL_REQUIRE(coo_col_host[e] >= 0 && coo_col_host[e] < n_cols, "column index out of range");
+  }
+  auto* o = new bl::SparseOperator();
+  o->n = n_rows;
+  o->n_rows = n_rows;
+  o->n_cols = n_cols;
+  o->nnz = nnz;
+  int rc = o->build(coo_row_host, coo_col_host);
+  if (rc != BL_OK) {
+    delete o;
+    return rc;
+  }
+  *op = o;
+  return BL_OK;
+}
+
+int bl_op_sparse_export_csr(const bl_operator_t* op, int32_t* row_ptr_host, int32_t* col_idx_host,
+                            int32_t* perm_host) {
+  auto* o = dynamic_cast<const bl::SparseOperator*>(op);
+  BL_REQUIRE(o != nullptr, "not a sparse operator");
+  if (row_ptr_host) std::copy(o->csr.row_ptr.begin(), o->csr.row_ptr.end(), row_ptr_host);
+  if (col_idx_host) std::copy(o->csr.col_idx.begin(), o->csr.col_idx.end(), col_idx_host);
+  if (perm_host) std::copy(o->csr.perm.begin(), o->csr.perm.end(), perm_host);
+  return BL_OK;
+}
+
+int bl_op_sparse_export_sell(const bl_operator_t* op, int transpose, int64_t* slice_ptr_host,
+                             int64_t* slot_of_csr_host) {
+  auto* o = dynamic_cast<const bl::SparseOperator*>(op);
+  BL_REQUIRE(o != nullptr, "not a sparse operator");
+  const auto& h = transpose ? o->sell_t_h : o->sell_h;
+  if (slice_ptr_host) std::copy(h.slice_ptr.begin(), h.slice_ptr.end(), slice_ptr_host);
+  if (slot_of_csr_host) std::copy(h.slot_of_csr.begin(), h.slot_of_csr.end(), slot_of_csr_host);
+  return BL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+"""Lanczos tridiagonalisation and the SLQ integrands built on it.
+
+Host-side mirror of `/root/reference/src/matfree_extensions/lanczos.py`:
+`tridiag`, `integrand_spd`, `integrand_spd_custom_vjp_reuse` with the reference's signatures
+and return structure.  `reortho="full"` runs Arnoldi and symmetrises (`lanczos.py:152-169`);
+`reortho="none"` runs the three-term recurrence and its adjoint (`lanczos.py:172-335`).  The
+O(n K) work is on the device; the K x K post-processing (`eigh`, `lanczos.py:48-59`) is host
+NumPy, as the survey marks it ("stays in JAX/NumPy, not a kernel target").
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from experiments_lanczos_adjoints_b200 import _lib
+from experiments_lanczos_adjoints_b200 import arnoldi
+from experiments_lanczos_adjoints_b200 import device as dev
+from experiments_lanczos_adjoints_b200.arnoldi import _cotangent_basis, _cotangent_vec, _ptr, _run, _Workspace
+
+
+def _vec_ws():
+    nbytes = _lib.load().bl_vec_workspace_bytes()
+    return dev.DeviceArray(((nbytes + 3) // 4,), np.float32), nbytes
+
+
+def device_dot(x: dev.DeviceArray, y: dev.DeviceArray, stream=None) -> float:
+    stream = stream or dev.default_stream()
+    out = dev.DeviceArray((), x.dtype)
+    ws, nbytes = _vec_ws()
+    _lib.call("bl_vec_dot", dev.dtype_code(x.dtype), x.size, x.ptr, y.ptr, out.ptr, ws.ptr, nbytes, stream.ptr)
+    return float(out.numpy(stream))
+
+
+def device_axpby(a, x, b, y, stream=None) -> dev.DeviceArray:
+    stream = stream or dev.default_stream()
+    out = dev.DeviceArray(x.shape, x.dtype)
+    _lib.call("bl_vec_axpby", dev.dtype_code(x.dtype), x.size, float(a), x.ptr, float(b), _ptr(y), out.ptr, stream.ptr)
+    return out
+
+
+class _TridiagFull:
+    """`_tridiag_reortho_full` (`lanczos.py:152-169`)."""
+
+    def __init__(self, op, krylov_depth, custom_vjp):
+        self.alg = arnoldi.hessenberg(op, krylov_depth, custom_vjp=custom_vjp, reortho="full")
+
+    @staticmethod
+    def _wrap(Qn, H, r, stream):
+        Hh = H.numpy(stream)
+        T = 0.5 * (Hh + Hh.T)  # lanczos.py:162
+        diags, offdiags = np.diag(T, 0).copy(), np.diag(T, 1).copy()
+        norm = np.sqrt(device_dot(r, r, stream)).astype(Hh.dtype)
+        remainder = (device_axpby(1.0 / norm, r, 0.0, None, stream), norm)
+        return (Qn.T, (diags, offdiags)), remainder
+
+    def __call__(self, vec, *params, stream=None):
+        stream = stream or dev.default_stream()
+        Qn, H, r, _c = self.alg(vec, *params, stream=stream)
+        return self._wrap(Qn, H, r, stream)
+
+    def vjp(self, vec, *params, stream=None):
+        stream = stream or dev.default_stream()
+        (Qn, H, r, _c), pull = self.alg.vjp(vec, *params, stream=stream)
+        out = self._wrap(Qn, H, r, stream)
+        K, dtype = H.shape[0], H.dtype
+        norm = float(out[1][1])
+
+        def pullback(cot):
+            (dQt, (dalpha, dbeta)), (dq_rem, dnorm) = cot
+            # cotangent of T = (H + H^T)/2 and its diagonals (lanczos.py:162-164)
+            dH = np.diag(np.asarray(dalpha, dtype=dtype))
+            if K > 1:
+                dbeta = np.asarray(dbeta, dtype=dtype)
+                dH = dH + 0.5 * (np.diag(dbeta, 1) + np.diag(dbeta, -1))
+            # cotangent of (r/||r||, ||r||) (lanczos.py:166)
+            dr = None
+            dq = _cotangent_vec(dq_rem, r.size, dtype)
+            dn = 0.0 if dnorm is None else float(np.asarray(dnorm))
+            if dq is not None or dn != 0.0:
+                coef_r = dn / norm
+                if dq is not None:
+                    coef_r -= device_dot(r, dq, stream) / norm**3
+                    dr = device_axpby(1.0 / norm, dq, coef_r, r, stream)
+                else:
+                    dr = device_axpby(coef_r, r, 0.0, None, stream)
+            dQ = None if dQt is None else _as_kn(dQt, K, r.size, dtype)
+            return pull((dQ, dH, dr, None))
+
+        return out, pullback
+
+
+def _as_kn(x, K, n, dtype):
+    """A `(K, n)` cotangent handed to the Arnoldi pullback, which expects `(n, K)`."""
+    if isinstance(x, dev.DeviceArray):
+        return x.T
+    return np.asarray(x, dtype=dtype).T
+
+
+class _TridiagNone:
+    """`_tridiag_reortho_none` (`lanczos.py:172-212`): three-term recurrence and its adjoint."""
+
+    def __init__(self, op, krylov_depth, custom_vjp):
+        arnoldi._require_operator(op)
+        self.op, self.K, self.custom_vjp = op, krylov_depth, custom_vjp
+        self._ws = _Workspace()
+
+    def _forward(self, vec, params, stream):
+        op, K = self.op, self.K
+        v = dev.asarray(vec)
+        n, dtype = v.shape[0], v.dtype
+        if not isinstance(K, (int, np.integer)) or K < 1 or K > n:
+            raise ValueError(f"Parameter depth {K} is outside the expected range")
+        bound = op.bind(params, dtype, stream)
+        ld = dev.basis_ld(n, dtype)
+        xs = dev.DeviceArray((K + 1, n), dtype, ld=ld)
+        alphas, betas = dev.DeviceArray((K,), dtype), dev.DeviceArray((K,), dtype)
+        nbytes = _lib.load().bl_lanczos3_workspace_bytes(n, K, dev.dtype_code(dtype))
+        ws = self._ws.get(("l3", n, K, dtype.str), nbytes)
+        _run(op, "bl_lanczos3_forward", op._handle, dev.dtype_code(dtype), n, K, v.ptr, xs.ptr, ld,
+             alphas.ptr, betas.ptr, ws.ptr, nbytes, stream.ptr)  # fmt: skip
+        return (xs, alphas, betas), (v, n, dtype, ld, nbytes, ws, bound)
+
+    @staticmethod
+    def _wrap(xs, alphas, betas, K, n, stream):
+        a, b = alphas.numpy(stream), betas.numpy(stream)
+        basis = dev.DeviceArray((K, n), xs.dtype, ld=xs.ld, owner=xs._owner, ptr=xs.ptr)
+        return (basis, (a, b[:-1].copy())), (xs.row(K), b[-1])  # lanczos.py:242-244
+
+    def __call__(self, vec, *params, stream=None):
+        stream = stream or dev.default_stream()
+        (xs, alphas, betas), (_, n, *_rest) = self._forward(vec, params, stream)
+        return self._wrap(xs, alphas, betas, self.K, n, stream)
+
+    def vjp(self, vec, *params, stream=None):
+        if not self.custom_vjp:
+            raise NotImplementedError("autodiff through the loop is not available; use custom_vjp=True")
+        if len(params) != 1:
+            raise TypeError("the three-term adjoint supports exactly one parameter array (lanczos.py:329)")
+        stream = stream or dev.default_stream()
+        (xs, alphas, betas), (v, n, dtype, ld, nbytes, ws, bound) = self._forward(vec, params, stream)
+        op, K = self.op, self.K
+        out = self._wrap(xs, alphas, betas, K, n, stream)
+        vnorm = dev.asarray(np.asarray([np.sqrt(device_dot(v, v, stream))], dtype=dtype))
+
+        def pullback(cot):
+            (dxs, (da, db)), (dx_last, db_last) = cot
+            dxs_b = None
+            dxs_h = None if dxs is None else np.asarray(dxs, dtype=dtype)
+            dxl_h = None if dx_last is None else np.asarray(dx_last, dtype=dtype)
+            if (dxs_h is not None and dxs_h.any()) or (dxl_h is not None and dxl_h.any()):
+                full = np.zeros((K + 1, n), dtype)
+                if dxs_h is not None:
+                    full[:K] = dxs_h
+                if dxl_h is not None:
+                    full[K] = dxl_h
+                dxs_b = dev.basis_from_host(full, dtype)
+            dal = dev.asarray(np.asarray(da, dtype=dtype).reshape(K))
+            dbe_h = np.zeros(K, dtype)
+            if K > 1 and db is not None:
+                dbe_h[: K - 1] = np.asarray(db, dtype=dtype)
+            if db_last is not None:
+                dbe_h[K - 1] = np.asarray(db_last, dtype=dtype)
+            dbe = dev.asarray(dbe_h)
+            op.bind(bound, dtype, stream)
+            op.grad_zero(dtype, stream)
+            dv = dev.DeviceArray((n,), dtype)
+            _run(op, "bl_lanczos3_adjoint", op._handle, dev.dtype_code(dtype), n, K, xs.ptr, ld,
+                 alphas.ptr, betas.ptr, _ptr(dxs_b), dal.ptr, dbe.ptr, vnorm.ptr, dv.ptr, ws.ptr,
+                 nbytes, stream.ptr)  # fmt: skip
+            (grad,) = op.grad_export(dtype, stream=stream)
+            return dv, grad
+
+        return out, pullback
+
+
+def tridiag(matvec, krylov_depth, /, *, reortho: str, custom_vjp: bool = True):
+    """Drop-in for `lanczos.tridiag` (`/root/reference/src/matfree_extensions/lanczos.py:142-149`):
+    returns `estimate(vec, *params) -> ((Q.T (K,n), (diags, offdiags)), (r/||r||, ||r||))`."""
+    if reortho == "full":
+        return _TridiagFull(matvec, krylov_depth, custom_vjp)
+    if reortho == "none":
+        return _TridiagNone(matvec, krylov_depth, custom_vjp)
+    msg = f"reortho={reortho} unsupported. Choose eiter {'full', 'none'}."
+    raise ValueError(msg)  # lanczos.py:148-149 (ValueError here, TypeError in arnoldi: quirk B9)
+
+
+# --------------------------------------------------------------------------------------------
+# SLQ integrands
+# --------------------------------------------------------------------------------------------
+
+
+def _matfun_derivative(matfun, x):
+    """f'(x) by the complex-step rule (exact to rounding for analytic NumPy functions such as
+    log / sqrt / exp); JAX derives f' by autodiff in the reference (`lanczos.py:56`)."""
+    h = 1e-30
+    return np.imag(matfun(np.asarray(x, dtype=np.float64) + 1j * h)) / h
+
+
+def _quadform_and_cotangents(matfun, matfun_grad, alpha, beta, want_grad):
+    """`e1^T f(T) e1` through `eigh` (`lanczos.py:48-59`) and, for the gradient, the closed-form
+    cotangents of `(diag, off_diag)` (Daleckii-Krein; the reference uses JAX autodiff of eigh)."""
+    a64, b64 = np.asarray(alpha, np.float64), np.asarray(beta, np.float64)
+    dense = np.diag(a64) + np.diag(b64, 1) + np.diag(b64, -1)
+    w, U = np.linalg.eigh(dense)
+    fw = np.asarray(matfun(w), dtype=np.float64)
+    value = float(np.dot(U[0], fw * U[0]))
+    if not want_grad:
+        return value, None, None, (w, U)
+    dfw = np.asarray((matfun_grad or (lambda x: _matfun_derivative(matfun, x)))(w), dtype=np.float64)
+    dw = w[:, None] - w[None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        F = (fw[:, None] - fw[None, :]) / dw
+    same = np.abs(dw) <= 1e-14 * max(1.0, float(np.abs(w).max()))
+    F[same] = (0.5 * (dfw[:, None] + dfw[None, :]))[same]
+    G = U @ (np.outer(U[0], U[0]) * F) @ U.T
+    return value, np.diag(G).copy(), np.diag(G, 1) + np.diag(G, -1), (w, U)
+
+
+class _IntegrandSPD:
+    def __init__(self, matfun, krylov_depth, matvec, reortho, use_adjoints, matfun_grad):
+        self.matfun, self.matfun_grad = matfun, matfun_grad
+        self.alg = tridiag(matvec, krylov_depth, custom_vjp=use_adjoints, reortho=reortho)
+
+    def __call__(self, v0, *parameters, stream=None):
+        stream = stream or dev.default_stream()
+        v0 = _flat(v0)
+        scale = np.sqrt(device_dot(v0, v0, stream))  # lanczos.py:25
+        u = device_axpby(1.0 / scale, v0, 0.0, None, stream)
+        (_basis, (diag, off)), _ = self.alg(u, *parameters, stream=stream)
+        value, *_ = _quadform_and_cotangents(self.matfun, self.matfun_grad, diag, off, False)
+        return diag.dtype.type(scale**2 * value)  # lanczos.py:59
+
+    def value_and_grad(self, v0, *parameters, stream=None, want_dv0=True):
+        """`jax.value_and_grad(quadform, argnums=(0, 1, ...))`: `(value, (dv0, *dparams))`."""
+        stream = stream or dev.default_stream()
+        v0 = _flat(v0)
+        scale = np.sqrt(device_dot(v0, v0, stream))
+        u = device_axpby(1.0 / scale, v0, 0.0, None, stream)
+        ((_basis, (diag, off)), _rem), pull = self.alg.vjp(u, *parameters, stream=stream)
+        g, dalpha, dbeta, _ = _quadform_and_cotangents(self.matfun, self.matfun_grad, diag, off, True)
+        s2 = scale**2
+        du, *dparams = pull(((None, (s2 * dalpha, s2 * dbeta)), (None, None)))
+        dv0 = None
+        if want_dv0:  # chain rule through u = v0/||v0|| and the scale**2 factor (lanczos.py:24-26,59)
+            udu = device_dot(u, du, stream)
+            tmp = device_axpby(1.0 / scale, du, -udu / scale, u, stream)
+            dv0 = device_axpby(2.0 * g, v0, 1.0, tmp, stream)
+        return diag.dtype.type(s2 * g), (dv0, *dparams)
+
+
+def _flat(v0):
+    v0 = dev.asarray(v0)
+    if v0.ndim != 1:  # ravel_pytree of a single array (lanczos.py:24)
+        v0 = dev.DeviceArray((v0.size,), v0.dtype, owner=v0._owner, ptr=v0.ptr)
+    return v0
+
+
+def integrand_spd(matfun, krylov_depth, matvec, /, *, reortho: str = "full", use_adjoints_for_tridiag: bool = True,
+                  matfun_grad=None):
+    """Drop-in for `lanczos.integrand_spd` (`/root/reference/src/matfree_extensions/lanczos.py:14-61`):
+    `quadform(v0, *parameters) -> ||v0||^2 e1^T f(T) e1`.  `matfun` acts on NumPy arrays
+    (`np.log`, ...); its derivative defaults to the complex-step rule (`matfun_grad` overrides)."""
+    return _IntegrandSPD(matfun, krylov_depth, matvec, reortho, use_adjoints_for_tridiag, matfun_grad)
+
+
+class _IntegrandSPDReuse:
+    def __init__(self, matfun, order, op, reortho, matfun_grad):
+        self.matfun, self.matfun_grad, self.op = matfun, matfun_grad, op
+        self.alg = tridiag(op, order, custom_vjp=False, reortho=reortho)  # lanczos.py:97
+
+    def value_and_grad(self, v0, *parameters, stream=None, want_dv0=True):
+        stream = stream or dev.default_stream()
+        v0 = _flat(v0)
+        scale = np.sqrt(device_dot(v0, v0, stream))
+        u = device_axpby(1.0 / scale, v0, 0.0, None, stream)
+        (basis, (diag, off)), _ = self.alg(u, *parameters, stream=stream)
+        value, _, _, (w, U) = _quadform_and_cotangents(self.matfun, self.matfun_grad, diag, off, False)
+        dfw = np.asarray((self.matfun_grad or (lambda x: _matfun_derivative(self.matfun, x)))(w))
+        sol = U @ (dfw * U[0])  # lanczos.py:112-113
+        # w1 = scale^2 * basis.T @ sol  (lanczos.py:114): a combination of basis rows
+        K, n, dtype = basis.shape[0], basis.shape[1], basis.dtype
+        w1 = dev.DeviceArray((n,), dtype)
+        coef = np.ascontiguousarray(scale**2 * sol, dtype=np.float64)
+        ws, nbytes = _vec_ws()
+        _lib.call("bl_rows_combine", dev.dtype_code(dtype), n, K, basis.ptr, basis.ld, coef.ctypes.data, 0,
+                  w1.ptr, ws.ptr, nbytes, stream.ptr)  # fmt: skip
+        stream.synchronize()
+        # gradient of  theta -> <w1, A(w2; theta)>  (lanczos.py:121), dv0 := 0 (lanczos.py:130-134)
+        op = self.op
+        op.grad_zero(dtype, stream)
+        op.vjp(u, w1, want_z=False, stream=stream)
+        grads = op.grad_export(dtype, stream=stream)
+        warnings.warn("Todo: implement gradient wrt v correctly", stacklevel=1)  # lanczos.py:127-128
+        dv0 = dev.zeros((n,), dtype) if want_dv0 else None
+        return diag.dtype.type(scale**2 * value), (dv0, *grads)
+
+    def __call__(self, v0, *parameters, stream=None):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return self.value_and_grad(v0, *parameters, stream=stream, want_dv0=False)[0]
+
+
+def integrand_spd_custom_vjp_reuse(matfun, order, matvec, /, *, reortho: str = "full", matfun_grad=None):
+    """Drop-in for `lanczos.integrand_spd_custom_vjp_reuse` (`lanczos.py:64-139`)."""
+    arnoldi._require_operator(matvec)
+    return _IntegrandSPDReuse(matfun, order, matvec, reortho, matfun_grad)

@@ -1,0 +1,183 @@
+/*
+ * b200_lanczos.h — C ABI of libb200lanczos.so (sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of pnkraemer/experiments-lanczos-adjoints:
+ * Arnoldi/Lanczos factorisation with full re-orthogonalisation, its hand-derived
+ * adjoint sweep, and the matvec back-ends they call.  The reference has no native
+ * boundary (it is pure JAX); each entry point below cites the reference function it
+ * replaces.  A reference maintainer binds these through `jax.ffi`
+ * or, as the Python host layer in this repo does, through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `*_dev` / unmarked data pointer is DEVICE
+ *     memory unless the name ends in `_host`;
+ *   - `dtype`: BL_F32 or BL_F64 — the arithmetic type of every vector/matrix argument of
+ *     that call (the reference follows the dtype of the input vector, arnoldi.py:64-65);
+ *   - Krylov bases are stored as K contiguous rows of length `ld` (row j = j-th basis
+ *     vector, i.e. the reference's `Q.T`, lanczos.py:165), `ld >= n`, `ld*sizeof(T)` a
+ *     multiple of 16, base pointers 16-byte aligned;
+ *   - small dense matrices (H, dH) are row-major K x K in `dtype`;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no host
+ *     synchronisation, no allocation inside the Krylov calls: the caller supplies a
+ *     workspace of `*_workspace_bytes()` bytes;
+ *   - return value 0 on success, otherwise a BL_E* code; `bl_last_error()` gives the
+ *     message (thread-local).
+ */
+#ifndef B200_LANCZOS_H
+#define B200_LANCZOS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { BL_F32 = 0, BL_F64 = 1 };
+enum {
+  BL_OK = 0,
+  BL_EINVAL = 1,   /* bad argument (shape, alignment, enum) */
+  BL_EDEPTH = 2,   /* krylov depth outside [1, n]: arnoldi.py:58-60 -> ValueError("depth") */
+  BL_ECUDA = 3,    /* CUDA runtime error, see bl_last_error() */
+  BL_ENOMEM = 4,
+  BL_ECALLBACK = 5 /* a user matvec callback returned non-zero */
+};
+
+const char* bl_last_error(void);
+const char* bl_version(void);
+
+/* ---- device runtime (thin wrappers so the host layer needs no other CUDA binding) ---- */
+int bl_device_count(int* count);
+int bl_set_device(int device);
+int bl_get_device(int* device);
+int bl_device_sm_count(int* count);
+int bl_malloc(void** ptr, size_t bytes);
+int bl_free(void* ptr);
+int bl_host_alloc(void** ptr, size_t bytes); /* pinned host memory */
+int bl_host_free(void* ptr);
+int bl_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void* stream);
+int bl_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream);
+int bl_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int bl_memset(void* dst, int value, size_t bytes, void* stream);
+int bl_stream_create(void** stream);
+int bl_stream_destroy(void* stream);
+int bl_stream_sync(void* stream);
+int bl_device_sync(void);
+int bl_event_create(void** event);
+int bl_event_destroy(void* event);
+int bl_event_record(void* event, void* stream);
+int bl_event_sync(void* event);
+int bl_event_elapsed_ms(void* start, void* stop, float* ms);
+/* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
+int bl_launch_count(uint64_t* count);
+
+/* ---- operators: the `matvec(v, *params)` callback of the reference ------------------
+ * An operator owns its index structures and a gradient accumulator for its parameters.
+ *   set_params : bind parameter values (device pointers, reference order)
+ *   matvec     : y = A(x; params)                     [what `matvec(v, *params)` returns]
+ *   vjp        : z = A^T lam  and  grad += d<lam, A(q; params)>/dparams
+ *                [what jax.vjp(lambda u, p: matvec(u, *p), q, params)(lam) returns,
+ *                 arnoldi.py:207-209]; z may be NULL (three-term adjoint, lanczos.py:328-329)
+ *   grad_zero / grad_export : reset / read the accumulator (one buffer per parameter).
+ */
+typedef struct bl_operator bl_operator_t;
+
+/* Sparse COO/BCOO operand (suite_sparse/benchmark.py:61-68, util/exp_util.py:35-42).
+ * One parameter: the COO `data` array (nnz values, COO order; duplicates are summed by the
+ * matvec and stay independent parameters).  Index work (COO -> CSR -> SELL-32 for A and
+ * A^T) happens here, on the host, and is bit-exact against oracle/operators.py. */
+int bl_op_sparse_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* coo_row_host,
+                        const int32_t* coo_col_host, bl_operator_t** op);
+/* CSR view of the index work, for the bit-exact tests: row_ptr[n_rows+1], col_idx[nnz],
+ * perm[nnz] (perm[k] = COO position of CSR slot k).  Any pointer may be NULL. */
+int bl_op_sparse_export_csr(const bl_operator_t* op, int32_t* row_ptr_host, int32_t* col_idx_host,
+                            int32_t* perm_host);
+/* SELL-32 view: slice_ptr[n_slices+1] (int64), slot_of_csr[nnz] (int64). */
+int bl_op_sparse_export_sell(const bl_operator_t* op, int transpose, int64_t* slice_ptr_host,
+                             int64_t* slot_of_csr_host);
+
+/* Dense operand of the reference's tests: mode 0 `p @ s` (test_hessenberg_forward.py:20),
+ * mode 1 `(p + p.T) @ s` (test_tridiag_adjoint.py:20-21).  One parameter: p (n x n row-major). */
+int bl_op_dense_create(int64_t n, int mode, bl_operator_t** op);
+
+/* Matrix-free Gram operator `(K(X,X) + noise I) v` (util/gp_util.py:69-184, 525-543).
+ * kind 0 Matern-3/2, 1 Matern-1/2, 2 RBF.  X_host is n x d row-major doubles (converted per
+ * dtype on bind).  Three parameters: raw_lengthscale (d), raw_outputscale (1), noise (1). */
+int bl_op_gram_create(int64_t n, int64_t d, int kind, const double* X_host, bl_operator_t** op);
+
+/* Wave-equation stencil operand (util/pde_util.py:126-157): state (u, du) of 2 g^2 values,
+ * A(u,du) = (du, scale^2 * conv3x3(stencil, edge_pad(u))).  One parameter: scale (g*g). */
+int bl_op_wave_create(int64_t grid, const double* stencil3x3_host, bl_operator_t** op);
+
+/* User-supplied matvec: the host layer passes C callbacks that enqueue work on `stream`.
+ * matvec_cb(user, dtype, x, y, stream); vjp_cb(user, dtype, q, lam, z_or_null, stream). */
+typedef int (*bl_matvec_cb)(void* user, int dtype, const void* x, void* y, void* stream);
+typedef int (*bl_vjp_cb)(void* user, int dtype, const void* q, const void* lam, void* z, void* stream);
+int bl_op_callback_create(int64_t n, bl_matvec_cb matvec_cb, bl_vjp_cb vjp_cb, void* user,
+                          bl_operator_t** op);
+
+int bl_op_destroy(bl_operator_t* op);
+int bl_op_size(const bl_operator_t* op, int64_t* n);
+int bl_op_num_params(const bl_operator_t* op, int* num);
+int bl_op_param_size(const bl_operator_t* op, int index, int64_t* numel);
+int bl_op_set_params(bl_operator_t* op, int dtype, const void* const* params, int num, void* stream);
+int bl_op_matvec(bl_operator_t* op, int dtype, const void* x, void* y, void* stream);
+int bl_op_vjp(bl_operator_t* op, int dtype, const void* q, const void* lam, void* z, void* stream);
+int bl_op_grad_zero(bl_operator_t* op, int dtype, void* stream);
+int bl_op_grad_export(bl_operator_t* op, int dtype, void* const* grads, int num, void* stream);
+
+/* ---- Arnoldi with CGS2 re-orthogonalisation and its adjoint (arnoldi.py) --------------- */
+size_t bl_arnoldi_workspace_bytes(int64_t n, int64_t krylov_depth, int dtype);
+
+/* arnoldi._forward (arnoldi.py:57-101).  second_pass != 0 performs the second
+ * Gram-Schmidt pass (`reortho_ != "none"`, arnoldi.py:91; the reference's default always
+ * does, arnoldi.py:26).  Outputs: Q (K rows, ld), H (K x K), r (n), c (1 element = 1/||v||). */
+int bl_arnoldi_forward(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_depth, int second_pass,
+                       const void* v, void* Q, int64_t ld, void* H, void* r, void* c,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* arnoldi._adjoint (arnoldi.py:104-220).  reortho_full != 0 re-projects lambda
+ * (`reortho == "full"`, arnoldi.py:201-204).  dQ (K rows, ld), dr, dc may be NULL (= zero
+ * cotangent, the SLQ case of SURVEY 3.3).  Lambda is a K x ld scratch basis supplied by the
+ * caller.  Output dv (n); parameter gradients accumulate in `op`. */
+int bl_arnoldi_adjoint(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_depth, int reortho_full,
+                       const void* Q, int64_t ld, const void* H, const void* r, const void* c,
+                       const void* dQ, const void* dH, const void* dr, const void* dc, void* dv,
+                       void* Lambda, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- three-term Lanczos without re-orthogonalisation and its adjoint (lanczos.py:215-335) */
+size_t bl_lanczos3_workspace_bytes(int64_t n, int64_t krylov_depth, int dtype);
+/* xs: K+1 rows (ld); alphas[K]; betas[K] (betas[K-1] is the remainder norm). */
+int bl_lanczos3_forward(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_depth, const void* v,
+                        void* xs, int64_t ld, void* alphas, void* betas, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* dxs: K+1 rows (ld) or NULL; dalphas[K], dbetas[K]; vnorm: 1 element (||v||, device).
+ * Output dv (n); the single parameter's gradient accumulates in `op` (lanczos.py:329). */
+int bl_lanczos3_adjoint(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_depth, const void* xs,
+                        int64_t ld, const void* alphas, const void* betas, const void* dxs,
+                        const void* dalphas, const void* dbetas, const void* vnorm, void* dv,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- small vector helpers used by the host-side wrappers (lanczos.py:162-167, 24-26) ---- */
+/* out[0] = sum_i x_i y_i  (device scalar, dtype) */
+int bl_vec_dot(int dtype, int64_t n, const void* x, const void* y, void* out, void* workspace,
+               size_t workspace_bytes, void* stream);
+/* out = a*x + b*y  (host scalars; y may be NULL when b == 0; out may alias x or y) */
+int bl_vec_axpby(int dtype, int64_t n, double a, const void* x, double b, const void* y, void* out,
+                 void* stream);
+/* rows x cols matrix, transpose copy (reference layout (n,K) <-> basis layout (K,ld)) */
+int bl_transpose(int dtype, int64_t rows, int64_t cols, const void* src, int64_t ld_src, void* dst,
+                 int64_t ld_dst, void* stream);
+/* out[j] = sum_i M[j, i] x[i] for j < nrows (rows of length ld; device output in dtype) */
+int bl_rows_dot(int dtype, int64_t n, int64_t nrows, const void* M, int64_t ld, const void* x,
+                void* out, void* workspace, size_t workspace_bytes, void* stream);
+/* out = sum_j coef_host[j] * M[j, :]  (+ out if accumulate) */
+int bl_rows_combine(int dtype, int64_t n, int64_t nrows, const void* M, int64_t ld,
+                    const double* coef_host, int accumulate, void* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+size_t bl_vec_workspace_bytes(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_LANCZOS_H */

@@ -1,0 +1,126 @@
+"""CPU-side checks: the C-ABI library loads, exports every symbol `include/b200_lanczos.h`
+declares, host logic (errors, index work) behaves like the reference — no compute calls."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from conftest import ROOT
+
+import experiments_lanczos_adjoints_b200 as bl
+from experiments_lanczos_adjoints_b200 import _lib
+from oracle import operators as oracle_ops
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200_lanczos.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bl_[a-z0-9_]+)\s*\(", text)) - {"bl_matvec_cb", "bl_vjp_cb"})
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.library_path())
+    names = header_symbols()
+    assert len(names) >= 50
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in _lib.load().bl_version()
+
+
+def test_workspace_queries_are_pure_host_functions():
+    lib = _lib.load()
+    small = lib.bl_arnoldi_workspace_bytes(1000, 10, _lib.BL_F32)
+    big = lib.bl_arnoldi_workspace_bytes(1_000_000, 100, _lib.BL_F64)
+    assert 0 < small < big < (1 << 31)
+    assert lib.bl_lanczos3_workspace_bytes(1000, 10, _lib.BL_F32) > 0
+    assert lib.bl_vec_workspace_bytes() > 0
+
+
+@pytest.mark.parametrize("reortho_wrong", [True, "full_with_sparsity", "None"])
+def test_hessenberg_raises_type_error_for_wrong_reortho(reortho_wrong):
+    # /root/reference/tests/test_arnoldi/test_hessenberg_forward.py:81-84
+    op = bl.operators.SparseOperator([0], [0], (2, 2))
+    with pytest.raises(TypeError, match="Unexpected input"):
+        bl.arnoldi.hessenberg(op, 1, reortho=reortho_wrong)
+
+
+def test_tridiag_raises_value_error_for_wrong_reortho():
+    # lanczos.py:148-149 raises ValueError for the same mistake
+    op = bl.operators.SparseOperator([0], [0], (2, 2))
+    with pytest.raises(ValueError, match="unsupported"):
+        bl.lanczos.tridiag(op, 1, reortho="partial")
+
+
+def test_plain_callable_is_rejected_loudly():
+    with pytest.raises(TypeError, match="operator object"):
+        bl.arnoldi.hessenberg(lambda s: s, 1, reortho="none")
+
+
+def test_custom_vjp_estimator_raises_outside_vjp():
+    est = bl.hutchinson.hutchinson_custom_vjp(lambda v, p: 0.0, lambda key: np.ones((1, 2)))
+    with pytest.raises(RuntimeError, match="oops"):  # hutchinson.py:24-30
+        est(0, 1.0)
+
+
+@pytest.mark.parametrize("seed,n,nnz", [(0, 1, 1), (1, 33, 200), (2, 1000, 7000), (3, 64, 0), (4, 257, 5000)])
+def test_sparse_index_work_is_bit_exact(seed, n, nnz):
+    """COO -> CSR -> SELL-32 (A and A^T) against oracle/operators.py, including duplicates,
+    empty rows, ragged last slice, nnz = 0."""
+    rng = np.random.default_rng(seed)
+    row = rng.integers(0, n, nnz).astype(np.int32)
+    col = rng.integers(0, n, nnz).astype(np.int32)
+    if nnz > 10:
+        row[5], col[5] = row[2], col[2]  # a duplicate entry
+    op = bl.operators.SparseOperator(row, col, (n, n))
+    row_ptr, col_idx, perm = op.export_csr()
+    r_ptr, c_idx, pm = oracle_ops.coo_to_csr(row, col, n)
+    assert np.array_equal(row_ptr, r_ptr) and np.array_equal(col_idx, c_idx) and np.array_equal(perm, pm)
+    slice_ptr, slot = op.export_sell()
+    s_ptr, s_slot = oracle_ops.csr_to_sell(r_ptr, n)
+    assert np.array_equal(slice_ptr, s_ptr) and np.array_equal(slot, s_slot)
+    slice_ptr_t, slot_t = op.export_sell(transpose=True)
+    rt_ptr, _, _ = oracle_ops.coo_to_csr(col, row, n)
+    st_ptr, st_slot = oracle_ops.csr_to_sell(rt_ptr, n)
+    assert np.array_equal(slice_ptr_t, st_ptr) and np.array_equal(slot_t, st_slot)
+
+
+def test_sparse_create_rejects_out_of_range_indices():
+    with pytest.raises(ValueError, match="out of range"):
+        bl.operators.SparseOperator([0, 5], [0, 1], (3, 3))
+
+
+def test_matrix_market_parameter_order_matches_mmread():
+    """`suite_sparse_load` order: stored lower triangle, then mirrored strict part
+    (/root/reference/src/matfree_extensions/util/exp_util.py:35-42)."""
+    import io
+
+    import scipy.io
+
+    text = "%%MatrixMarket matrix coordinate real symmetric\n3 3 4\n1 1 2.0\n2 1 -1.0\n3 2 -0.5\n3 3 4.0\n"
+    m = scipy.io.mmread(io.StringIO(text))
+    r, c, d = oracle_ops.mm_expand_symmetric([0, 1, 2, 2], [0, 0, 1, 2], [2.0, -1.0, -0.5, 4.0])
+    assert np.array_equal(m.row, r) and np.array_equal(m.col, c) and np.array_equal(m.data, d)
+
+
+def test_quadform_cotangents_match_finite_differences():
+    from experiments_lanczos_adjoints_b200.lanczos import _quadform_and_cotangents
+
+    rng = np.random.default_rng(0)
+    a, b = 2.0 + rng.uniform(size=6), 0.3 * rng.uniform(size=5)
+    val, da, db, _ = _quadform_and_cotangents(np.log, None, a, b, True)
+    eps = 1e-6
+    for i in range(6):
+        e = np.zeros(6)
+        e[i] = eps
+        fd = (_quadform_and_cotangents(np.log, None, a + e, b, False)[0]
+              - _quadform_and_cotangents(np.log, None, a - e, b, False)[0]) / (2 * eps)  # fmt: skip
+        assert abs(fd - da[i]) < 1e-8
+    for i in range(5):
+        e = np.zeros(5)
+        e[i] = eps
+        fd = (_quadform_and_cotangents(np.log, None, a, b + e, False)[0]
+              - _quadform_and_cotangents(np.log, None, a, b - e, False)[0]) / (2 * eps)  # fmt: skip
+        assert abs(fd - db[i]) < 1e-8

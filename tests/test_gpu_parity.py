@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the host layer -> C ABI) against
+ (1) the golden vectors produced by the reference's own sources (tests/golden),
+ (2) the NumPy oracle on seeded inputs at sizes the oracle finishes in seconds,
+ (3) size-independent properties at BASELINE.json's full size (n = 1M, K = 100).
+Tolerances (BASELINE.json north_star): fp32 1e-5 on tridiagonal coefficients / log-dets and
+1e-4 on gradients; fp64 1e-10 on all three; integer index work bit-exact."""
+
+import numpy as np
+import pytest
+from conftest import golden, golden_names, rel_err
+
+import experiments_lanczos_adjoints_b200 as bl
+from oracle import krylov, operators
+
+pytestmark = pytest.mark.gpu
+
+F32_VAL, F32_GRAD, F64 = 1e-5, 1e-4, 1e-10
+
+
+def dt(g):
+    return np.float64 if bool(g["x64"]) else np.float32
+
+
+def tol(g, grad=False):
+    return F64 if bool(g["x64"]) else (F32_GRAD if grad else F32_VAL)
+
+
+def dense_op(g):
+    return bl.operators.DenseOperator(len(g["v"]), sym=str(g["matvec"]) == "sym")
+
+
+@pytest.mark.parametrize("name", golden_names("arnoldi_"))
+def test_arnoldi_matches_reference_golden(name):
+    g = golden(name)
+    d, K, n = dt(g), int(g["K"]), len(g["v"])
+    alg = bl.arnoldi.hessenberg(dense_op(g), K, reortho=str(g["reortho"]), reortho_vjp=str(g["reortho_vjp"]))
+    (Q, H, r, c), pull = bl.vjp(alg, g["v"].astype(d), g["A"].astype(d))
+    assert Q.shape == (n, K) and H.shape == (K, K) and r.shape == (n,) and c.shape == ()
+    Qh, Hh, rh = Q.numpy(), H.numpy(), r.numpy()
+    if "hilbert" in name:
+        # cond ~ 1e13: only the reference's own identities hold (test_hessenberg_forward.py:58-66)
+        A = g["A"] + g["A"].T if str(g["matvec"]) == "sym" else g["A"]
+        small = np.sqrt(np.finfo(d).eps)
+        assert np.allclose(A @ Qh - Qh @ Hh - np.outer(rh, np.eye(K)[-1]), 0.0, atol=small)
+        assert np.allclose(Qh.T @ Qh, np.eye(K), atol=small)
+        assert np.allclose(Qh[:, 0], float(c) * g["v"], atol=small)
+        return
+    for mine, ref in ((Qh, "Q"), (Hh, "H"), (float(c), "c")):
+        assert rel_err(mine, g[ref]) < 2 * tol(g), ref
+    if K < n:
+        assert rel_err(rh, g["r"]) < 2 * tol(g)
+    dv, dp = pull(tuple(g[k].astype(d) for k in ("dQ", "dH", "dr", "dc")))
+    assert rel_err(dv.numpy(), g["dv_adjoint"]) < 2 * tol(g, True)
+    assert rel_err(dp.numpy(), g["dp_adjoint"]) < 2 * tol(g, True)
+
+
+@pytest.mark.parametrize("name", golden_names("tridiag_"))
+def test_tridiag_matches_reference_golden(name):
+    g = golden(name)
+    d, K, n = dt(g), int(g["K"]), len(g["v"])
+    alg = bl.lanczos.tridiag(dense_op(g), K, reortho=str(g["reortho"]))
+    ((Qt, (alpha, beta)), (q_rem, b_rem)), pull = bl.vjp(alg, g["v"].astype(d), g["A"].astype(d))
+    assert Qt.shape == (K, n) and alpha.shape == (K,) and beta.shape == (K - 1,)
+    # 3-term Lanczos without re-orthogonalisation loses orthogonality: rounding-order
+    # differences grow with K (the reference tests it at 1e-1, test_tridiag_forward.py:29-30)
+    loose = 1e3 if (str(g["reortho"]) == "none" and K > 5) else 1.0
+    assert rel_err(alpha, g["alpha"]) < loose * tol(g)
+    assert rel_err(beta, g["beta"]) < loose * tol(g)
+    assert rel_err(Qt.numpy(), g["Qt"]) < loose * 10 * tol(g)
+    if K == n:
+        return
+    assert rel_err(q_rem.numpy(), g["q_rem"]) < loose * 10 * tol(g)
+    assert rel_err(b_rem, g["b_rem"]) < loose * 10 * tol(g)
+    cot = ((g["dQt"], (g["dalpha"], g["dbeta"])), (g["dq_rem"], g["db_rem"]))
+    dv, dp = pull(cot)
+    assert rel_err(dv.numpy(), g["dv_adjoint"]) < loose * 5 * tol(g, True)
+    assert rel_err(dp.numpy(), g["dp_adjoint"]) < loose * 5 * tol(g, True)
+
+
+@pytest.mark.parametrize("name", golden_names("sparse_coo_"))
+def test_sparse_operand_matches_reference_golden(name):
+    g = golden(name)
+    d, K, n = dt(g), int(g["K"]), int(g["n"])
+    op = bl.operators.SparseOperator(g["row"], g["col"], (n, n))
+    # the matvec itself (BCOO @ x sums duplicates)
+    x = g["v"].astype(d)
+    y = op(x, g["data"].astype(d)).numpy()
+    y_ref = operators.CooOperator(g["row"], g["col"], (n, n)).matvec(g["v"], g["data"])
+    assert rel_err(y, y_ref) < tol(g)
+    alg = bl.lanczos.tridiag(op, K, reortho=str(g["reortho"]))
+    ((Qt, (alpha, beta)), _), pull = bl.vjp(alg, x, g["data"].astype(d))
+    assert rel_err(alpha, g["alpha"]) < tol(g) and rel_err(beta, g["beta"]) < tol(g)
+    cot = ((g["dQt"], (g["dalpha"], g["dbeta"])), (g["dq_rem"], g["db_rem"]))
+    dv, dp = pull(cot)
+    assert rel_err(dv.numpy(), g["dv"]) < 5 * tol(g, True)
+    assert rel_err(dp.numpy(), g["dp"]) < 5 * tol(g, True)  # parameter gradient in COO order
+    dv0, dp0 = pull(((None, (g["dalpha"], g["dbeta"])), (None, None)))  # SLQ-style cotangent
+    assert rel_err(dv0.numpy(), g["dv_slqcot"]) < 5 * tol(g, True)
+    assert rel_err(dp0.numpy(), g["dp_slqcot"]) < 5 * tol(g, True)
+
+
+@pytest.mark.parametrize("name", golden_names("slq_"))
+def test_slq_value_and_grad_match_reference_golden(name):
+    g = golden(name)
+    d, K = dt(g), int(g["K"])
+    n = g["probes"].shape[1]
+    op = bl.operators.DenseOperator(n, sym=str(g["matvec"]) == "sym")
+    integrand = bl.lanczos.integrand_spd(np.log, K, op)
+    probes = g["probes"].astype(d)
+    A = g["A"].astype(d)
+    vals = np.array([integrand(p, A) for p in probes])
+    assert rel_err(vals, g["probe_values_adjoint"]) < tol(g)
+    estimate = bl.hutchinson.hutchinson(integrand, lambda key: probes)
+    assert rel_err(estimate(None, A), g["value_adjoint"]) < tol(g)
+    value, grad = bl.value_and_grad(estimate, argnums=1)(None, A)
+    assert rel_err(value, g["value_adjoint"]) < tol(g)
+    assert rel_err(grad.numpy(), g["grad_adjoint"]) < tol(g, True)
+    _, (dv0, _dA) = integrand.value_and_grad(probes[0], A)
+    assert rel_err(dv0.numpy(), g["probe_dv0_adjoint"][0]) < 5 * tol(g, True)
+    reuse = bl.lanczos.integrand_spd_custom_vjp_reuse(np.log, K, op)
+    est_r = bl.hutchinson.hutchinson_nograd(reuse, lambda key: probes)
+    with pytest.warns(UserWarning):
+        value_r, (grad_r,) = est_r.value_and_grad(None, A)
+    assert rel_err(value_r, g["value_reuse"]) < tol(g)
+    assert rel_err(grad_r.numpy(), g["grad_reuse"]) < tol(g, True)
+
+
+@pytest.mark.parametrize("name", golden_names("gp_kernels_"))
+@pytest.mark.parametrize("kind", ["matern32", "matern12", "rbf"])
+def test_gram_operator_matches_reference_golden(name, kind):
+    g = golden(name)
+    d = dt(g)
+    amp = 1000.0 if kind == "matern12" else 5.0  # see tests/test_oracle_golden.py
+    op = bl.operators.GramOperator(g["X"], kind=kind)
+    params = (g["raw_lengthscale"].astype(d), g["raw_outputscale"].astype(d), np.zeros((), d))
+    y = op(g["v"].astype(d), *params).numpy()
+    assert rel_err(y, g[f"{kind}_y"]) < amp * tol(g)
+    op.grad_zero(d)
+    z = op.vjp(bl.asarray(g["v"].astype(d)), bl.asarray(g["lam"].astype(d))).numpy()
+    dls, dos, dnoise = (a.numpy() for a in op.grad_export(d))
+    assert rel_err(z, g[f"{kind}_dv"]) < amp * tol(g)
+    if kind != "matern12":
+        assert rel_err(dls, g[f"{kind}_dls"]) < amp * tol(g, True)
+    assert rel_err(dos, g[f"{kind}_dos"]) < amp * tol(g, True)
+    assert rel_err(dnoise, g["lam"] @ g["v"]) < tol(g, True)
+
+
+def test_wave_operator_and_arnoldi_match_reference_golden():
+    g = golden("pde_wave_g8_k6_f64")
+    grid, K = int(g["g"]), int(g["K"])
+    op = bl.operators.WaveStencilOperator(grid, g["stencil"])
+    y0, lam, scale = g["y0"].ravel(), g["lam"].ravel(), g["scale"]
+    assert rel_err(op(y0, scale).numpy(), g["rhs"].ravel()) < 1e-12
+    op.grad_zero(np.float64)
+    z = op.vjp(bl.asarray(y0), bl.asarray(lam)).numpy()
+    (dscale,) = op.grad_export(np.float64)
+    assert rel_err(z, g["rhs_dx"].ravel()) < 1e-12
+    assert rel_err(dscale.numpy(), g["rhs_dscale"]) < 1e-12
+    # expm action (1/c) Q expm(dt H) e1 and its gradient through the Arnoldi adjoint (pde_util.py:260-266)
+    import scipy.linalg
+
+    alg = bl.arnoldi.hessenberg(op, K, reortho="full")
+    (Q, H, r, c), pull = bl.vjp(alg, y0, scale)
+    Hh, ch, t1, u = H.numpy(), float(c), float(g["t1"]), g["u"].ravel()
+    E = scipy.linalg.expm(t1 * Hh)
+    out = (Q.numpy() @ E[:, 0]) / ch
+    assert rel_err(out, g["expm_out"].ravel()) < 1e-10
+    yv = E[:, 0]
+    dQ = np.outer(u, yv) / ch
+    dy = (Q.numpy().T @ u) / ch
+    dc = -np.dot(u, Q.numpy() @ yv) / ch**2
+    e1 = np.zeros(K)
+    e1[0] = 1.0
+    dH = t1 * scipy.linalg.expm_frechet(t1 * Hh.T, np.outer(dy, e1), compute_expm=False)
+    dy0, dsc = pull((dQ, dH, None, dc))
+    assert rel_err(dy0.numpy(), g["loss_dy0"].ravel()) < 1e-9
+    assert rel_err(dsc.numpy(), g["loss_dscale"]) < 1e-9
+
+
+# ---- seeded random problems against the oracle ---------------------------------------------
+def banded_spd(n, per_row, seed, max_off=2000):
+    """Synthetic SPD operand in `suite_sparse_load` layout: diagonal, strict lower, mirrored."""
+    rng = np.random.default_rng(seed)
+    offs = np.sort(rng.choice(np.arange(1, min(max_off, n - 1) + 1), size=per_row, replace=False))
+    lo_r = np.concatenate([np.arange(o, n) for o in offs])
+    lo_c = np.concatenate([np.arange(0, n - o) for o in offs])
+    vals = -rng.uniform(0.0, 1.0, lo_r.size)
+    row = np.concatenate([np.arange(n), lo_r, lo_c]).astype(np.int32)
+    col = np.concatenate([np.arange(n), lo_c, lo_r]).astype(np.int32)
+    data = np.concatenate([np.full(n, 2.0 * per_row + 2.0), vals, vals])
+    return row, col, data
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,K", [(20000, 30), (4099, 17), (1, 1), (5, 5)])
+def test_sparse_tridiag_and_adjoint_match_oracle(dtype, n, K):
+    """Ragged sizes (n not a multiple of the vector width / slice height), n = 1, K = n."""
+    rng = np.random.default_rng(n + K)
+    if n >= 100:
+        row, col, data = banded_spd(n, 4, seed=n)
+    else:
+        row = np.arange(n, dtype=np.int32)
+        col = row.copy()
+        data = 1.0 + np.arange(n, dtype=np.float64)
+    v = rng.standard_normal(n) + 2.0
+    op = bl.operators.SparseOperator(row, col, (n, n))
+    alg = bl.lanczos.tridiag(op, K, reortho="full")
+    ((Qt, (alpha, beta)), (q_rem, b_rem)), pull = bl.vjp(alg, v.astype(dtype), data.astype(dtype))
+    ref = krylov.tridiag(operators.CsrFastOperator(row, col, (n, n)), K, reortho="full")
+    ((Qt_r, (alpha_r, beta_r)), (q_r, b_r)), pull_r = ref.vjp(v, data)
+    t_val, t_grad = (F64, F64) if dtype == np.float64 else (F32_VAL, F32_GRAD)
+    assert rel_err(alpha, alpha_r) < t_val
+    if K > 1:
+        assert rel_err(beta, beta_r) < t_val
+    if K == n:
+        return
+    dalpha, dbeta = rng.standard_normal(K), rng.standard_normal(K - 1)
+    dv, dp = pull(((None, (dalpha, dbeta)), (None, None)))
+    z = np.zeros_like
+    dv_r, dp_r = pull_r(((z(Qt_r), (dalpha, dbeta)), (z(q_r), z(b_r))))
+    assert rel_err(dv.numpy(), dv_r) < 10 * t_grad
+    assert rel_err(dp.numpy(), dp_r) < 10 * t_grad
+    # dense cotangent on every output (the published benchmark recipe, benchmark.py:95-96)
+    cot = ((rng.standard_normal((K, n)), (dalpha, dbeta)), (rng.standard_normal(n), rng.standard_normal()))
+    dv, dp = pull(cot)
+    dv_r, dp_r = pull_r(cot)
+    assert rel_err(dv.numpy(), dv_r) < 10 * t_grad
+    assert rel_err(dp.numpy(), dp_r) < 10 * t_grad
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lanczos3_matches_oracle(dtype):
+    n, K = 3001, 12
+    row, col, data = banded_spd(n, 3, seed=5)
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(n)
+    op = bl.operators.SparseOperator(row, col, (n, n))
+    alg = bl.lanczos.tridiag(op, K, reortho="none")
+    ((xs, (a, b)), (x_last, b_last)), pull = bl.vjp(alg, v.astype(dtype), data.astype(dtype))
+    ref = krylov.tridiag(operators.CsrFastOperator(row, col, (n, n)), K, reortho="none")
+    ((xs_r, (a_r, b_r)), (xl_r, bl_r)), pull_r = ref.vjp(v, data)
+    t_val, t_grad = (1e-9, 1e-8) if dtype == np.float64 else (5e-5, 5e-4)
+    assert rel_err(a, a_r) < t_val and rel_err(b, b_r) < t_val and rel_err(b_last, bl_r) < t_val
+    assert rel_err(xs.numpy(), xs_r) < 10 * t_val
+    cot = ((rng.standard_normal((K, n)), (rng.standard_normal(K), rng.standard_normal(K - 1))),
+           (rng.standard_normal(n), rng.standard_normal()))  # fmt: skip
+    dv, dp = pull(cot)
+    dv_r, dp_r = pull_r(cot)
+    assert rel_err(dv.numpy(), dv_r) < t_grad and rel_err(dp.numpy(), dp_r) < t_grad
+
+
+def test_callback_operator_runs_user_matvec():
+    """An arbitrary user matvec written against DeviceArrays (the reference's `matvec` callable)."""
+    n, K = 500, 6
+    row, col, data = banded_spd(n, 2, seed=9, max_off=50)
+    inner = bl.operators.SparseOperator(row, col, (n, n))
+    inner.bind((data,), np.float64)
+
+    def matvec(x):
+        return inner.matvec(x)
+
+    op = bl.operators.CallbackOperator(n, matvec)
+    v = np.random.default_rng(0).standard_normal(n)
+    Q, H, r, c = bl.arnoldi.hessenberg(op, K, reortho="full")(v)
+    Q2, H2, r2, c2 = bl.arnoldi.hessenberg(inner, K, reortho="full")(v, data)
+    assert rel_err(H.numpy(), H2.numpy()) < 1e-14 and rel_err(r.numpy(), r2.numpy()) < 1e-14
+
+    def bad(x):
+        raise KeyError("boom")
+
+    with pytest.raises(KeyError, match="boom"):
+        bl.arnoldi.hessenberg(bl.operators.CallbackOperator(n, bad), K, reortho="full")(v)
+
+
+def test_depth_errors_match_reference():
+    # /root/reference/tests/test_arnoldi/test_hessenberg_forward.py:69-78
+    op = bl.operators.DenseOperator(2)
+    for depth in (0, 3):
+        with pytest.raises(ValueError, match="depth"):
+            bl.arnoldi.hessenberg(op, depth, reortho="none")(np.ones(2), np.eye(2))
+
+
+# ---- BASELINE.json full size: properties that need no oracle run ----------------------------
+@pytest.mark.parametrize("dtype", [np.float32])
+def test_full_size_properties(dtype):
+    """n = 1M, ~10 nnz/row, K = 100 (BASELINE config 2): Arnoldi identities, orthogonality and
+    linearity of the adjoint in its cotangent, checked with device reductions."""
+    n, K = 1_000_000, 100
+    row, col, data = banded_spd(n, 5, seed=0)  # 1 + 2*5 = 11 entries per row
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(n).astype(dtype)
+    op = bl.operators.SparseOperator(row, col, (n, n))
+    alg = bl.lanczos.tridiag(op, K, reortho="full")
+    ((Qt, (alpha, beta)), (q_rem, b_rem)), pull = bl.vjp(alg, v, data.astype(dtype))
+    Qh = Qt.numpy()  # (K, n) host copy, 400 MB
+    gram = Qh[:, ::7].astype(np.float64) @ Qh[:, ::7].T.astype(np.float64)  # sampled rows only for speed
+    full = Qh.astype(np.float64) @ Qh.T.astype(np.float64)
+    assert np.abs(full - np.eye(K)).max() < 5e-5, np.abs(full - np.eye(K)).max()
+    del gram
+    # A Q^T = Q^T T + e_K (q b)^T on a few columns (test_tridiag_forward.py:56-58)
+    A = operators.CsrFastOperator(row, col, (n, n))
+    T = np.diag(alpha) + np.diag(beta, 1) + np.diag(beta, -1)
+    for j in (0, K // 2, K - 1):
+        lhs = A.matvec(Qh[j].astype(np.float64), data)
+        rhs = T[j] @ Qh
+        if j == K - 1:
+            rhs = rhs + q_rem.numpy() * b_rem
+        assert rel_err(lhs, rhs) < 5e-5
+    assert np.all(beta > 0.1)  # no breakdown on this operand
+    # linearity of the adjoint in the cotangent
+    c1 = (rng.standard_normal(K), rng.standard_normal(K - 1))
+    c2 = (rng.standard_normal(K), rng.standard_normal(K - 1))
+    dv1, dp1 = pull(((None, c1), (None, None)))
+    dv2, dp2 = pull(((None, c2), (None, None)))
+    dv3, dp3 = pull(((None, (c1[0] + 2 * c2[0], c1[1] + 2 * c2[1])), (None, None)))
+    assert rel_err(dv3.numpy(), dv1.numpy() + 2 * dv2.numpy()) < 1e-4
+    assert rel_err(dp3.numpy(), dp1.numpy() + 2 * dp2.numpy()) < 1e-4
