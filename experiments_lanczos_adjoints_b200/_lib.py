@@ -47,6 +47,8 @@ SIGNATURES = {
     "bl_event_sync": (_i32, [_vp]),
     "bl_event_elapsed_ms": (_i32, [_vp, _vp, C.POINTER(C.c_float)]),
     "bl_launch_count": (_i32, [C.POINTER(C.c_uint64)]),
+    "bl_profile_begin": (_i32, []),
+    "bl_profile_end": (_i32, [C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bl_op_sparse_create": (_i32, [_i64, _i64, _i64, _vp, _vp, _pvp]),
     "bl_op_sparse_export_csr": (_i32, [_vp, _vp, _vp, _vp]),
     "bl_op_sparse_export_sell": (_i32, [_vp, _i32, _vp, _vp]),

@@ -53,6 +53,21 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();
 
+// Optional per-launch event bracket (bl_profile_begin/end).  No-ops unless profiling is on.
+bool prof_enabled();
+void prof_start(int cls, double bytes, cudaStream_t s);
+void prof_stop(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s;
+  bool on;
+  ProfScope(int cls, double bytes, cudaStream_t stream) : s(stream), on(prof_enabled()) {
+    if (on) prof_start(cls, bytes, s);
+  }
+  ~ProfScope() {
+    if (on) prof_stop(s);
+  }
+};
+
 // ---- device-side helpers ----------------------------------------------------------------
 template <typename T>
 struct Vec;  // 16-byte vector of T

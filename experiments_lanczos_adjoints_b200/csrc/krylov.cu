@@ -84,6 +84,7 @@ template <typename T>
 int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_t n, Epi epi, cudaStream_t s) {
   epi.red = c.red;
   epi.scal = c.scal;
+  ProfScope prof(BL_PROF_DOTS, (double)(blk.nrows + 1) * n * sizeof(T), s);
   k_dots<T><<<g.dots, kDotsThreads, 0, s>>>(blk, x, n, c.partials_dots, c.counters + 0, epi);
   BL_LAUNCHED();
   return BL_OK;
@@ -96,6 +97,8 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
   a.epi.red = c.red;
   a.epi.scal = c.scal;
   const size_t smem = (size_t)(a.blk[0].nrows + a.blk[1].nrows + 1) * sizeof(T);
+  ProfScope prof(BL_PROF_COMBINE,
+                 (double)(a.blk[0].nrows + a.blk[1].nrows + a.nvec + 1 + (a.out2 ? 1 : 0)) * a.n * sizeof(T), s);
   if (norm)
     k_combine<T, true><<<g.combine, kCombineThreads, smem, s>>>(a);
   else
@@ -107,6 +110,7 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
 template <typename T>
 int launch_scale_copy(int64_t n, const T* x, double mul, const double* div_ptr, T* out, int64_t n_pad, cudaStream_t s) {
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(16 * sm_count(), (n_pad + 255) / 256));
+  ProfScope prof(BL_PROF_OTHER, 2.0 * n * sizeof(T), s);
   k_scale_copy<T><<<blocks, 256, 0, s>>>(n, x, mul, div_ptr, out, n_pad);
   BL_LAUNCHED();
   return BL_OK;
@@ -171,7 +175,10 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool secon
     // v /= length; Q[:, i] = v                                                 arnoldi.py:80-81
     BL_CHECK(launch_scale_copy<T>(n, r, 1.0, c.scal + S_LEN, qi, ld, s));
     // v = matvec(v, *params)                                                   arnoldi.py:84
-    BL_CHECK(op->matvec(dtype, qi, r, s));
+    {
+      ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype), s);
+      BL_CHECK(op->matvec(dtype, qi, r, s));
+    }
     const int m = i + 1;
     {  // h = Q^H v (active columns only)                                       arnoldi.py:87
       Epi e;
@@ -310,7 +317,10 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
       BL_CHECK(launch_scale_copy<T>(n, lam, 1.0, nullptr, Lrow, n, s));
     }
     // (A^T lambda, dparams += ...) = vjp of matvec at (q_idx, params)            arnoldi.py:207-209
-    BL_CHECK(op->vjp(dtype, Q + (int64_t)idx * ld, Lrow, z, s));
+    {
+      ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
+      BL_CHECK(op->vjp(dtype, Q + (int64_t)idx * ld, Lrow, z, s));
+    }
     {  // Gamma[idx, :] and the coefficients of the back-substitution             arnoldi.py:212-218
       Epi e;
       e.mode = EPI_ADJ_GAMMA;

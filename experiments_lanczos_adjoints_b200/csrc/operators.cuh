@@ -15,6 +15,9 @@ struct bl_operator {
   virtual int vjp(int dtype, const void* q, const void* lam, void* z, cudaStream_t s) = 0;
   virtual int grad_zero(int dtype, cudaStream_t s) = 0;
   virtual int grad_export(int dtype, void* const* grads, int num, cudaStream_t s) = 0;
+  // ALGORITHMIC bytes of one matvec / one vjp (roofline report); default: vectors only
+  virtual double matvec_bytes(int dtype) const { return 2.0 * n * (dtype == BL_F32 ? 4 : 8); }
+  virtual double vjp_bytes(int dtype) const { return 3.0 * n * (dtype == BL_F32 ? 4 : 8); }
 };
 
 namespace bl {

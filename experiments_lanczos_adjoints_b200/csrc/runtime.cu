@@ -1,5 +1,6 @@
 // Device runtime wrappers of the C ABI (memory, streams, events) and error plumbing.
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -9,6 +10,40 @@ static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
 
 void set_error(const std::string& msg) { t_error = msg; }
+
+namespace {
+struct ProfRecord {
+  int cls;
+  double bytes;
+  cudaEvent_t a, b;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+bool prof_enabled() { return g_prof_on; }
+void prof_start(int cls, double bytes, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRecord r{cls, bytes, prof_event(), prof_event()};
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void prof_stop(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, s);
+}
 
 int sm_count() {
   static int cached = 0;
@@ -134,6 +169,35 @@ int bl_event_sync(void* event) {
 int bl_event_elapsed_ms(void* start, void* stop, float* ms) {
   BL_REQUIRE(ms != nullptr, "ms is NULL");
   BL_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+  return BL_OK;
+}
+int bl_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(bl::g_prof_mu);
+  for (auto& r : bl::g_prof) {
+    bl::g_prof_pool.push_back(r.a);
+    bl::g_prof_pool.push_back(r.b);
+  }
+  bl::g_prof.clear();
+  bl::g_prof_on = true;
+  return BL_OK;
+}
+int bl_profile_end(uint64_t* counts, double* ms, double* bytes) {
+  BL_REQUIRE(counts && ms && bytes, "NULL argument");
+  BL_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(bl::g_prof_mu);
+  bl::g_prof_on = false;
+  for (int c = 0; c < BL_PROF_NCLASS; ++c) counts[c] = 0, ms[c] = 0.0, bytes[c] = 0.0;
+  for (auto& r : bl::g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      counts[r.cls] += 1;
+      ms[r.cls] += t;
+      bytes[r.cls] += r.bytes;
+    }
+    bl::g_prof_pool.push_back(r.a);
+    bl::g_prof_pool.push_back(r.b);
+  }
+  bl::g_prof.clear();
   return BL_OK;
 }
 int bl_launch_count(uint64_t* count) {

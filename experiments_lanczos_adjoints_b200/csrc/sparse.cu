@@ -213,6 +213,15 @@ struct SparseOperator : bl_operator {
 
   int num_params() const override { return 1; }
   int64_t param_size(int) const override { return nnz; }
+  // operator nnz(w+4)+4(n+1) (+ x, y); with cotangent nnz(3w+4)+4(n+1) (+ q, lam, z)
+  double matvec_bytes(int dtype) const override {
+    const double w = dtype == BL_F32 ? 4 : 8;
+    return nnz * (w + 4) + 4.0 * (n_rows + 1) + 2.0 * n_rows * w;
+  }
+  double vjp_bytes(int dtype) const override {
+    const double w = dtype == BL_F32 ? 4 : 8;
+    return nnz * (3 * w + 4) + 4.0 * (n_rows + 1) + 3.0 * n_rows * w;
+  }
 
   int build(const int32_t* row, const int32_t* col) {
     csr = coo_to_csr(n_rows, nnz, row, col);

@@ -55,7 +55,8 @@ class Operator:
         if len(params) != len(shapes):
             raise TypeError(f"operator takes {len(shapes)} parameter array(s), got {len(params)}")
         arrays = []
-        for p, (numel,) in zip(params, shapes):
+        for p, shape in zip(params, shapes):
+            numel = int(np.prod(shape, dtype=np.int64))
             a = dev.asarray(p, dtype=dtype)
             if a.size != numel:
                 raise ValueError(f"parameter has {a.size} elements, expected {numel}")

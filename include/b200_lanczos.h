@@ -71,6 +71,16 @@ int bl_event_elapsed_ms(void* start, void* stop, float* ms);
 /* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
 int bl_launch_count(uint64_t* count);
 
+/* Per-kernel-class device timing for the roofline report.  Between begin and end every
+ * streaming launch of the Krylov loops is bracketed by CUDA events on its own stream; end
+ * synchronises and returns, per class, the launch count, the summed event time (ms) and the
+ * summed ALGORITHMIC bytes (rows*n*w for basis rows, n*w per dense vector read or written,
+ * nnz*(w+4)+4(n+1) for the sparse operand).  Classes: */
+enum { BL_PROF_DOTS = 0, BL_PROF_COMBINE = 1, BL_PROF_MATVEC = 2, BL_PROF_VJP = 3, BL_PROF_OTHER = 4,
+       BL_PROF_NCLASS = 5 };
+int bl_profile_begin(void);
+int bl_profile_end(uint64_t* counts, double* ms, double* bytes); /* arrays of BL_PROF_NCLASS */
+
 /* ---- operators: the `matvec(v, *params)` callback of the reference ------------------
  * An operator owns its index structures and a gradient accumulator for its parameters.
  *   set_params : bind parameter values (device pointers, reference order)
