@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Lanczos (full re-orthogonalisation) forward + adjoint.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): sparse SPD operator, n = 1M rows, 11 entries per row
+(COO layout of `suite_sparse_load`), Krylov depth 100, fp32, cotangents on the tridiagonal
+coefficients (the SLQ case).  One bench "step" = one forward + one adjoint sweep = 100 Krylov
+steps; the metric is Krylov steps per second, `depth / (t_fwd + t_adj)`.
+
+N > 1 (launched by torchrun, one rank per GPU): every rank runs the forward + adjoint of its
+own probe vector on a replicated operator (probe sharding) and the step ends with a
+single NCCL all-reduce of the parameter cotangent; weak scaling.
+
+`--impl reference`: the reference's algorithm on the host CPUs (the NumPy/SciPy oracle port —
+JAX is not installed in this image, so the reference itself cannot run), bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS = int(os.environ.get("BL_BENCH_N", 1_000_000))
+DEPTH = int(os.environ.get("BL_BENCH_DEPTH", 100))
+BANDS = 5
+METRIC = "Lanczos fwd+adjoint steps/sec at n=1M, K=100; achieved HBM GB/s vs peak"
+UNIT = "krylov_steps/s"
+
+
+def algorithmic_bytes(n, nnz, K, w):
+    """compulsory traffic with the best legal fusion, active columns only."""
+    fwd = 3 * n * w * K * (K + 1) / 2 + K * (nnz * (w + 4) + 4 * (n + 1)) + 8 * K * n * w
+    adj = 3 * n * w * K * (K + 1) + K * (nnz * (3 * w + 4) + 4 * (n + 1)) + 10 * K * n * w
+    return fwd, adj
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _sample(self):
+        nv = self._nvml
+        if nv is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+            names = {
+                "hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+            }
+            for name, bit in names.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self._sample()
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "source": "unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml"}  # fmt: skip
+
+
+def build_workload(seed=0):
+    from experiments_lanczos_adjoints_b200 import synthetic
+
+    row, col, data = synthetic.banded_spd_coo(N_ROWS, bands=BANDS, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    dalpha, dbeta = rng.standard_normal(DEPTH), rng.standard_normal(DEPTH - 1)
+    return row, col, data, dalpha, dbeta
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(row, col, data, dalpha, dbeta, depth, dtype, seed=0):
+    """One forward + adjoint of the reference's algorithm (oracle port) on the host CPUs."""
+    from oracle import krylov, operators
+
+    n = N_ROWS
+    op = operators.CsrFastOperator(row, col, (n, n))
+    v = np.random.default_rng(seed + 7).standard_normal(n).astype(dtype)
+    alg = krylov.tridiag(op, depth, reortho="full")
+    t0 = time.perf_counter()
+    ((Qt, _), (q_rem, b_rem)), pull = alg.vjp(v, data.astype(dtype))
+    pull(((np.zeros_like(Qt), (dalpha[:depth].astype(dtype), dbeta[: depth - 1].astype(dtype))),
+          (np.zeros_like(q_rem), np.zeros((), dtype))))  # fmt: skip
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(row, col, data, dalpha, dbeta, sample_depth=16):
+    cores = os.cpu_count() or 1
+    t = cpu_reference_run(row, col, data, dalpha, dbeta, sample_depth, np.float32)
+    return {
+        "value": sample_depth / t, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"n={N_ROWS}, nnz={len(data)}, fp32, one forward+adjoint at Krylov depth {sample_depth} "
+                  f"({t:.1f} s; cost per Krylov step grows with depth, so depth {DEPTH} is slower per step); "
+                  "NumPy/SciPy oracle port, BLAS threads = all cores (JAX not installed: the reference "
+                  "itself cannot run)",
+    }  # fmt: skip
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    row, col, data, dalpha, dbeta = build_workload()
+    depth = int(os.environ.get("BL_REF_DEPTH", 12))
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_run(row, col, data, dalpha, dbeta, depth, np.float32)
+    times = [cpu_reference_run(row, col, data, dalpha, dbeta, depth, np.float32) for _ in range(max(1, args.steps))]
+    t = float(np.mean(times))
+    value = depth / t
+    cores = os.cpu_count() or 1
+    sample = (f"each step = one forward+adjoint at Krylov depth {depth} (bounded sample of depth {DEPTH}) on "
+              f"n={N_ROWS}, nnz={len(data)}, fp32; NumPy/SciPy oracle port of the reference algorithm "
+              "(JAX is not installed, the reference itself cannot be imported)")  # fmt: skip
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"sparse SPD COO n={N_ROWS} nnz={len(data)} depth={DEPTH} fwd+adjoint"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))  # fmt: skip
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-timed steps only (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import experiments_lanczos_adjoints_b200 as bl
+    from experiments_lanczos_adjoints_b200 import plan as bl_plan
+    from experiments_lanczos_adjoints_b200 import synthetic
+
+    bl.set_device(local_rank)
+    dtype = np.float32 if args.dtype == "f32" else np.float64
+    w = np.dtype(dtype).itemsize
+    row, col, data, dalpha, dbeta = build_workload()
+    nnz = len(data)
+    op = bl.operators.SparseOperator(row, col, (N_ROWS, N_ROWS))
+    plan = bl_plan.TridiagAdjointPlan(op, DEPTH, dtype)
+    stream = plan.stream
+
+    # pinned host buffers for the end-to-end path; one probe vector per rank
+    v_host = bl_plan.pinned_empty((N_ROWS,), dtype)
+    v_host[:] = np.random.default_rng(100 + rank).standard_normal(N_ROWS)
+    p_host = bl_plan.pinned_empty((nnz,), dtype)
+    p_host[:] = data
+    dH_host = bl_plan.pinned_empty((DEPTH, DEPTH), dtype)
+    dH_host[:] = synthetic.slq_cotangent_dH(dalpha, dbeta, dtype)
+    out_H = bl_plan.pinned_empty((DEPTH, DEPTH), dtype)
+    out_dv = bl_plan.pinned_empty((N_ROWS,), dtype)
+    out_g = [bl_plan.pinned_empty((nnz,), dtype)]
+
+    plan.set_vector(v_host)
+    plan.set_params(p_host)
+    plan.set_cotangent(dH_host)
+    grad_t = None
+    if dist is not None:
+        import torch
+
+        grad_t = torch.as_tensor(plan.grads[0], device=f"cuda:{local_rank}")
+
+    def step_device():
+        plan.run()
+        if dist is not None:  # probe sharding: one all-reduce of the parameter cotangent per step
+            stream.synchronize()
+            dist.all_reduce(grad_t)
+
+    def barrier():
+        if dist is not None:
+            import torch
+
+            torch.cuda.synchronize()
+            dist.barrier()
+        bl.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = bl.Event(), bl.Event()
+        launches0 = bl.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        if dist is not None:
+            import torch
+
+            torch.cuda.synchronize()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_ms(e1)
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, bl.launch_count() - launches0
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total, launches = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    ms_per_step = ms_total / args.steps
+    value = world * DEPTH / (ms_per_step * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_per_step, "gpu_launches": launches, "quick": True}))
+        return
+    # end-to-end through the host-buffer entry point: H2D (v, params, dH) + fwd + adjoint + D2H
+    io = {}
+
+    def step_host():
+        io["h2d"], io["d2h"] = plan.run_host(v_host, [p_host], dH_host, out_H, out_dv, out_g)
+        if dist is not None:
+            dist.all_reduce(grad_t)
+
+    for _ in range(2):
+        step_host()
+    e2e_steps = max(2, args.steps // 2)
+    ms_e2e, _ = timed(step_host, e2e_steps)
+    e2e_value = world * DEPTH / (ms_e2e / e2e_steps * 1e-3)
+
+    # per-kernel-class timing of one more step (events around every launch)
+    prof = bl_plan.profile(plan.run)
+    peak, peak_src = measured_peaks()
+    fwd_b, adj_b = algorithmic_bytes(N_ROWS, nnz, DEPTH, w)
+    step_gbs = (fwd_b + adj_b) / (ms_per_step * 1e-3) / 1e9
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    dom_gbs = d["algorithmic_bytes"] / max(d["ms"], 1e-9) / 1e6
+    prof_total = sum(c["ms"] for c in prof.values())
+    roofline = {
+        "bound": "hbm", "kernel": {"dots": "k_dots", "combine": "k_combine", "matvec": "k_sell_spmv", "vjp": "k_sell_vjp",
+                                   "other": "k_scale_copy"}[dom],
+        "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "peak_source": peak_src,
+        "traffic": None, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / max(1, d["launches"]),
+        "share_of_step": d["ms"] / max(prof_total, 1e-9),
+        "whole_step": {"algorithmic_gb": (fwd_b + adj_b) / 1e9, "achieved": step_gbs, "frac": step_gbs / peak},
+        "classes": {k: {"launches": c["launches"], "ms": round(c["ms"], 4),
+                        "gbs": c["algorithmic_bytes"] / max(c["ms"], 1e-9) / 1e6} for k, c in prof.items()},
+    }  # fmt: skip
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"sparse SPD COO operator n={N_ROWS} nnz={nnz} ({2 * BANDS + 1}/row), Lanczos full "
+                            f"reortho depth {DEPTH}, forward + adjoint (cotangents on alpha/beta)",
+                "per_gpu": "one probe vector per GPU per step; parameter cotangent all-reduced once per step",
+                "l2": f"inputs larger than L2 (basis Q {DEPTH * N_ROWS * w / 1e6:.0f} MB + adjoint basis, 126 MB L2)",
+            },
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
+                    "ms_per_step": ms_e2e / e2e_steps},
+            "roofline": roofline,
+        }  # fmt: skip
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(row, col, data, dalpha, dbeta)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

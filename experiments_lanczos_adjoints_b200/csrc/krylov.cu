@@ -4,7 +4,10 @@
 //   bl_lanczos3_*       <- lanczos._forward / _adjoint        (lanczos.py:215-335)
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "krylov_kernels.cuh"
+#include "stream_kernels.cuh"
 #include "operators.cuh"
 
 namespace bl {
@@ -80,12 +83,62 @@ void carve_common(Workspace& w, int64_t K, Common& c) {
   c.partials_comb = static_cast<double*>(w.take((size_t)kMaxCombineGrid * 8));
 }
 
+// BL_STREAM=0 forces the register-staged (LDG) kernels; default: TMA-staged kernels for n >= 8192.
+int stream_mode() {
+  static int mode = [] {
+    const char* e = std::getenv("BL_STREAM");
+    return e ? std::atoi(e) : 1;
+  }();
+  return mode;
+}
+bool use_tma(int64_t n) { return stream_mode() != 0 && n >= 8192; }
+
+template <typename T>
+constexpr int dots_tile() { return 4096 / (int)sizeof(T); }  // 4 KB row segments
+
+template <typename T>
+int tma_grid(int64_t n, int tile) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(2 * sm_count(), kMaxDotsGrid), (n + tile - 1) / tile));
+}
+
+template <typename F>
+int set_smem(F* kernel, size_t bytes) {
+  BL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return BL_OK;
+}
+
+RowSource row_source(const RowBlock& b0, const RowBlock* b1, size_t w) {
+  RowSource r;
+  r.base0 = static_cast<const char*>(b0.base) + (long long)b0.row0 * b0.ld * (long long)w;
+  r.ldb0 = b0.ld * (long long)w;
+  r.n0 = b0.nrows;
+  if (b1 && b1->nrows > 0) {
+    r.base1 = static_cast<const char*>(b1->base) + (long long)b1->row0 * b1->ld * (long long)w;
+    r.ldb1 = b1->ld * (long long)w;
+    r.n1 = b1->nrows;
+  }
+  return r;
+}
+
 template <typename T>
 int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_t n, Epi epi, cudaStream_t s) {
   epi.red = c.red;
   epi.scal = c.scal;
   ProfScope prof(BL_PROF_DOTS, (double)(blk.nrows + 1) * n * sizeof(T), s);
-  k_dots<T><<<g.dots, kDotsThreads, 0, s>>>(blk, x, n, c.partials_dots, c.counters + 0, epi);
+  if (use_tma(n)) {
+    constexpr int TILE = dots_tile<T>();
+    const size_t smem = (size_t)kStages * kGroup * TILE * sizeof(T) + 2 * kStages * 8 + (size_t)blk.nrows * 8 + 16;
+    static bool once = false;
+    if (!once) {
+      BL_CHECK(set_smem(k_dots_tma<T, TILE>, 100 * 1024));
+      once = true;
+    }
+    BL_REQUIRE(smem <= 100 * 1024, "too many rows for k_dots_tma");
+    k_dots_tma<T, TILE><<<tma_grid<T>(n, TILE), kStreamThreads, smem, s>>>(
+        row_source(blk, nullptr, sizeof(T)), blk.nrows, x, n, c.partials_dots, c.counters + 0, epi);
+  } else {
+    k_dots<T><<<g.dots, kDotsThreads, 0, s>>>(blk, x, n, c.partials_dots, c.counters + 0, epi);
+  }
   BL_LAUNCHED();
   return BL_OK;
 }
@@ -96,14 +149,94 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
   a.counter = c.counters + 1;
   a.epi.red = c.red;
   a.epi.scal = c.scal;
-  const size_t smem = (size_t)(a.blk[0].nrows + a.blk[1].nrows + 1) * sizeof(T);
-  ProfScope prof(BL_PROF_COMBINE,
-                 (double)(a.blk[0].nrows + a.blk[1].nrows + a.nvec + 1 + (a.out2 ? 1 : 0)) * a.n * sizeof(T), s);
-  if (norm)
-    k_combine<T, true><<<g.combine, kCombineThreads, smem, s>>>(a);
-  else
-    k_combine<T, false><<<g.combine, kCombineThreads, smem, s>>>(a);
+  const int nrows = a.blk[0].nrows + a.blk[1].nrows;
+  ProfScope prof(BL_PROF_COMBINE, (double)(nrows + a.nvec + 1 + (a.out2 ? 1 : 0)) * a.n * sizeof(T), s);
+  if (use_tma(a.n) && nrows >= 4) {
+    constexpr int TILE = kConsumerThreads * Vec<T>::N;
+    CombineTmaArgs t;
+    t.n = a.n;
+    t.out = a.out;
+    t.out2 = a.out2;
+    t.nvec = a.nvec;
+    for (int k = 0; k < a.nvec; ++k) t.vec[k] = a.vec[k];
+    t.src = row_source(a.blk[0], &a.blk[1], sizeof(T));
+    t.coef0 = a.blk[0].coef ? a.blk[0].coef + a.blk[0].coef0 : nullptr;
+    t.sign0 = a.blk[0].sign;
+    t.coef1 = a.blk[1].coef ? a.blk[1].coef + a.blk[1].coef0 : nullptr;
+    t.sign1 = a.blk[1].sign;
+    t.out_div_ptr = a.out_div_ptr;
+    t.out_mul_ptr = a.out_mul_ptr;
+    t.partials = a.partials;
+    t.counter = a.counter;
+    t.epi = a.epi;
+    const size_t smem = (size_t)kStages * kGroup * TILE * sizeof(T) + 2 * kStages * 8 + (size_t)nrows * sizeof(T) + 16;
+    static bool once = false;
+    if (!once) {
+      BL_CHECK(set_smem(k_combine_tma<T, true>, 100 * 1024));
+      BL_CHECK(set_smem(k_combine_tma<T, false>, 100 * 1024));
+      once = true;
+    }
+    BL_REQUIRE(smem <= 100 * 1024, "too many rows for k_combine_tma");
+    const int grid = tma_grid<T>(a.n, TILE);
+    if (norm)
+      k_combine_tma<T, true><<<grid, kStreamThreads, smem, s>>>(t);
+    else
+      k_combine_tma<T, false><<<grid, kStreamThreads, smem, s>>>(t);
+  } else {
+    const size_t smem = (size_t)(nrows + 1) * sizeof(T);
+    if (norm)
+      k_combine<T, true><<<g.combine, kCombineThreads, smem, s>>>(a);
+    else
+      k_combine<T, false><<<g.combine, kCombineThreads, smem, s>>>(a);
+  }
   BL_LAUNCHED();
+  return BL_OK;
+}
+
+// Fused "x' = x + sign * sum_j coef_j row_j ; red[j] = <row_j, x'>" (second Gram-Schmidt pass).
+// Returns false if the tile does not fit shared memory (caller falls back to combine + dots).
+template <typename T, int EPT>
+int launch_project_ept(const Common& c, const RowBlock& blk, const T* x, T* out, int64_t n, Epi epi, cudaStream_t s) {
+  constexpr int TILE = kConsumerThreads * EPT;
+  const int ngroups = (blk.nrows + kGroup - 1) / kGroup;
+  const size_t smem = (((size_t)ngroups * kGroup * (TILE + 1) + TILE) * sizeof(T) + 15) / 16 * 16 +
+                      (size_t)(ngroups + 1) * 8 + (size_t)blk.nrows * 8 + 16;
+  static bool once = false;
+  if (!once) {
+    BL_CHECK(set_smem(k_project_tma<T, EPT>, 225 * 1024));
+    once = true;
+  }
+  epi.red = c.red;
+  epi.scal = c.scal;
+  ProfScope prof(BL_PROF_COMBINE, (double)(blk.nrows + 2) * n * sizeof(T), s);
+  k_project_tma<T, EPT><<<tma_grid<T>(n, TILE), kStreamThreads, smem, s>>>(
+      row_source(blk, nullptr, sizeof(T)), blk.nrows, x, out, n, blk.coef + blk.coef0, blk.sign, c.partials_dots,
+      c.counters + 0, epi);
+  BL_LAUNCHED();
+  return BL_OK;
+}
+
+template <typename T>
+bool project_fits(int nrows, int ept, size_t budget) {
+  const size_t tile = (size_t)kConsumerThreads * ept;
+  const size_t rows_pad = (size_t)(nrows + kGroup - 1) / kGroup * kGroup;
+  return (rows_pad * (tile + 1) + tile) * sizeof(T) + rows_pad + nrows * 8 + 64 <= budget;
+}
+
+// fused = 1 on return if the fused kernel ran
+template <typename T>
+int launch_project(const Common& c, const RowBlock& blk, const T* x, T* out, int64_t n, Epi epi, cudaStream_t s,
+                   bool* fused) {
+  *fused = false;
+  if (!use_tma(n) || stream_mode() == 2) return BL_OK;
+  constexpr size_t two_per_sm = 110 * 1024, one_per_sm = 222 * 1024;
+  constexpr int EMAX = 16 / (int)sizeof(T);  // 4 floats / 2 doubles per thread
+  *fused = true;
+  if (project_fits<T>(blk.nrows, EMAX, two_per_sm)) return launch_project_ept<T, EMAX>(c, blk, x, out, n, epi, s);
+  if (EMAX == 4 && project_fits<T>(blk.nrows, 2, two_per_sm))
+    return launch_project_ept<T, (EMAX == 4 ? 2 : 1)>(c, blk, x, out, n, epi, s);
+  if (project_fits<T>(blk.nrows, 1, one_per_sm)) return launch_project_ept<T, 1>(c, blk, x, out, n, epi, s);
+  *fused = false;
   return BL_OK;
 }
 
@@ -190,35 +323,46 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool secon
       e.coef = c.coefA;
       BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, m), r, n, e, s));
     }
-    {  // v = v - Q h                                                           arnoldi.py:88
+    Epi norm_epi;  // length = sqrt(v . v); h[i+1] = length                      arnoldi.py:95-98
+    norm_epi.mode = EPI_FWD_NORM;
+    norm_epi.i = i;
+    norm_epi.K = K;
+    norm_epi.H = H;
+    bool fused = false;
+    if (second_pass) {
+      // v = v - Q h and, from the same read of Q, h2 = Q^H v (the second pass's coefficients;
+      // h itself is not updated, arnoldi.py:92)
+      Epi e;
+      e.mode = EPI_FWD_B;
+      e.m = m;
+      e.coef = c.coefB;
+      BL_CHECK(launch_project<T>(c, rows(Q, ld, 0, m, c.coefA, -1.0), r, r, n, e, s, &fused));
+    }
+    if (!fused) {  // v = v - Q h                                               arnoldi.py:88
       CombineArgs a;
       a.n = n;
       a.out = r;
       a.nvec = 1;
       a.vec[0] = term(r);
       a.blk[0] = rows(Q, ld, 0, m, c.coefA, -1.0);
-      a.epi.mode = EPI_FWD_NORM;
-      a.epi.i = i;
-      a.epi.K = K;
-      a.epi.H = H;
+      a.epi = norm_epi;
       BL_CHECK(launch_combine<T>(g, c, a, !second_pass, s));
+      if (second_pass) {
+        Epi e;
+        e.mode = EPI_FWD_B;
+        e.m = m;
+        e.coef = c.coefB;
+        BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, m), r, n, e, s));
+      }
     }
-    if (second_pass) {  // v = v - Q (Q^H v); h is not updated                  arnoldi.py:91-92
-      Epi e;
-      e.mode = EPI_FWD_B;
-      e.m = m;
-      e.coef = c.coefB;
-      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, m), r, n, e, s));
+    if (second_pass) {  // v = v - Q (Q^H v)                                    arnoldi.py:91-92
       CombineArgs a;
       a.n = n;
       a.out = r;
       a.nvec = 1;
       a.vec[0] = term(r);
       a.blk[0] = rows(Q, ld, 0, m, c.coefB, -1.0);
-      a.epi.mode = EPI_FWD_NORM;  // length = sqrt(v . v); h[i+1] = length       arnoldi.py:95-98
-      a.epi.i = i;
-      a.epi.K = K;
-      a.epi.H = H;
+      a.epi = norm_epi;
       BL_CHECK(launch_combine<T>(g, c, a, true, s));
     }
   }
@@ -247,6 +391,8 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
 
   BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
   BL_CUDA(cudaMemsetAsync(Gamma, 0, (size_t)K * K * 8, s));
+  if (ld > n)  // row buffers are zero-padded up to ld (contract of the TMA-staged kernels)
+    BL_CUDA(cudaMemset2DAsync(Lambda + n, (size_t)ld * sizeof(T), 0, (size_t)(ld - n) * sizeof(T), (size_t)K, s));
 
   // eta = dH e_K - Q^T dr ; lambda_K = dr + Q eta                             arnoldi.py:119-120
   {

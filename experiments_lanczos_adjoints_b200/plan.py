@@ -1,0 +1,133 @@
+"""Pre-planned forward + adjoint of `lanczos.tridiag(..., reortho="full")`.
+
+The function objects in `arnoldi.py` / `lanczos.py` mirror the reference's call structure
+(allocate outputs per call, return arrays).  A training / SLQ loop calls the same forward and
+adjoint thousands of times on one operand shape; this plan owns every buffer (basis `Q`,
+adjoint basis `Lambda`, `H`, workspace, gradient) once and re-enqueues the two C-ABI calls —
+no allocation, no host synchronisation inside `run()`.  Same arithmetic, same C entry points
+(`bl_arnoldi_forward`, `bl_arnoldi_adjoint`).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from experiments_lanczos_adjoints_b200 import _lib
+from experiments_lanczos_adjoints_b200 import device as dev
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """NumPy array backed by page-locked host memory (fast, truly asynchronous H2D/D2H)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    p = C.c_void_p()
+    _lib.call("bl_host_alloc", C.byref(p), max(1, nbytes))
+    buf = (C.c_char * max(1, nbytes)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    _PINNED[arr.ctypes.data] = p.value  # freed at interpreter exit with the CUDA context
+    return arr
+
+
+_PINNED = {}
+
+
+class TridiagAdjointPlan:
+    """`(Q^T, alpha, beta), r = tridiag(op, K, reortho="full")(v, params)` followed by the adjoint
+    for cotangents on `(alpha, beta)` (the SLQ case) or on every output."""
+
+    def __init__(self, op, krylov_depth: int, dtype, stream: dev.Stream | None = None):
+        self.op, self.K, self.dtype = op, int(krylov_depth), np.dtype(dtype)
+        self.n = op.n
+        self.stream = stream or dev.default_stream()
+        n, K = self.n, self.K
+        if K < 1 or K > n:
+            raise ValueError(f"Parameter depth {K} is outside the expected range")
+        self.code = dev.dtype_code(self.dtype)
+        self.ld = dev.basis_ld(n, self.dtype)
+        self.Q = dev.DeviceArray((K, n), self.dtype, ld=self.ld)
+        self.Lam = dev.DeviceArray((K, n), self.dtype, ld=self.ld)
+        self.H = dev.DeviceArray((K, K), self.dtype)
+        self.dH = dev.DeviceArray((K, K), self.dtype)
+        self.r = dev.DeviceArray((n,), self.dtype)
+        self.c = dev.DeviceArray((), self.dtype)
+        self.v = dev.DeviceArray((n,), self.dtype)
+        self.dv = dev.DeviceArray((n,), self.dtype)
+        self.params = [dev.DeviceArray(tuple(s) or (1,), self.dtype) for s in op.param_shapes()]
+        self.grads = [dev.DeviceArray(tuple(s) or (1,), self.dtype) for s in op.param_shapes()]
+        self.ws_bytes = _lib.load().bl_arnoldi_workspace_bytes(n, K, self.code)
+        self.ws = dev.DeviceArray(((self.ws_bytes + 3) // 4,), np.float32)
+        self._pptr = (C.c_void_p * max(1, len(self.params)))(*[p.ptr for p in self.params])
+        self._gptr = (C.c_void_p * max(1, len(self.grads)))(*[g.ptr for g in self.grads])
+
+    # -- uploads (async on the plan's stream; pass pinned arrays for true overlap) ----------
+    def _h2d(self, dst: dev.DeviceArray, host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        _lib.call("bl_memcpy_h2d", dst.ptr, host.ctypes.data, host.nbytes, self.stream.ptr)
+        return host.nbytes
+
+    def set_vector(self, v_host):
+        return self._h2d(self.v, v_host)
+
+    def set_params(self, *params_host):
+        return sum(self._h2d(d, h) for d, h in zip(self.params, params_host))
+
+    def set_cotangent(self, dH_host):
+        return self._h2d(self.dH, dH_host)
+
+    # -- the two sweeps -----------------------------------------------------------------------
+    def forward(self):
+        s = self.stream.ptr
+        _lib.call("bl_op_set_params", self.op._handle, self.code, self._pptr, len(self.params), s)
+        _lib.call("bl_arnoldi_forward", self.op._handle, self.code, self.n, self.K, 1, self.v.ptr, self.Q.ptr,
+                  self.ld, self.H.ptr, self.r.ptr, self.c.ptr, self.ws.ptr, self.ws_bytes, s)  # fmt: skip
+
+    def adjoint(self, dQ=None, dr=None):
+        s = self.stream.ptr
+        _lib.call("bl_op_grad_zero", self.op._handle, self.code, s)
+        _lib.call("bl_arnoldi_adjoint", self.op._handle, self.code, self.n, self.K, 1, self.Q.ptr, self.ld,
+                  self.H.ptr, self.r.ptr, self.c.ptr, dQ.ptr if dQ is not None else None, self.dH.ptr,
+                  dr.ptr if dr is not None else None, None, self.dv.ptr, self.Lam.ptr, self.ws.ptr,
+                  self.ws_bytes, s)  # fmt: skip
+        _lib.call("bl_op_grad_export", self.op._handle, self.code, self._gptr, len(self.grads), s)
+
+    def run(self):
+        """One forward + adjoint, enqueued back to back (no host sync)."""
+        self.forward()
+        self.adjoint()
+
+    # -- host-buffer entry point (the e2e path of bench.py) -----------------------------------
+    def run_host(self, v_host, params_host, dH_host, out_H, out_dv, out_grads):
+        """Host buffers in, host buffers out: H2D of `(v, params, dH)`, forward + adjoint, D2H of
+        `(H, dv, dparams)`; synchronises once at the end.  Returns (h2d_bytes, d2h_bytes)."""
+        h2d = self.set_vector(v_host) + self.set_params(*params_host) + self.set_cotangent(dH_host)
+        self.run()
+        d2h = 0
+        for src, dst in [(self.H, out_H), (self.dv, out_dv), *zip(self.grads, out_grads)]:
+            _lib.call("bl_memcpy_d2h", dst.ctypes.data, src.ptr, dst.nbytes, self.stream.ptr)
+            d2h += dst.nbytes
+        self.stream.synchronize()
+        return h2d, d2h
+
+    def coefficients(self):
+        """`(alpha, beta)` of the last forward (`lanczos.py:162-164`); synchronises."""
+        H = self.H.numpy(self.stream)
+        T = 0.5 * (H + H.T)
+        return np.diag(T, 0).copy(), np.diag(T, 1).copy()
+
+
+def profile(fn):
+    """Run `fn()` with per-kernel-class event timing; returns
+    `{class: {"launches", "ms", "algorithmic_bytes"}}` (see `bl_profile_begin` in the header)."""
+    names = ["dots", "combine", "matvec", "vjp", "other"]
+    _lib.call("bl_profile_begin")
+    try:
+        fn()
+    finally:
+        counts = (C.c_uint64 * 5)()
+        ms = (C.c_double * 5)()
+        nbytes = (C.c_double * 5)()
+        _lib.call("bl_profile_end", counts, ms, nbytes)
+    return {nm: {"launches": int(counts[i]), "ms": float(ms[i]), "algorithmic_bytes": float(nbytes[i])}
+            for i, nm in enumerate(names)}  # fmt: skip
