@@ -101,6 +101,33 @@ int tma_grid(int64_t n, int tile) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(2 * sm_count(), kMaxDotsGrid), (n + tile - 1) / tile));
 }
 
+// Launch with the programmatic-dependent-launch attribute (BL_PDL=0 disables it): the kernel's
+// prologue and its first TMA loads overlap the tail (imbalance, last-block reduction) of the
+// kernel in front of it; the kernel itself executes griddepcontrol.wait before reading anything
+// its predecessor wrote.
+bool pdl_enabled() {
+  static int mode = [] {
+    const char* e = std::getenv("BL_PDL");
+    return e ? std::atoi(e) : 1;
+  }();
+  return mode != 0;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename F>
 int set_smem(F* kernel, size_t bytes) {
   BL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -134,8 +161,9 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
       once = true;
     }
     BL_REQUIRE(smem <= 100 * 1024, "too many rows for k_dots_tma");
-    k_dots_tma<T, TILE><<<tma_grid<T>(n, TILE), kStreamThreads, smem, s>>>(
-        row_source(blk, nullptr, sizeof(T)), blk.nrows, x, n, c.partials_dots, c.counters + 0, epi);
+    BL_CUDA(launch_pdl(k_dots_tma<T, TILE>, tma_grid<T>(n, TILE), kStreamThreads, smem, s,
+                       row_source(blk, nullptr, sizeof(T)), blk.nrows, x, (long long)n, c.partials_dots,
+                       c.counters + 0, epi));
   } else {
     k_dots<T><<<g.dots, kDotsThreads, 0, s>>>(blk, x, n, c.partials_dots, c.counters + 0, epi);
   }
@@ -179,9 +207,9 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
     BL_REQUIRE(smem <= 100 * 1024, "too many rows for k_combine_tma");
     const int grid = tma_grid<T>(a.n, TILE);
     if (norm)
-      k_combine_tma<T, true><<<grid, kStreamThreads, smem, s>>>(t);
+      BL_CUDA(launch_pdl(k_combine_tma<T, true>, grid, kStreamThreads, smem, s, t));
     else
-      k_combine_tma<T, false><<<grid, kStreamThreads, smem, s>>>(t);
+      BL_CUDA(launch_pdl(k_combine_tma<T, false>, grid, kStreamThreads, smem, s, t));
   } else {
     const size_t smem = (size_t)(nrows + 1) * sizeof(T);
     if (norm)
@@ -209,9 +237,9 @@ int launch_project_ept(const Common& c, const RowBlock& blk, const T* x, T* out,
   epi.red = c.red;
   epi.scal = c.scal;
   ProfScope prof(BL_PROF_COMBINE, (double)(blk.nrows + 2) * n * sizeof(T), s);
-  k_project_tma<T, EPT><<<tma_grid<T>(n, TILE), kStreamThreads, smem, s>>>(
-      row_source(blk, nullptr, sizeof(T)), blk.nrows, x, out, n, blk.coef + blk.coef0, blk.sign, c.partials_dots,
-      c.counters + 0, epi);
+  BL_CUDA(launch_pdl(k_project_tma<T, EPT>, tma_grid<T>(n, TILE), kStreamThreads, smem, s,
+                     row_source(blk, nullptr, sizeof(T)), blk.nrows, x, out, (long long)n, blk.coef + blk.coef0,
+                     blk.sign, c.partials_dots, c.counters + 0, epi));
   BL_LAUNCHED();
   return BL_OK;
 }

@@ -56,17 +56,49 @@ __device__ __forceinline__ ColumnRange block_columns(long long n, int tile) {
 }
 
 // Fixed-order cross-block reduction + epilogue, run by the last block (all threads call it).
+// Latency-bound (one block reads gridDim.x * nrows doubles from L2), so every lane issues all of
+// its loads for two rows before the first add: <= 10 independent 16-byte loads in flight.
 template <typename T>
 __device__ __forceinline__ void reduce_partials_and_epilogue(int nrows, const double* __restrict__ partials,
                                                              const Epi& epi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int G = gridDim.x;
-  for (int j = warp; j < nrows; j += nwarps) {
-    const double* p = partials + (size_t)j * G;
-    double s = 0.0;
-    for (int b = lane; b < G; b += 32) s += __ldcg(p + b);
-    s = warp_sum(s);
-    if (lane == 0) epi.red[j] = s;
+  if ((G & 1) == 0 && G <= 320) {
+    const int nv = G >> 1;  // 16-byte vectors per row
+    for (int j = warp; j < nrows; j += 2 * nwarps) {
+      const int j2 = j + nwarps < nrows ? j + nwarps : j;  // second row (or the same one again)
+      const double2* p0 = reinterpret_cast<const double2*>(partials + (size_t)j * G);
+      const double2* p1 = reinterpret_cast<const double2*>(partials + (size_t)j2 * G);
+      double2 v0[5], v1[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int i = lane + 32 * k;
+        const int ic = i < nv ? i : 0;
+        v0[k] = __ldcg(p0 + ic);
+        v1[k] = __ldcg(p1 + ic);
+        if (i >= nv) v0[k] = v1[k] = make_double2(0.0, 0.0);
+      }
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        s0 += v0[k].x + v0[k].y;
+        s1 += v1[k].x + v1[k].y;
+      }
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      if (lane == 0) {
+        epi.red[j] = s0;
+        if (j2 != j) epi.red[j2] = s1;
+      }
+    }
+  } else {
+    for (int j = warp; j < nrows; j += nwarps) {
+      const double* p = partials + (size_t)j * G;
+      double s = 0.0;
+      for (int b = lane; b < G; b += 32) s += __ldcg(p + b);
+      s = warp_sum(s);
+      if (lane == 0) epi.red[j] = s;
+    }
   }
   __syncthreads();
   run_epilogue<T>(epi);
@@ -96,12 +128,13 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
   }
   for (int j = threadIdx.x; j < nrows; j += blockDim.x) acc_s[j] = 0.0;
   __syncthreads();
+  tma::griddep_launch_dependents();
 
   const ColumnRange cr = block_columns<T>(n, TILE);
   const int ngroups = (nrows + kGroup - 1) / kGroup;
 
   if (warp == kConsumerWarps) {
-    if (lane == 0) {  // ---- producer ----
+    if (lane == 0) {  // ---- producer: basis rows are older than the predecessor kernel, no wait ----
       int it = 0;
       for (int t = 0; t < cr.ntiles; ++t) {
         const long long tc0 = cr.c0 + (long long)t * TILE;
@@ -120,6 +153,7 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
       }
     }
   } else {  // ---- consumers: warp w takes row g*8 + w of every stage ----
+    tma::griddep_wait();  // x (and everything else in global memory) may come from the predecessor
     int it = 0;
     for (int t = 0; t < cr.ntiles; ++t) {
       const long long tc0 = cr.c0 + (long long)t * TILE;
@@ -221,16 +255,9 @@ k_combine_tma(CombineTmaArgs a) {
       tma::mbar_init(empty + s, kConsumerWarps);
     }
     tma::fence_barrier_init();
-    oscale[0] = a.out_mul_ptr ? static_cast<T>(*a.out_mul_ptr) : T(1);
-    oscale[1] = a.out_div_ptr ? static_cast<T>(*a.out_div_ptr) : T(1);
-  }
-  for (int j = threadIdx.x; j < nrows; j += blockDim.x)
-    coef[j] = j < a.src.n0 ? static_cast<T>(a.sign0 * a.coef0[j]) : static_cast<T>(a.sign1 * a.coef1[j - a.src.n0]);
-  if (threadIdx.x < a.nvec) {
-    const VecTerm& v = a.vec[threadIdx.x];
-    vcoef[threadIdx.x] = static_cast<T>(v.coef_imm * (v.coef_ptr ? *v.coef_ptr : 1.0));
   }
   __syncthreads();
+  tma::griddep_launch_dependents();
 
   const ColumnRange cr = block_columns<T>(a.n, TILE);
   const int ngroups = (nrows + kGroup - 1) / kGroup;
@@ -257,6 +284,19 @@ k_combine_tma(CombineTmaArgs a) {
     }
   } else {
     const int tid = threadIdx.x;  // 0..255: one 16-byte vector of every staged row
+    // coefficients and scalars come from the predecessor's epilogue: wait for it first
+    tma::griddep_wait();
+    if (tid == 0) {
+      oscale[0] = a.out_mul_ptr ? static_cast<T>(*a.out_mul_ptr) : T(1);
+      oscale[1] = a.out_div_ptr ? static_cast<T>(*a.out_div_ptr) : T(1);
+    }
+    for (int j = tid; j < nrows; j += kConsumerThreads)
+      coef[j] = j < a.src.n0 ? static_cast<T>(a.sign0 * a.coef0[j]) : static_cast<T>(a.sign1 * a.coef1[j - a.src.n0]);
+    if (tid < a.nvec) {
+      const VecTerm& v = a.vec[tid];
+      vcoef[tid] = static_cast<T>(v.coef_imm * (v.coef_ptr ? *v.coef_ptr : 1.0));
+    }
+    tma::named_bar_sync(2, kConsumerThreads);
     int it = 0;
     for (int t = 0; t < cr.ntiles; ++t) {
       const long long tc0 = cr.c0 + (long long)t * TILE;
@@ -386,10 +426,9 @@ k_project_tma(RowSource src, int nrows, const T* x, T* out, long long n, const d
     tma::mbar_init(tile_free, kConsumerWarps);
     tma::fence_barrier_init();
   }
-  for (int j = threadIdx.x; j < ngroups * kGroup; j += blockDim.x)
-    coef[j] = j < nrows ? static_cast<T>(sign * coef_in[j]) : T(0);
   for (int j = threadIdx.x; j < nrows; j += blockDim.x) acc_s[j] = 0.0;
   __syncthreads();
+  tma::griddep_launch_dependents();
 
   const ColumnRange cr = block_columns<T>(n, TILE);
 
@@ -411,6 +450,10 @@ k_project_tma(RowSource src, int nrows, const T* x, T* out, long long n, const d
     }
   } else {
     const int tid = threadIdx.x;
+    tma::griddep_wait();  // coefficients come from the predecessor's epilogue
+    for (int j = tid; j < ngroups * kGroup; j += kConsumerThreads)
+      coef[j] = j < nrows ? static_cast<T>(sign * coef_in[j]) : T(0);
+    tma::named_bar_sync(2, kConsumerThreads);
     for (int t = 0; t < cr.ntiles; ++t) {
       const long long tc0 = cr.c0 + (long long)t * TILE;
       const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
@@ -450,21 +493,40 @@ k_project_tma(RowSource src, int nrows, const T* x, T* out, long long n, const d
       V xv[LV];
 #pragma unroll
       for (int u = 0; u < LV; ++u) xv[u] = reinterpret_cast<const V*>(xs)[lane + 32 * u];
-      for (int j = warp; j < nrows; j += kConsumerWarps) {
-        const V* row = reinterpret_cast<const V*>(tile_s + (size_t)j * TILE);
-        T a0 = T(0);
+      // four rows per iteration: four independent reduction chains hide the shuffle latency
+      for (int j = warp; j < nrows; j += 4 * kConsumerWarps) {
+        T a[4];
 #pragma unroll
-        for (int u = 0; u < LV; ++u) {
-          if ((lane + 32 * u) * VN < len) {
-            T q[VN], xx[VN];
-            vec_unpack(row[lane + 32 * u], q);
-            vec_unpack(xv[u], xx);
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int jj = j + q4 * kConsumerWarps;
+          a[q4] = T(0);
+          if (jj < nrows) {
+            const V* row = reinterpret_cast<const V*>(tile_s + (size_t)jj * TILE);
 #pragma unroll
-            for (int k = 0; k < VN; ++k) a0 = fma(q[k], xx[k], a0);
+            for (int u = 0; u < LV; ++u) {
+              if ((lane + 32 * u) * VN < len) {
+                T q[VN], xx[VN];
+                vec_unpack(row[lane + 32 * u], q);
+                vec_unpack(xv[u], xx);
+#pragma unroll
+                for (int k = 0; k < VN; ++k) a[q4] = fma(q[k], xx[k], a[q4]);
+              }
+            }
           }
         }
-        double sacc = warp_sum(static_cast<double>(a0));
-        if (lane == 0) acc_s[j] += sacc;
+        double d[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) d[q4] = static_cast<double>(a[q4]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) d[q4] += __shfl_xor_sync(0xffffffffu, d[q4], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            if (j + q4 * kConsumerWarps < nrows) acc_s[j + q4 * kConsumerWarps] += d[q4];
+        }
       }
       __syncwarp();
       if (lane == 0) tma::mbar_arrive(tile_free);

@@ -84,5 +84,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor is still draining; it must execute
+// `griddep_wait` before touching anything the predecessor wrote.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 }  // namespace tma
 }  // namespace bl
