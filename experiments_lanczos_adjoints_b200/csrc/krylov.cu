@@ -105,6 +105,24 @@ int tma_grid(int64_t n, int tile) {
 // prologue and its first TMA loads overlap the tail (imbalance, last-block reduction) of the
 // kernel in front of it; the kernel itself executes griddepcontrol.wait before reading anything
 // its predecessor wrote.
+// L2 "snake" order (BL_SNAKE=0 disables it): consecutive streaming kernels walk the basis in
+// opposite directions, so a kernel starts on the tiles its predecessor read last — the part of
+// the basis that is still in the 126 MB L2.  Each block owns the same column range in every
+// kernel (same grid, same partition), which makes the reuse exact.
+bool snake_enabled() {
+  static int mode = [] {
+    const char* e = std::getenv("BL_SNAKE");
+    return e ? std::atoi(e) : 1;
+  }();
+  return mode != 0;
+}
+thread_local int g_direction = 0;  // toggled per streaming launch; host-side launch order is the stream order
+int next_direction() {
+  if (!snake_enabled()) return 0;
+  g_direction ^= 1;
+  return g_direction;
+}
+
 bool pdl_enabled() {
   static int mode = [] {
     const char* e = std::getenv("BL_PDL");
@@ -163,7 +181,7 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
     BL_REQUIRE(smem <= 100 * 1024, "too many rows for k_dots_tma");
     BL_CUDA(launch_pdl(k_dots_tma<T, TILE>, tma_grid<T>(n, TILE), kStreamThreads, smem, s,
                        row_source(blk, nullptr, sizeof(T)), blk.nrows, x, (long long)n, c.partials_dots,
-                       c.counters + 0, epi));
+                       c.counters + 0, epi, next_direction()));
   } else {
     k_dots<T><<<g.dots, kDotsThreads, 0, s>>>(blk, x, n, c.partials_dots, c.counters + 0, epi);
   }
@@ -196,6 +214,7 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
     t.out_mul_ptr = a.out_mul_ptr;
     t.partials = a.partials;
     t.counter = a.counter;
+    t.reverse = next_direction();
     t.epi = a.epi;
     const size_t smem = (size_t)kStages * kGroup * TILE * sizeof(T) + 2 * kStages * 8 + (size_t)nrows * sizeof(T) + 16;
     static bool once = false;
@@ -239,7 +258,7 @@ int launch_project_ept(const Common& c, const RowBlock& blk, const T* x, T* out,
   ProfScope prof(BL_PROF_COMBINE, (double)(blk.nrows + 2) * n * sizeof(T), s);
   BL_CUDA(launch_pdl(k_project_tma<T, EPT>, tma_grid<T>(n, TILE), kStreamThreads, smem, s,
                      row_source(blk, nullptr, sizeof(T)), blk.nrows, x, out, (long long)n, blk.coef + blk.coef0,
-                     blk.sign, c.partials_dots, c.counters + 0, epi));
+                     blk.sign, c.partials_dots, c.counters + 0, epi, next_direction()));
   BL_LAUNCHED();
   return BL_OK;
 }

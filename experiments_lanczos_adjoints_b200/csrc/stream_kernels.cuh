@@ -108,7 +108,7 @@ __device__ __forceinline__ void reduce_partials_and_epilogue(int nrows, const do
 template <typename T, int TILE>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, double* __restrict__ partials,
-           unsigned int* counter, Epi epi) {
+           unsigned int* counter, Epi epi, int reverse) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int XV = TILE / (32 * VN);  // x vectors per lane
@@ -136,11 +136,13 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
   if (warp == kConsumerWarps) {
     if (lane == 0) {  // ---- producer: basis rows are older than the predecessor kernel, no wait ----
       int it = 0;
-      for (int t = 0; t < cr.ntiles; ++t) {
+      for (int tt = 0; tt < cr.ntiles; ++tt) {
+        const int t = reverse ? cr.ntiles - 1 - tt : tt;
         const long long tc0 = cr.c0 + (long long)t * TILE;
         const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
         const uint32_t bytes = (uint32_t)len * sizeof(T);
-        for (int g = 0; g < ngroups; ++g, ++it) {
+        for (int gg = 0; gg < ngroups; ++gg, ++it) {
+          const int g = reverse ? ngroups - 1 - gg : gg;
           const int s = it % kStages;
           tma::mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
           const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
@@ -155,7 +157,8 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
   } else {  // ---- consumers: warp w takes row g*8 + w of every stage ----
     tma::griddep_wait();  // x (and everything else in global memory) may come from the predecessor
     int it = 0;
-    for (int t = 0; t < cr.ntiles; ++t) {
+    for (int tt = 0; tt < cr.ntiles; ++tt) {
+      const int t = reverse ? cr.ntiles - 1 - tt : tt;
       const long long tc0 = cr.c0 + (long long)t * TILE;
       const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
       V xr[XV];
@@ -177,7 +180,8 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
         }
         xr[u] = vec_pack(tmp);
       }
-      for (int g = 0; g < ngroups; ++g, ++it) {
+      for (int gg = 0; gg < ngroups; ++gg, ++it) {
+        const int g = reverse ? ngroups - 1 - gg : gg;
         const int s = it % kStages;
         tma::mbar_wait(full + s, (it / kStages) & 1);
         const int j = g * kGroup + warp;
@@ -229,6 +233,7 @@ struct CombineTmaArgs {
   const double* out_mul_ptr = nullptr;
   double* partials = nullptr;
   unsigned int* counter = nullptr;
+  int reverse = 0;  // walk tiles and row groups backwards (L2 "snake" order, see krylov.cu)
   Epi epi;
 };
 
@@ -261,16 +266,19 @@ k_combine_tma(CombineTmaArgs a) {
 
   const ColumnRange cr = block_columns<T>(a.n, TILE);
   const int ngroups = (nrows + kGroup - 1) / kGroup;
+  const int reverse = a.reverse;
   double ss = 0.0;
 
   if (warp == kConsumerWarps) {
     if (lane == 0) {
       int it = 0;
-      for (int t = 0; t < cr.ntiles; ++t) {
+      for (int tt = 0; tt < cr.ntiles; ++tt) {
+        const int t = reverse ? cr.ntiles - 1 - tt : tt;
         const long long tc0 = cr.c0 + (long long)t * TILE;
         const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
         const uint32_t bytes = (uint32_t)len * sizeof(T);
-        for (int g = 0; g < ngroups; ++g, ++it) {
+        for (int gg = 0; gg < ngroups; ++gg, ++it) {
+          const int g = reverse ? ngroups - 1 - gg : gg;
           const int s = it % kStages;
           tma::mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
           const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
@@ -298,7 +306,8 @@ k_combine_tma(CombineTmaArgs a) {
     }
     tma::named_bar_sync(2, kConsumerThreads);
     int it = 0;
-    for (int t = 0; t < cr.ntiles; ++t) {
+    for (int tt = 0; tt < cr.ntiles; ++tt) {
+      const int t = reverse ? cr.ntiles - 1 - tt : tt;
       const long long tc0 = cr.c0 + (long long)t * TILE;
       const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
       const long long col = tc0 + (long long)tid * VN;
@@ -320,7 +329,8 @@ k_combine_tma(CombineTmaArgs a) {
           for (int k = 0; k < VN; ++k) acc[k] = fma(vcoef[v], e[k], acc[k]);
         }
       }
-      for (int g = 0; g < ngroups; ++g, ++it) {
+      for (int gg = 0; gg < ngroups; ++gg, ++it) {
+        const int g = reverse ? ngroups - 1 - gg : gg;
         const int s = it % kStages;
         tma::mbar_wait(full + s, (it / kStages) & 1);
         const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
@@ -405,7 +415,7 @@ __device__ __forceinline__ void load_ept(const T* p, T (&e)[EPT]) {
 template <typename T, int EPT>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 k_project_tma(RowSource src, int nrows, const T* x, T* out, long long n, const double* __restrict__ coef_in,
-              double sign, double* __restrict__ partials, unsigned int* counter, Epi epi) {
+              double sign, double* __restrict__ partials, unsigned int* counter, Epi epi, int reverse) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int TILE = kConsumerThreads * EPT;
@@ -434,12 +444,14 @@ k_project_tma(RowSource src, int nrows, const T* x, T* out, long long n, const d
 
   if (warp == kConsumerWarps) {
     if (lane == 0) {
-      for (int t = 0; t < cr.ntiles; ++t) {
+      for (int tt = 0; tt < cr.ntiles; ++tt) {
+        const int t = reverse ? cr.ntiles - 1 - tt : tt;
         const long long tc0 = cr.c0 + (long long)t * TILE;
         const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
         const uint32_t bytes = (uint32_t)len * sizeof(T);
-        tma::mbar_wait(tile_free, (t & 1) ^ 1);  // both sweeps of the previous tile are done
-        for (int g = 0; g < ngroups; ++g) {
+        tma::mbar_wait(tile_free, (tt & 1) ^ 1);  // both sweeps of the previous tile are done
+        for (int gg = 0; gg < ngroups; ++gg) {
+          const int g = reverse ? ngroups - 1 - gg : gg;
           const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
           tma::mbar_arrive_expect_tx(full + g, bytes * rows_here);
           for (int r = 0; r < rows_here; ++r)
@@ -454,7 +466,8 @@ k_project_tma(RowSource src, int nrows, const T* x, T* out, long long n, const d
     for (int j = tid; j < ngroups * kGroup; j += kConsumerThreads)
       coef[j] = j < nrows ? static_cast<T>(sign * coef_in[j]) : T(0);
     tma::named_bar_sync(2, kConsumerThreads);
-    for (int t = 0; t < cr.ntiles; ++t) {
+    for (int tt = 0; tt < cr.ntiles; ++tt) {
+      const int t = reverse ? cr.ntiles - 1 - tt : tt;
       const long long tc0 = cr.c0 + (long long)t * TILE;
       const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
       // ---- sweep 1: x' = x + sum_j coef_j row_j (thread <-> EPT consecutive columns) ----
@@ -464,8 +477,9 @@ k_project_tma(RowSource src, int nrows, const T* x, T* out, long long n, const d
         const long long col = tc0 + (long long)tid * EPT + k;
         acc[k] = (tid * EPT + k < len && col < n) ? x[col] : T(0);
       }
-      for (int g = 0; g < ngroups; ++g) {
-        tma::mbar_wait(full + g, t & 1);
+      for (int gg = 0; gg < ngroups; ++gg) {
+        const int g = reverse ? ngroups - 1 - gg : gg;
+        tma::mbar_wait(full + g, tt & 1);
         const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
         const T* st = tile_s + (size_t)g * kGroup * TILE + tid * EPT;
         const T* cf = coef + g * kGroup;
