@@ -5,6 +5,9 @@
 #include <algorithm>
 
 #include <cstdlib>
+#ifndef BL_DOTS_TILE_BYTES
+#define BL_DOTS_TILE_BYTES 4096
+#endif
 
 #include "krylov_kernels.cuh"
 #include "stream_kernels.cuh"
@@ -94,7 +97,7 @@ int stream_mode() {
 bool use_tma(int64_t n) { return stream_mode() != 0 && n >= 8192; }
 
 template <typename T>
-constexpr int dots_tile() { return 4096 / (int)sizeof(T); }  // 4 KB row segments
+constexpr int dots_tile() { return BL_DOTS_TILE_BYTES / (int)sizeof(T); }  // row segment per copy
 
 template <typename T>
 int tma_grid(int64_t n, int tile) {
@@ -172,13 +175,14 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
   ProfScope prof(BL_PROF_DOTS, (double)(blk.nrows + 1) * n * sizeof(T), s);
   if (use_tma(n)) {
     constexpr int TILE = dots_tile<T>();
-    const size_t smem = (size_t)kStages * kGroup * TILE * sizeof(T) + 2 * kStages * 8 + (size_t)blk.nrows * 8 + 16;
+    const size_t smem = (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 4) * 8 +
+                        (size_t)blk.nrows * 8 + 16;
     static bool once = false;
     if (!once) {
-      BL_CHECK(set_smem(k_dots_tma<T, TILE>, 100 * 1024));
+      BL_CHECK(set_smem(k_dots_tma<T, TILE>, 112 * 1024));
       once = true;
     }
-    BL_REQUIRE(smem <= 100 * 1024, "too many rows for k_dots_tma");
+    BL_REQUIRE(smem <= 112 * 1024, "too many rows for k_dots_tma");
     BL_CUDA(launch_pdl(k_dots_tma<T, TILE>, tma_grid<T>(n, TILE), kStreamThreads, smem, s,
                        row_source(blk, nullptr, sizeof(T)), blk.nrows, x, (long long)n, c.partials_dots,
                        c.counters + 0, epi, next_direction()));
@@ -197,7 +201,7 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
   a.epi.scal = c.scal;
   const int nrows = a.blk[0].nrows + a.blk[1].nrows;
   ProfScope prof(BL_PROF_COMBINE, (double)(nrows + a.nvec + 1 + (a.out2 ? 1 : 0)) * a.n * sizeof(T), s);
-  if (use_tma(a.n) && nrows >= 4) {
+  if (use_tma(a.n) && nrows + a.nvec >= 4) {
     constexpr int TILE = kConsumerThreads * Vec<T>::N;
     CombineTmaArgs t;
     t.n = a.n;
@@ -216,7 +220,8 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
     t.counter = a.counter;
     t.reverse = next_direction();
     t.epi = a.epi;
-    const size_t smem = (size_t)kStages * kGroup * TILE * sizeof(T) + 2 * kStages * 8 + (size_t)nrows * sizeof(T) + 16;
+    const size_t smem = (size_t)kStages * kGroup * TILE * sizeof(T) + 2 * kStages * 8 +
+                        (size_t)(nrows + 2 * kGroup) * sizeof(T) + 16;
     static bool once = false;
     if (!once) {
       BL_CHECK(set_smem(k_combine_tma<T, true>, 100 * 1024));
@@ -240,49 +245,121 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
   return BL_OK;
 }
 
-// Fused "x' = x + sign * sum_j coef_j row_j ; red[j] = <row_j, x'>" (second Gram-Schmidt pass).
-// Returns false if the tile does not fit shared memory (caller falls back to combine + dots).
-template <typename T, int EPT>
-int launch_project_ept(const Common& c, const RowBlock& blk, const T* x, T* out, int64_t n, Epi epi, cudaStream_t s) {
-  constexpr int TILE = kConsumerThreads * EPT;
-  const int ngroups = (blk.nrows + kGroup - 1) / kGroup;
-  const size_t smem = (((size_t)ngroups * kGroup * (TILE + 1) + TILE) * sizeof(T) + 15) / 16 * 16 +
-                      (size_t)(ngroups + 1) * 8 + (size_t)blk.nrows * 8 + 16;
+// ---- tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point) --------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Row-major [rows x ld] basis buffer, box = [8 rows x box_cols]; out-of-range elements read as 0.
+int make_basis_map(CUtensorMap* map, int dtype, const void* base, int64_t ld, int64_t rows, int box_cols) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  BL_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)std::max<int64_t>(rows, 1)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * dtype_size(dtype)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kGroup};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(map, dtype == BL_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return BL_ECUDA;
+  }
+  return BL_OK;
+}
+
+// Host-side description of a fused combine + dots launch (k_fused_tma).
+struct FusedSpec {
+  int64_t n = 0;
+  void* out = nullptr;
+  int nvec = 0;
+  VecTerm vec[kMaxVecTerms];
+  RowBlock res;             // resident rows (dots wanted): coefficient of row j = sign * coef[coef0 + j]
+  RowBlock str0, str1;      // streamed-only rows
+  int64_t rows_total0 = 0;  // row extent of the buffers behind str0 / str1 (for the tensor maps)
+  int64_t rows_total1 = 0;
+  const double* out_div_ptr = nullptr;
+  Epi epi;
+};
+
+template <typename T, int TILE>
+int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, cudaStream_t s) {
+  constexpr int BOXC = TILE > 256 ? 256 : TILE;
+  const FusedLayout L = fused_layout<T, TILE>(f.res.nrows, f.str0.nrows, f.str1.nrows, f.nvec);
   static bool once = false;
   if (!once) {
-    BL_CHECK(set_smem(k_project_tma<T, EPT>, 225 * 1024));
+    BL_CHECK(set_smem(k_fused_tma<T, TILE>, 225 * 1024));
     once = true;
   }
-  epi.red = c.red;
-  epi.scal = c.scal;
-  ProfScope prof(BL_PROF_COMBINE, (double)(blk.nrows + 2) * n * sizeof(T), s);
-  BL_CUDA(launch_pdl(k_project_tma<T, EPT>, tma_grid<T>(n, TILE), kStreamThreads, smem, s,
-                     row_source(blk, nullptr, sizeof(T)), blk.nrows, x, out, (long long)n, blk.coef + blk.coef0,
-                     blk.sign, c.partials_dots, c.counters + 0, epi, next_direction()));
+  FusedArgs a;
+  const char* res_base = static_cast<const char*>(f.res.base) + (int64_t)f.res.row0 * f.res.ld * (int64_t)sizeof(T);
+  BL_CHECK(make_basis_map(&a.map_res, dtype, res_base, f.res.ld, f.res.nrows, BOXC));
+  if (f.str0.nrows > 0)
+    BL_CHECK(make_basis_map(&a.map_str0, dtype, f.str0.base, f.str0.ld, f.rows_total0, BOXC));
+  else
+    a.map_str0 = a.map_res;
+  if (f.str1.nrows > 0)
+    BL_CHECK(make_basis_map(&a.map_str1, dtype, f.str1.base, f.str1.ld, f.rows_total1, BOXC));
+  else
+    a.map_str1 = a.map_res;
+  a.n = f.n;
+  a.out = f.out;
+  a.nvec = f.nvec;
+  for (int k = 0; k < f.nvec; ++k) a.vec[k] = f.vec[k];
+  a.nres = f.res.nrows;
+  a.coef_res = f.res.coef + f.res.coef0;
+  a.sign_res = f.res.sign;
+  a.nstr0 = f.str0.nrows;
+  a.row_str0 = f.str0.row0;
+  a.coef_str0 = f.str0.coef ? f.str0.coef + f.str0.coef0 : nullptr;
+  a.sign_str0 = f.str0.sign;
+  a.nstr1 = f.str1.nrows;
+  a.row_str1 = f.str1.row0;
+  a.coef_str1 = f.str1.coef ? f.str1.coef + f.str1.coef0 : nullptr;
+  a.sign_str1 = f.str1.sign;
+  a.out_div_ptr = f.out_div_ptr;
+  a.partials = c.partials_dots;
+  a.counter = c.counters + 0;
+  a.epi = f.epi;
+  a.epi.red = c.red;
+  a.epi.scal = c.scal;
+  a.reverse = next_direction();
+  const int nrows = f.res.nrows + f.str0.nrows + f.str1.nrows;
+  ProfScope prof(BL_PROF_COMBINE, (double)(nrows + f.nvec + 1) * f.n * sizeof(T), s);
+  BL_CUDA(launch_pdl(k_fused_tma<T, TILE>, tma_grid<T>(f.n, TILE), kStreamThreads, L.total_bytes, s, a));
   BL_LAUNCHED();
   return BL_OK;
 }
 
+// `*fused` is false on return when no tile shape fits shared memory or the TMA path is off;
+// the caller then runs combine and dots separately.
 template <typename T>
-bool project_fits(int nrows, int ept, size_t budget) {
-  const size_t tile = (size_t)kConsumerThreads * ept;
-  const size_t rows_pad = (size_t)(nrows + kGroup - 1) / kGroup * kGroup;
-  return (rows_pad * (tile + 1) + tile) * sizeof(T) + rows_pad + nrows * 8 + 64 <= budget;
-}
-
-// fused = 1 on return if the fused kernel ran
-template <typename T>
-int launch_project(const Common& c, const RowBlock& blk, const T* x, T* out, int64_t n, Epi epi, cudaStream_t s,
-                   bool* fused) {
+int launch_fused(const Common& c, const FusedSpec& f, int dtype, cudaStream_t s, bool* fused) {
   *fused = false;
-  if (!use_tma(n) || stream_mode() == 2) return BL_OK;
-  constexpr size_t two_per_sm = 110 * 1024, one_per_sm = 222 * 1024;
-  constexpr int EMAX = 16 / (int)sizeof(T);  // 4 floats / 2 doubles per thread
+  if (!use_tma(f.n) || stream_mode() == 2 || f.n >= ((int64_t)1 << 31)) return BL_OK;
+  constexpr size_t two_per_sm = 113 * 1024;
+  constexpr int TMAX = 4096 / (int)sizeof(T);  // 1024 floats / 512 doubles
+  const int nr = f.res.nrows, n0 = f.str0.nrows, n1 = f.str1.nrows, nv = f.nvec;
   *fused = true;
-  if (project_fits<T>(blk.nrows, EMAX, two_per_sm)) return launch_project_ept<T, EMAX>(c, blk, x, out, n, epi, s);
-  if (EMAX == 4 && project_fits<T>(blk.nrows, 2, two_per_sm))
-    return launch_project_ept<T, (EMAX == 4 ? 2 : 1)>(c, blk, x, out, n, epi, s);
-  if (project_fits<T>(blk.nrows, 1, one_per_sm)) return launch_project_ept<T, 1>(c, blk, x, out, n, epi, s);
+  if (fused_layout<T, TMAX>(nr, n0, n1, nv).total_bytes <= two_per_sm) return launch_fused_tile<T, TMAX>(c, f, dtype, s);
+  if (fused_layout<T, TMAX / 2>(nr, n0, n1, nv).total_bytes <= two_per_sm)
+    return launch_fused_tile<T, TMAX / 2>(c, f, dtype, s);
+  if (fused_layout<T, TMAX / 4>(nr, n0, n1, nv).total_bytes <= two_per_sm)
+    return launch_fused_tile<T, TMAX / 4>(c, f, dtype, s);
+  if (fused_layout<T, TMAX / 8>(nr, n0, n1, nv).total_bytes <= two_per_sm)
+    return launch_fused_tile<T, TMAX / 8>(c, f, dtype, s);
   *fused = false;
   return BL_OK;
 }
@@ -383,7 +460,14 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool secon
       e.mode = EPI_FWD_B;
       e.m = m;
       e.coef = c.coefB;
-      BL_CHECK(launch_project<T>(c, rows(Q, ld, 0, m, c.coefA, -1.0), r, r, n, e, s, &fused));
+      FusedSpec f;
+      f.n = n;
+      f.out = r;
+      f.nvec = 1;
+      f.vec[0] = term(r);
+      f.res = rows(Q, ld, 0, m, c.coefA, -1.0);
+      f.epi = e;
+      BL_CHECK(launch_fused<T>(c, f, dtype, s, &fused));
     }
     if (!fused) {  // v = v - Q h                                               arnoldi.py:88
       CombineArgs a;
@@ -486,19 +570,22 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
     BL_LAUNCHED();
   }
 
+  bool have_reproj = false;  // coefA already holds p - P lambda for this idx (fused into the previous step)
   for (int idx = K - 1; idx >= 0; --idx) {
     T* Lrow = Lambda + (int64_t)idx * ld;
     if (reortho_full) {
       // lambda -= P^T (P lambda) - P^T p, rows <= idx+1 of P = Q^T              arnoldi.py:201-204
       const int mact = std::min(idx + 2, K);
-      Epi e;
-      e.mode = EPI_ADJ_REPROJ;
-      e.i = idx;
-      e.K = K;
-      e.m = mact;
-      e.dH = dH;
-      e.coef = c.coefA;
-      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, mact), lam, n, e, s));
+      if (!have_reproj) {
+        Epi e;
+        e.mode = EPI_ADJ_REPROJ;
+        e.i = idx;
+        e.K = K;
+        e.m = mact;
+        e.dH = dH;
+        e.coef = c.coefA;
+        BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, mact), lam, n, e, s));
+      }
       CombineArgs a;
       a.n = n;
       a.out = Lrow;  // Lambda[:, idx] = lambda                                   arnoldi.py:216
@@ -528,7 +615,35 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
       e.coef2 = c.coefC;
       BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, idx + 1), z, n, e, s));
     }
-    {  // lambda = (Pi_xi[idx] + Q gamma_row - alpha lambda + A^T lambda - Lambda beta_plus) / beta_minus
+    // lambda = (Pi_xi[idx] + Q gamma_row - alpha lambda + A^T lambda - Lambda beta_plus) / beta_minus
+    have_reproj = false;
+    if (reortho_full && idx > 0) {
+      // ... fused with the NEXT step's re-projection dots t = P lambda (rows 0..idx of Q are the
+      // active rows of P at idx-1): one read of those rows serves both          arnoldi.py:202,217-219
+      FusedSpec f;
+      f.n = n;
+      f.out = lam;
+      int nv = 0;
+      if (dQ) f.vec[nv++] = term(dQ + (int64_t)idx * ld);
+      f.vec[nv++] = term(r, 1.0, c.scal + S_ETA_IDX);
+      f.vec[nv++] = term(Lrow, 1.0, c.scal + S_NEG_ALPHA);
+      f.vec[nv++] = term(z);
+      f.nvec = nv;
+      f.res = rows(Q, ld, 0, idx + 1, c.coefB, 1.0);
+      f.str0 = rows(Q, ld, idx + 1, K - idx - 1, c.coefB, 1.0, idx + 1);
+      f.str1 = rows(Lambda, ld, idx + 1, K - idx - 1, c.coefC, 1.0, idx + 1);
+      f.rows_total0 = K;
+      f.rows_total1 = K;
+      f.out_div_ptr = c.scal + S_BETA_MINUS;
+      f.epi.mode = EPI_ADJ_REPROJ;
+      f.epi.i = idx - 1;
+      f.epi.K = K;
+      f.epi.m = idx + 1;
+      f.epi.dH = dH;
+      f.epi.coef = c.coefA;
+      BL_CHECK(launch_fused<T>(c, f, dtype, s, &have_reproj));
+    }
+    if (!have_reproj) {
       CombineArgs a;
       a.n = n;
       a.out = lam;

@@ -2,17 +2,19 @@
 //
 //   k_dots_tma    : red[j] = <row_j, x>                      pass A of CGS2, adjoint re-projection
 //   k_combine_tma : out = s * (sum_k a_k vec_k + sum_j c_j row_j) (+ ||out||^2)   pass C, adjoint back-substitution
-//   k_project_tma : x' = x - sum_j c_j row_j  AND  red[j] = <row_j, x'> from ONE read of the rows   (pass B)
+//   k_fused_tma   : out = combine(...)  AND  red[j] = <row_j, out> from ONE read of the rows  (pass B; adjoint)
 //
 // Persistent blocks (2 per SM): block b owns a contiguous, balanced range of columns and walks it
 // in tiles.  Warp 8 lane 0 is the producer: for every tile and every group of 8 basis rows it
 // issues one bulk copy per row segment into a shared-memory stage; warps 0-7 consume.  In
-// k_project_tma the whole [m x TILE] tile stays resident so the second Gram-Schmidt projection
-// reads the rows from shared memory instead of HBM.
+// k_fused_tma the rows that are needed twice stay resident for the tile, so the second use
+// reads shared memory instead of HBM.
 //
 // Contract: row buffers are zero-padded up to `ld` (ld*sizeof(T) % 16 == 0), so the 16-byte
 // vector that straddles `n` can be copied and multiplied without masking.
 #pragma once
+
+#include <cuda.h>
 
 #include "krylov_kernels.cuh"
 #include "tma_pipeline.cuh"
@@ -105,6 +107,9 @@ __device__ __forceinline__ void reduce_partials_and_epilogue(int nrows, const do
 }
 
 // ---------------------------------------------------------------------------------------------
+// red[j] = <row_j, x>.  The x tile travels through its own double-buffered TMA slot so the
+// consumers never wait on a global load; basis rows are prefetched before griddepcontrol.wait
+// (they are older than the predecessor kernel), x — usually the predecessor's output — after it.
 template <typename T, int TILE>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, double* __restrict__ partials,
@@ -113,16 +118,23 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
   constexpr int VN = Vec<T>::N;
   constexpr int XV = TILE / (32 * VN);  // x vectors per lane
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* stages = reinterpret_cast<T*>(smem_raw);  // [kStages][kGroup][TILE]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kGroup * TILE * sizeof(T));
+  T* stages = reinterpret_cast<T*>(smem_raw);                       // [kStages][kGroup][TILE]
+  T* xs = stages + (size_t)kStages * kGroup * TILE;                 // [2][TILE]
+  uint64_t* full = reinterpret_cast<uint64_t*>(xs + 2 * TILE);
   uint64_t* empty = full + kStages;
-  double* acc_s = reinterpret_cast<double*>(empty + kStages);  // [nrows]
+  uint64_t* xfull = empty + kStages;   // [2]
+  uint64_t* xempty = xfull + 2;        // [2]
+  double* acc_s = reinterpret_cast<double*>(xempty + 2);            // [nrows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       tma::mbar_init(full + s, 1);
       tma::mbar_init(empty + s, kConsumerWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
+      tma::mbar_init(xfull + s, 1);
+      tma::mbar_init(xempty + s, kConsumerWarps);
     }
     tma::fence_barrier_init();
   }
@@ -134,52 +146,74 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
   const int ngroups = (nrows + kGroup - 1) / kGroup;
 
   if (warp == kConsumerWarps) {
-    if (lane == 0) {  // ---- producer: basis rows are older than the predecessor kernel, no wait ----
-      int it = 0;
-      for (int tt = 0; tt < cr.ntiles; ++tt) {
+    if (lane == 0) {  // ---- producer ----
+      const int total = cr.ntiles * ngroups;
+      bool waited = false;
+      auto issue_x = [&](int tt) {
         const int t = reverse ? cr.ntiles - 1 - tt : tt;
         const long long tc0 = cr.c0 + (long long)t * TILE;
         const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
-        const uint32_t bytes = (uint32_t)len * sizeof(T);
-        for (int gg = 0; gg < ngroups; ++gg, ++it) {
-          const int g = reverse ? ngroups - 1 - gg : gg;
-          const int s = it % kStages;
-          tma::mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
-          const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
-          tma::mbar_arrive_expect_tx(full + s, bytes * rows_here);
-          T* dst = stages + (size_t)s * kGroup * TILE;
-          for (int r = 0; r < rows_here; ++r)
-            tma::bulk_g2s(dst + (size_t)r * TILE, src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes,
-                          full + s);
+        const int b = tt & 1;
+        tma::mbar_wait(xempty + b, ((tt >> 1) & 1) ^ 1);
+        tma::mbar_arrive_expect_tx(xfull + b, (uint32_t)len * sizeof(T));
+        tma::bulk_g2s(xs + (size_t)b * TILE, x + tc0, (uint32_t)len * sizeof(T), xfull + b);
+      };
+      for (int it = 0; it < total; ++it) {
+        const int tt = it / ngroups, gg = it - tt * ngroups;
+        // x runs one tile ahead of the rows: x(0), x(1) right after the wait, x(tt+1) when tile tt starts
+        if (!waited && (it == kStages || (gg == 0 && tt > 0))) {
+          tma::griddep_wait();
+          waited = true;
+          issue_x(0);
+          if (cr.ntiles > 1) issue_x(1);
         }
+        if (gg == 0 && tt > 0 && tt + 1 < cr.ntiles) issue_x(tt + 1);
+        const int t = reverse ? cr.ntiles - 1 - tt : tt;
+        const int g = reverse ? ngroups - 1 - gg : gg;
+        const long long tc0 = cr.c0 + (long long)t * TILE;
+        const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
+        const uint32_t bytes = (uint32_t)len * sizeof(T);
+        const int s = it % kStages;
+        tma::mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
+        const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
+        tma::mbar_arrive_expect_tx(full + s, bytes * rows_here);
+        T* dst = stages + (size_t)s * kGroup * TILE;
+        for (int r = 0; r < rows_here; ++r)
+          tma::bulk_g2s(dst + (size_t)r * TILE, src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes, full + s);
+      }
+      if (!waited && total > 0) {
+        tma::griddep_wait();
+        issue_x(0);
+        if (cr.ntiles > 1) issue_x(1);
       }
     }
   } else {  // ---- consumers: warp w takes row g*8 + w of every stage ----
-    tma::griddep_wait();  // x (and everything else in global memory) may come from the predecessor
     int it = 0;
     for (int tt = 0; tt < cr.ntiles; ++tt) {
       const int t = reverse ? cr.ntiles - 1 - tt : tt;
       const long long tc0 = cr.c0 + (long long)t * TILE;
       const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
+      const int b = tt & 1;
+      tma::mbar_wait(xfull + b, (tt >> 1) & 1);
       V xr[XV];
 #pragma unroll
       for (int u = 0; u < XV; ++u) {
         const int e = (lane + 32 * u) * VN;
-        const long long col = tc0 + e;
         T tmp[VN];
 #pragma unroll
         for (int k = 0; k < VN; ++k) tmp[k] = T(0);
         if (e < len) {
-          if (col + VN <= n) {
-            vec_unpack(__ldg(reinterpret_cast<const V*>(x + col)), tmp);
-          } else {
+          vec_unpack(reinterpret_cast<const V*>(xs + (size_t)b * TILE)[lane + 32 * u], tmp);
+          if (tc0 + e + VN > n) {  // the vector that straddles n: x is not zero-padded
 #pragma unroll
             for (int k = 0; k < VN; ++k)
-              if (col + k < n) tmp[k] = x[col + k];
+              if (tc0 + e + k >= n) tmp[k] = T(0);
           }
         }
         xr[u] = vec_pack(tmp);
       }
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(xempty + b);
       for (int gg = 0; gg < ngroups; ++gg, ++it) {
         const int g = reverse ? ngroups - 1 - gg : gg;
         const int s = it % kStages;
@@ -203,13 +237,19 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
               }
             }
           }
+          // release the stage before the (latency-bound) warp reduction: with three stages in
+          // the ring every cycle a stage is held costs bytes in flight
+          __syncwarp();
+          if (lane == 0) tma::mbar_arrive(empty + s);
           double sacc = warp_sum(static_cast<double>(a0) + static_cast<double>(a1));
           if (lane == 0) acc_s[j] += sacc;  // row j is always handled by this warp: no race
+        } else {
+          __syncwarp();
+          if (lane == 0) tma::mbar_arrive(empty + s);
         }
-        __syncwarp();
-        if (lane == 0) tma::mbar_arrive(empty + s);
       }
     }
+    tma::griddep_wait();  // blocks with no tile must still order their partial writes after the predecessor
   }
   __syncthreads();
   for (int j = threadIdx.x; j < nrows; j += blockDim.x) partials[(size_t)j * gridDim.x + blockIdx.x] = acc_s[j];
@@ -218,13 +258,17 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// out = s * sum_j c_j row_j (+ ||out||^2): dense vector terms are rows too (src.nv leading
+// single-row sources), so everything the consumers read arrives through the TMA pipeline.
+// Row order inside a tile: basis groups first (prefetched before griddepcontrol.wait), the
+// group(s) holding vector terms last (they may be the predecessor's output).
 struct CombineTmaArgs {
   long long n = 0;
   void* out = nullptr;
   void* out2 = nullptr;
   int nvec = 0;
   VecTerm vec[kMaxVecTerms];
-  RowSource src;
+  RowSource src;                  // basis blocks only
   const double* coef0 = nullptr;  // coefficients of block 0 rows (already offset)
   double sign0 = 1.0;
   const double* coef1 = nullptr;
@@ -247,13 +291,14 @@ k_combine_tma(CombineTmaArgs a) {
   T* stages = reinterpret_cast<T*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kGroup * TILE * sizeof(T));
   uint64_t* empty = full + kStages;
-  T* coef = reinterpret_cast<T*>(empty + kStages);  // [nrows]
+  T* coef = reinterpret_cast<T*>(empty + kStages);  // [ngb*8 + 8]: basis rows, then the vector group
   __shared__ double red_smem[32];
-  __shared__ T vcoef[kMaxVecTerms];
   __shared__ T oscale[2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nrows = a.src.n0 + a.src.n1;
+  const int nbasis = a.src.n0 + a.src.n1;
+  const int ngb = (nbasis + kGroup - 1) / kGroup;   // basis groups
+  const int ngroups = ngb + (a.nvec > 0 ? 1 : 0);   // + one group of vector terms (nvec <= 8)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       tma::mbar_init(full + s, 1);
@@ -265,28 +310,39 @@ k_combine_tma(CombineTmaArgs a) {
   tma::griddep_launch_dependents();
 
   const ColumnRange cr = block_columns<T>(a.n, TILE);
-  const int ngroups = (nrows + kGroup - 1) / kGroup;
   const int reverse = a.reverse;
   double ss = 0.0;
 
   if (warp == kConsumerWarps) {
     if (lane == 0) {
       int it = 0;
+      bool waited = false;
       for (int tt = 0; tt < cr.ntiles; ++tt) {
         const int t = reverse ? cr.ntiles - 1 - tt : tt;
         const long long tc0 = cr.c0 + (long long)t * TILE;
         const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
         const uint32_t bytes = (uint32_t)len * sizeof(T);
         for (int gg = 0; gg < ngroups; ++gg, ++it) {
-          const int g = reverse ? ngroups - 1 - gg : gg;
+          const bool vec_group = gg >= ngb;
+          const int g = vec_group ? gg : (reverse ? ngb - 1 - gg : gg);
           const int s = it % kStages;
+          if (vec_group && !waited) {
+            tma::griddep_wait();
+            waited = true;
+          }
           tma::mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
-          const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
-          tma::mbar_arrive_expect_tx(full + s, bytes * rows_here);
           T* dst = stages + (size_t)s * kGroup * TILE;
-          for (int r = 0; r < rows_here; ++r)
-            tma::bulk_g2s(dst + (size_t)r * TILE, a.src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes,
-                          full + s);
+          if (vec_group) {
+            tma::mbar_arrive_expect_tx(full + s, bytes * a.nvec);
+            for (int r = 0; r < a.nvec; ++r)
+              tma::bulk_g2s(dst + (size_t)r * TILE, static_cast<const T*>(a.vec[r].ptr) + tc0, bytes, full + s);
+          } else {
+            const int rows_here = nbasis - g * kGroup < kGroup ? nbasis - g * kGroup : kGroup;
+            tma::mbar_arrive_expect_tx(full + s, bytes * rows_here);
+            for (int r = 0; r < rows_here; ++r)
+              tma::bulk_g2s(dst + (size_t)r * TILE, a.src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes,
+                            full + s);
+          }
         }
       }
     }
@@ -298,11 +354,17 @@ k_combine_tma(CombineTmaArgs a) {
       oscale[0] = a.out_mul_ptr ? static_cast<T>(*a.out_mul_ptr) : T(1);
       oscale[1] = a.out_div_ptr ? static_cast<T>(*a.out_div_ptr) : T(1);
     }
-    for (int j = tid; j < nrows; j += kConsumerThreads)
-      coef[j] = j < a.src.n0 ? static_cast<T>(a.sign0 * a.coef0[j]) : static_cast<T>(a.sign1 * a.coef1[j - a.src.n0]);
-    if (tid < a.nvec) {
-      const VecTerm& v = a.vec[tid];
-      vcoef[tid] = static_cast<T>(v.coef_imm * (v.coef_ptr ? *v.coef_ptr : 1.0));
+    for (int j = tid; j < ngb * kGroup; j += kConsumerThreads)
+      coef[j] = j >= nbasis ? T(0)
+                            : (j < a.src.n0 ? static_cast<T>(a.sign0 * a.coef0[j])
+                                            : static_cast<T>(a.sign1 * a.coef1[j - a.src.n0]));
+    if (tid < kGroup) {
+      T c = T(0);
+      if (tid < a.nvec) {
+        const VecTerm& v = a.vec[tid];
+        c = static_cast<T>(v.coef_imm * (v.coef_ptr ? *v.coef_ptr : 1.0));
+      }
+      coef[ngb * kGroup + tid] = c;
     }
     tma::named_bar_sync(2, kConsumerThreads);
     int it = 0;
@@ -316,24 +378,12 @@ k_combine_tma(CombineTmaArgs a) {
       T acc[VN];
 #pragma unroll
       for (int k = 0; k < VN; ++k) acc[k] = T(0);
-      if (live) {
-        for (int v = 0; v < a.nvec; ++v) {
-          T e[VN];
-          if (fullvec) {
-            vec_unpack(reinterpret_cast<const V*>(a.vec[v].ptr)[col / VN], e);
-          } else {
-#pragma unroll
-            for (int k = 0; k < VN; ++k) e[k] = col + k < a.n ? static_cast<const T*>(a.vec[v].ptr)[col + k] : T(0);
-          }
-#pragma unroll
-          for (int k = 0; k < VN; ++k) acc[k] = fma(vcoef[v], e[k], acc[k]);
-        }
-      }
       for (int gg = 0; gg < ngroups; ++gg, ++it) {
-        const int g = reverse ? ngroups - 1 - gg : gg;
+        const bool vec_group = gg >= ngb;
+        const int g = vec_group ? gg : (reverse ? ngb - 1 - gg : gg);
         const int s = it % kStages;
         tma::mbar_wait(full + s, (it / kStages) & 1);
-        const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
+        const int rows_here = vec_group ? a.nvec : (nbasis - g * kGroup < kGroup ? nbasis - g * kGroup : kGroup);
         if (live) {
           const V* st = reinterpret_cast<const V*>(stages + (size_t)s * kGroup * TILE) + tid;
           const T* cf = coef + g * kGroup;
@@ -409,148 +459,353 @@ __device__ __forceinline__ void load_ept(const T* p, T (&e)[EPT]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused second Gram-Schmidt pass: x' = x - sum_j c_j row_j (written to `out`), then
-// red[j] = <row_j, x'> from the tile that is still resident in shared memory.
-// EPT = elements per consumer thread in sweep 1; TILE = 256 * EPT columns.
-template <typename T, int EPT>
+// Fused "combine, then dots against part of the rows" from ONE read of the basis:
+//   out   = ( sum_v a_v vec_v + sum_{j < nres} c_j res_j + sum_k d_k str_k ) / div
+//   red_j = < res_j , out >        for the resident rows j < nres
+// Used for (i) the second Gram-Schmidt pass of the forward step (v' = v - Q h, h2 = Q^T v';
+// arnoldi.py:88-92) and (ii) the adjoint's back-substitution fused with the next step's
+// re-projection dots (lambda' = (...)/beta_minus, t = P lambda'; arnoldi.py:217-219 + 202-204).
+//
+// Data movement: 2-D tiled TMA through tensor maps — one instruction per [8 rows x TILE] box.
+// The resident rows of a tile live in one of TWO shared-memory buffers, so the producer loads
+// tile t+1 while the consumers run both sweeps over tile t (loads never drain); streamed-only
+// rows go through a 3-slot ring; dense vector terms through a double-buffered slot.
+// Sweep 1: thread <-> (column, row-split) accumulates the combination as boxes land.
+// Sweep 2: warp w <-> row 8g+w takes the dots from shared memory and releases each box.
+struct alignas(64) FusedArgs {
+  CUtensorMap map_res;   // resident block: rows [0, nres) of one basis buffer (row extent = nres)
+  CUtensorMap map_str0;  // streamed block 0 (rows [row_str0, row_str0 + nstr0))
+  CUtensorMap map_str1;  // streamed block 1
+  long long n = 0;
+  void* out = nullptr;
+  int nvec = 0;
+  VecTerm vec[kMaxVecTerms];
+  int nres = 0;
+  const double* coef_res = nullptr;
+  double sign_res = 1.0;
+  int nstr0 = 0, row_str0 = 0;
+  const double* coef_str0 = nullptr;
+  double sign_str0 = 1.0;
+  int nstr1 = 0, row_str1 = 0;
+  const double* coef_str1 = nullptr;
+  double sign_str1 = 1.0;
+  const double* out_div_ptr = nullptr;
+  double* partials = nullptr;
+  unsigned int* counter = nullptr;
+  int reverse = 0;
+  Epi epi;
+};
+
+struct FusedLayout {
+  size_t res, ring, vec, part, xs, coef, elems;  // element offsets
+  size_t bar_bytes, acc_bytes, total_bytes;
+  int GR, GS0, GS1, GS;
+};
+
+template <typename T, int TILE>
+__host__ __device__ inline FusedLayout fused_layout(int nres, int nstr0, int nstr1, int nvec) {
+  constexpr int RS = kConsumerThreads * Vec<T>::N / TILE;  // row split of sweep 1
+  FusedLayout L;
+  L.GR = (nres + kGroup - 1) / kGroup;
+  L.GS0 = (nstr0 + kGroup - 1) / kGroup;
+  L.GS1 = (nstr1 + kGroup - 1) / kGroup;
+  L.GS = L.GS0 + L.GS1;
+  size_t o = 0;
+  L.res = o;  o += (size_t)2 * L.GR * kGroup * TILE;
+  L.ring = o; o += L.GS > 0 ? (size_t)kStages * kGroup * TILE : 0;
+  L.vec = o;  o += (size_t)2 * (nvec > 0 ? nvec : 1) * TILE;
+  L.part = o; o += (size_t)RS * TILE;
+  L.xs = o;   o += (size_t)2 * TILE;
+  L.coef = o; o += (size_t)(L.GR + L.GS) * kGroup + kGroup;
+  L.elems = o;
+  L.bar_bytes = (size_t)(4 * L.GR + 2 * kStages + 4) * 8;
+  L.acc_bytes = (size_t)nres * 8;
+  L.total_bytes = (L.elems * sizeof(T) + 127) / 128 * 128 + L.bar_bytes + L.acc_bytes + 64;
+  return L;
+}
+
+template <typename T, int TILE>
 __global__ void __launch_bounds__(kStreamThreads, 2)
-k_project_tma(RowSource src, int nrows, const T* x, T* out, long long n, const double* __restrict__ coef_in,
-              double sign, double* __restrict__ partials, unsigned int* counter, Epi epi, int reverse) {
+k_fused_tma(const __grid_constant__ FusedArgs a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
-  constexpr int TILE = kConsumerThreads * EPT;
-  constexpr int LV = TILE / (32 * VN);  // 16-byte vectors per lane in sweep 2
+  constexpr int EPT = VN;                                // sweep 1: one 16-byte vector per thread and row
+  constexpr int RS = kConsumerThreads * VN / TILE;       // ... rows r == h (mod RS) of every group
+  constexpr int LV = TILE / (32 * VN);                   // vectors per lane (sweep 2)
+  constexpr int GRMAX = 16;                              // sweep-2 lane accumulators (nres <= 128)
+  static_assert(RS >= 1 && RS <= kGroup && TILE * RS == kConsumerThreads * VN, "bad tile");
+  constexpr int BOXC = TILE > 256 ? 256 : TILE;                                // box columns (<= 256)
+  constexpr int NBOX = TILE / BOXC;
+  static_assert(LV >= 1, "tile too small");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int ngroups = (nrows + kGroup - 1) / kGroup;
-  T* tile_s = reinterpret_cast<T*>(smem_raw);                    // [ngroups*8][TILE]
-  T* xs = tile_s + (size_t)ngroups * kGroup * TILE;              // [TILE]   x' of the tile
-  T* coef = xs + TILE;                                           // [ngroups*8]
-  uint64_t* full = reinterpret_cast<uint64_t*>(
-      smem_raw + (((size_t)ngroups * kGroup * (TILE + 1) + TILE) * sizeof(T) + 15) / 16 * 16);  // [ngroups]
-  uint64_t* tile_free = full + ngroups;
-  double* acc_s = reinterpret_cast<double*>(tile_free + 1);      // [nrows]
+  const int nres = a.nres, nvec = a.nvec;
+  const FusedLayout L = fused_layout<T, TILE>(nres, a.nstr0, a.nstr1, nvec);
+  const int GR = L.GR, GS = L.GS, GS0 = L.GS0;
+  T* base = reinterpret_cast<T*>(smem_raw);
+  T* res_s = base + L.res;    // [2][GR*8][TILE]
+  T* ring_s = base + L.ring;  // [3][8][TILE]
+  T* vec_s = base + L.vec;    // [2][nvec][TILE]
+  T* part_s = base + L.part;  // [RS][TILE]
+  T* xs = base + L.xs;        // [2][TILE]
+  T* coef = base + L.coef;    // [GR*8][GS*8][8]
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(smem_raw + (L.elems * sizeof(T) + 127) / 128 * 128);  // [2][GR]
+  uint64_t* res_empty = res_full + 2 * GR;      // [2][GR]
+  uint64_t* ring_full = res_empty + 2 * GR;     // [3]
+  uint64_t* ring_empty = ring_full + kStages;   // [3]
+  uint64_t* x_full = ring_empty + kStages;      // [2]
+  uint64_t* x_empty = x_full + 2;               // [2]
+  double* acc_s = reinterpret_cast<double*>(x_empty + 2);  // [nres]
+  __shared__ T oscale;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int g = 0; g < ngroups; ++g) tma::mbar_init(full + g, 1);
-    tma::mbar_init(tile_free, kConsumerWarps);
+    for (int g = 0; g < 2 * GR; ++g) {
+      tma::mbar_init(res_full + g, 1);
+      tma::mbar_init(res_empty + g, kConsumerWarps);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      tma::mbar_init(ring_full + s, 1);
+      tma::mbar_init(ring_empty + s, kConsumerWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
+      tma::mbar_init(x_full + s, 1);
+      tma::mbar_init(x_empty + s, kConsumerWarps);
+    }
     tma::fence_barrier_init();
   }
-  for (int j = threadIdx.x; j < nrows; j += blockDim.x) acc_s[j] = 0.0;
+  for (int j = threadIdx.x; j < nres; j += blockDim.x) acc_s[j] = 0.0;
   __syncthreads();
   tma::griddep_launch_dependents();
 
-  const ColumnRange cr = block_columns<T>(n, TILE);
+  const ColumnRange cr = block_columns<T>(a.n, TILE);
+  const int reverse = a.reverse;
+  constexpr uint32_t kBoxBytes = (uint32_t)kGroup * TILE * sizeof(T);
 
   if (warp == kConsumerWarps) {
-    if (lane == 0) {
-      for (int tt = 0; tt < cr.ntiles; ++tt) {
+    if (lane == 0) {  // ---- producer ----
+      tma::prefetch_tensormap(&a.map_res);
+      if (GS > 0) {
+        tma::prefetch_tensormap(&a.map_str0);
+        tma::prefetch_tensormap(&a.map_str1);
+      }
+      bool waited = false;
+      int its = 0;      // running index of streamed groups (ring position)
+      int vec_next = 0; // next tile whose vector terms have to be issued
+      auto issue_vec = [&](int tt) {
+        if (nvec == 0) return;
         const int t = reverse ? cr.ntiles - 1 - tt : tt;
         const long long tc0 = cr.c0 + (long long)t * TILE;
         const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
         const uint32_t bytes = (uint32_t)len * sizeof(T);
-        tma::mbar_wait(tile_free, (tt & 1) ^ 1);  // both sweeps of the previous tile are done
-        for (int gg = 0; gg < ngroups; ++gg) {
-          const int g = reverse ? ngroups - 1 - gg : gg;
-          const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
-          tma::mbar_arrive_expect_tx(full + g, bytes * rows_here);
-          for (int r = 0; r < rows_here; ++r)
-            tma::bulk_g2s(tile_s + (size_t)(g * kGroup + r) * TILE,
-                          src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes, full + g);
+        const int b = tt & 1;
+        tma::mbar_wait(x_empty + b, ((tt >> 1) & 1) ^ 1);
+        tma::mbar_arrive_expect_tx(x_full + b, bytes * nvec);
+        for (int v = 0; v < nvec; ++v)
+          tma::bulk_g2s(vec_s + ((size_t)b * nvec + v) * TILE, static_cast<const T*>(a.vec[v].ptr) + tc0, bytes,
+                        x_full + b);
+      };
+      for (int tt = 0; tt < cr.ntiles; ++tt) {
+        const int t = reverse ? cr.ntiles - 1 - tt : tt;
+        const int tc0 = (int)(cr.c0 + (long long)t * TILE);
+        const int b = tt & 1;
+        const uint32_t ph = (tt >> 1) & 1;
+        if (waited && vec_next <= tt) issue_vec(vec_next++);
+        for (int gg = 0; gg < GR; ++gg) {
+          const int g = reverse ? GR - 1 - gg : gg;
+          tma::mbar_wait(res_empty + b * GR + g, ph ^ 1);  // sweep 2 of tile tt-2 released this box
+          tma::mbar_arrive_expect_tx(res_full + b * GR + g, kBoxBytes);
+          T* dst = res_s + ((size_t)b * GR + g) * kGroup * TILE;
+#pragma unroll
+          for (int bx = 0; bx < NBOX; ++bx)
+            tma::tensor_g2s_2d(dst + (size_t)bx * kGroup * BOXC, &a.map_res, tc0 + bx * BOXC, g * kGroup,
+                               res_full + b * GR + g);
+        }
+        if (!waited && (tt == 1 || cr.ntiles == 1 || GS > 0)) {
+          // the resident rows of the first two tiles were prefetched; everything else may be the
+          // predecessor's output and has to wait for it
+          tma::griddep_wait();
+          waited = true;
+          issue_vec(vec_next++);
+          if (tt == 1) issue_vec(vec_next++);
+        }
+        for (int gs = 0; gs < GS; ++gs, ++its) {
+          const int s = its % kStages;
+          tma::mbar_wait(ring_empty + s, ((its / kStages) & 1) ^ 1);
+          tma::mbar_arrive_expect_tx(ring_full + s, kBoxBytes);
+          T* dst = ring_s + (size_t)s * kGroup * TILE;
+          const bool first = gs < GS0;
+          const void* map = first ? &a.map_str0 : &a.map_str1;
+          const int row = first ? a.row_str0 + gs * kGroup : a.row_str1 + (gs - GS0) * kGroup;
+#pragma unroll
+          for (int bx = 0; bx < NBOX; ++bx)
+            tma::tensor_g2s_2d(dst + (size_t)bx * kGroup * BOXC, map, tc0 + bx * BOXC, row, ring_full + s);
         }
       }
     }
   } else {
     const int tid = threadIdx.x;
-    tma::griddep_wait();  // coefficients come from the predecessor's epilogue
-    for (int j = tid; j < ngroups * kGroup; j += kConsumerThreads)
-      coef[j] = j < nrows ? static_cast<T>(sign * coef_in[j]) : T(0);
+    const int c = (tid % (TILE / VN)) * VN;  // first column of this thread inside the tile
+    const int h = tid / (TILE / VN);         // row-split index: this thread takes rows r == h (mod RS)
+    tma::griddep_wait();  // coefficients / scalars come from the predecessor's epilogue
+    if (tid == 0) oscale = a.out_div_ptr ? static_cast<T>(*a.out_div_ptr) : T(1);
+    for (int j = tid; j < GR * kGroup; j += kConsumerThreads)
+      coef[j] = j < nres ? static_cast<T>(a.sign_res * a.coef_res[j]) : T(0);
+    for (int j = tid; j < GS * kGroup; j += kConsumerThreads) {
+      T cv = T(0);
+      if (j < GS0 * kGroup) {
+        if (j < a.nstr0) cv = static_cast<T>(a.sign_str0 * a.coef_str0[j]);
+      } else if (j - GS0 * kGroup < a.nstr1) {
+        cv = static_cast<T>(a.sign_str1 * a.coef_str1[j - GS0 * kGroup]);
+      }
+      coef[GR * kGroup + j] = cv;
+    }
+    if (tid < kGroup) {
+      T cv = T(0);
+      if (tid < nvec) {
+        const VecTerm& v = a.vec[tid];
+        cv = static_cast<T>(v.coef_imm * (v.coef_ptr ? *v.coef_ptr : 1.0));
+      }
+      coef[(GR + GS) * kGroup + tid] = cv;
+    }
     tma::named_bar_sync(2, kConsumerThreads);
+    const T* cvec = coef + (GR + GS) * kGroup;
+    int its = 0;
+    // sweep-2 partial dots stay in registers across tiles (one per group: row 8g + warp) and are
+    // reduced across lanes once, after the last tile
+    T lane_acc[GRMAX];
+#pragma unroll
+    for (int g = 0; g < GRMAX; ++g) lane_acc[g] = T(0);
     for (int tt = 0; tt < cr.ntiles; ++tt) {
       const int t = reverse ? cr.ntiles - 1 - tt : tt;
       const long long tc0 = cr.c0 + (long long)t * TILE;
       const int len = (int)((cr.c1 - tc0) < TILE ? (cr.c1 - tc0) : TILE);
-      // ---- sweep 1: x' = x + sum_j coef_j row_j (thread <-> EPT consecutive columns) ----
+      const int b = tt & 1;
+      const uint32_t ph = (tt >> 1) & 1;
+      // ---- sweep 1: thread <-> (one 16-byte vector of columns, rows r == h mod RS of every group) ----
       T acc[EPT];
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) {
-        const long long col = tc0 + (long long)tid * EPT + k;
-        acc[k] = (tid * EPT + k < len && col < n) ? x[col] : T(0);
+      for (int k = 0; k < EPT; ++k) acc[k] = T(0);
+      if (nvec > 0) {
+        tma::mbar_wait(x_full + b, ph);
+        if (h == 0 && c < len) {
+          for (int v = 0; v < nvec; ++v) {
+            T e[EPT];
+            load_ept<T, EPT>(vec_s + ((size_t)b * nvec + v) * TILE + c, e);
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) acc[k] = fma(cvec[v], e[k], acc[k]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(x_empty + b);
       }
-      for (int gg = 0; gg < ngroups; ++gg) {
-        const int g = reverse ? ngroups - 1 - gg : gg;
-        tma::mbar_wait(full + g, tt & 1);
-        const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
-        const T* st = tile_s + (size_t)g * kGroup * TILE + tid * EPT;
+      // element (row r, column cc) of a [8][TILE] slot built from NBOX boxes of [8][BOXC]
+      const int boff = (c / BOXC) * kGroup * BOXC + (c % BOXC);
+      for (int gg = 0; gg < GR; ++gg) {
+        const int g = reverse ? GR - 1 - gg : gg;
+        tma::mbar_wait(res_full + b * GR + g, ph);
+        const T* st = res_s + ((size_t)b * GR + g) * kGroup * TILE + boff;
         const T* cf = coef + g * kGroup;
-        if (tid * EPT < len) {
 #pragma unroll
-          for (int r = 0; r < kGroup; ++r) {
-            if (r < rows_here) {
-              T e[EPT];
-              load_ept<T, EPT>(st + (size_t)r * TILE, e);
+        for (int r = 0; r < kGroup / RS; ++r) {
+          const int rr = r * RS + h;
+          T e[EPT];
+          load_ept<T, EPT>(st + (size_t)rr * BOXC, e);
 #pragma unroll
-              for (int k = 0; k < EPT; ++k) acc[k] = fma(cf[r], e[k], acc[k]);
-            }
+          for (int k = 0; k < EPT; ++k) acc[k] = fma(cf[rr], e[k], acc[k]);
+        }
+      }
+      for (int gs = 0; gs < GS; ++gs, ++its) {
+        const int s = its % kStages;
+        tma::mbar_wait(ring_full + s, (its / kStages) & 1);
+        const T* st = ring_s + (size_t)s * kGroup * TILE + boff;
+        const T* cf = coef + (GR + gs) * kGroup;
+#pragma unroll
+        for (int r = 0; r < kGroup / RS; ++r) {
+          const int rr = r * RS + h;
+          T e[EPT];
+          load_ept<T, EPT>(st + (size_t)rr * BOXC, e);
+#pragma unroll
+          for (int k = 0; k < EPT; ++k) acc[k] = fma(cf[rr], e[k], acc[k]);
+        }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(ring_empty + s);
+      }
+      if (RS > 1) {  // combine the row-split partial sums
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) part_s[(size_t)h * TILE + c + k] = acc[k];
+        tma::named_bar_sync(1, kConsumerThreads);
+        if (h == 0) {
+#pragma unroll
+          for (int k = 0; k < EPT; ++k) {
+            T sacc = T(0);
+#pragma unroll
+            for (int hh = 0; hh < RS; ++hh) sacc += part_s[(size_t)hh * TILE + c + k];
+            acc[k] = sacc;
           }
         }
       }
+      T* xcur = xs + (size_t)b * TILE;
+      if (h == 0) {
+        T val[EPT];
+        bool all_ok = true;
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) {
-        const long long col = tc0 + (long long)tid * EPT + k;
-        const bool ok = tid * EPT + k < len && col < n;
-        xs[tid * EPT + k] = ok ? acc[k] : T(0);
-        if (ok) out[col] = acc[k];
+        for (int k = 0; k < EPT; ++k) {
+          const bool ok = c + k < len && tc0 + c + k < a.n;
+          val[k] = ok ? acc[k] / oscale : T(0);
+          all_ok = all_ok && ok;
+        }
+        *reinterpret_cast<V*>(xcur + c) = vec_pack(val);
+        if (all_ok) {
+          *reinterpret_cast<V*>(static_cast<T*>(a.out) + tc0 + c) = vec_pack(val);
+        } else {
+#pragma unroll
+          for (int k = 0; k < EPT; ++k)
+            if (c + k < len && tc0 + c + k < a.n) static_cast<T*>(a.out)[tc0 + c + k] = val[k];
+        }
       }
       tma::named_bar_sync(1, kConsumerThreads);
-      // ---- sweep 2: red[j] += <row_j, x'>, warp w owns rows w, w+8, ... ----
+      // ---- sweep 2: red[8g + w] += <row, out tile>; boxes released in the order they get refilled ----
       V xv[LV];
 #pragma unroll
-      for (int u = 0; u < LV; ++u) xv[u] = reinterpret_cast<const V*>(xs)[lane + 32 * u];
-      // four rows per iteration: four independent reduction chains hide the shuffle latency
-      for (int j = warp; j < nrows; j += 4 * kConsumerWarps) {
-        T a[4];
+      for (int u = 0; u < LV; ++u) xv[u] = reinterpret_cast<const V*>(xcur)[lane + 32 * u];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int jj = j + q4 * kConsumerWarps;
-          a[q4] = T(0);
-          if (jj < nrows) {
-            const V* row = reinterpret_cast<const V*>(tile_s + (size_t)jj * TILE);
+      for (int gg = 0; gg < GRMAX; ++gg) {
+        if (gg < GR) {
+          const int g = reverse ? GR - 1 - gg : gg;
+          if (g * kGroup + warp < nres) {
+            const T* slot = res_s + ((size_t)b * GR + g) * kGroup * TILE;
+            T p = T(0);
 #pragma unroll
             for (int u = 0; u < LV; ++u) {
-              if ((lane + 32 * u) * VN < len) {
-                T q[VN], xx[VN];
-                vec_unpack(row[lane + 32 * u], q);
-                vec_unpack(xv[u], xx);
+              const int cc = (lane + 32 * u) * VN;  // column inside the tile
+              const V qv = *reinterpret_cast<const V*>(slot + (cc / BOXC) * kGroup * BOXC + warp * BOXC + (cc % BOXC));
+              T q[VN], xx[VN];
+              vec_unpack(qv, q);
+              vec_unpack(xv[u], xx);
 #pragma unroll
-                for (int k = 0; k < VN; ++k) a[q4] = fma(q[k], xx[k], a[q4]);
-              }
+              for (int k = 0; k < VN; ++k) p = fma(q[k], xx[k], p);
             }
+            lane_acc[gg] += p;
           }
-        }
-        double d[4];
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) d[q4] = static_cast<double>(a[q4]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) d[q4] += __shfl_xor_sync(0xffffffffu, d[q4], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            if (j + q4 * kConsumerWarps < nrows) acc_s[j + q4 * kConsumerWarps] += d[q4];
+          __syncwarp();
+          if (lane == 0) tma::mbar_arrive(res_empty + b * GR + g);
         }
       }
-      __syncwarp();
-      if (lane == 0) tma::mbar_arrive(tile_free);
-      tma::named_bar_sync(1, kConsumerThreads);  // xs is rewritten by the next tile's sweep 1
+    }
+    // one cross-lane reduction per row for the whole block
+#pragma unroll
+    for (int gg = 0; gg < GRMAX; ++gg) {
+      if (gg < GR) {
+        const int g = reverse ? GR - 1 - gg : gg;
+        const double d = warp_sum(static_cast<double>(lane_acc[gg]));
+        if (lane == 0 && g * kGroup + warp < nres) acc_s[g * kGroup + warp] = d;
+      }
     }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < nrows; j += blockDim.x) partials[(size_t)j * gridDim.x + blockIdx.x] = acc_s[j];
-  if (!last_block_done(counter)) return;
-  reduce_partials_and_epilogue<T>(nrows, partials, epi);
+  for (int j = threadIdx.x; j < nres; j += blockDim.x) a.partials[(size_t)j * gridDim.x + blockIdx.x] = acc_s[j];
+  if (!last_block_done(a.counter)) return;
+  reduce_partials_and_epilogue<T>(nres, a.partials, a.epi);
 }
 
 }  // namespace bl

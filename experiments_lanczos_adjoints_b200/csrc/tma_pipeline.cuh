@@ -79,6 +79,21 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   return p;
 }
 
+// 2-D tiled TMA load through a tensor map (`cp.async.bulk.tensor`, SASS UTMALDG): one
+// instruction moves a [box_rows x box_cols] box; elements outside the tensor are zero-filled
+// and the mbarrier always receives the full box size.
+__device__ __forceinline__ void tensor_g2s_2d(void* dst_smem, const void* tensor_map, int col, int row,
+                                              uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(tensor_map)), "r"(col), "r"(row), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const void* tensor_map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tensor_map)) : "memory");
+}
+
 // named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
