@@ -263,12 +263,13 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // Row-major [rows x ld] basis buffer, box = [8 rows x box_cols]; out-of-range elements read as 0.
-int make_basis_map(CUtensorMap* map, int dtype, const void* base, int64_t ld, int64_t rows, int box_cols) {
+int make_basis_map(CUtensorMap* map, int dtype, const void* base, int64_t ld, int64_t rows, int box_cols,
+                   int box_rows = kGroup) {
   EncodeTiledFn fn = encode_tiled_fn();
   BL_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
   const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)std::max<int64_t>(rows, 1)};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * dtype_size(dtype)};
-  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kGroup};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estride[2] = {1, 1};
   CUresult r = fn(map, dtype == BL_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
                   const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -295,9 +296,9 @@ struct FusedSpec {
 };
 
 template <typename T, int TILE>
-int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, cudaStream_t s) {
+int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, int sr, cudaStream_t s) {
   constexpr int BOXC = TILE > 256 ? 256 : TILE;
-  const FusedLayout L = fused_layout<T, TILE>(f.res.nrows, f.str0.nrows, f.str1.nrows, f.nvec);
+  const FusedLayout L = fused_layout<T, TILE>(f.res.nrows, f.str0.nrows, f.str1.nrows, f.nvec, sr);
   static bool once = false;
   if (!once) {
     BL_CHECK(set_smem(k_fused_tma<T, TILE>, 225 * 1024));
@@ -307,11 +308,11 @@ int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, cudaStream
   const char* res_base = static_cast<const char*>(f.res.base) + (int64_t)f.res.row0 * f.res.ld * (int64_t)sizeof(T);
   BL_CHECK(make_basis_map(&a.map_res, dtype, res_base, f.res.ld, f.res.nrows, BOXC));
   if (f.str0.nrows > 0)
-    BL_CHECK(make_basis_map(&a.map_str0, dtype, f.str0.base, f.str0.ld, f.rows_total0, BOXC));
+    BL_CHECK(make_basis_map(&a.map_str0, dtype, f.str0.base, f.str0.ld, f.rows_total0, BOXC, sr));
   else
     a.map_str0 = a.map_res;
   if (f.str1.nrows > 0)
-    BL_CHECK(make_basis_map(&a.map_str1, dtype, f.str1.base, f.str1.ld, f.rows_total1, BOXC));
+    BL_CHECK(make_basis_map(&a.map_str1, dtype, f.str1.base, f.str1.ld, f.rows_total1, BOXC, sr));
   else
     a.map_str1 = a.map_res;
   a.n = f.n;
@@ -330,6 +331,7 @@ int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, cudaStream
   a.coef_str1 = f.str1.coef ? f.str1.coef + f.str1.coef0 : nullptr;
   a.sign_str1 = f.str1.sign;
   a.out_div_ptr = f.out_div_ptr;
+  a.sr = sr;
   a.partials = c.partials_dots;
   a.counter = c.counters + 0;
   a.epi = f.epi;
@@ -353,13 +355,20 @@ int launch_fused(const Common& c, const FusedSpec& f, int dtype, cudaStream_t s,
   constexpr int TMAX = 4096 / (int)sizeof(T);  // 1024 floats / 512 doubles
   const int nr = f.res.nrows, n0 = f.str0.nrows, n1 = f.str1.nrows, nv = f.nvec;
   *fused = true;
-  if (fused_layout<T, TMAX>(nr, n0, n1, nv).total_bytes <= two_per_sm) return launch_fused_tile<T, TMAX>(c, f, dtype, s);
-  if (fused_layout<T, TMAX / 2>(nr, n0, n1, nv).total_bytes <= two_per_sm)
-    return launch_fused_tile<T, TMAX / 2>(c, f, dtype, s);
-  if (fused_layout<T, TMAX / 4>(nr, n0, n1, nv).total_bytes <= two_per_sm)
-    return launch_fused_tile<T, TMAX / 4>(c, f, dtype, s);
-  if (fused_layout<T, TMAX / 8>(nr, n0, n1, nv).total_bytes <= two_per_sm)
-    return launch_fused_tile<T, TMAX / 8>(c, f, dtype, s);
+  // widest tile that leaves room for two blocks per SM; streamed rows travel in groups of 32,
+  // 16 or 8 rows per ring stage (bigger stages amortise the per-stage barrier traffic)
+  const int srs[3] = {32, 16, 8};
+  for (int k = 0; k < 3; ++k) {
+    const int sr = (n0 + n1 > 0) ? srs[k] : kGroup;
+    if (fused_layout<T, TMAX>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm) return launch_fused_tile<T, TMAX>(c, f, dtype, sr, s);
+    if (fused_layout<T, TMAX / 2>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm)
+      return launch_fused_tile<T, TMAX / 2>(c, f, dtype, sr, s);
+    if (fused_layout<T, TMAX / 4>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm)
+      return launch_fused_tile<T, TMAX / 4>(c, f, dtype, sr, s);
+    if (fused_layout<T, TMAX / 8>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm)
+      return launch_fused_tile<T, TMAX / 8>(c, f, dtype, sr, s);
+    if (n0 + n1 == 0) break;
+  }
   *fused = false;
   return BL_OK;
 }

@@ -493,6 +493,7 @@ struct alignas(64) FusedArgs {
   double* partials = nullptr;
   unsigned int* counter = nullptr;
   int reverse = 0;
+  int sr = kGroup;  // rows per streamed group (box rows of map_str0/1): 8, 16 or 32
   Epi epi;
 };
 
@@ -503,20 +504,20 @@ struct FusedLayout {
 };
 
 template <typename T, int TILE>
-__host__ __device__ inline FusedLayout fused_layout(int nres, int nstr0, int nstr1, int nvec) {
+__host__ __device__ inline FusedLayout fused_layout(int nres, int nstr0, int nstr1, int nvec, int sr) {
   constexpr int RS = kConsumerThreads * Vec<T>::N / TILE;  // row split of sweep 1
   FusedLayout L;
   L.GR = (nres + kGroup - 1) / kGroup;
-  L.GS0 = (nstr0 + kGroup - 1) / kGroup;
-  L.GS1 = (nstr1 + kGroup - 1) / kGroup;
+  L.GS0 = (nstr0 + sr - 1) / sr;
+  L.GS1 = (nstr1 + sr - 1) / sr;
   L.GS = L.GS0 + L.GS1;
   size_t o = 0;
   L.res = o;  o += (size_t)2 * L.GR * kGroup * TILE;
-  L.ring = o; o += L.GS > 0 ? (size_t)kStages * kGroup * TILE : 0;
+  L.ring = o; o += L.GS > 0 ? (size_t)kStages * sr * TILE : 0;
   L.vec = o;  o += (size_t)2 * (nvec > 0 ? nvec : 1) * TILE;
   L.part = o; o += (size_t)RS * TILE;
   L.xs = o;   o += (size_t)2 * TILE;
-  L.coef = o; o += (size_t)(L.GR + L.GS) * kGroup + kGroup;
+  L.coef = o; o += (size_t)L.GR * kGroup + (size_t)L.GS * sr + kGroup;
   L.elems = o;
   L.bar_bytes = (size_t)(4 * L.GR + 2 * kStages + 4) * 8;
   L.acc_bytes = (size_t)nres * 8;
@@ -539,15 +540,16 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
   static_assert(LV >= 1, "tile too small");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nres = a.nres, nvec = a.nvec;
-  const FusedLayout L = fused_layout<T, TILE>(nres, a.nstr0, a.nstr1, nvec);
+  const int SR = a.sr;
+  const FusedLayout L = fused_layout<T, TILE>(nres, a.nstr0, a.nstr1, nvec, SR);
   const int GR = L.GR, GS = L.GS, GS0 = L.GS0;
   T* base = reinterpret_cast<T*>(smem_raw);
   T* res_s = base + L.res;    // [2][GR*8][TILE]
-  T* ring_s = base + L.ring;  // [3][8][TILE]
+  T* ring_s = base + L.ring;  // [3][SR][TILE]
   T* vec_s = base + L.vec;    // [2][nvec][TILE]
   T* part_s = base + L.part;  // [RS][TILE]
   T* xs = base + L.xs;        // [2][TILE]
-  T* coef = base + L.coef;    // [GR*8][GS*8][8]
+  T* coef = base + L.coef;    // [GR*8][GS*SR][8]
   uint64_t* res_full = reinterpret_cast<uint64_t*>(smem_raw + (L.elems * sizeof(T) + 127) / 128 * 128);  // [2][GR]
   uint64_t* res_empty = res_full + 2 * GR;      // [2][GR]
   uint64_t* ring_full = res_empty + 2 * GR;     // [3]
@@ -631,14 +633,14 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
         for (int gs = 0; gs < GS; ++gs, ++its) {
           const int s = its % kStages;
           tma::mbar_wait(ring_empty + s, ((its / kStages) & 1) ^ 1);
-          tma::mbar_arrive_expect_tx(ring_full + s, kBoxBytes);
-          T* dst = ring_s + (size_t)s * kGroup * TILE;
+          tma::mbar_arrive_expect_tx(ring_full + s, (uint32_t)SR * TILE * sizeof(T));
+          T* dst = ring_s + (size_t)s * SR * TILE;
           const bool first = gs < GS0;
           const void* map = first ? &a.map_str0 : &a.map_str1;
-          const int row = first ? a.row_str0 + gs * kGroup : a.row_str1 + (gs - GS0) * kGroup;
+          const int row = first ? a.row_str0 + gs * SR : a.row_str1 + (gs - GS0) * SR;
 #pragma unroll
           for (int bx = 0; bx < NBOX; ++bx)
-            tma::tensor_g2s_2d(dst + (size_t)bx * kGroup * BOXC, map, tc0 + bx * BOXC, row, ring_full + s);
+            tma::tensor_g2s_2d(dst + (size_t)bx * SR * BOXC, map, tc0 + bx * BOXC, row, ring_full + s);
         }
       }
     }
@@ -650,12 +652,12 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
     if (tid == 0) oscale = a.out_div_ptr ? static_cast<T>(*a.out_div_ptr) : T(1);
     for (int j = tid; j < GR * kGroup; j += kConsumerThreads)
       coef[j] = j < nres ? static_cast<T>(a.sign_res * a.coef_res[j]) : T(0);
-    for (int j = tid; j < GS * kGroup; j += kConsumerThreads) {
+    for (int j = tid; j < GS * SR; j += kConsumerThreads) {
       T cv = T(0);
-      if (j < GS0 * kGroup) {
+      if (j < GS0 * SR) {
         if (j < a.nstr0) cv = static_cast<T>(a.sign_str0 * a.coef_str0[j]);
-      } else if (j - GS0 * kGroup < a.nstr1) {
-        cv = static_cast<T>(a.sign_str1 * a.coef_str1[j - GS0 * kGroup]);
+      } else if (j - GS0 * SR < a.nstr1) {
+        cv = static_cast<T>(a.sign_str1 * a.coef_str1[j - GS0 * SR]);
       }
       coef[GR * kGroup + j] = cv;
     }
@@ -665,10 +667,10 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
         const VecTerm& v = a.vec[tid];
         cv = static_cast<T>(v.coef_imm * (v.coef_ptr ? *v.coef_ptr : 1.0));
       }
-      coef[(GR + GS) * kGroup + tid] = cv;
+      coef[GR * kGroup + GS * SR + tid] = cv;
     }
     tma::named_bar_sync(2, kConsumerThreads);
-    const T* cvec = coef + (GR + GS) * kGroup;
+    const T* cvec = coef + GR * kGroup + GS * SR;
     int its = 0;
     // sweep-2 partial dots stay in registers across tiles (one per group: row 8g + warp) and are
     // reduced across lanes once, after the last tile
@@ -717,10 +719,10 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
       for (int gs = 0; gs < GS; ++gs, ++its) {
         const int s = its % kStages;
         tma::mbar_wait(ring_full + s, (its / kStages) & 1);
-        const T* st = ring_s + (size_t)s * kGroup * TILE + boff;
-        const T* cf = coef + (GR + gs) * kGroup;
-#pragma unroll
-        for (int r = 0; r < kGroup / RS; ++r) {
+        const T* st = ring_s + (size_t)s * SR * TILE + (c / BOXC) * SR * BOXC + (c % BOXC);
+        const T* cf = coef + GR * kGroup + gs * SR;
+#pragma unroll 4
+        for (int r = 0; r < SR / RS; ++r) {
           const int rr = r * RS + h;
           T e[EPT];
           load_ept<T, EPT>(st + (size_t)rr * BOXC, e);
