@@ -297,8 +297,8 @@ def main():
     dom_gbs = d["algorithmic_bytes"] / max(d["ms"], 1e-9) / 1e6
     prof_total = sum(c["ms"] for c in prof.values())
     roofline = {
-        "bound": "hbm", "kernel": {"dots": "k_dots", "combine": "k_combine", "matvec": "k_sell_spmv", "vjp": "k_sell_vjp",
-                                   "other": "k_scale_copy"}[dom],
+        "bound": "hbm", "kernel": {"dots": "k_dots_tma", "combine": "k_combine_tma", "matvec": "k_sell_spmv",
+                                   "vjp": "k_sell_vjp", "other": "k_scale_copy", "fused": "k_fused_tma"}[dom],
         "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "peak_source": peak_src,
         "traffic": None, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / max(1, d["launches"]),
         "share_of_step": d["ms"] / max(prof_total, 1e-9),

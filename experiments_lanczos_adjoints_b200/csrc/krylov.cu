@@ -339,7 +339,7 @@ int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, int sr, cu
   a.epi.scal = c.scal;
   a.reverse = next_direction();
   const int nrows = f.res.nrows + f.str0.nrows + f.str1.nrows;
-  ProfScope prof(BL_PROF_COMBINE, (double)(nrows + f.nvec + 1) * f.n * sizeof(T), s);
+  ProfScope prof(BL_PROF_FUSED, (double)(nrows + f.nvec + 1) * f.n * sizeof(T), s);
   BL_CUDA(launch_pdl(k_fused_tma<T, TILE>, tma_grid<T>(f.n, TILE), kStreamThreads, L.total_bytes, s, a));
   BL_LAUNCHED();
   return BL_OK;

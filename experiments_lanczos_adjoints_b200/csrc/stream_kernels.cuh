@@ -772,7 +772,8 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
       for (int u = 0; u < LV; ++u) xv[u] = reinterpret_cast<const V*>(xcur)[lane + 32 * u];
 #pragma unroll
       for (int gg = 0; gg < GRMAX; ++gg) {
-        if (gg < GR) {
+        if (gg >= GR) break;  // (unrolled for static register indexing; skip the unused copies)
+        {
           const int g = reverse ? GR - 1 - gg : gg;
           if (g * kGroup + warp < nres) {
             const T* slot = res_s + ((size_t)b * GR + g) * kGroup * TILE;
@@ -797,7 +798,8 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
     // one cross-lane reduction per row for the whole block
 #pragma unroll
     for (int gg = 0; gg < GRMAX; ++gg) {
-      if (gg < GR) {
+      if (gg >= GR) break;
+      {
         const int g = reverse ? GR - 1 - gg : gg;
         const double d = warp_sum(static_cast<double>(lane_acc[gg]));
         if (lane == 0 && g * kGroup + warp < nres) acc_s[g * kGroup + warp] = d;

@@ -120,14 +120,14 @@ class TridiagAdjointPlan:
 def profile(fn):
     """Run `fn()` with per-kernel-class event timing; returns
     `{class: {"launches", "ms", "algorithmic_bytes"}}` (see `bl_profile_begin` in the header)."""
-    names = ["dots", "combine", "matvec", "vjp", "other"]
+    names = ["dots", "combine", "matvec", "vjp", "other", "fused"]
     _lib.call("bl_profile_begin")
     try:
         fn()
     finally:
-        counts = (C.c_uint64 * 5)()
-        ms = (C.c_double * 5)()
-        nbytes = (C.c_double * 5)()
+        counts = (C.c_uint64 * len(names))()
+        ms = (C.c_double * len(names))()
+        nbytes = (C.c_double * len(names))()
         _lib.call("bl_profile_end", counts, ms, nbytes)
     return {nm: {"launches": int(counts[i]), "ms": float(ms[i]), "algorithmic_bytes": float(nbytes[i])}
             for i, nm in enumerate(names)}  # fmt: skip

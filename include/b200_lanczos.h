@@ -77,7 +77,8 @@ int bl_launch_count(uint64_t* count);
  * summed ALGORITHMIC bytes (rows*n*w for basis rows, n*w per dense vector read or written,
  * nnz*(w+4)+4(n+1) for the sparse operand).  Classes: */
 enum { BL_PROF_DOTS = 0, BL_PROF_COMBINE = 1, BL_PROF_MATVEC = 2, BL_PROF_VJP = 3, BL_PROF_OTHER = 4,
-       BL_PROF_NCLASS = 5 };
+       BL_PROF_FUSED = 5, /* fused combine + dots (one read of the basis for both) */
+       BL_PROF_NCLASS = 6 };
 int bl_profile_begin(void);
 int bl_profile_end(uint64_t* counts, double* ms, double* bytes); /* arrays of BL_PROF_NCLASS */
 
