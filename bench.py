@@ -159,7 +159,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"sparse SPD COO n={N_ROWS} nnz={len(data)} depth={DEPTH} fwd+adjoint"},
+        "config": {"workload": f"sparse SPD COO operator n={N_ROWS} nnz={len(data)} ({2 * BANDS + 1}/row), Lanczos full "
+                               f"reortho depth {DEPTH}, forward + adjoint (cotangents on alpha/beta)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))  # fmt: skip
@@ -184,6 +185,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         import torch
         import torch.distributed as dist
 
