@@ -13,13 +13,14 @@
 #include <vector>
 
 #include "operators.cuh"
+#include "tma_pipeline.cuh"
 
 namespace bl {
 namespace {
 
 constexpr int kMaxDim = 32;
-constexpr int kTileI = 128;  // rows per block (one per thread)
-constexpr int kTileJ = 128;  // columns staged per iteration
+constexpr int kTileI = 128;  // threads per block; a block owns kTileI * RI rows
+constexpr int kTileJ = 64;   // points per staged column tile
 
 template <typename T>
 __device__ __forceinline__ T softplus_t(T x) {  // gp_util.py:188-199 (beta = 1, threshold = 20)
@@ -41,19 +42,23 @@ struct Eps<double> {
   static __device__ __forceinline__ double v() { return 2.220446049250313e-16; }
 };
 
-// scaled inputs xs = fac * x / softplus(raw_ls), squared norms, constrained scales
+// scaled inputs xs = fac * x / softplus(raw_ls) in a zero-padded [n][DP] layout (16-byte rows, so
+// a column tile is one contiguous TMA bulk copy), squared norms, constrained scales
 template <typename T>
-__global__ void k_gram_prepare(int64_t n, int d, int kind, const double* __restrict__ X,
+__global__ void k_gram_prepare(int64_t n, int d, int dp, int kind, const double* __restrict__ X,
                                const T* __restrict__ raw_ls, const T* __restrict__ raw_os,
                                T* __restrict__ xs, T* __restrict__ xx, T* __restrict__ consts) {
   const T fac = kind == 0 ? sqrt(T(3)) : T(1);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     T s = T(0);
-    for (int k = 0; k < d; ++k) {
-      const T ls = softplus_t(raw_ls[k]);
-      const T v = fac * static_cast<T>(X[i * d + k]) / ls;
-      xs[i * d + k] = v;
-      s = fma(v, v, s);  // jnp.dot(x, x)
+    for (int k = 0; k < dp; ++k) {
+      T v = T(0);
+      if (k < d) {
+        const T ls = softplus_t(raw_ls[k]);
+        v = fac * static_cast<T>(X[i * d + k]) / ls;
+        s = fma(v, v, s);  // jnp.dot(x, x)
+      }
+      xs[i * dp + k] = v;
     }
     xx[i] = s;
   }
@@ -79,96 +84,143 @@ __device__ __forceinline__ void kernel_eval(int kind, T sigma, T s2, T& k, T& dk
   }
 }
 
-// Row-tile x column-split sweep.  grid = (ceil(n/kTileI), jsplit).
+// Register-tiled sweep: a block owns kTileI * RI rows (thread t: rows i0 + t + 128 r), column
+// tiles of kTileJ points arrive by TMA bulk copies (double-buffered: scaled inputs, squared
+// norms, v / lam, q); every staged point is reused for RI kernel evaluations from registers.
+// grid = (row tiles, column splits).
 //   ADJ == false: part[split][i] = sum_{j in split} k_ij v_j
 //   ADJ == true : part[split][i] = sum_j k_ij lam_j ; block partial sums of
 //                 d_sigma = sum lam_i q_j k_ij / sigma and  d_ls[k] = sum lam_i q_j dk_ij (x_ik - x_jk)^2
-template <typename T, bool ADJ>
+template <typename T, int DP, int RI, bool ADJ>
 __global__ void __launch_bounds__(kTileI)
 k_gram_sweep(int64_t n, int d, int kind, const T* __restrict__ xs, const T* __restrict__ xx,
              const T* __restrict__ consts, const T* __restrict__ v, const T* __restrict__ q,
              T* __restrict__ part, double* __restrict__ gpart /* [blocks][d+1] */) {
-  extern __shared__ unsigned char smem_raw[];
-  T* sx = reinterpret_cast<T*>(smem_raw);  // [kTileJ][d]
-  T* sxx = sx + (size_t)kTileJ * d;        // [kTileJ]
-  T* sv = sxx + kTileJ;                    // [kTileJ]  v_j   (ADJ: lam_j)
-  T* sq = sv + kTileJ;                     // [kTileJ]  (ADJ: q_j)
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NV = DP / VN;
+  __shared__ __align__(128) T sx[2][kTileJ * DP];
+  __shared__ __align__(16) T sxx[2][kTileJ];
+  __shared__ __align__(16) T sv[2][kTileJ];
+  __shared__ __align__(16) T sq[2][kTileJ];
+  __shared__ uint64_t full[2];
   __shared__ double red_smem[32];
 
-  const int64_t i = (int64_t)blockIdx.x * kTileI + threadIdx.x;
-  const bool live = i < n;
+  const int tid = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * (kTileI * RI);
   const T sigma = consts[0];
-  T xi[kMaxDim];
+  T xi[RI][DP], xxi[RI], lam_i[RI];
+  bool live[RI];
 #pragma unroll
-  for (int k = 0; k < kMaxDim; ++k) xi[k] = (live && k < d) ? xs[i * d + k] : T(0);
-  const T xxi = live ? xx[i] : T(0);
-  const T lam_i = (ADJ && live) ? v[i] : T(0);
+  for (int r = 0; r < RI; ++r) {
+    const int64_t i = i0 + tid + (int64_t)kTileI * r;
+    live[r] = i < n;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xi[r][k] = live[r] ? xs[i * DP + k] : T(0);
+    xxi[r] = live[r] ? xx[i] : T(0);
+    lam_i[r] = (ADJ && live[r]) ? v[i] : T(0);
+  }
 
   const int64_t per = ((n + gridDim.y - 1) / gridDim.y + kTileJ - 1) / kTileJ * kTileJ;
   const int64_t j0 = per * blockIdx.y;
   const int64_t j1 = j0 + per < n ? j0 + per : n;
+  const int ntiles = j0 < j1 ? (int)((j1 - j0 + kTileJ - 1) / kTileJ) : 0;
 
-  double y_acc = 0.0, dsig_acc = 0.0;
-  double dls_acc[kMaxDim];
-#pragma unroll
-  for (int k = 0; k < kMaxDim; ++k) dls_acc[k] = 0.0;
-
-  for (int64_t jt = j0; jt < j1; jt += kTileJ) {
+  if (tid == 0) {
+    tma::mbar_init(full + 0, 1);
+    tma::mbar_init(full + 1, 1);
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t) {
+    const int b = t & 1;
+    const int64_t jt = j0 + (int64_t)t * kTileJ;
     const int w = (int)((j1 - jt) < kTileJ ? (j1 - jt) : kTileJ);
-    __syncthreads();
-    for (int e = threadIdx.x; e < w * d; e += blockDim.x) sx[e] = xs[jt * d + e];
-    for (int e = threadIdx.x; e < w; e += blockDim.x) {
-      sxx[e] = xx[jt + e];
-      sv[e] = v[jt + e];
-      if (ADJ) sq[e] = q[jt + e];
-    }
-    __syncthreads();
-    T y_t = T(0), dsig_t = T(0);
-    T dls_t[kMaxDim];
+    const uint32_t wv = (uint32_t)((w + VN - 1) / VN * VN) * sizeof(T);  // 16-byte granules
+    const uint32_t bx = (uint32_t)w * DP * sizeof(T);
+    tma::mbar_arrive_expect_tx(full + b, bx + wv * (ADJ ? 3u : 2u));
+    tma::bulk_g2s(sx[b], xs + jt * DP, bx, full + b);
+    tma::bulk_g2s(sxx[b], xx + jt, wv, full + b);
+    tma::bulk_g2s(sv[b], v + jt, wv, full + b);
+    if (ADJ) tma::bulk_g2s(sq[b], q + jt, wv, full + b);
+  };
+  if (tid == 0 && ntiles > 0) issue(0);
+
+  double y_acc[RI], dsig_acc = 0.0, dls_acc[DP];
 #pragma unroll
-    for (int k = 0; k < kMaxDim; ++k) dls_t[k] = T(0);
+  for (int r = 0; r < RI; ++r) y_acc[r] = 0.0;
+#pragma unroll
+  for (int k = 0; k < DP; ++k) dls_acc[k] = 0.0;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int b = t & 1;
+    if (tid == 0 && t + 1 < ntiles) issue(t + 1);  // stage (t+1)&1 was released by the barrier below
+    tma::mbar_wait(full + b, (t >> 1) & 1);
+    const int64_t jt = j0 + (int64_t)t * kTileJ;
+    const int w = (int)((j1 - jt) < kTileJ ? (j1 - jt) : kTileJ);
+    T y_t[RI], dsig_t = T(0), dls_t[DP];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) y_t[r] = T(0);
+#pragma unroll
+    for (int k = 0; k < DP; ++k) dls_t[k] = T(0);
     for (int jj = 0; jj < w; ++jj) {
-      const T* xj = sx + (size_t)jj * d;
-      T dot = T(0);
+      T xj[DP];
 #pragma unroll
-      for (int k = 0; k < kMaxDim; ++k)
-        if (k < d) dot = fma(xi[k], xj[k], dot);
-      T s2 = xxi + sxx[jj] - T(2) * dot;  // gp_util.py:92
-      const bool pos = s2 > T(0);
-      s2 = pos ? s2 : T(0);  // jnp.maximum(0.0, scaled)
-      T kij, dk;
-      kernel_eval<T>(kind, sigma, s2, kij, dk);
-      y_t = fma(kij, sv[jj], y_t);
-      if (ADJ) {
-        const T wgt = lam_i * sq[jj];
-        dsig_t = fma(wgt, kij, dsig_t);
-        const T g = pos ? wgt * dk : T(0);
+      for (int u = 0; u < NV; ++u) {
+        T tmp[VN];
+        vec_unpack(reinterpret_cast<const V*>(sx[b] + (size_t)jj * DP)[u], tmp);  // broadcast load
 #pragma unroll
-        for (int k = 0; k < kMaxDim; ++k)
-          if (k < d) {
-            const T diff = xi[k] - xj[k];
+        for (int k = 0; k < VN; ++k) xj[u * VN + k] = tmp[k];
+      }
+      const T xxj = sxx[b][jj], vj = sv[b][jj];
+      const T qj = ADJ ? sq[b][jj] : T(0);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        T dot = T(0);
+#pragma unroll
+        for (int k = 0; k < DP; ++k) dot = fma(xi[r][k], xj[k], dot);
+        T s2 = xxi[r] + xxj - T(2) * dot;  // gp_util.py:92
+        const bool pos = s2 > T(0);
+        s2 = pos ? s2 : T(0);  // jnp.maximum(0.0, scaled)
+        T kij, dk;
+        kernel_eval<T>(kind, sigma, s2, kij, dk);
+        y_t[r] = fma(kij, vj, y_t[r]);
+        if (ADJ) {
+          const T wgt = lam_i[r] * qj;
+          dsig_t = fma(wgt, kij, dsig_t);
+          const T g = pos ? wgt * dk : T(0);
+#pragma unroll
+          for (int k = 0; k < DP; ++k) {
+            const T diff = xi[r][k] - xj[k];
             dls_t[k] = fma(g, diff * diff, dls_t[k]);
           }
+        }
       }
     }
-    y_acc += static_cast<double>(y_t);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) y_acc[r] += static_cast<double>(y_t[r]);
     if (ADJ) {
       dsig_acc += static_cast<double>(dsig_t);
 #pragma unroll
-      for (int k = 0; k < kMaxDim; ++k)
-        if (k < d) dls_acc[k] += static_cast<double>(dls_t[k]);
+      for (int k = 0; k < DP; ++k) dls_acc[k] += static_cast<double>(dls_t[k]);
     }
+    __syncthreads();  // everyone is done with stage b
   }
-  if (live) part[(int64_t)blockIdx.y * n + i] = static_cast<T>(y_acc);
-  if (ADJ) {
-    const int b = blockIdx.y * gridDim.x + blockIdx.x;
-    double r = block_sum(live ? dsig_acc : 0.0, red_smem);
-    if (threadIdx.x == 0) gpart[(size_t)b * (d + 1) + d] = r;
 #pragma unroll
-    for (int k = 0; k < kMaxDim; ++k)
+  for (int r = 0; r < RI; ++r) {
+    const int64_t i = i0 + tid + (int64_t)kTileI * r;
+    if (live[r]) part[(int64_t)blockIdx.y * n + i] = static_cast<T>(y_acc[r]);
+  }
+  if (ADJ) {
+    // rows that are not live carry lam_i = 0, so their sums are already zero
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    double rsum = block_sum(dsig_acc, red_smem);
+    if (tid == 0) gpart[(size_t)blk * (d + 1) + d] = rsum;
+#pragma unroll
+    for (int k = 0; k < DP; ++k)
       if (k < d) {
-        r = block_sum(live ? dls_acc[k] : 0.0, red_smem);
-        if (threadIdx.x == 0) gpart[(size_t)b * (d + 1) + k] = r;
+        rsum = block_sum(dls_acc[k], red_smem);
+        if (tid == 0) gpart[(size_t)blk * (d + 1) + k] = rsum;
       }
   }
 }
@@ -226,20 +278,23 @@ struct GramOperator : bl_operator {
   int num_params() const override { return 3; }
   int64_t param_size(int i) const override { return i == 0 ? d : 1; }
 
-  int nblocks_i() const { return (int)((n + kTileI - 1) / kTileI); }
+  // padded point dimension (multiple of 4) and rows per thread
+  int dp() const { return d <= 4 ? 4 : d <= 8 ? 8 : d <= 12 ? 12 : d <= 16 ? 16 : 32; }
+  int ri() const { return dp() <= 16 ? 4 : 2; }
+  int nblocks_i() const { return (int)((n + (int64_t)kTileI * ri() - 1) / ((int64_t)kTileI * ri())); }
 
   template <typename T>
   int set_params_t(cudaStream_t s) {
-    BL_CHECK(xs.ensure((size_t)n * d * sizeof(T)));
-    BL_CHECK(xx.ensure((size_t)n * sizeof(T)));
+    BL_CHECK(xs.ensure(((size_t)n + kTileJ) * dp() * sizeof(T)));
+    BL_CHECK(xx.ensure(((size_t)n + kTileJ) * sizeof(T)));
     BL_CHECK(consts.ensure(4 * sizeof(T)));
     jsplit = std::max(1, std::min<int>(64, (4 * sm_count() + nblocks_i() - 1) / nblocks_i()));
     BL_CHECK(part.ensure((size_t)jsplit * n * sizeof(T)));
     BL_CHECK(gpart.ensure((size_t)jsplit * nblocks_i() * (d + 1) * sizeof(double)));
     BL_CHECK(grad.ensure((size_t)(d + 2) * sizeof(T)));
     k_gram_prepare<T><<<std::min<int>(1024, (int)((n + 255) / 256)), 256, 0, s>>>(
-        n, (int)d, kind, X.as<double>(), static_cast<const T*>(raw_ls), static_cast<const T*>(raw_os), xs.as<T>(),
-        xx.as<T>(), consts.as<T>());
+        n, (int)d, dp(), kind, X.as<double>(), static_cast<const T*>(raw_ls), static_cast<const T*>(raw_os),
+        xs.as<T>(), xx.as<T>(), consts.as<T>());
     BL_LAUNCHED();
     return BL_OK;
   }
@@ -254,12 +309,22 @@ struct GramOperator : bl_operator {
     return dtype == BL_F32 ? set_params_t<float>(s) : set_params_t<double>(s);
   }
 
+  template <typename T, int DP, int RI, bool ADJ>
+  void launch_sweep(const T* v, const T* q, cudaStream_t s) {
+    dim3 grid(nblocks_i(), jsplit);
+    k_gram_sweep<T, DP, RI, ADJ><<<grid, kTileI, 0, s>>>(n, (int)d, kind, xs.as<T>(), xx.as<T>(), consts.as<T>(), v, q,
+                                                          part.as<T>(), gpart.as<double>());
+  }
+
   template <typename T, bool ADJ>
   int sweep(const T* v, const T* q, T* y, cudaStream_t s) {
-    const size_t smem = ((size_t)kTileJ * d + 3 * kTileJ) * sizeof(T);
-    dim3 grid(nblocks_i(), jsplit);
-    k_gram_sweep<T, ADJ><<<grid, kTileI, smem, s>>>(n, (int)d, kind, xs.as<T>(), xx.as<T>(), consts.as<T>(), v, q,
-                                                     part.as<T>(), gpart.as<double>());
+    switch (dp()) {
+      case 4: launch_sweep<T, 4, 4, ADJ>(v, q, s); break;
+      case 8: launch_sweep<T, 8, 4, ADJ>(v, q, s); break;
+      case 12: launch_sweep<T, 12, 4, ADJ>(v, q, s); break;
+      case 16: launch_sweep<T, 16, 4, ADJ>(v, q, s); break;
+      default: launch_sweep<T, 32, 2, ADJ>(v, q, s); break;
+    }
     BL_LAUNCHED();
     if (y) {
       k_gram_finish<T><<<std::min<int>(1024, (int)((n + 255) / 256)), 256, 0, s>>>(
