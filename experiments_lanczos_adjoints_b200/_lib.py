@@ -15,6 +15,7 @@ from experiments_lanczos_adjoints_b200 import build as _build
 BL_F32, BL_F64 = 0, 1
 BL_OK, BL_EINVAL, BL_EDEPTH, BL_ECUDA, BL_ENOMEM, BL_ECALLBACK = range(6)
 
+ALLREDUCE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 MATVEC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 VJP_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 
@@ -49,6 +50,7 @@ SIGNATURES = {
     "bl_launch_count": (_i32, [C.POINTER(C.c_uint64)]),
     "bl_profile_begin": (_i32, []),
     "bl_profile_end": (_i32, [C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "bl_dist_set_reduce_hook": (_i32, [ALLREDUCE_CB, _vp]),
     "bl_op_sparse_create": (_i32, [_i64, _i64, _i64, _vp, _vp, _pvp]),
     "bl_op_sparse_export_csr": (_i32, [_vp, _vp, _vp, _vp]),
     "bl_op_sparse_export_sell": (_i32, [_vp, _i32, _vp, _vp]),

@@ -108,6 +108,26 @@ int tma_grid(int64_t n, int tile) {
 // prologue and its first TMA loads overlap the tail (imbalance, last-block reduction) of the
 // kernel in front of it; the kernel itself executes griddepcontrol.wait before reading anything
 // its predecessor wrote.
+// Row sharding: cross-rank SUM of the reduced values between a kernel's local reduction and the
+// epilogue that consumes them (bl_dist_set_reduce_hook).
+thread_local bl_allreduce_cb g_reduce_hook = nullptr;
+thread_local void* g_reduce_user = nullptr;
+
+// Runs `epi` after the hook: the kernel in front was launched with EPI_NONE and left the local
+// sums in red[0..count).
+template <typename T>
+int finish_sharded(const Common& c, Epi epi, int count, cudaStream_t s) {
+  if (g_reduce_hook(g_reduce_user, c.red, count, s) != 0) {
+    set_error("all-reduce hook failed");
+    return BL_ECALLBACK;
+  }
+  epi.red = c.red;
+  epi.scal = c.scal;
+  k_epilogue_only<T><<<1, 256, 0, s>>>(epi);
+  BL_LAUNCHED();
+  return BL_OK;
+}
+
 // L2 "snake" order (BL_SNAKE=0 disables it): consecutive streaming kernels walk the basis in
 // opposite directions, so a kernel starts on the tiles its predecessor read last — the part of
 // the basis that is still in the 126 MB L2.  Each block owns the same column range in every
@@ -172,6 +192,10 @@ template <typename T>
 int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_t n, Epi epi, cudaStream_t s) {
   epi.red = c.red;
   epi.scal = c.scal;
+  const Epi full_epi = epi;
+  const bool sharded = g_reduce_hook != nullptr;
+  if (sharded) epi.mode = EPI_NONE;
+  {
   ProfScope prof(BL_PROF_DOTS, (double)(blk.nrows + 1) * n * sizeof(T), s);
   if (use_tma(n)) {
     constexpr int TILE = dots_tile<T>();
@@ -190,6 +214,8 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
     k_dots<T><<<g.dots, kDotsThreads, 0, s>>>(blk, x, n, c.partials_dots, c.counters + 0, epi);
   }
   BL_LAUNCHED();
+  }
+  if (sharded) return finish_sharded<T>(c, full_epi, blk.nrows, s);
   return BL_OK;
 }
 
@@ -199,7 +225,11 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
   a.counter = c.counters + 1;
   a.epi.red = c.red;
   a.epi.scal = c.scal;
+  const Epi full_epi = a.epi;
+  const bool sharded = norm && g_reduce_hook != nullptr;
+  if (sharded) a.epi.mode = EPI_NONE;
   const int nrows = a.blk[0].nrows + a.blk[1].nrows;
+  {
   ProfScope prof(BL_PROF_COMBINE, (double)(nrows + a.nvec + 1 + (a.out2 ? 1 : 0)) * a.n * sizeof(T), s);
   if (use_tma(a.n) && nrows + a.nvec >= 4) {
     constexpr int TILE = kConsumerThreads * Vec<T>::N;
@@ -242,6 +272,8 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
       k_combine<T, false><<<g.combine, kCombineThreads, smem, s>>>(a);
   }
   BL_LAUNCHED();
+  }
+  if (sharded) return finish_sharded<T>(c, full_epi, 1, s);
   return BL_OK;
 }
 
@@ -337,11 +369,17 @@ int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, int sr, cu
   a.epi = f.epi;
   a.epi.red = c.red;
   a.epi.scal = c.scal;
+  const Epi full_epi = a.epi;
+  const bool sharded = g_reduce_hook != nullptr;
+  if (sharded) a.epi.mode = EPI_NONE;
   a.reverse = next_direction();
   const int nrows = f.res.nrows + f.str0.nrows + f.str1.nrows;
-  ProfScope prof(BL_PROF_FUSED, (double)(nrows + f.nvec + 1) * f.n * sizeof(T), s);
-  BL_CUDA(launch_pdl(k_fused_tma<T, TILE>, tma_grid<T>(f.n, TILE), kStreamThreads, L.total_bytes, s, a));
-  BL_LAUNCHED();
+  {
+    ProfScope prof(BL_PROF_FUSED, (double)(nrows + f.nvec + 1) * f.n * sizeof(T), s);
+    BL_CUDA(launch_pdl(k_fused_tma<T, TILE>, tma_grid<T>(f.n, TILE), kStreamThreads, L.total_bytes, s, a));
+    BL_LAUNCHED();
+  }
+  if (sharded) return finish_sharded<T>(c, full_epi, f.res.nrows, s);
   return BL_OK;
 }
 
@@ -572,6 +610,10 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
     BL_LAUNCHED();
     k_gram_reduce<<<(K * K + 255) / 256, 256, 0, s>>>(K * K, gram_parts, gram_partial, Gmat);
     BL_LAUNCHED();
+    if (g_reduce_hook && g_reduce_hook(g_reduce_user, Gmat, K * K, s) != 0) {
+      set_error("all-reduce hook failed");
+      return BL_ECALLBACK;
+    }
   }
   {
     dim3 grid(K, (K + 127) / 128);
@@ -824,6 +866,12 @@ int lanczos3_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, const T* 
 using namespace bl;
 
 extern "C" {
+
+int bl_dist_set_reduce_hook(bl_allreduce_cb hook, void* user) {
+  g_reduce_hook = hook;
+  g_reduce_user = user;
+  return BL_OK;
+}
 
 size_t bl_arnoldi_workspace_bytes(int64_t n, int64_t K, int dtype) {
   const size_t ld = align_up((size_t)n, 64);

@@ -285,7 +285,7 @@ struct SparseOperator : bl_operator {
 
   template <typename T>
   int vjp_t(const T* q, const T* lam, T* z, cudaStream_t s) {
-    const int64_t rows = std::max(n_rows, n_cols);
+    const int64_t rows = z ? std::max(n_rows, n_cols) : n_rows;
     const int64_t threads = ((rows + kSlice - 1) / kSlice) * kSlice;
     const int blocks = (int)((threads + 255) / 256);
     if (blocks > 0) {
@@ -299,7 +299,7 @@ struct SparseOperator : bl_operator {
 
   int vjp(int dtype, const void* q, const void* lam, void* z, cudaStream_t s) override {
     BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
-    BL_REQUIRE(n_rows == n_cols, "vjp needs a square operator");
+    BL_REQUIRE(n_rows == n_cols || z == nullptr, "A^T lam needs a square operator (pass z = NULL for the gradient only)");
     return dtype == BL_F32
                ? vjp_t<float>(static_cast<const float*>(q), static_cast<const float*>(lam), static_cast<float*>(z), s)
                : vjp_t<double>(static_cast<const double*>(q), static_cast<const double*>(lam), static_cast<double*>(z), s);

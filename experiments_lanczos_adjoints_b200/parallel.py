@@ -134,3 +134,166 @@ def hutchinson_sharded(integrand_fun, /, sample_fun, group=None):
     """Probe-sharded Hutchinson estimator: same call signature and (up to summation order) the
     same value / gradient as `hutchinson.hutchinson` on one GPU."""
     return _ShardedEstimator(integrand_fun, sample_fun, group)
+
+
+# ---------------------------------------------------------------------------------------------
+# Row sharding: one large operator split by rows over the GPUs (SURVEY 8e, second half)
+# ---------------------------------------------------------------------------------------------
+class _RawDeviceBuffer:
+    """`__cuda_array_interface__` view of a raw device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}  # fmt: skip
+
+
+def _as_torch(ptr, count, dtype):
+    import torch
+
+    typestr = np.dtype(dtype).str
+    return torch.as_tensor(_RawDeviceBuffer(ptr, count, typestr), device="cuda")
+
+
+class row_sharded:
+    """Context manager: while active, every reduction of the Krylov loops on this thread is
+    summed over the ranks of `group` (bl_dist_set_reduce_hook) — the Arnoldi / Lanczos calls then
+    operate on the LOCAL rows of every vector and produce the same `H`, coefficients and scalars
+    on every rank.  Collectives are enqueued on the library's stream (no host synchronisation)."""
+
+    def __init__(self, group=None):
+        from experiments_lanczos_adjoints_b200 import _lib
+
+        self.group = group
+        self._lib = _lib
+
+        def hook(_user, values, count, stream):
+            try:
+                import torch.distributed as dist
+
+                if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+                    return 0  # one rank: the local sums are the global sums
+                import torch
+
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                    dist.all_reduce(_as_torch(values, count, np.float64), group=self.group)
+                return 0
+            except Exception as exc:  # pragma: no cover - surfaced as BL_ECALLBACK
+                self.error = exc
+                return 1
+
+        self.error = None
+        self._cb = _lib.ALLREDUCE_CB(hook)
+
+    def __enter__(self):
+        self._lib.call("bl_dist_set_reduce_hook", self._cb, None)
+        return self
+
+    def __exit__(self, *exc):
+        import ctypes as C
+
+        self._lib.call("bl_dist_set_reduce_hook", C.cast(None, self._lib.ALLREDUCE_CB), None)
+        return False
+
+
+def shard_coo_rows(row, col, n, rank, world):
+    """Index work of the row-sharded sparse operand (pure host, bit-exact, testable on CPU).
+
+    Uniform chunks of `chunk = ceil(n / world)` rows; rank r owns global rows
+    `[r*chunk, min(n, (r+1)*chunk))` and a gathered vector has `world*chunk` entries whose index
+    is the global row index.  Returns `(chunk, idx_a, row_a, col_a, idx_b, row_b, col_b)`:
+    `idx_a` = COO positions of the entries in the local rows of A (local row index `row_a`, global
+    column `col_a`); `idx_b` / `row_b` / `col_b` the same for the local rows of A^T."""
+    row = np.asarray(row, dtype=np.int64)
+    col = np.asarray(col, dtype=np.int64)
+    chunk = -(-int(n) // world)
+    lo, hi = rank * chunk, min(int(n), (rank + 1) * chunk)
+    idx_a = np.nonzero((row >= lo) & (row < hi))[0]
+    idx_b = np.nonzero((col >= lo) & (col < hi))[0]
+    return (chunk, idx_a, (row[idx_a] - lo).astype(np.int32), col[idx_a].astype(np.int32),
+            idx_b, (col[idx_b] - lo).astype(np.int32), row[idx_b].astype(np.int32))  # fmt: skip
+
+
+class RowShardedSparseOperator:
+    """The sparse COO operand with its rows sharded over the ranks of `group`.
+
+    `matvec`: all-gather of the local piece of x (NCCL), then the local rows of A;
+    `vjp`: all-gather of q and lambda, local rows of A^T for `A^T lambda`, local rows of A for the
+    parameter cotangent (`d theta_e` is local to the owner of row_e).  Built on two rectangular
+    `SparseOperator`s; plugs into the Krylov loops as a `CallbackOperator`."""
+
+    def __init__(self, row, col, n, group=None):
+        from experiments_lanczos_adjoints_b200 import operators as ops
+
+        dist = _dist()
+        self.group = group
+        self.rank = dist.get_rank(group) if dist else 0
+        self.world = dist.get_world_size(group) if dist else 1
+        self.n_global, self.nnz = int(n), len(row)
+        (self.chunk, self.idx_a, row_a, col_a, self.idx_b, row_b, col_b) = shard_coo_rows(
+            row, col, n, self.rank, self.world)  # fmt: skip
+        width = self.chunk * self.world
+        self.A = ops.SparseOperator(row_a, col_a, (self.chunk, width))
+        self.B = ops.SparseOperator(row_b, col_b, (self.chunk, width))
+        self._gathered = {}
+        self.callback = ops.CallbackOperator(self.chunk, self._matvec, self._vjp, num_params=1)
+        self.callback.bind = self._bind
+        self.callback.grad_zero = self._grad_zero
+        self.callback.grad_export = self._grad_export
+
+    # vectors ------------------------------------------------------------------------------
+    def local_slice(self, x_global):
+        """Local piece (zero-padded to `chunk`) of a global host vector."""
+        out = np.zeros(self.chunk, dtype=np.asarray(x_global).dtype)
+        lo = self.rank * self.chunk
+        hi = min(self.n_global, lo + self.chunk)
+        out[: hi - lo] = np.asarray(x_global)[lo:hi]
+        return out
+
+    def _gather(self, x_loc, slot):
+        full = self._gathered.get((slot, x_loc.dtype.str))
+        if full is None:
+            full = dev.empty((self.chunk * self.world,), x_loc.dtype)
+            self._gathered[(slot, x_loc.dtype.str)] = full
+        if self.world == 1:
+            from experiments_lanczos_adjoints_b200 import _lib
+
+            _lib.call("bl_memcpy_d2d", full.ptr, x_loc.ptr, x_loc.size * x_loc.dtype.itemsize, dev.default_stream().ptr)
+            return full
+        import torch
+        import torch.distributed as dist
+
+        with torch.cuda.stream(torch.cuda.ExternalStream(dev.default_stream().ptr)):
+            dist.all_gather_into_tensor(torch.as_tensor(full, device="cuda"), torch.as_tensor(x_loc, device="cuda"),
+                                        group=self.group)  # fmt: skip
+        return full
+
+    # operator protocol ----------------------------------------------------------------------
+    def _bind(self, params, dtype, stream=None):
+        (data,) = params
+        data = np.asarray(data)
+        self.A.bind((data[self.idx_a],), dtype)
+        self.B.bind((data[self.idx_b],), dtype)
+        self._dtype = np.dtype(dtype)
+        return [data]
+
+    def _matvec(self, x_loc):
+        return self.A.matvec(self._gather(x_loc, "x"))
+
+    def _vjp(self, q_loc, lam_loc):
+        q_full = self._gather(q_loc, "q")
+        lam_full = self._gather(lam_loc, "lam")
+        z = self.B.matvec(lam_full)
+        self.A.vjp(q_full, lam_loc, want_z=False)
+        return z, ()
+
+    def _grad_zero(self, dtype, stream=None):
+        self.A.grad_zero(dtype)
+
+    def _grad_export(self, dtype, like=None, stream=None):
+        """Parameter cotangent in global COO order (each entry is owned by exactly one rank; one
+        all-reduce assembles the full vector)."""
+        (g_loc,) = self.A.grad_export(dtype)
+        full = np.zeros(self.nnz, dtype=np.float64)
+        full[self.idx_a] = g_loc.numpy()
+        (full,) = all_reduce_sum([full], self.group)
+        return [full.astype(dtype)]

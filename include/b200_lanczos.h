@@ -82,6 +82,17 @@ enum { BL_PROF_DOTS = 0, BL_PROF_COMBINE = 1, BL_PROF_MATVEC = 2, BL_PROF_VJP = 
 int bl_profile_begin(void);
 int bl_profile_end(uint64_t* counts, double* ms, double* bytes); /* arrays of BL_PROF_NCLASS */
 
+/* ---- row sharding: one large operator split by rows over several GPUs (one process each) ----
+ * Every rank owns the same row range of every Krylov vector (`n` in the Krylov calls is the LOCAL
+ * length).  The only cross-rank data the loops need are the reduced dot products / norms: when a
+ * hook is installed, each streaming kernel stops after its local reduction, the hook is called
+ * with the device array of `count` doubles (it must enqueue an in-place SUM all-reduce on
+ * `stream`, e.g. ncclAllReduce), and the epilogue that consumes the numbers runs afterwards.
+ * The hook is per host thread; NULL removes it.  The matvec's own exchange (all-gather / halo)
+ * belongs to the operator (bl_op_callback_create). */
+typedef int (*bl_allreduce_cb)(void* user, double* values_dev, int count, void* stream);
+int bl_dist_set_reduce_hook(bl_allreduce_cb hook, void* user);
+
 /* ---- operators: the `matvec(v, *params)` callback of the reference ------------------
  * An operator owns its index structures and a gradient accumulator for its parameters.
  *   set_params : bind parameter values (device pointers, reference order)

@@ -272,6 +272,30 @@ def test_callback_operator_runs_user_matvec():
         bl.arnoldi.hessenberg(bl.operators.CallbackOperator(n, bad), K, reortho="full")(v)
 
 
+def test_row_sharded_path_with_one_rank_matches_plain_path():
+    """The row-sharded code path (local reduction -> all-reduce hook -> separate epilogue kernel,
+    operand = all-gather + rectangular local rows of A and A^T) on a single rank must reproduce the
+    plain path; the 2-GPU run is `scripts/run_row_sharded.py` (profiles/r1_row_sharded.json)."""
+    from experiments_lanczos_adjoints_b200 import parallel
+
+    n, K = 20000, 12
+    row, col, data = banded_spd(n, 4, seed=3)
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal(n)
+    dalpha, dbeta = rng.standard_normal(K), rng.standard_normal(K - 1)
+    plain = bl.lanczos.tridiag(bl.operators.SparseOperator(row, col, (n, n)), K, reortho="full")
+    ((_, (a0, b0)), _), pull0 = bl.vjp(plain, v, data)
+    dv0, dp0 = pull0(((None, (dalpha, dbeta)), (None, None)))
+    op = parallel.RowShardedSparseOperator(row, col, n)
+    sharded = bl.lanczos.tridiag(op.callback, K, reortho="full")
+    with parallel.row_sharded():
+        ((_, (a1, b1)), _), pull1 = bl.vjp(sharded, op.local_slice(v), data)
+        dv1, dp1 = pull1(((None, (dalpha, dbeta)), (None, None)))
+    assert rel_err(a1, a0) < 1e-13 and rel_err(b1, b0) < 1e-13
+    assert rel_err(dv1.numpy(), dv0.numpy()) < 1e-12
+    assert rel_err(dp1, dp0.numpy()) < 1e-12
+
+
 def test_depth_errors_match_reference():
     # /root/reference/tests/test_arnoldi/test_hessenberg_forward.py:69-78
     op = bl.operators.DenseOperator(2)

@@ -26,6 +26,24 @@ def test_shard_bounds_partition_exactly(num, world):
     assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("n,world", [(10, 2), (11, 4), (5, 8)])
+def test_row_shard_index_work_covers_every_entry_once(n, world):
+    """Row-sharded sparse operand: every COO entry lands in exactly one rank's A block and one
+    rank's A^T block; local indices map back to the global ones (bit-exact host work)."""
+    rng = np.random.default_rng(n)
+    row, col = rng.integers(0, n, 40), rng.integers(0, n, 40)
+    seen_a, seen_b = np.zeros(40, int), np.zeros(40, int)
+    for r in range(world):
+        chunk, idx_a, row_a, col_a, idx_b, row_b, col_b = parallel.shard_coo_rows(row, col, n, r, world)
+        assert chunk * world >= n
+        seen_a[idx_a] += 1
+        seen_b[idx_b] += 1
+        assert np.array_equal(row_a + r * chunk, row[idx_a]) and np.array_equal(col_a, col[idx_a])
+        assert np.array_equal(row_b + r * chunk, col[idx_b]) and np.array_equal(col_b, row[idx_b])
+        assert row_a.max(initial=0) < chunk and row_b.max(initial=0) < chunk
+    assert np.all(seen_a == 1) and np.all(seen_b == 1)
+
+
 WORKER = textwrap.dedent(
     """
     import os, sys
