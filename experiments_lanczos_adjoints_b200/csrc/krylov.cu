@@ -388,7 +388,8 @@ int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, int sr, cu
 template <typename T>
 int launch_fused(const Common& c, const FusedSpec& f, int dtype, cudaStream_t s, bool* fused) {
   *fused = false;
-  if (!use_tma(f.n) || stream_mode() == 2 || f.n >= ((int64_t)1 << 31)) return BL_OK;
+  // k_fused_tma keeps one register accumulator per resident box: at most 16 boxes = 128 rows
+  if (!use_tma(f.n) || stream_mode() == 2 || f.n >= ((int64_t)1 << 31) || f.res.nrows > 128) return BL_OK;
   constexpr size_t two_per_sm = 113 * 1024;
   constexpr int TMAX = 4096 / (int)sizeof(T);  // 1024 floats / 512 doubles
   const int nr = f.res.nrows, n0 = f.str0.nrows, n1 = f.str1.nrows, nv = f.nvec;

@@ -26,6 +26,7 @@ constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = 32 * kConsumerWarps;
 constexpr int kStreamThreads = kConsumerThreads + 32;  // + producer warp
 constexpr int kStages = 3;
+constexpr int kBoxesPerBarrier = 4;  // fused kernel: resident boxes ([8 x TILE]) that share one mbarrier
 
 struct RowSource {  // rows [0, n0) from block 0, [n0, n0 + n1) from block 1
   const char* base0 = nullptr;
@@ -519,7 +520,7 @@ __host__ __device__ inline FusedLayout fused_layout(int nres, int nstr0, int nst
   L.xs = o;   o += (size_t)2 * TILE;
   L.coef = o; o += (size_t)L.GR * kGroup + (size_t)L.GS * sr + kGroup;
   L.elems = o;
-  L.bar_bytes = (size_t)(4 * L.GR + 2 * kStages + 4) * 8;
+  L.bar_bytes = (size_t)(4 * ((L.GR + 3) / 4) + 2 * kStages + 4) * 8;
   L.acc_bytes = (size_t)nres * 8;
   L.total_bytes = (L.elems * sizeof(T) + 127) / 128 * 128 + L.bar_bytes + L.acc_bytes + 64;
   return L;
@@ -550,9 +551,10 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
   T* part_s = base + L.part;  // [RS][TILE]
   T* xs = base + L.xs;        // [2][TILE]
   T* coef = base + L.coef;    // [GR*8][GS*SR][8]
-  uint64_t* res_full = reinterpret_cast<uint64_t*>(smem_raw + (L.elems * sizeof(T) + 127) / 128 * 128);  // [2][GR]
-  uint64_t* res_empty = res_full + 2 * GR;      // [2][GR]
-  uint64_t* ring_full = res_empty + 2 * GR;     // [3]
+  const int GQ = (GR + kBoxesPerBarrier - 1) / kBoxesPerBarrier;  // barrier groups of resident boxes
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(smem_raw + (L.elems * sizeof(T) + 127) / 128 * 128);  // [2][GQ]
+  uint64_t* res_empty = res_full + 2 * GQ;      // [2][GQ]
+  uint64_t* ring_full = res_empty + 2 * GQ;     // [3]
   uint64_t* ring_empty = ring_full + kStages;   // [3]
   uint64_t* x_full = ring_empty + kStages;      // [2]
   uint64_t* x_empty = x_full + 2;               // [2]
@@ -561,7 +563,7 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int g = 0; g < 2 * GR; ++g) {
+    for (int g = 0; g < 2 * GQ; ++g) {
       tma::mbar_init(res_full + g, 1);
       tma::mbar_init(res_empty + g, kConsumerWarps);
     }
@@ -612,15 +614,20 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
         const int b = tt & 1;
         const uint32_t ph = (tt >> 1) & 1;
         if (waited && vec_next <= tt) issue_vec(vec_next++);
-        for (int gg = 0; gg < GR; ++gg) {
-          const int g = reverse ? GR - 1 - gg : gg;
-          tma::mbar_wait(res_empty + b * GR + g, ph ^ 1);  // sweep 2 of tile tt-2 released this box
-          tma::mbar_arrive_expect_tx(res_full + b * GR + g, kBoxBytes);
-          T* dst = res_s + ((size_t)b * GR + g) * kGroup * TILE;
+        for (int qq = 0; qq < GQ; ++qq) {  // kBoxesPerBarrier boxes per mbarrier
+          const int q = reverse ? GQ - 1 - qq : qq;
+          const int g_lo = q * kBoxesPerBarrier;
+          const int nb = GR - g_lo < kBoxesPerBarrier ? GR - g_lo : kBoxesPerBarrier;
+          tma::mbar_wait(res_empty + b * GQ + q, ph ^ 1);  // sweep 2 of tile tt-2 released these boxes
+          tma::mbar_arrive_expect_tx(res_full + b * GQ + q, kBoxBytes * nb);
+          for (int gi = 0; gi < nb; ++gi) {
+            const int g = g_lo + gi;
+            T* dst = res_s + ((size_t)b * GR + g) * kGroup * TILE;
 #pragma unroll
-          for (int bx = 0; bx < NBOX; ++bx)
-            tma::tensor_g2s_2d(dst + (size_t)bx * kGroup * BOXC, &a.map_res, tc0 + bx * BOXC, g * kGroup,
-                               res_full + b * GR + g);
+            for (int bx = 0; bx < NBOX; ++bx)
+              tma::tensor_g2s_2d(dst + (size_t)bx * kGroup * BOXC, &a.map_res, tc0 + bx * BOXC, g * kGroup,
+                                 res_full + b * GQ + q);
+          }
         }
         if (!waited && (tt == 1 || cr.ntiles == 1 || GS > 0)) {
           // the resident rows of the first two tiles were prefetched; everything else may be the
@@ -702,18 +709,23 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
       }
       // element (row r, column cc) of a [8][TILE] slot built from NBOX boxes of [8][BOXC]
       const int boff = (c / BOXC) * kGroup * BOXC + (c % BOXC);
-      for (int gg = 0; gg < GR; ++gg) {
-        const int g = reverse ? GR - 1 - gg : gg;
-        tma::mbar_wait(res_full + b * GR + g, ph);
-        const T* st = res_s + ((size_t)b * GR + g) * kGroup * TILE + boff;
-        const T* cf = coef + g * kGroup;
+      for (int qq = 0; qq < GQ; ++qq) {
+        const int q = reverse ? GQ - 1 - qq : qq;
+        const int g_lo = q * kBoxesPerBarrier;
+        const int nb = GR - g_lo < kBoxesPerBarrier ? GR - g_lo : kBoxesPerBarrier;
+        tma::mbar_wait(res_full + b * GQ + q, ph);
+        for (int gi = 0; gi < nb; ++gi) {
+          const int g = g_lo + gi;
+          const T* st = res_s + ((size_t)b * GR + g) * kGroup * TILE + boff;
+          const T* cf = coef + g * kGroup;
 #pragma unroll
-        for (int r = 0; r < kGroup / RS; ++r) {
-          const int rr = r * RS + h;
-          T e[EPT];
-          load_ept<T, EPT>(st + (size_t)rr * BOXC, e);
+          for (int r = 0; r < kGroup / RS; ++r) {
+            const int rr = r * RS + h;
+            T e[EPT];
+            load_ept<T, EPT>(st + (size_t)rr * BOXC, e);
 #pragma unroll
-          for (int k = 0; k < EPT; ++k) acc[k] = fma(cf[rr], e[k], acc[k]);
+            for (int k = 0; k < EPT; ++k) acc[k] = fma(cf[rr], e[k], acc[k]);
+          }
         }
       }
       for (int gs = 0; gs < GS; ++gs, ++its) {
@@ -771,38 +783,62 @@ k_fused_tma(const __grid_constant__ FusedArgs a) {
 #pragma unroll
       for (int u = 0; u < LV; ++u) xv[u] = reinterpret_cast<const V*>(xcur)[lane + 32 * u];
 #pragma unroll
-      for (int gg = 0; gg < GRMAX; ++gg) {
-        if (gg >= GR) break;  // (unrolled for static register indexing; skip the unused copies)
-        {
-          const int g = reverse ? GR - 1 - gg : gg;
-          if (g * kGroup + warp < nres) {
-            const T* slot = res_s + ((size_t)b * GR + g) * kGroup * TILE;
+      for (int qq = 0; qq < GRMAX / kBoxesPerBarrier; ++qq) {
+        if (qq >= GQ) break;  // (unrolled for static register indexing; skip the unused copies)
+        const int q = reverse ? GQ - 1 - qq : qq;
+        const int g_lo = q * kBoxesPerBarrier;
+        // all shared-memory loads of the (up to four) boxes first, then the FMAs
+        V qv[kBoxesPerBarrier][LV];
+#pragma unroll
+        for (int gi = 0; gi < kBoxesPerBarrier; ++gi) {
+          const int g = g_lo + gi;
+          const bool on = g < GR && g * kGroup + warp < nres;
+          const T* slot = res_s + ((size_t)b * GR + (on ? g : g_lo)) * kGroup * TILE;
+#pragma unroll
+          for (int u = 0; u < LV; ++u) {
+            const int cc = (lane + 32 * u) * VN;  // column inside the tile
+            qv[gi][u] = *reinterpret_cast<const V*>(slot + (cc / BOXC) * kGroup * BOXC + warp * BOXC + (cc % BOXC));
+          }
+        }
+#pragma unroll
+        for (int gi = 0; gi < kBoxesPerBarrier; ++gi) {
+          const int g = g_lo + gi;
+          if (g < GR && g * kGroup + warp < nres) {
             T p = T(0);
 #pragma unroll
             for (int u = 0; u < LV; ++u) {
-              const int cc = (lane + 32 * u) * VN;  // column inside the tile
-              const V qv = *reinterpret_cast<const V*>(slot + (cc / BOXC) * kGroup * BOXC + warp * BOXC + (cc % BOXC));
-              T q[VN], xx[VN];
-              vec_unpack(qv, q);
+              T qq4[VN], xx[VN];
+              vec_unpack(qv[gi][u], qq4);
               vec_unpack(xv[u], xx);
 #pragma unroll
-              for (int k = 0; k < VN; ++k) p = fma(q[k], xx[k], p);
+              for (int k = 0; k < VN; ++k) p = fma(qq4[k], xx[k], p);
             }
-            lane_acc[gg] += p;
+            lane_acc[qq * kBoxesPerBarrier + gi] += p;
           }
-          __syncwarp();
-          if (lane == 0) tma::mbar_arrive(res_empty + b * GR + g);
         }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(res_empty + b * GQ + q);
       }
     }
     // one cross-lane reduction per row for the whole block
 #pragma unroll
-    for (int gg = 0; gg < GRMAX; ++gg) {
-      if (gg >= GR) break;
-      {
-        const int g = reverse ? GR - 1 - gg : gg;
-        const double d = warp_sum(static_cast<double>(lane_acc[gg]));
-        if (lane == 0 && g * kGroup + warp < nres) acc_s[g * kGroup + warp] = d;
+    for (int qq = 0; qq < GRMAX / kBoxesPerBarrier; ++qq) {
+      if (qq >= GQ) break;
+      const int q = reverse ? GQ - 1 - qq : qq;
+      double d[kBoxesPerBarrier];
+#pragma unroll
+      for (int gi = 0; gi < kBoxesPerBarrier; ++gi) d[gi] = static_cast<double>(lane_acc[qq * kBoxesPerBarrier + gi]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int gi = 0; gi < kBoxesPerBarrier; ++gi) d[gi] += __shfl_xor_sync(0xffffffffu, d[gi], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int gi = 0; gi < kBoxesPerBarrier; ++gi) {
+          const int j = (q * kBoxesPerBarrier + gi) * kGroup + warp;
+          if (j < nres) acc_s[j] = d[gi];
+        }
       }
     }
   }
