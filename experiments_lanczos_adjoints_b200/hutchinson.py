@@ -71,10 +71,26 @@ def _mean(values):
     return np.mean(np.stack([np.asarray(v) for v in values]), axis=0)
 
 
+def _resident(parameters, like):
+    """Upload host parameter arrays once per estimate (not once per probe)."""
+    dtype = like.dtype if hasattr(like, "dtype") else np.asarray(like).dtype
+    if np.dtype(dtype) not in (np.dtype(np.float32), np.dtype(np.float64)):
+        return parameters
+    out = []
+    for p in parameters:
+        if isinstance(p, np.ndarray) and p.dtype.kind == "f" and p.ndim >= 1 and p.size >= 4096:
+            p = dev.asarray(p.reshape(-1) if p.ndim > 1 else p, dtype=dtype) if p.ndim == 1 else p
+        out.append(p)
+    return tuple(out)
+
+
 def probe_sum(integrand_fun, samples, parameters, *, with_grad=False):
     """Sum (not mean) of the integrand over probes; gradients stay on the device."""
     total, grads, count = 0.0, None, 0
-    for vec in _probe_rows(samples):
+    rows = _probe_rows(samples)
+    if len(rows):
+        parameters = _resident(parameters, rows[0])
+    for vec in rows:
         if with_grad:
             val, (_dv0, *dp) = integrand_fun.value_and_grad(vec, *parameters, want_dv0=False)
             if grads is None:
