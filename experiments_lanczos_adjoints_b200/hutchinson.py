@@ -27,7 +27,8 @@ def split(key, num: int = 2):
     """`jax.random.split` stand-in: `num` independent child keys."""
     if not isinstance(key, np.random.SeedSequence):
         key = np.random.SeedSequence(int(np.asarray(key).sum()))
-    return key.spawn(num)
+    # a pure function of the key (SeedSequence.spawn is stateful): same key -> same children
+    return [np.random.SeedSequence(entropy=key.entropy, spawn_key=tuple(key.spawn_key) + (i,)) for i in range(num)]
 
 
 def _generator(key):

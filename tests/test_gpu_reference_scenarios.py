@@ -1,0 +1,173 @@
+"""The reference's own test scenarios, replayed on the CUDA path through the mirrored API.
+Each test names the reference test it restates; inputs are seeded NumPy (JAX's PRNG stream is
+not reproducible here), the assertions and tolerances are the reference's."""
+
+import numpy as np
+import pytest
+
+import experiments_lanczos_adjoints_b200 as bl
+from experiments_lanczos_adjoints_b200 import arnoldi, hutchinson, lanczos
+
+pytestmark = pytest.mark.gpu
+
+
+def symmetric_matrix_from_eigenvalues(eigvals, seed=0):
+    """Stand-in for `matfree.test_util.symmetric_matrix_from_eigenvalues`: Q diag(e) Q^T."""
+    n = len(eigvals)
+    Q, _ = np.linalg.qr(np.random.default_rng(seed).standard_normal((n, n)))
+    return (Q * np.asarray(eigvals)) @ Q.T
+
+
+def dense_tridiag(d, o):
+    return np.diag(d) + np.diag(o, 1) + np.diag(o, -1)
+
+
+@pytest.mark.parametrize("reortho", ["full", "none"])
+def test_full_rank_reconstruction_is_exact(reortho, ndim=12):
+    # /root/reference/tests/test_lanczos/test_tridiag_forward.py:9-36
+    eigvals = np.arange(1.0, 2.0, step=1 / ndim)
+    matrix = symmetric_matrix_from_eigenvalues(eigvals).astype(np.float32)
+    vector = np.flip(np.arange(1.0, 1.0 + ndim)).astype(np.float32).copy()
+    algorithm = lanczos.tridiag(bl.operators.DenseOperator(ndim), ndim, reortho=reortho)
+    (vecs, tri), _ = algorithm(vector, matrix)
+    Q = vecs.numpy()
+    tols = {"atol": 1e-5, "rtol": 1e-5} if reortho == "full" else {"atol": 1e-1, "rtol": 1e-1}
+    assert np.allclose(Q.T @ dense_tridiag(*tri) @ Q, matrix, **tols)
+    assert np.allclose(Q @ Q.T, np.eye(ndim), **tols)
+    assert np.allclose(Q.T @ Q, np.eye(ndim), **tols)
+
+
+@pytest.mark.parametrize("krylov_depth", [1, 5, 11])
+@pytest.mark.parametrize("reortho", ["full", "none"])
+def test_mid_rank_reconstruction_satisfies_decomposition(krylov_depth, reortho, ndim=12):
+    # /root/reference/tests/test_lanczos/test_tridiag_forward.py:41-58
+    eigvals = np.arange(1.0, 2.0, step=1 / ndim)
+    matrix = symmetric_matrix_from_eigenvalues(eigvals).astype(np.float32)
+    vector = np.flip(np.arange(1.0, 1.0 + ndim)).astype(np.float32).copy()
+    algorithm = lanczos.tridiag(bl.operators.DenseOperator(ndim), krylov_depth, reortho=reortho)
+    (vecs, tri), (q, b) = algorithm(vector, matrix)
+    Q, T = vecs.numpy(), dense_tridiag(*tri)
+    e_K = np.eye(krylov_depth)[-1]
+    assert np.allclose(matrix @ Q.T, Q.T @ T + np.outer(e_K, q.numpy() * b).T, atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("krylov_depth", [1, 5, 10])
+@pytest.mark.parametrize("reortho", ["none", "full"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_decomposition_is_satisfied(krylov_depth, reortho, dtype, nrows=10):
+    # /root/reference/tests/test_arnoldi/test_hessenberg_forward.py:10-37 (real dtypes)
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((nrows, nrows)).astype(dtype)
+    v = rng.standard_normal(nrows).astype(dtype)
+    Q, H, r, c = arnoldi.hessenberg(bl.operators.DenseOperator(nrows), krylov_depth, reortho=reortho)(v, A)
+    assert Q.shape == (nrows, krylov_depth) and H.shape == (krylov_depth, krylov_depth)
+    assert r.shape == (nrows,) and c.shape == ()
+    Q, H, r, c = Q.numpy(), H.numpy(), r.numpy(), float(c)
+    small = np.sqrt(np.finfo(dtype).eps)
+    e0, ek = np.eye(krylov_depth)[[0, -1], :]
+    assert np.allclose(A @ Q - Q @ H - np.outer(r, ek), 0.0, atol=small, rtol=small)
+    assert np.allclose(Q.T @ Q - np.eye(krylov_depth), 0.0, atol=small, rtol=small)
+    assert np.allclose(Q @ e0, c * v, atol=small, rtol=small)
+
+
+@pytest.mark.parametrize("krylov_depth", [1, 5, 10])
+def test_reorthogonalisation_improves_the_estimate(krylov_depth, nrows=10):
+    # /root/reference/tests/test_arnoldi/test_hessenberg_forward.py:40-66 (Hilbert matrix)
+    a = np.arange(nrows)
+    A = (1 / (1 + a[:, None] + a[None, :])).astype(np.float32)
+    v = np.random.default_rng(2).standard_normal(nrows).astype(np.float32)
+    Q, H, r, c = arnoldi.hessenberg(bl.operators.DenseOperator(nrows), krylov_depth, reortho="full")(v, A)
+    Q, H, r, c = Q.numpy(), H.numpy(), r.numpy(), float(c)
+    small = np.sqrt(np.finfo(np.float32).eps)
+    e0, ek = np.eye(krylov_depth)[[0, -1], :]
+    assert np.allclose(A @ Q - Q @ H - np.outer(r, ek), 0.0, atol=small, rtol=small)
+    assert np.allclose(Q.T @ Q - np.eye(krylov_depth), 0.0, atol=small, rtol=small)
+    assert np.allclose(Q @ e0, c * v, atol=small, rtol=small)
+
+
+@pytest.mark.parametrize("reortho", ["full", "none"])
+def test_adjoint_matches_finite_differences(reortho, nrows=15, krylov_depth=10):
+    """/root/reference/tests/test_arnoldi/test_hessenberg_adjoint.py:53-99 compares the adjoint with
+    autodiff in fp64 (replayed against the stored autodiff VJPs in tests/golden).  Autodiff through
+    the loop does not exist here, so this is the independent check: a central finite difference of
+    <cotangent, outputs> along random directions, dense cotangents on all of (Q, H, r, c), on a
+    well-conditioned operand (on the reference's Hilbert matrix the difference quotient itself is
+    only good to a few percent)."""
+    rng = np.random.default_rng(2)
+    spd = symmetric_matrix_from_eigenvalues(1.0 + rng.uniform(size=nrows), seed=3)
+    A = np.tril(spd) - 0.5 * np.diag(np.diag(spd))
+    v = rng.standard_normal(nrows)
+    alg = arnoldi.hessenberg(bl.operators.DenseOperator(nrows, sym=True), krylov_depth, reortho=reortho)
+    (Q, H, r, c), pull = bl.vjp(alg, v, A)
+    cot = (rng.standard_normal((nrows, krylov_depth)), rng.standard_normal((krylov_depth, krylov_depth)),
+           rng.standard_normal(nrows), rng.standard_normal())  # fmt: skip
+    dv, dA = pull(cot)
+
+    def phi(vv, AA):
+        Q, H, r, c = alg(vv, AA)
+        return (np.sum(cot[0] * Q.numpy()) + np.sum(cot[1] * H.numpy()) + np.sum(cot[2] * r.numpy())
+                + cot[3] * float(c))  # fmt: skip
+
+    for _ in range(3):
+        dvv, dAA = rng.standard_normal(nrows), rng.standard_normal((nrows, nrows))
+        eps = 1e-6
+        fd = (phi(v + eps * dvv, A + eps * dAA) - phi(v - eps * dvv, A - eps * dAA)) / (2 * eps)
+        an = np.dot(dv.numpy(), dvv) + np.sum(dA.numpy() * dAA)
+        if reortho == "full":
+            assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (fd, an)
+        else:  # without the re-projection the adjoint is only as exact as the basis is orthogonal
+            assert abs(fd - an) <= 1e-4 * max(1.0, abs(an)), (fd, an)
+
+
+def test_integrand_spd_value_matches_dense_logdet_quadform(n=10):
+    """/root/reference/tests/test_lanczos/test_integrand_spd_value_and_grad.py: at full Krylov depth
+    the quadrature is exact: v^T log(A) v, and the parameter gradient is that of the dense formula."""
+    eigvals = np.arange(0.0, 1.0 + n) + 1.0
+    A = symmetric_matrix_from_eigenvalues(eigvals)
+    P = np.triu(A) - np.diag(0.5 * np.diag(A))  # _sym(): matvec = (p + p.T) @ x
+    rng = np.random.default_rng(2)
+    v = rng.integers(0, 2, n + 1) * 2.0 - 1.0
+    integrand = lanczos.integrand_spd(np.log, n + 1, bl.operators.DenseOperator(n + 1, sym=True))
+    w, U = np.linalg.eigh(A)
+    logA = (U * np.log(w)) @ U.T
+    assert np.allclose(integrand(v, P), v @ logA @ v, rtol=1e-8)
+    value, (_, grad) = integrand.value_and_grad(v, P)
+    eps = 1e-6
+    dP = np.triu(rng.standard_normal((n + 1, n + 1)))
+    fd = (integrand(v, P + eps * dP) - integrand(v, P - eps * dP)) / (2 * eps)
+    assert abs(fd - np.sum(grad.numpy() * dP)) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_custom_vjp_is_similar_but_different(n=3):
+    # /root/reference/tests/test_hutchinson.py:9-37 (10 000 probes: forward identical, backward
+    # sampled with a different key: different, but within 25 %)
+    eigvals = np.arange(0.0, 1.0 + n) + 1.0
+    A = symmetric_matrix_from_eigenvalues(eigvals)
+    op = bl.operators.DenseOperator(n + 1)
+    sampler = hutchinson.sampler_rademacher(np.ones(n + 1), num=2000)
+    integrand = lanczos.integrand_spd(np.log, n // 2 + 1, op)
+    est_ref = hutchinson.hutchinson(integrand, sampler)
+    est_custom = hutchinson.hutchinson_custom_vjp(integrand, sampler)
+    key = hutchinson.prng_key(2)
+    value_custom, vjp_custom = bl.vjp(est_custom, key, A)
+    value_ref, (grad_ref,) = est_ref.value_and_grad(key, A)
+    assert np.allclose(value_custom, value_ref)
+    _, grad_custom = vjp_custom(1.0)
+    g_c, g_r = np.asarray(grad_custom), np.asarray(grad_ref)
+    assert not np.allclose(g_c, g_r)
+    assert np.linalg.norm(g_c - g_r) < 0.25 * np.linalg.norm(g_r)
+    with pytest.raises(RuntimeError, match="oops"):
+        est_custom(key, A)
+
+
+def test_hutchinson_batch_averages_split_keys():
+    # /root/reference/src/matfree_extensions/hutchinson.py:57-65
+    op = bl.operators.DenseOperator(4)
+    A = symmetric_matrix_from_eigenvalues([1.0, 2.0, 3.0, 4.0])
+    integrand = lanczos.integrand_spd(np.log, 4, op)
+    est = hutchinson.hutchinson_nograd(integrand, hutchinson.sampler_rademacher(np.ones(4), num=50))
+    batched = hutchinson.hutchinson_batch(est, num=4)
+    key = hutchinson.prng_key(0)
+    expected = np.mean([est(k, A) for k in hutchinson.split(key, 4)])
+    assert np.allclose(batched(key, A), expected)
+    assert abs(batched(key, A) - np.log([1.0, 2.0, 3.0, 4.0]).sum()) < 0.5
