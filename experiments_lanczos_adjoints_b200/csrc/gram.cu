@@ -65,18 +65,25 @@ __global__ void k_gram_prepare(int64_t n, int d, int dp, int kind, const double*
   if (blockIdx.x == 0 && threadIdx.x == 0) consts[0] = softplus_t(raw_os[0]);
 }
 
-template <typename T>
-__device__ __forceinline__ void kernel_eval(int kind, T sigma, T s2, T& k, T& dk_ds2) {
+// exp(-s) and sqrt on the hot path.  fp32: MUFU-based (ex2.approx / rsqrt.approx, ~2 ulp), which
+// keeps the matvec well inside the 1e-5 parity bound; fp64: the IEEE library routines.
+__device__ __forceinline__ float exp_neg(float s) { return __expf(-s); }
+__device__ __forceinline__ double exp_neg(double s) { return exp(-s); }
+__device__ __forceinline__ float sqrt_pos(float x) { return x * rsqrtf(x); }  // x >= eps > 0
+__device__ __forceinline__ double sqrt_pos(double x) { return sqrt(x); }
+
+template <typename T, int KIND>
+__device__ __forceinline__ void kernel_eval(T sigma, T s2, T& k, T& dk_ds2) {
   // value and derivative w.r.t. the clamped squared distance
-  if (kind == 2) {  // RBF: sigma exp(-s2/2)
-    k = sigma * exp(-s2 / T(2));
-    dk_ds2 = -k / T(2);
+  if (KIND == 2) {  // RBF: sigma exp(-s2/2)
+    k = sigma * exp_neg(s2 * T(0.5));
+    dk_ds2 = -k * T(0.5);
   } else {
-    const T s = sqrt(s2 + Eps<T>::v());
-    const T e = exp(-s);
-    if (kind == 0) {  // Matern-3/2: sigma (1+s) e^{-s};  dk/ds = -sigma s e^{-s};  ds/ds2 = 1/(2s)
+    const T s = sqrt_pos(s2 + Eps<T>::v());
+    const T e = exp_neg(s);
+    if (KIND == 0) {  // Matern-3/2: sigma (1+s) e^{-s};  dk/ds = -sigma s e^{-s};  ds/ds2 = 1/(2s)
       k = sigma * (T(1) + s) * e;
-      dk_ds2 = -sigma * e / T(2);
+      dk_ds2 = -sigma * e * T(0.5);
     } else {  // Matern-1/2: sigma e^{-s}
       k = sigma * e;
       dk_ds2 = -k / (T(2) * s);
@@ -91,9 +98,9 @@ __device__ __forceinline__ void kernel_eval(int kind, T sigma, T s2, T& k, T& dk
 //   ADJ == false: part[split][i] = sum_{j in split} k_ij v_j
 //   ADJ == true : part[split][i] = sum_j k_ij lam_j ; block partial sums of
 //                 d_sigma = sum lam_i q_j k_ij / sigma and  d_ls[k] = sum lam_i q_j dk_ij (x_ik - x_jk)^2
-template <typename T, int DP, int RI, bool ADJ>
+template <typename T, int DP, int RI, bool ADJ, int KIND>
 __global__ void __launch_bounds__(kTileI)
-k_gram_sweep(int64_t n, int d, int kind, const T* __restrict__ xs, const T* __restrict__ xx,
+k_gram_sweep(int64_t n, int d, const T* __restrict__ xs, const T* __restrict__ xx,
              const T* __restrict__ consts, const T* __restrict__ v, const T* __restrict__ q,
              T* __restrict__ part, double* __restrict__ gpart /* [blocks][d+1] */) {
   using V = typename Vec<T>::type;
@@ -183,7 +190,7 @@ k_gram_sweep(int64_t n, int d, int kind, const T* __restrict__ xs, const T* __re
         const bool pos = s2 > T(0);
         s2 = pos ? s2 : T(0);  // jnp.maximum(0.0, scaled)
         T kij, dk;
-        kernel_eval<T>(kind, sigma, s2, kij, dk);
+        kernel_eval<T, KIND>(sigma, s2, kij, dk);
         y_t[r] = fma(kij, vj, y_t[r]);
         if (ADJ) {
           const T wgt = lam_i[r] * qj;
@@ -312,8 +319,16 @@ struct GramOperator : bl_operator {
   template <typename T, int DP, int RI, bool ADJ>
   void launch_sweep(const T* v, const T* q, cudaStream_t s) {
     dim3 grid(nblocks_i(), jsplit);
-    k_gram_sweep<T, DP, RI, ADJ><<<grid, kTileI, 0, s>>>(n, (int)d, kind, xs.as<T>(), xx.as<T>(), consts.as<T>(), v, q,
-                                                          part.as<T>(), gpart.as<double>());
+#define BL_GRAM_LAUNCH(KIND)                                                                                  \
+  k_gram_sweep<T, DP, RI, ADJ, KIND><<<grid, kTileI, 0, s>>>(n, (int)d, xs.as<T>(), xx.as<T>(), consts.as<T>(), v, \
+                                                             q, part.as<T>(), gpart.as<double>())
+    if (kind == 0)
+      BL_GRAM_LAUNCH(0);
+    else if (kind == 1)
+      BL_GRAM_LAUNCH(1);
+    else
+      BL_GRAM_LAUNCH(2);
+#undef BL_GRAM_LAUNCH
   }
 
   template <typename T, bool ADJ>
