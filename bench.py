@@ -37,6 +37,13 @@ METRIC = "Lanczos fwd+adjoint steps/sec at n=1M, K=100; achieved HBM GB/s vs pea
 UNIT = "krylov_steps/s"
 
 
+# DRAM traffic of the dominant kernel from one `ncu --set full` capture (profiles/r1_prof_r1_fused.md):
+# k_fused_tma<float,128>, adjoint step idx = 14 (15 resident + 170 streamed basis rows + 4 vectors + out),
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, next to the algorithmic bytes of that launch.
+NCU_TRAFFIC = {"k_fused_tma": {"traffic": 815.0e6 + 7.0e6, "algorithmic": 190 * 4.0e6,
+                               "launch": "adjoint idx=14, fp32, n=1M", "source": "profiles/r1_prof_r1_fused.md"}}
+
+
 def algorithmic_bytes(n, nnz, K, w):
     """compulsory traffic with the best legal fusion, active columns only."""
     fwd = 3 * n * w * K * (K + 1) / 2 + K * (nnz * (w + 4) + 4 * (n + 1)) + 8 * K * n * w
@@ -299,11 +306,13 @@ def main():
     d = prof[dom]
     dom_gbs = d["algorithmic_bytes"] / max(d["ms"], 1e-9) / 1e6
     prof_total = sum(c["ms"] for c in prof.values())
+    KERNEL_OF = {"dots": "k_dots_tma", "combine": "k_combine_tma", "matvec": "k_sell_spmv", "vjp": "k_sell_vjp",
+                 "other": "k_scale_copy", "fused": "k_fused_tma"}
     roofline = {
-        "bound": "hbm", "kernel": {"dots": "k_dots_tma", "combine": "k_combine_tma", "matvec": "k_sell_spmv",
-                                   "vjp": "k_sell_vjp", "other": "k_scale_copy", "fused": "k_fused_tma"}[dom],
+        "bound": "hbm", "kernel": KERNEL_OF[dom],
         "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "peak_source": peak_src,
-        "traffic": None, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / max(1, d["launches"]),
+        "traffic": NCU_TRAFFIC.get(KERNEL_OF[dom], {}).get("traffic"),
+        "traffic_capture": NCU_TRAFFIC.get(KERNEL_OF[dom]), "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / max(1, d["launches"]),
         "share_of_step": d["ms"] / max(prof_total, 1e-9),
         "whole_step": {"algorithmic_gb": (fwd_b + adj_b) / 1e9, "achieved": step_gbs, "frac": step_gbs / peak},
         "classes": {k: {"launches": c["launches"], "ms": round(c["ms"], 4),

@@ -30,6 +30,24 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in _lib.load().bl_version()
 
 
+def test_header_is_valid_c_and_library_links_from_c(tmp_path):
+    """Compile tests/c_abi_smoke.c with gcc against include/b200_lanczos.h and run it."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib = _lib.library_path()
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, lib,
+                    "-Wl,-rpath," + os.path.dirname(lib)], check=True)  # fmt: skip
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "c abi ok" in out.stdout
+
+
 def test_workspace_queries_are_pure_host_functions():
     lib = _lib.load()
     small = lib.bl_arnoldi_workspace_bytes(1000, 10, _lib.BL_F32)
