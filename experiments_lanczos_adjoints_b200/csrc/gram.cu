@@ -65,28 +65,73 @@ __global__ void k_gram_prepare(int64_t n, int d, int dp, int kind, const double*
   if (blockIdx.x == 0 && threadIdx.x == 0) consts[0] = softplus_t(raw_os[0]);
 }
 
-// exp(-s) and sqrt on the hot path.  fp32: MUFU-based (ex2.approx / rsqrt.approx, ~2 ulp), which
-// keeps the matvec well inside the 1e-5 parity bound; fp64: the IEEE library routines.
-__device__ __forceinline__ float exp_neg(float s) { return __expf(-s); }
-__device__ __forceinline__ double exp_neg(double s) { return exp(-s); }
-__device__ __forceinline__ float sqrt_pos(float x) { return x * rsqrtf(x); }  // x >= eps > 0
-__device__ __forceinline__ double sqrt_pos(double x) { return sqrt(x); }
+// ---- two rows at a time -----------------------------------------------------------------------
+// Blackwell issues packed FP32 pairs (`fma.rn.f32x2`, SASS FFMA2): one FMA-pipe slot does two
+// multiply-adds.  Every thread owns RI rows; rows (2p, 2p+1) travel as one pair through the
+// distance contraction and the kernel epilogue, which halves the FMA-pipe work per kernel entry.
+// fp64 uses the same code with a plain two-element struct.
+template <typename T>
+struct P2 {
+  T a, b;
+};
+template <>
+struct P2<float> {
+  float2 v;
+};
 
-template <typename T, int KIND>
-__device__ __forceinline__ void kernel_eval(T sigma, T s2, T& k, T& dk_ds2) {
-  // value and derivative w.r.t. the clamped squared distance
+__device__ __forceinline__ P2<float> p2_set(float x, float y) { return {make_float2(x, y)}; }
+__device__ __forceinline__ P2<double> p2_set(double x, double y) { return {x, y}; }
+template <typename T>
+__device__ __forceinline__ P2<T> p2_splat(T x) { return p2_set(x, x); }
+__device__ __forceinline__ float p2_lo(const P2<float>& p) { return p.v.x; }
+__device__ __forceinline__ float p2_hi(const P2<float>& p) { return p.v.y; }
+__device__ __forceinline__ double p2_lo(const P2<double>& p) { return p.a; }
+__device__ __forceinline__ double p2_hi(const P2<double>& p) { return p.b; }
+__device__ __forceinline__ P2<float> p2_fma(const P2<float>& x, const P2<float>& y, const P2<float>& z) {
+  return {__ffma2_rn(x.v, y.v, z.v)};
+}
+__device__ __forceinline__ P2<double> p2_fma(const P2<double>& x, const P2<double>& y, const P2<double>& z) {
+  return {fma(x.a, y.a, z.a), fma(x.b, y.b, z.b)};
+}
+__device__ __forceinline__ P2<float> p2_mul(const P2<float>& x, const P2<float>& y) { return {__fmul2_rn(x.v, y.v)}; }
+__device__ __forceinline__ P2<double> p2_mul(const P2<double>& x, const P2<double>& y) { return {x.a * y.a, x.b * y.b}; }
+__device__ __forceinline__ P2<float> p2_add(const P2<float>& x, const P2<float>& y) { return {__fadd2_rn(x.v, y.v)}; }
+__device__ __forceinline__ P2<double> p2_add(const P2<double>& x, const P2<double>& y) { return {x.a + y.a, x.b + y.b}; }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(-s) for a pair: fp32 = ex2.approx(-s * log2(e)) per component (MUFU), fp64 = library exp
+__device__ __forceinline__ P2<float> p2_exp_neg(const P2<float>& s) {
+  const P2<float> t = p2_mul(s, p2_splat(-1.4426950408889634f));
+  return p2_set(ex2_approx(p2_lo(t)), ex2_approx(p2_hi(t)));
+}
+__device__ __forceinline__ P2<double> p2_exp_neg(const P2<double>& s) { return {exp(-s.a), exp(-s.b)}; }
+// sqrt of strictly positive numbers: fp32 = x * rsqrt.approx(x), fp64 = IEEE sqrt
+__device__ __forceinline__ P2<float> p2_sqrt_pos(const P2<float>& x) {
+  return p2_mul(x, p2_set(rsqrtf(p2_lo(x)), rsqrtf(p2_hi(x))));
+}
+__device__ __forceinline__ P2<double> p2_sqrt_pos(const P2<double>& x) { return {sqrt(x.a), sqrt(x.b)}; }
+template <typename T>
+__device__ __forceinline__ P2<T> p2_recip(const P2<T>& x) { return p2_set(T(1) / p2_lo(x), T(1) / p2_hi(x)); }
+
+// value and derivative (w.r.t. the clamped squared distance) of two kernel entries
+template <typename T, int KIND, bool ADJ>
+__device__ __forceinline__ void kernel_eval2(const P2<T>& sigma, const P2<T>& s2, P2<T>& k, P2<T>& dk_ds2) {
   if (KIND == 2) {  // RBF: sigma exp(-s2/2)
-    k = sigma * exp_neg(s2 * T(0.5));
-    dk_ds2 = -k * T(0.5);
+    k = p2_mul(sigma, p2_exp_neg(p2_mul(s2, p2_splat(T(0.5)))));
+    if (ADJ) dk_ds2 = p2_mul(k, p2_splat(T(-0.5)));
   } else {
-    const T s = sqrt_pos(s2 + Eps<T>::v());
-    const T e = exp_neg(s);
-    if (KIND == 0) {  // Matern-3/2: sigma (1+s) e^{-s};  dk/ds = -sigma s e^{-s};  ds/ds2 = 1/(2s)
-      k = sigma * (T(1) + s) * e;
-      dk_ds2 = -sigma * e * T(0.5);
-    } else {  // Matern-1/2: sigma e^{-s}
-      k = sigma * e;
-      dk_ds2 = -k / (T(2) * s);
+    const P2<T> s = p2_sqrt_pos(p2_add(s2, p2_splat(Eps<T>::v())));
+    const P2<T> e = p2_mul(sigma, p2_exp_neg(s));  // sigma e^{-s}
+    if (KIND == 0) {  // Matern-3/2: sigma (1+s) e^{-s};  dk/ds2 = -sigma e^{-s} / 2
+      k = p2_fma(s, e, e);
+      if (ADJ) dk_ds2 = p2_mul(e, p2_splat(T(-0.5)));
+    } else {  // Matern-1/2: sigma e^{-s};  dk/ds2 = -k / (2 s)
+      k = e;
+      if (ADJ) dk_ds2 = p2_mul(p2_mul(e, p2_splat(T(-0.5))), p2_recip(s));
     }
   }
 }
@@ -115,17 +160,21 @@ k_gram_sweep(int64_t n, int d, const T* __restrict__ xs, const T* __restrict__ x
 
   const int tid = threadIdx.x;
   const int64_t i0 = (int64_t)blockIdx.x * (kTileI * RI);
-  const T sigma = consts[0];
-  T xi[RI][DP], xxi[RI], lam_i[RI];
+  static_assert(RI % 2 == 0, "rows are processed in pairs");
+  constexpr int RP = RI / 2;
+  const P2<T> sigma2 = p2_splat(consts[0]);
+  P2<T> xi[RP][DP], xxi[RP], lam_i[RP];  // rows (2p, 2p+1) of this thread as packed pairs
   bool live[RI];
 #pragma unroll
-  for (int r = 0; r < RI; ++r) {
-    const int64_t i = i0 + tid + (int64_t)kTileI * r;
-    live[r] = i < n;
+  for (int p = 0; p < RP; ++p) {
+    const int64_t ia = i0 + tid + (int64_t)kTileI * (2 * p), ib = ia + kTileI;
+    live[2 * p] = ia < n;
+    live[2 * p + 1] = ib < n;
 #pragma unroll
-    for (int k = 0; k < DP; ++k) xi[r][k] = live[r] ? xs[i * DP + k] : T(0);
-    xxi[r] = live[r] ? xx[i] : T(0);
-    lam_i[r] = (ADJ && live[r]) ? v[i] : T(0);
+    for (int k = 0; k < DP; ++k)
+      xi[p][k] = p2_set(live[2 * p] ? xs[ia * DP + k] : T(0), live[2 * p + 1] ? xs[ib * DP + k] : T(0));
+    xxi[p] = p2_set(live[2 * p] ? xx[ia] : T(0), live[2 * p + 1] ? xx[ib] : T(0));
+    lam_i[p] = p2_set((ADJ && live[2 * p]) ? v[ia] : T(0), (ADJ && live[2 * p + 1]) ? v[ib] : T(0));
   }
 
   const int64_t per = ((n + gridDim.y - 1) / gridDim.y + kTileJ - 1) / kTileJ * kTileJ;
@@ -165,11 +214,11 @@ k_gram_sweep(int64_t n, int d, const T* __restrict__ xs, const T* __restrict__ x
     tma::mbar_wait(full + b, (t >> 1) & 1);
     const int64_t jt = j0 + (int64_t)t * kTileJ;
     const int w = (int)((j1 - jt) < kTileJ ? (j1 - jt) : kTileJ);
-    T y_t[RI], dsig_t = T(0), dls_t[DP];
+    P2<T> y_t[RP], dsig_t = p2_splat(T(0)), dls_t[DP];
 #pragma unroll
-    for (int r = 0; r < RI; ++r) y_t[r] = T(0);
+    for (int p = 0; p < RP; ++p) y_t[p] = p2_splat(T(0));
 #pragma unroll
-    for (int k = 0; k < DP; ++k) dls_t[k] = T(0);
+    for (int k = 0; k < DP; ++k) dls_t[k] = p2_splat(T(0));
     for (int jj = 0; jj < w; ++jj) {
       T xj[DP];
 #pragma unroll
@@ -179,37 +228,43 @@ k_gram_sweep(int64_t n, int d, const T* __restrict__ xs, const T* __restrict__ x
 #pragma unroll
         for (int k = 0; k < VN; ++k) xj[u * VN + k] = tmp[k];
       }
-      const T xxj = sxx[b][jj], vj = sv[b][jj];
-      const T qj = ADJ ? sq[b][jj] : T(0);
+      const P2<T> xxj = p2_splat(sxx[b][jj]), vj = p2_splat(sv[b][jj]);
+      const P2<T> qj = p2_splat(ADJ ? sq[b][jj] : T(0));
 #pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        T dot = T(0);
+      for (int p = 0; p < RP; ++p) {
+        P2<T> dot = p2_splat(T(0));
 #pragma unroll
-        for (int k = 0; k < DP; ++k) dot = fma(xi[r][k], xj[k], dot);
-        T s2 = xxi[r] + xxj - T(2) * dot;  // gp_util.py:92
-        const bool pos = s2 > T(0);
-        s2 = pos ? s2 : T(0);  // jnp.maximum(0.0, scaled)
-        T kij, dk;
-        kernel_eval<T, KIND>(sigma, s2, kij, dk);
-        y_t[r] = fma(kij, vj, y_t[r]);
+        for (int k = 0; k < DP; ++k) dot = p2_fma(xi[p][k], p2_splat(xj[k]), dot);
+        // s2 = |x|^2 + |y|^2 - 2 x.y, clamped at zero                          gp_util.py:92-95
+        const P2<T> raw = p2_fma(dot, p2_splat(T(-2)), p2_add(xxi[p], xxj));
+        const bool pos_a = p2_lo(raw) > T(0), pos_b = p2_hi(raw) > T(0);
+        const P2<T> s2 = p2_set(pos_a ? p2_lo(raw) : T(0), pos_b ? p2_hi(raw) : T(0));
+        P2<T> kij, dk;
+        kernel_eval2<T, KIND, ADJ>(sigma2, s2, kij, dk);
+        y_t[p] = p2_fma(kij, vj, y_t[p]);
         if (ADJ) {
-          const T wgt = lam_i[r] * qj;
-          dsig_t = fma(wgt, kij, dsig_t);
-          const T g = pos ? wgt * dk : T(0);
+          const P2<T> wgt = p2_mul(lam_i[p], qj);
+          dsig_t = p2_fma(wgt, kij, dsig_t);
+          // derivative of max(0, .) is zero where it clamps
+          const P2<T> g = p2_mul(p2_mul(wgt, dk), p2_set(pos_a ? T(1) : T(0), pos_b ? T(1) : T(0)));
 #pragma unroll
           for (int k = 0; k < DP; ++k) {
-            const T diff = xi[r][k] - xj[k];
-            dls_t[k] = fma(g, diff * diff, dls_t[k]);
+            const P2<T> diff = p2_add(xi[p][k], p2_splat(-xj[k]));
+            dls_t[k] = p2_fma(g, p2_mul(diff, diff), dls_t[k]);
           }
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < RI; ++r) y_acc[r] += static_cast<double>(y_t[r]);
+    for (int p = 0; p < RP; ++p) {
+      y_acc[2 * p] += static_cast<double>(p2_lo(y_t[p]));
+      y_acc[2 * p + 1] += static_cast<double>(p2_hi(y_t[p]));
+    }
     if (ADJ) {
-      dsig_acc += static_cast<double>(dsig_t);
+      dsig_acc += static_cast<double>(p2_lo(dsig_t)) + static_cast<double>(p2_hi(dsig_t));
 #pragma unroll
-      for (int k = 0; k < DP; ++k) dls_acc[k] += static_cast<double>(dls_t[k]);
+      for (int k = 0; k < DP; ++k)
+        dls_acc[k] += static_cast<double>(p2_lo(dls_t[k])) + static_cast<double>(p2_hi(dls_t[k]));
     }
     __syncthreads();  // everyone is done with stage b
   }
