@@ -3,6 +3,7 @@
 //   bl_arnoldi_adjoint  <- arnoldi._adjoint / _adjoint_step   (arnoldi.py:104-220)
 //   bl_lanczos3_*       <- lanczos._forward / _adjoint        (lanczos.py:215-335)
 #include <algorithm>
+#include <type_traits>
 
 #include <cstdlib>
 #ifndef BL_DOTS_TILE_BYTES
@@ -390,24 +391,27 @@ int launch_fused(const Common& c, const FusedSpec& f, int dtype, cudaStream_t s,
   *fused = false;
   // k_fused_tma keeps one register accumulator per resident box: at most 16 boxes = 128 rows
   if (!use_tma(f.n) || stream_mode() == 2 || f.n >= ((int64_t)1 << 31) || f.res.nrows > 128) return BL_OK;
+  // every tile pays a fixed chain (exchange, barriers, sweep hand-over) of about a microsecond: with
+  // fewer than ~16 rows per tile that costs more than the second read of the rows it saves
+  if (f.res.nrows + f.str0.nrows + f.str1.nrows < 16) return BL_OK;
   constexpr size_t two_per_sm = 113 * 1024;
   constexpr int TMAX = 4096 / (int)sizeof(T);  // 1024 floats / 512 doubles
   const int nr = f.res.nrows, n0 = f.str0.nrows, n1 = f.str1.nrows, nv = f.nvec;
   *fused = true;
-  // widest tile that leaves room for two blocks per SM; streamed rows travel in groups of 32,
-  // 16 or 8 rows per ring stage (bigger stages amortise the per-stage barrier traffic)
-  const int srs[3] = {32, 16, 8};
-  for (int k = 0; k < 3; ++k) {
-    const int sr = (n0 + n1 > 0) ? srs[k] : kGroup;
-    if (fused_layout<T, TMAX>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm) return launch_fused_tile<T, TMAX>(c, f, dtype, sr, s);
-    if (fused_layout<T, TMAX / 2>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm)
-      return launch_fused_tile<T, TMAX / 2>(c, f, dtype, sr, s);
-    if (fused_layout<T, TMAX / 4>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm)
-      return launch_fused_tile<T, TMAX / 4>(c, f, dtype, sr, s);
-    if (fused_layout<T, TMAX / 8>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm)
-      return launch_fused_tile<T, TMAX / 8>(c, f, dtype, sr, s);
-    if (n0 + n1 == 0) break;
-  }
+  // widest tile that leaves room for two blocks per SM (the per-tile hand-over between the two
+  // sweeps is a fixed cost); then the largest streamed-row group (32, 16 or 8 rows per ring stage)
+  // that still fits
+  auto pick_sr = [&](auto tile_tag) -> int {
+    constexpr int TILE = decltype(tile_tag)::value;
+    if (n0 + n1 == 0) return fused_layout<T, TILE>(nr, n0, n1, nv, kGroup).total_bytes <= two_per_sm ? kGroup : 0;
+    for (int sr : {32, 16, 8})
+      if (fused_layout<T, TILE>(nr, n0, n1, nv, sr).total_bytes <= two_per_sm) return sr;
+    return 0;
+  };
+  if (int sr = pick_sr(std::integral_constant<int, TMAX>{})) return launch_fused_tile<T, TMAX>(c, f, dtype, sr, s);
+  if (int sr = pick_sr(std::integral_constant<int, TMAX / 2>{})) return launch_fused_tile<T, TMAX / 2>(c, f, dtype, sr, s);
+  if (int sr = pick_sr(std::integral_constant<int, TMAX / 4>{})) return launch_fused_tile<T, TMAX / 4>(c, f, dtype, sr, s);
+  if (int sr = pick_sr(std::integral_constant<int, TMAX / 8>{})) return launch_fused_tile<T, TMAX / 8>(c, f, dtype, sr, s);
   *fused = false;
   return BL_OK;
 }

@@ -34,9 +34,12 @@ __device__ __forceinline__ T conv_at(const T* __restrict__ u, int64_t g, int64_t
 template <typename T>
 __global__ void k_wave_matvec(int64_t g, Stencil st, const T* __restrict__ scale, const T* __restrict__ x,
                               T* __restrict__ y) {
+  // 2-D launch: blockIdx.y = grid row, x = column (no 64-bit div/mod per point; rows are contiguous)
   const int64_t gg = g * g;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < gg; p += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = p / g, j = p % g;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = blockIdx.y; i < g; i += gridDim.y) {
+    if (j >= g) continue;
+    const int64_t p = i * g + j;
     y[p] = x[gg + p];  // d/dt u = du
     const T sc = scale[p];
     y[gg + p] = conv_at<T>(x, g, i, j, st) * (sc * sc);  // fx * constrain(scale), constrain = square
@@ -78,8 +81,10 @@ template <typename T>
 __global__ void k_wave_vjp_a(int64_t g, Stencil st, const T* __restrict__ scale, const T* __restrict__ q,
                              const T* __restrict__ lam, T* __restrict__ tmp, T* __restrict__ z, T* __restrict__ grad) {
   const int64_t gg = g * g;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < gg; p += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = p / g, j = p % g;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = blockIdx.y; i < g; i += gridDim.y) {
+    if (j >= g) continue;
+    const int64_t p = i * g + j;
     const T sc = scale[p], ld = lam[gg + p];
     tmp[p] = sc * sc * ld;
     grad[p] = fma(T(2) * sc * ld, conv_at<T>(q, g, i, j, st), grad[p]);
@@ -90,9 +95,9 @@ __global__ void k_wave_vjp_a(int64_t g, Stencil st, const T* __restrict__ scale,
 // z_u = conv^T(tmp)
 template <typename T>
 __global__ void k_wave_vjp_b(int64_t g, Stencil st, const T* __restrict__ tmp, T* __restrict__ z) {
-  const int64_t gg = g * g;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < gg; p += (int64_t)gridDim.x * blockDim.x)
-    z[p] = conv_t_at<T>(tmp, g, p / g, p % g, st);
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = blockIdx.y; i < g; i += gridDim.y)
+    if (j < g) z[i * g + j] = conv_t_at<T>(tmp, g, i, j, st);
 }
 
 }  // namespace
@@ -106,7 +111,7 @@ struct WaveOperator : bl_operator {
 
   int num_params() const override { return 1; }
   int64_t param_size(int) const override { return g * g; }
-  int blocks() const { return (int)std::min<int64_t>(16 * sm_count(), (g * g + 255) / 256); }
+  dim3 blocks() const { return dim3((unsigned)((g + 255) / 256), (unsigned)std::min<int64_t>(g, 65535)); }
 
   int set_params(int dtype, const void* const* params, int num, cudaStream_t) override {
     BL_REQUIRE(num == 1 && params && params[0], "wave operator takes one parameter (scale, g x g)");
