@@ -3,6 +3,9 @@
 //   bl_arnoldi_adjoint  <- arnoldi._adjoint / _adjoint_step   (arnoldi.py:104-220)
 //   bl_lanczos3_*       <- lanczos._forward / _adjoint        (lanczos.py:215-335)
 #include <algorithm>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <type_traits>
 
 #include <cstdlib>
@@ -170,9 +173,19 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// The dynamic shared-memory opt-in is a per-device function attribute: cache it per (kernel,
+// device) so that one process may drive several GPUs from different host threads.
 template <typename F>
 int set_smem(F* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  BL_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), dev);
+  if (done.count(key)) return BL_OK;
   BL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  done.insert(key);
   return BL_OK;
 }
 
@@ -202,11 +215,7 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
     constexpr int TILE = dots_tile<T>();
     const size_t smem = (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 4) * 8 +
                         (size_t)blk.nrows * 8 + 16;
-    static bool once = false;
-    if (!once) {
-      BL_CHECK(set_smem(k_dots_tma<T, TILE>, 112 * 1024));
-      once = true;
-    }
+    BL_CHECK(set_smem(k_dots_tma<T, TILE>, 112 * 1024));
     BL_REQUIRE(smem <= 112 * 1024, "too many rows for k_dots_tma");
     BL_CUDA(launch_pdl(k_dots_tma<T, TILE>, tma_grid<T>(n, TILE), kStreamThreads, smem, s,
                        row_source(blk, nullptr, sizeof(T)), blk.nrows, x, (long long)n, c.partials_dots,
@@ -253,12 +262,8 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
     t.epi = a.epi;
     const size_t smem = (size_t)kStages * kGroup * TILE * sizeof(T) + 2 * kStages * 8 +
                         (size_t)(nrows + 2 * kGroup) * sizeof(T) + 16;
-    static bool once = false;
-    if (!once) {
-      BL_CHECK(set_smem(k_combine_tma<T, true>, 100 * 1024));
-      BL_CHECK(set_smem(k_combine_tma<T, false>, 100 * 1024));
-      once = true;
-    }
+    BL_CHECK(set_smem(k_combine_tma<T, true>, 100 * 1024));
+    BL_CHECK(set_smem(k_combine_tma<T, false>, 100 * 1024));
     BL_REQUIRE(smem <= 100 * 1024, "too many rows for k_combine_tma");
     const int grid = tma_grid<T>(a.n, TILE);
     if (norm)
@@ -332,11 +337,7 @@ template <typename T, int TILE>
 int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, int sr, cudaStream_t s) {
   constexpr int BOXC = TILE > 256 ? 256 : TILE;
   const FusedLayout L = fused_layout<T, TILE>(f.res.nrows, f.str0.nrows, f.str1.nrows, f.nvec, sr);
-  static bool once = false;
-  if (!once) {
-    BL_CHECK(set_smem(k_fused_tma<T, TILE>, 225 * 1024));
-    once = true;
-  }
+  BL_CHECK(set_smem(k_fused_tma<T, TILE>, 225 * 1024));
   FusedArgs a;
   const char* res_base = static_cast<const char*>(f.res.base) + (int64_t)f.res.row0 * f.res.ld * (int64_t)sizeof(T);
   BL_CHECK(make_basis_map(&a.map_res, dtype, res_base, f.res.ld, f.res.nrows, BOXC));

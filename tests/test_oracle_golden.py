@@ -168,3 +168,29 @@ def test_wave_stencil_and_expm_action_match_reference():
     dy0, dsc = krylov.expm_action_vjp(op, K, float(g["t1"]), y0, (scale,), g["u"].ravel())
     assert rel_err(dy0, g["loss_dy0"].ravel()) < 1e-9
     assert rel_err(dsc, g["loss_dscale"]) < 1e-9
+
+
+@pytest.mark.parametrize("krylov_depth", [1, 5, 10])
+def test_oracle_arnoldi_forward_supports_complex(krylov_depth, nrows=10):
+    """/root/reference/tests/test_arnoldi/test_hessenberg_forward.py:10-37 with dtype=complex: the
+    forward pass conjugates (`arnoldi.py:66,87,92,95`); the CUDA path is real-only."""
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((nrows, nrows)) + 1j * rng.standard_normal((nrows, nrows))
+    v = rng.standard_normal(nrows) + 1j * rng.standard_normal(nrows)
+    Q, H, r, c = krylov.arnoldi_forward(operators.DenseOperator(), krylov_depth, v, A)
+    small = np.sqrt(np.finfo(np.float64).eps)
+    e0, ek = np.eye(krylov_depth)[[0, -1], :]
+    assert np.allclose(A @ Q - Q @ H - np.outer(r, ek), 0.0, atol=small)
+    assert np.allclose(Q.T.conj() @ Q - np.eye(krylov_depth), 0.0, atol=small)
+    assert np.allclose(Q @ e0, c * v, atol=small)
+
+
+def test_oracle_error_conventions():
+    # arnoldi.py:16-19 (TypeError), :58-60 (ValueError "depth"), lanczos.py:148-149 (ValueError)
+    with pytest.raises(TypeError, match="Unexpected input"):
+        krylov.Hessenberg(operators.DenseOperator(), 1, reortho="None")
+    for depth in (0, 3):
+        with pytest.raises(ValueError, match="depth"):
+            krylov.Hessenberg(operators.DenseOperator(), depth, reortho="none")(np.ones(2), np.eye(2))
+    with pytest.raises(ValueError, match="unsupported"):
+        krylov.tridiag(operators.DenseOperator(), 1, reortho="partial")
