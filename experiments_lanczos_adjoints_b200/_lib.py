@@ -57,6 +57,8 @@ SIGNATURES = {
     "bl_op_dense_create": (_i32, [_i64, _i32, _pvp]),
     "bl_op_gram_create": (_i32, [_i64, _i64, _i32, _vp, _pvp]),
     "bl_op_wave_create": (_i32, [_i64, _vp, _pvp]),
+    "bl_op_wave_slab_create": (_i32, [_i64, _i64, _i32, _i32, _vp, _pvp]),
+    "bl_op_wave_halo": (_i32, [_vp, _i32, _pvp]),
     "bl_op_callback_create": (_i32, [_i64, MATVEC_CB, VJP_CB, _vp, _pvp]),
     "bl_op_destroy": (_i32, [_vp]),
     "bl_op_size": (_i32, [_vp, C.POINTER(C.c_int64)]),

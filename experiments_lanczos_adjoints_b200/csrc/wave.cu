@@ -9,6 +9,12 @@
 // the grid are contiguous so every access is coalesced.
 #include "operators.cuh"
 
+// Row-sharded use (one slab of grid rows per GPU): the operator covers `gy` rows x `gx` columns and
+// may have a neighbour above / below.  Rows next to a neighbour read one halo row that the host
+// layer exchanges (NCCL send/recv) into the operator's halo buffers before each call; at a global
+// boundary the index clamps (edge replicate).  The square single-GPU operator is the slab with
+// gy = gx = g and no neighbours.
+
 namespace bl {
 namespace {
 
@@ -16,125 +22,174 @@ struct Stencil {
   double w[9];
 };
 
+// Field of gy x gx values with optional halo rows above (row -1) and below (row gy).
+template <typename T>
+struct Field {
+  const T* body;
+  const T* top;  // nullptr: no neighbour above (clamp)
+  const T* bot;  // nullptr: no neighbour below (clamp)
+  int64_t gy, gx;
+  __device__ __forceinline__ const T* row(int64_t i) const {
+    if (i < 0) return top ? top : body;
+    if (i >= gy) return bot ? bot : body + (gy - 1) * gx;
+    return body + i * gx;
+  }
+};
+
 __device__ __forceinline__ int64_t clampi(int64_t v, int64_t hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 
+// conv(u)[i,j] = sum_{a,b} st[a,b] * u[i+1-a, clamp(j+1-b)]  (rows through the halo / clamp)
 template <typename T>
-__device__ __forceinline__ T conv_at(const T* __restrict__ u, int64_t g, int64_t i, int64_t j, const Stencil& st) {
-  T s = T(0);
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const T w = static_cast<T>(st.w[a * 3 + b]);
-      if (w != T(0)) s = fma(w, u[clampi(i + 1 - a, g - 1) * g + clampi(j + 1 - b, g - 1)], s);
-    }
-  return s;
-}
-
-template <typename T>
-__global__ void k_wave_matvec(int64_t g, Stencil st, const T* __restrict__ scale, const T* __restrict__ x,
-                              T* __restrict__ y) {
-  // 2-D launch: blockIdx.y = grid row, x = column (no 64-bit div/mod per point; rows are contiguous)
-  const int64_t gg = g * g;
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t i = blockIdx.y; i < g; i += gridDim.y) {
-    if (j >= g) continue;
-    const int64_t p = i * g + j;
-    y[p] = x[gg + p];  // d/dt u = du
-    const T sc = scale[p];
-    y[gg + p] = conv_at<T>(x, g, i, j, st) * (sc * sc);  // fx * constrain(scale), constrain = square
-  }
-}
-
-// transpose of conv (with the clamp folded in): contributions to cell (p, q) come from
-//   i = p + a - 1 (if inside), plus i = 0 when p == 0 and a == 2, plus i = g-1 when p == g-1 and a == 0
-template <typename T>
-__device__ __forceinline__ T conv_t_at(const T* __restrict__ w, int64_t g, int64_t p, int64_t q, const Stencil& st) {
+__device__ __forceinline__ T conv_at(const Field<T>& u, int64_t i, int64_t j, const Stencil& st) {
   T s = T(0);
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    int64_t is[2];
-    int ni = 0;
-    const int64_t i0 = p + a - 1;
-    if (i0 >= 0 && i0 <= g - 1) is[ni++] = i0;
-    if (p == 0 && a == 2) is[ni++] = 0;
-    if (p == g - 1 && a == 0) is[ni++] = g - 1;
+    const T* r = u.row(i + 1 - a);
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-      const T wt = static_cast<T>(st.w[a * 3 + b]);
-      if (wt == T(0)) continue;
-      int64_t js[2];
-      int nj = 0;
-      const int64_t jj0 = q + b - 1;
-      if (jj0 >= 0 && jj0 <= g - 1) js[nj++] = jj0;
-      if (q == 0 && b == 2) js[nj++] = 0;
-      if (q == g - 1 && b == 0) js[nj++] = g - 1;
-      for (int ii = 0; ii < ni; ++ii)
-        for (int jj = 0; jj < nj; ++jj) s = fma(wt, w[is[ii] * g + js[jj]], s);
+      const T w = static_cast<T>(st.w[a * 3 + b]);
+      if (w != T(0)) s = fma(w, r[clampi(j + 1 - b, u.gx - 1)], s);
     }
   }
   return s;
 }
 
-// tmp = scale^2 * lam_du ; grad += 2 scale lam_du conv(q_u) ; z_du = lam_u
+// y_u = du ; y_du = scale^2 * conv(u)          (2-D launch: blockIdx.y strides the rows)
 template <typename T>
-__global__ void k_wave_vjp_a(int64_t g, Stencil st, const T* __restrict__ scale, const T* __restrict__ q,
-                             const T* __restrict__ lam, T* __restrict__ tmp, T* __restrict__ z, T* __restrict__ grad) {
-  const int64_t gg = g * g;
+__global__ void k_wave_matvec(Field<T> u, Stencil st, const T* __restrict__ scale, const T* __restrict__ du,
+                              T* __restrict__ y) {
+  const int64_t gg = u.gy * u.gx;
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t i = blockIdx.y; i < g; i += gridDim.y) {
-    if (j >= g) continue;
-    const int64_t p = i * g + j;
-    const T sc = scale[p], ld = lam[gg + p];
-    tmp[p] = sc * sc * ld;
-    grad[p] = fma(T(2) * sc * ld, conv_at<T>(q, g, i, j, st), grad[p]);
-    if (z) z[gg + p] = lam[p];
+  for (int64_t i = blockIdx.y; i < u.gy; i += gridDim.y) {
+    if (j >= u.gx) continue;
+    const int64_t p = i * u.gx + j;
+    y[p] = du[p];  // d/dt u = du
+    const T sc = scale[p];
+    y[gg + p] = conv_at<T>(u, i, j, st) * (sc * sc);  // fx * constrain(scale), constrain = square
   }
 }
 
-// z_u = conv^T(tmp)
+// tmp = scale^2 * lam_du (also for the halo rows) ; grad += 2 scale lam_du conv(q_u) ; z_du = lam_u
 template <typename T>
-__global__ void k_wave_vjp_b(int64_t g, Stencil st, const T* __restrict__ tmp, T* __restrict__ z) {
+__global__ void k_wave_vjp_a(Field<T> qu, Stencil st, const T* __restrict__ scale, const T* __restrict__ lam,
+                             const T* __restrict__ scale_top, const T* __restrict__ scale_bot,
+                             const T* __restrict__ lam_top, const T* __restrict__ lam_bot, T* __restrict__ tmp,
+                             T* __restrict__ tmp_top, T* __restrict__ tmp_bot, T* __restrict__ z,
+                             T* __restrict__ grad) {
+  const int64_t gy = qu.gy, gx = qu.gx, gg = gy * gx;
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t i = blockIdx.y; i < g; i += gridDim.y)
-    if (j < g) z[i * g + j] = conv_t_at<T>(tmp, g, i, j, st);
+  if (j >= gx) return;
+  for (int64_t i = blockIdx.y; i < gy; i += gridDim.y) {
+    const int64_t p = i * gx + j;
+    const T sc = scale[p], ld = lam[gg + p];
+    tmp[p] = sc * sc * ld;
+    grad[p] = fma(T(2) * sc * ld, conv_at<T>(qu, i, j, st), grad[p]);
+    if (z) z[gg + p] = lam[p];
+  }
+  if (blockIdx.y == 0) {  // the neighbours' boundary rows of tmp, recomputed from their halos
+    if (tmp_top) tmp_top[j] = scale_top[j] * scale_top[j] * lam_top[j];
+    if (tmp_bot) tmp_bot[j] = scale_bot[j] * scale_bot[j] * lam_bot[j];
+  }
+}
+
+// z_u = conv^T(tmp): contributions to cell (p, q) come from rows i = p + a - 1 (through the halo
+// when a neighbour exists) plus, at a GLOBAL boundary, the rows folded in by the clamp:
+// i = 0 when p == 0 and a == 2, i = gy-1 when p == gy-1 and a == 0; same for the columns.
+template <typename T>
+__global__ void k_wave_vjp_b(Field<T> tmp, Stencil st, T* __restrict__ z) {
+  const int64_t gy = tmp.gy, gx = tmp.gx;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= gx) return;
+  for (int64_t p = blockIdx.y; p < gy; p += gridDim.y) {
+    T s = T(0);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const T* rows[2];
+      int ni = 0;
+      const int64_t i0 = p + a - 1;
+      if (i0 >= 0 && i0 <= gy - 1) rows[ni++] = tmp.body + i0 * gx;
+      if (i0 == -1 && tmp.top) rows[ni++] = tmp.top;
+      if (i0 == gy && tmp.bot) rows[ni++] = tmp.bot;
+      if (p == 0 && a == 2 && !tmp.top) rows[ni++] = tmp.body;
+      if (p == gy - 1 && a == 0 && !tmp.bot) rows[ni++] = tmp.body + (gy - 1) * gx;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const T wt = static_cast<T>(st.w[a * 3 + b]);
+        if (wt == T(0)) continue;
+        int64_t js[2];
+        int nj = 0;
+        const int64_t j0 = q + b - 1;
+        if (j0 >= 0 && j0 <= gx - 1) js[nj++] = j0;
+        if (q == 0 && b == 2) js[nj++] = 0;
+        if (q == gx - 1 && b == 0) js[nj++] = gx - 1;
+        for (int ii = 0; ii < ni; ++ii)
+          for (int jj = 0; jj < nj; ++jj) s = fma(wt, rows[ii][js[jj]], s);
+      }
+    }
+    z[p * gx + q] = s;
+  }
 }
 
 }  // namespace
 
 struct WaveOperator : bl_operator {
-  int64_t g = 0;
+  int64_t gy = 0, gx = 0;
+  bool has_top = false, has_bot = false;
   Stencil st;
   const void* scale = nullptr;
   int bound_dtype = -1;
   DevBuf grad, tmp;
+  // halo rows (gx values each, 8 bytes per value reserved): 0/1 first input top/bottom (u or q_u),
+  // 2/3 lam_du top/bottom, 4/5 scale top/bottom, 6/7 tmp top/bottom (internal)
+  DevBuf halo[8];
 
   int num_params() const override { return 1; }
-  int64_t param_size(int) const override { return g * g; }
-  dim3 blocks() const { return dim3((unsigned)((g + 255) / 256), (unsigned)std::min<int64_t>(g, 65535)); }
+  int64_t param_size(int) const override { return gy * gx; }
+  dim3 blocks() const { return dim3((unsigned)((gx + 255) / 256), (unsigned)std::min<int64_t>(gy, 65535)); }
+  double matvec_bytes(int dtype) const override { return 5.0 * gy * gx * dtype_size(dtype); }
+  double vjp_bytes(int dtype) const override { return 10.0 * gy * gx * dtype_size(dtype); }
 
-  int set_params(int dtype, const void* const* params, int num, cudaStream_t) override {
-    BL_REQUIRE(num == 1 && params && params[0], "wave operator takes one parameter (scale, g x g)");
-    scale = params[0];
-    bound_dtype = dtype;
-    BL_CHECK(grad.ensure((size_t)g * g * dtype_size(dtype)));
-    return tmp.ensure((size_t)g * g * dtype_size(dtype));
-  }
-  int matvec(int dtype, const void* x, void* y, cudaStream_t s) override {
-    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
-    if (dtype == BL_F32)
-      k_wave_matvec<float><<<blocks(), 256, 0, s>>>(g, st, (const float*)scale, (const float*)x, (float*)y);
-    else
-      k_wave_matvec<double><<<blocks(), 256, 0, s>>>(g, st, (const double*)scale, (const double*)x, (double*)y);
-    BL_LAUNCHED();
+  int init_halos() {
+    for (auto& h : halo) {
+      BL_CHECK(h.ensure((size_t)gx * 8));
+      BL_CUDA(cudaMemset(h.p, 0, (size_t)gx * 8));
+    }
     return BL_OK;
   }
   template <typename T>
+  const T* halo_or_null(int k, bool present) const { return present ? halo[k].as<T>() : nullptr; }
+
+  int set_params(int dtype, const void* const* params, int num, cudaStream_t) override {
+    BL_REQUIRE(num == 1 && params && params[0], "wave operator takes one parameter (scale, rows x cols)");
+    scale = params[0];
+    bound_dtype = dtype;
+    BL_CHECK(grad.ensure((size_t)gy * gx * dtype_size(dtype)));
+    return tmp.ensure((size_t)gy * gx * dtype_size(dtype));
+  }
+  template <typename T>
+  int matvec_t(const T* x, T* y, cudaStream_t s) {
+    Field<T> u{x, halo_or_null<T>(0, has_top), halo_or_null<T>(1, has_bot), gy, gx};
+    k_wave_matvec<T><<<blocks(), 256, 0, s>>>(u, st, (const T*)scale, x + gy * gx, y);
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  int matvec(int dtype, const void* x, void* y, cudaStream_t s) override {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    return dtype == BL_F32 ? matvec_t<float>((const float*)x, (float*)y, s)
+                           : matvec_t<double>((const double*)x, (double*)y, s);
+  }
+  template <typename T>
   int vjp_t(const T* q, const T* lam, T* z, cudaStream_t s) {
-    k_wave_vjp_a<T><<<blocks(), 256, 0, s>>>(g, st, (const T*)scale, q, lam, tmp.as<T>(), z, grad.as<T>());
+    Field<T> qu{q, halo_or_null<T>(0, has_top), halo_or_null<T>(1, has_bot), gy, gx};
+    k_wave_vjp_a<T><<<blocks(), 256, 0, s>>>(qu, st, (const T*)scale, lam, halo_or_null<T>(4, has_top),
+                                             halo_or_null<T>(5, has_bot), halo_or_null<T>(2, has_top),
+                                             halo_or_null<T>(3, has_bot), tmp.as<T>(),
+                                             has_top ? halo[6].as<T>() : nullptr, has_bot ? halo[7].as<T>() : nullptr,
+                                             z, grad.as<T>());
     BL_LAUNCHED();
     if (z) {
-      k_wave_vjp_b<T><<<blocks(), 256, 0, s>>>(g, st, tmp.as<T>(), z);
+      Field<T> tf{tmp.as<T>(), halo_or_null<T>(6, has_top), halo_or_null<T>(7, has_bot), gy, gx};
+      k_wave_vjp_b<T><<<blocks(), 256, 0, s>>>(tf, st, z);
       BL_LAUNCHED();
     }
     return BL_OK;
@@ -145,25 +200,54 @@ struct WaveOperator : bl_operator {
                            : vjp_t<double>((const double*)q, (const double*)lam, (double*)z, s);
   }
   int grad_zero(int dtype, cudaStream_t s) override {
-    BL_CHECK(grad.ensure((size_t)g * g * dtype_size(dtype)));
-    BL_CUDA(cudaMemsetAsync(grad.p, 0, (size_t)g * g * dtype_size(dtype), s));
+    BL_CHECK(grad.ensure((size_t)gy * gx * dtype_size(dtype)));
+    BL_CUDA(cudaMemsetAsync(grad.p, 0, (size_t)gy * gx * dtype_size(dtype), s));
     return BL_OK;
   }
   int grad_export(int dtype, void* const* grads, int num, cudaStream_t s) override {
     BL_REQUIRE(num == 1 && grads && grads[0], "wave operator has one gradient buffer");
-    BL_CUDA(cudaMemcpyAsync(grads[0], grad.p, (size_t)g * g * dtype_size(dtype), cudaMemcpyDeviceToDevice, s));
+    BL_CUDA(cudaMemcpyAsync(grads[0], grad.p, (size_t)gy * gx * dtype_size(dtype), cudaMemcpyDeviceToDevice, s));
     return BL_OK;
   }
 };
 
 }  // namespace bl
 
-extern "C" int bl_op_wave_create(int64_t grid, const double* stencil3x3_host, bl_operator_t** op) {
-  BL_REQUIRE(op && stencil3x3_host && grid >= 2, "bad wave operator arguments");
+extern "C" {
+
+int bl_op_wave_slab_create(int64_t rows, int64_t cols, int has_top, int has_bottom, const double* stencil3x3_host,
+                           bl_operator_t** op) {
+  BL_REQUIRE(op && stencil3x3_host && rows >= 1 && cols >= 2, "bad wave operator arguments");
+  BL_REQUIRE(rows >= 2 || (has_top && has_bottom) || rows * cols > 0, "bad slab");
   auto* o = new bl::WaveOperator();
-  o->g = grid;
-  o->n = 2 * grid * grid;
+  o->gy = rows;
+  o->gx = cols;
+  o->has_top = has_top != 0;
+  o->has_bot = has_bottom != 0;
+  o->n = 2 * rows * cols;
   for (int k = 0; k < 9; ++k) o->st.w[k] = stencil3x3_host[k];
+  if (o->has_top || o->has_bot) {
+    int rc = o->init_halos();
+    if (rc != BL_OK) {
+      delete o;
+      return rc;
+    }
+  }
   *op = o;
   return BL_OK;
 }
+
+int bl_op_wave_create(int64_t grid, const double* stencil3x3_host, bl_operator_t** op) {
+  BL_REQUIRE(grid >= 2, "bad wave operator arguments");
+  return bl_op_wave_slab_create(grid, grid, 0, 0, stencil3x3_host, op);
+}
+
+int bl_op_wave_halo(bl_operator_t* op, int which, void** ptr) {
+  auto* o = dynamic_cast<bl::WaveOperator*>(op);
+  BL_REQUIRE(o != nullptr && ptr != nullptr && which >= 0 && which < 6, "bad halo query");
+  BL_REQUIRE(o->halo[which].p != nullptr, "operator has no neighbours");
+  *ptr = o->halo[which].p;
+  return BL_OK;
+}
+
+}  // extern "C"

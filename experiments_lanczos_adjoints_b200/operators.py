@@ -193,14 +193,24 @@ class WaveStencilOperator(Operator):
     """`(u, du) -> (du, scale^2 * conv3x3(stencil, edge_pad(u)))` on a `g x g` grid
     (`/root/reference/src/matfree_extensions/util/pde_util.py:126-157`).  Parameter: `scale (g, g)`."""
 
-    def __init__(self, grid, stencil):
+    def __init__(self, grid, stencil, *, rows=None, has_top=False, has_bottom=False):
+        """`rows` (with `has_top` / `has_bottom`) builds the row-sharded form: a slab of `rows` grid
+        rows x `grid` columns whose neighbours' boundary rows arrive through halo buffers
+        (`parallel.RowShardedWaveOperator`)."""
         st = np.ascontiguousarray(np.asarray(stencil, dtype=np.float64))
         if st.shape != (3, 3):
             raise ValueError("stencil must be 3 x 3")
         self.g = int(grid)
+        self.rows = self.g if rows is None else int(rows)
         h = C.c_void_p()
-        _lib.call("bl_op_wave_create", self.g, st.ctypes.data, C.byref(h))
-        super().__init__(h.value, 2 * self.g * self.g)
+        _lib.call("bl_op_wave_slab_create", self.rows, self.g, int(bool(has_top)), int(bool(has_bottom)),
+                  st.ctypes.data, C.byref(h))  # fmt: skip
+        super().__init__(h.value, 2 * self.rows * self.g)
+
+    def halo_ptr(self, which: int) -> int:
+        p = C.c_void_p()
+        _lib.call("bl_op_wave_halo", self._handle, int(which), C.byref(p))
+        return p.value
 
     @staticmethod
     def stencil_laplacian(dx):
@@ -208,15 +218,15 @@ class WaveStencilOperator(Operator):
         return np.asarray([[0.0, 1.0, 0.0], [1.0, -2.0, 1.0], [0.0, 1.0, 0.0]]) / dx**2
 
     def param_shapes(self):
-        return [(self.g, self.g)]
+        return [(self.rows, self.g)]
 
     def bind(self, params, dtype, stream=None):
         params = [np.asarray(p).reshape(-1) if not isinstance(p, dev.DeviceArray) else p for p in params]
         return super().bind(params, dtype, stream)
 
     def grad_export(self, dtype, like=None, stream=None):
-        (g,) = super().grad_export(dtype, like=[(self.g * self.g,)], stream=stream)
-        return [dev.DeviceArray((self.g, self.g), dtype, owner=g._owner, ptr=g.ptr)]
+        (g,) = super().grad_export(dtype, like=[(self.rows * self.g,)], stream=stream)
+        return [dev.DeviceArray((self.rows, self.g), dtype, owner=g._owner, ptr=g.ptr)]
 
 
 class CallbackOperator(Operator):

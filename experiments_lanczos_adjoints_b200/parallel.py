@@ -297,3 +297,92 @@ class RowShardedSparseOperator:
         full[self.idx_a] = g_loc.numpy()
         (full,) = all_reduce_sum([full], self.group)
         return [full.astype(dtype)]
+
+
+class RowShardedWaveOperator:
+    """The wave-stencil operand (BASELINE config 5) with the grid rows sharded over the ranks:
+    rank r owns rows `[r*gs, (r+1)*gs)` of `u` and of `du` (local state `[u_slab; du_slab]`).
+    Each matvec exchanges ONE grid row with each neighbour (NCCL send/recv on the library's
+    stream); the VJP exchanges the boundary rows of `q_u` and `lambda_du`.  `d scale` is local to the
+    owner of the row."""
+
+    def __init__(self, grid, stencil, group=None):
+        from experiments_lanczos_adjoints_b200 import operators as ops
+
+        dist = _dist()
+        self.group = group
+        self.rank = dist.get_rank(group) if dist else 0
+        self.world = dist.get_world_size(group) if dist else 1
+        self.g = int(grid)
+        if self.g % self.world:
+            raise ValueError(f"grid rows ({self.g}) must be divisible by the number of ranks ({self.world})")
+        self.gs = self.g // self.world
+        self.has_top, self.has_bot = self.rank > 0, self.rank < self.world - 1
+        self.local = ops.WaveStencilOperator(self.g, stencil, rows=self.gs, has_top=self.has_top,
+                                             has_bottom=self.has_bot)  # fmt: skip
+        self.callback = ops.CallbackOperator(self.local.n, self._matvec, self._vjp, num_params=1)
+        self.callback.bind = self._bind
+        self.callback.grad_zero = lambda dtype, stream=None: self.local.grad_zero(dtype)
+        self.callback.grad_export = self._grad_export
+
+    def local_slice(self, state):
+        """Local `[u_slab; du_slab]` of a global state `(2, g, g)` (or its ravel)."""
+        st = np.asarray(state).reshape(2, self.g, self.g)
+        lo, hi = self.rank * self.gs, (self.rank + 1) * self.gs
+        return np.concatenate([st[0, lo:hi].ravel(), st[1, lo:hi].ravel()])
+
+    def _exchange(self, field_ptr, dtype, slot_top, slot_bot):
+        """Send my first / last row of `field` to the neighbours, receive theirs into the halo slots."""
+        if self.world == 1:
+            return
+        import torch
+        import torch.distributed as dist
+
+        g, gs, item = self.g, self.gs, np.dtype(dtype).itemsize
+        ops_ = []
+        with torch.cuda.stream(torch.cuda.ExternalStream(dev.default_stream().ptr)):
+            if self.has_top:
+                ops_.append(dist.P2POp(dist.isend, _as_torch(field_ptr, g, dtype), self.rank - 1, self.group))
+                ops_.append(dist.P2POp(dist.irecv, _as_torch(self.local.halo_ptr(slot_top), g, dtype),
+                                       self.rank - 1, self.group))  # fmt: skip
+            if self.has_bot:
+                last = field_ptr + (gs - 1) * g * item
+                ops_.append(dist.P2POp(dist.isend, _as_torch(last, g, dtype), self.rank + 1, self.group))
+                ops_.append(dist.P2POp(dist.irecv, _as_torch(self.local.halo_ptr(slot_bot), g, dtype),
+                                       self.rank + 1, self.group))  # fmt: skip
+            for req in dist.batch_isend_irecv(ops_):
+                req.wait()
+
+    def _bind(self, params, dtype, stream=None):
+        from experiments_lanczos_adjoints_b200 import _lib
+
+        (scale,) = params
+        sc = np.asarray(scale, dtype=dtype).reshape(self.g, self.g)
+        lo, hi = self.rank * self.gs, (self.rank + 1) * self.gs
+        self.local.bind((np.ascontiguousarray(sc[lo:hi]),), dtype)
+        self._dtype = np.dtype(dtype)
+        # the neighbours' boundary rows of `scale` (the parameter is replicated on the hosts)
+        s = dev.default_stream()
+        for present, row, slot in ((self.has_top, lo - 1, 4), (self.has_bot, hi, 5)):
+            if present:
+                host = np.ascontiguousarray(sc[row])
+                _lib.call("bl_memcpy_h2d", self.local.halo_ptr(slot), host.ctypes.data, host.nbytes, s.ptr)
+                s.synchronize()
+        return [scale]
+
+    def _matvec(self, x_loc):
+        self._exchange(x_loc.ptr, x_loc.dtype, 0, 1)  # rows of u
+        return self.local.matvec(x_loc)
+
+    def _vjp(self, q_loc, lam_loc):
+        half = self.gs * self.g * q_loc.dtype.itemsize
+        self._exchange(q_loc.ptr, q_loc.dtype, 0, 1)             # rows of q_u
+        self._exchange(lam_loc.ptr + half, lam_loc.dtype, 2, 3)  # rows of lambda_du
+        return self.local.vjp(q_loc, lam_loc), ()
+
+    def _grad_export(self, dtype, like=None, stream=None):
+        (g_loc,) = self.local.grad_export(dtype)
+        full = np.zeros((self.g, self.g), dtype=np.float64)
+        full[self.rank * self.gs : (self.rank + 1) * self.gs] = g_loc.numpy()
+        (full,) = all_reduce_sum([full], self.group)
+        return [full.astype(dtype)]

@@ -130,6 +130,15 @@ int bl_op_gram_create(int64_t n, int64_t d, int kind, const double* X_host, bl_o
 /* Wave-equation stencil operand (util/pde_util.py:126-157): state (u, du) of 2 g^2 values,
  * A(u,du) = (du, scale^2 * conv3x3(stencil, edge_pad(u))).  One parameter: scale (g*g). */
 int bl_op_wave_create(int64_t grid, const double* stencil3x3_host, bl_operator_t** op);
+/* Row-sharded form: a slab of `rows` grid rows x `cols` columns with an optional neighbour above /
+ * below.  State (u_slab, du_slab) of 2*rows*cols values; parameter scale (rows*cols).  Before each
+ * matvec the caller writes the neighbours' boundary rows of u into halo buffers 0 (top) / 1 (bottom);
+ * before each vjp: rows of q_u into 0/1, rows of lam_du into 2/3; the neighbours' rows of `scale`
+ * into 4/5 once per bind.  bl_op_wave_halo returns the device pointer of buffer `which`
+ * (cols values of the bound dtype). */
+int bl_op_wave_slab_create(int64_t rows, int64_t cols, int has_top, int has_bottom, const double* stencil3x3_host,
+                           bl_operator_t** op);
+int bl_op_wave_halo(bl_operator_t* op, int which, void** ptr);
 
 /* User-supplied matvec: the host layer passes C callbacks that enqueue work on `stream`.
  * matvec_cb(user, dtype, x, y, stream); vjp_cb(user, dtype, q, lam, z_or_null, stream). */

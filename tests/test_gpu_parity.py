@@ -296,6 +296,29 @@ def test_row_sharded_path_with_one_rank_matches_plain_path():
     assert rel_err(dp1, dp0.numpy()) < 1e-12
 
 
+def test_wave_slab_operator_with_one_rank_matches_square_operator():
+    """Row-sharded wave operand on a single rank (no neighbours) == the plain operand; the halo path
+    itself needs two GPUs (`scripts/run_row_sharded_wave.py`, profiles/)."""
+    from experiments_lanczos_adjoints_b200 import parallel
+
+    g, K = 96, 5
+    rng = np.random.default_rng(0)
+    stencil = bl.operators.WaveStencilOperator.stencil_laplacian(1.0)
+    y0 = rng.standard_normal((2, g, g))
+    scale = 0.3 + 0.05 * rng.standard_normal((g, g))
+    dH = rng.standard_normal((K, K))
+    plain = bl.arnoldi.hessenberg(bl.operators.WaveStencilOperator(g, stencil), K, reortho="full")
+    (Q0, H0, r0, c0), pull0 = bl.vjp(plain, y0.ravel(), scale)
+    dv0, ds0 = pull0((None, dH, None, None))
+    op = parallel.RowShardedWaveOperator(g, stencil)
+    sharded = bl.arnoldi.hessenberg(op.callback, K, reortho="full")
+    with parallel.row_sharded():
+        (Q1, H1, r1, c1), pull1 = bl.vjp(sharded, op.local_slice(y0), scale)
+        dv1, ds1 = pull1((None, dH, None, None))
+    assert rel_err(H1.numpy(), H0.numpy()) < 1e-13 and rel_err(r1.numpy(), r0.numpy()) < 1e-12
+    assert rel_err(dv1.numpy(), dv0.numpy()) < 1e-12 and rel_err(ds1, ds0.numpy()) < 1e-12
+
+
 def test_depth_errors_match_reference():
     # /root/reference/tests/test_arnoldi/test_hessenberg_forward.py:69-78
     op = bl.operators.DenseOperator(2)
