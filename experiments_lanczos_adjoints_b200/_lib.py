@@ -56,6 +56,8 @@ SIGNATURES = {
     "bl_op_sparse_export_sell": (_i32, [_vp, _i32, _vp, _vp]),
     "bl_op_dense_create": (_i32, [_i64, _i32, _pvp]),
     "bl_op_gram_create": (_i32, [_i64, _i64, _i32, _vp, _pvp]),
+    "bl_op_gram_set_path": (_i32, [_vp, _i32]),
+    "bl_op_gram_tile_distances": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "bl_op_wave_create": (_i32, [_i64, _vp, _pvp]),
     "bl_op_wave_slab_create": (_i32, [_i64, _i64, _i32, _i32, _vp, _pvp]),
     "bl_op_wave_halo": (_i32, [_vp, _i32, _pvp]),

@@ -12,6 +12,11 @@
 // column tile and reused by every row of the block).
 #include <vector>
 
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
+#include "gram_tc.cuh"
 #include "operators.cuh"
 #include "tma_pipeline.cuh"
 
@@ -336,6 +341,21 @@ struct GramOperator : bl_operator {
   const void* noise = nullptr;
   int bound_dtype = -1;
   int jsplit = 1;
+  // tensor-core path (fp32, d <= 20): packed TF32 operands, see gram_tc.cuh
+  int path = 0;  // 0 = automatic, 1 = FP32 ALU kernel, 2 = tcgen05 kernel
+  DevBuf opA, opB, xt, dbg;
+  int64_t npad = 0;
+  int tc_split = 1;
+
+  bool tc_eligible(int dtype) const { return dtype == BL_F32 && d <= 20; }
+  bool use_tc(int dtype) const {
+    if (!tc_eligible(dtype) || path == 1) return false;
+    if (path == 2) return true;
+    const char* env = std::getenv("BL_GRAM_PATH");  // "alu" / "tc": A/B comparisons without recompiling
+    return !(env && std::string(env) == "alu");
+  }
+  int tc_rowtiles() const { return (int)((n + gramtc::kM - 1) / gramtc::kM); }
+  int tc_gparts() const { return tc_rowtiles() * tc_split; }
 
   int num_params() const override { return 3; }
   int64_t param_size(int i) const override { return i == 0 ? d : 1; }
@@ -351,13 +371,108 @@ struct GramOperator : bl_operator {
     BL_CHECK(xx.ensure(((size_t)n + kTileJ) * sizeof(T)));
     BL_CHECK(consts.ensure(4 * sizeof(T)));
     jsplit = std::max(1, std::min<int>(64, (4 * sm_count() + nblocks_i() - 1) / nblocks_i()));
-    BL_CHECK(part.ensure((size_t)jsplit * n * sizeof(T)));
-    BL_CHECK(gpart.ensure((size_t)jsplit * nblocks_i() * (d + 1) * sizeof(double)));
+    const bool tc = use_tc(sizeof(T) == 4 ? BL_F32 : BL_F64);
+    if (tc) plan_tc();
+    BL_CHECK(part.ensure((size_t)std::max(jsplit, tc_split) * n * sizeof(T)));
+    BL_CHECK(gpart.ensure((size_t)std::max(jsplit * nblocks_i(), tc_gparts()) * (d + 1) * sizeof(double)));
     BL_CHECK(grad.ensure((size_t)(d + 2) * sizeof(T)));
     k_gram_prepare<T><<<std::min<int>(1024, (int)((n + 255) / 256)), 256, 0, s>>>(
         n, (int)d, dp(), kind, X.as<double>(), static_cast<const T*>(raw_ls), static_cast<const T*>(raw_os),
         xs.as<T>(), xx.as<T>(), consts.as<T>());
     BL_LAUNCHED();
+    if (tc) BL_CHECK(pack_tc(s));
+    return BL_OK;
+  }
+
+  // ---- tensor-core path ------------------------------------------------------------------
+  // column splits: balance waves of one-CTA-per-SM blocks against the per-CTA prologue (~1 tile)
+  void plan_tc() {
+    npad = (n + gramtc::kN - 1) / gramtc::kN * gramtc::kN;
+    const int tiles = (int)(npad / gramtc::kN), sms = sm_count();
+    double best = 1e300;
+    tc_split = 1;
+    for (int sp = 1; sp <= std::min(tiles, 64); ++sp) {
+      const int per = (tiles + sp - 1) / sp;
+      const int waves = (tc_rowtiles() * sp + sms - 1) / sms;
+      const double cost = (double)waves * (per + 1.0);
+      if (cost < best - 1e-9) best = cost, tc_split = sp;
+    }
+  }
+  int pack_tc(cudaStream_t s) {
+    const int slots = gramtc::slots_for((int)d);
+    BL_CHECK(opA.ensure((size_t)npad * slots * sizeof(float)));
+    BL_CHECK(opB.ensure((size_t)npad * slots * sizeof(float)));
+    BL_CHECK(xt.ensure((size_t)npad * gramtc::kXtRows * sizeof(float)));
+    gramtc::k_gram_tc_pack<<<std::min<int>(1024, (int)((npad + 127) / 128)), 128, 0, s>>>(
+        n, npad, (int)d, dp(), slots, xs.as<float>(), xx.as<float>(), opA.as<float>(), opB.as<float>(), xt.as<float>());
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  template <int KIND, bool ADJ, int D>
+  int launch_tc(const float* v, const float* q, float* dbg_out, int dbg_bx, int dbg_by, cudaStream_t s) {
+    const int slots = gramtc::slots_for((int)d);
+    const gramtc::Plan pl = gramtc::make_plan(slots, ADJ);
+    auto kernel = gramtc::k_gram_tc_sweep<KIND, ADJ, D>;
+    {
+      static std::mutex mu;
+      static std::map<int, bool> done;
+      int dev = 0;
+      BL_CUDA(cudaGetDevice(&dev));
+      std::lock_guard<std::mutex> lk(mu);
+      if (!done[dev]) {  // the request depends on d: opt in to the architectural maximum once
+        cudaFuncAttributes fa;
+        BL_CUDA(cudaFuncGetAttributes(&fa, kernel));
+        BL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes));
+        done[dev] = true;
+      }
+    }
+    kernel<<<dim3(tc_rowtiles(), tc_split), gramtc::kThreads, pl.total, s>>>(
+        n, npad, (int)d, slots, opA.as<float>(), opB.as<float>(), xt.as<float>(), xx.as<float>(), consts.as<float>(), v,
+        q,
+        part.as<float>(), gpart.as<double>(), dbg_out, dbg_bx, dbg_by);
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  template <int KIND, bool ADJ>
+  int launch_tc_d(const float* v, const float* q, float* dbg_out, int bx, int by, cudaStream_t s) {
+    if (!ADJ) return launch_tc<KIND, false, 1>(v, q, dbg_out, bx, by, s);
+    if (d <= 3) return launch_tc<KIND, ADJ, ADJ ? 3 : 1>(v, q, dbg_out, bx, by, s);
+    if (d <= 4) return launch_tc<KIND, ADJ, ADJ ? 4 : 1>(v, q, dbg_out, bx, by, s);
+    if (d <= 6) return launch_tc<KIND, ADJ, ADJ ? 6 : 1>(v, q, dbg_out, bx, by, s);
+    if (d <= 8) return launch_tc<KIND, ADJ, ADJ ? 8 : 1>(v, q, dbg_out, bx, by, s);
+    if (d <= 9) return launch_tc<KIND, ADJ, ADJ ? 9 : 1>(v, q, dbg_out, bx, by, s);
+    if (d <= 12) return launch_tc<KIND, ADJ, ADJ ? 12 : 1>(v, q, dbg_out, bx, by, s);
+    if (d <= 16) return launch_tc<KIND, ADJ, ADJ ? 16 : 1>(v, q, dbg_out, bx, by, s);
+    return launch_tc<KIND, ADJ, ADJ ? 20 : 1>(v, q, dbg_out, bx, by, s);
+  }
+  template <bool ADJ>
+  int sweep_tc(const float* v, const float* q, float* y, float* dbg_out, int bx, int by, cudaStream_t s) {
+    if (kind == 0)
+      BL_CHECK((launch_tc_d<0, ADJ>(v, q, dbg_out, bx, by, s)));
+    else if (kind == 1)
+      BL_CHECK((launch_tc_d<1, ADJ>(v, q, dbg_out, bx, by, s)));
+    else
+      BL_CHECK((launch_tc_d<2, ADJ>(v, q, dbg_out, bx, by, s)));
+    if (y) {
+      k_gram_finish<float><<<std::min<int>(1024, (int)((n + 255) / 256)), 256, 0, s>>>(
+          n, tc_split, part.as<float>(), static_cast<const float*>(noise), v, y);
+      BL_LAUNCHED();
+    }
+    return BL_OK;
+  }
+  // diagnostic: the tensor-core accumulator (x_i.x_j - |x_j|^2/2) of the tile (rows 128 bi .., columns 256 bj ..)
+  int tile_distances(int64_t bi, int64_t bj, float* out_host, cudaStream_t s) {
+    BL_REQUIRE(bound_dtype == BL_F32 && use_tc(BL_F32), "tile distances need the fp32 tensor-core path (bind first)");
+    const int64_t per = (npad / gramtc::kN + tc_split - 1) / tc_split;
+    BL_REQUIRE(bi >= 0 && bi < tc_rowtiles() && bj >= 0 && bj < npad / gramtc::kN && bj % per == 0,
+               "tile index out of range (column tile must be the first tile of a split)");
+    BL_CHECK(dbg.ensure((size_t)gramtc::kM * gramtc::kN * sizeof(float)));
+    BL_CUDA(cudaMemsetAsync(dbg.p, 0, dbg.bytes, s));
+    // any vector works as v: only the accumulator is reported
+    BL_CHECK((sweep_tc<false>(xx.as<float>(), nullptr, nullptr, dbg.as<float>(), (int)bi, (int)(bj / per), s)));
+    BL_CUDA(cudaMemcpyAsync(out_host, dbg.p, dbg.bytes, cudaMemcpyDeviceToHost, s));
+    BL_CUDA(cudaStreamSynchronize(s));
     return BL_OK;
   }
 
@@ -406,14 +521,19 @@ struct GramOperator : bl_operator {
 
   int matvec(int dtype, const void* x, void* y, cudaStream_t s) override {
     BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    if (use_tc(dtype)) return sweep_tc<false>((const float*)x, nullptr, (float*)y, nullptr, 0, 0, s);
     return dtype == BL_F32 ? sweep<float, false>((const float*)x, nullptr, (float*)y, s)
                            : sweep<double, false>((const double*)x, nullptr, (double*)y, s);
   }
 
   template <typename T>
   int vjp_t(const T* q, const T* lam, T* z, cudaStream_t s) {
-    BL_CHECK((sweep<T, true>(lam, q, z, s)));
-    k_gram_grad_finish<T><<<(int)d + 2, 256, 0, s>>>((int)d, jsplit * nblocks_i(), gpart.as<double>(),
+    const bool tc = use_tc(sizeof(T) == 4 ? BL_F32 : BL_F64);
+    if (tc)
+      BL_CHECK((sweep_tc<true>((const float*)lam, (const float*)q, (float*)z, nullptr, 0, 0, s)));
+    else
+      BL_CHECK((sweep<T, true>(lam, q, z, s)));
+    k_gram_grad_finish<T><<<(int)d + 2, 256, 0, s>>>((int)d, tc ? tc_gparts() : jsplit * nblocks_i(), gpart.as<double>(),
                                                       static_cast<const T*>(raw_ls), static_cast<const T*>(raw_os),
                                                       consts.as<T>(), n, lam, q, grad.as<T>());
     BL_LAUNCHED();
@@ -444,6 +564,22 @@ struct GramOperator : bl_operator {
 };
 
 }  // namespace bl
+
+extern "C" int bl_op_gram_set_path(bl_operator_t* op, int path) {
+  auto* o = dynamic_cast<bl::GramOperator*>(op);
+  BL_REQUIRE(o != nullptr && path >= 0 && path <= 2, "bad gram path (0 automatic, 1 ALU, 2 tensor cores)");
+  BL_REQUIRE(path != 2 || o->d <= 20, "the tensor-core path supports d <= 20");
+  o->path = path;
+  o->bound_dtype = -1;  // operands are packed at bind time
+  return BL_OK;
+}
+
+extern "C" int bl_op_gram_tile_distances(bl_operator_t* op, int64_t row_tile, int64_t col_tile, float* out_host,
+                                         void* stream) {
+  auto* o = dynamic_cast<bl::GramOperator*>(op);
+  BL_REQUIRE(o != nullptr && out_host != nullptr, "bad arguments");
+  return o->tile_distances(row_tile, col_tile, out_host, bl::as_stream(stream));
+}
 
 extern "C" int bl_op_gram_create(int64_t n, int64_t d, int kind, const double* X_host, bl_operator_t** op) {
   BL_REQUIRE(op && X_host && n > 0 && d > 0 && d <= bl::kMaxDim && kind >= 0 && kind <= 2,

@@ -168,8 +168,11 @@ class GramOperator(Operator):
     Parameters, in order: `raw_lengthscale (d,)`, `raw_outputscale ()`, `noise ()`."""
 
     KINDS = {"matern32": 0, "matern12": 1, "rbf": 2}
+    PATHS = {"auto": 0, "alu": 1, "tensor": 2}
 
-    def __init__(self, X, kind="matern32"):
+    def __init__(self, X, kind="matern32", path="auto"):
+        """`path`: which kernel evaluates the pairwise distances in fp32 -- "tensor" (tcgen05, TF32
+        hi/lo split operands), "alu" (FP32 pipes) or "auto" (tensor cores when d <= 20)."""
         X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
         if X.ndim != 2:
             raise ValueError("X must be (n, d)")
@@ -177,6 +180,16 @@ class GramOperator(Operator):
         h = C.c_void_p()
         _lib.call("bl_op_gram_create", X.shape[0], X.shape[1], self.KINDS[kind], X.ctypes.data, C.byref(h))
         super().__init__(h.value, X.shape[0])
+        if path != "auto":
+            _lib.call("bl_op_gram_set_path", self._handle, self.PATHS[path])
+
+    def tile_distances(self, row_tile=0, col_tile=0, stream=None):
+        """Diagnostic: the tensor-core accumulator `x_i.x_j - |x_j|^2 / 2` (scaled inputs) of one
+        128 x 256 tile (after `bind`); `s2_ij = |x_i|^2 - 2 acc_ij`."""
+        out = np.empty((128, 256), dtype=np.float32)
+        s = stream or dev.default_stream()
+        _lib.call("bl_op_gram_tile_distances", self._handle, int(row_tile), int(col_tile), out.ctypes.data, s.ptr)
+        return out
 
     def param_shapes(self):
         return [(self.d,), (), ()]

@@ -126,6 +126,15 @@ int bl_op_dense_create(int64_t n, int mode, bl_operator_t** op);
  * kind 0 Matern-3/2, 1 Matern-1/2, 2 RBF.  X_host is n x d row-major doubles (converted per
  * dtype on bind).  Three parameters: raw_lengthscale (d), raw_outputscale (1), noise (1). */
 int bl_op_gram_create(int64_t n, int64_t d, int kind, const double* X_host, bl_operator_t** op);
+/* Which kernel evaluates the pairwise distances of an fp32 Gram operator: 0 automatic (tensor cores
+ * when d <= 20), 1 FP32 ALU kernel, 2 tcgen05 kernel (TF32 hi/lo split operands, fp32 accumulator in
+ * TMEM; gram_tc.cuh).  fp64 always uses the FP64 ALU kernel.  Takes effect at the next bind. */
+int bl_op_gram_set_path(bl_operator_t* op, int path);
+/* Diagnostic for the parity tests of the contraction itself: the tensor-core accumulator
+ * x_i.x_j - |x_j|^2/2 of the scaled inputs (gp_util.py:87-92; s2_ij = |x_i|^2 - 2 acc_ij, the row term
+ * is added in the epilogue) for the tile of rows [128 row_tile, +128) x columns [256 col_tile, +256),
+ * written to out_host[128][256] (fp32; entries beyond n are padding).  col_tile must be the first tile of a column split.  Synchronises `stream`. */
+int bl_op_gram_tile_distances(bl_operator_t* op, int64_t row_tile, int64_t col_tile, float* out_host, void* stream);
 
 /* Wave-equation stencil operand (util/pde_util.py:126-157): state (u, du) of 2 g^2 values,
  * A(u,du) = (du, scale^2 * conv3x3(stencil, edge_pad(u))).  One parameter: scale (g*g). */
