@@ -1,4 +1,4 @@
-"""One Gram matvec + one VJP at the UCI-protein shape (ncu target).  KIND / DTYPE / GP_N from the environment."""
+"""One Gram matvec + one VJP at the UCI-protein shape (ncu target).  KIND / DTYPE / GP_N / GRAM_PATH from the environment."""
 import os
 import sys
 
@@ -12,7 +12,7 @@ kind = os.environ.get("KIND", "matern32")
 dtype = np.float32 if os.environ.get("DTYPE", "f32") == "f32" else np.float64
 rng = np.random.default_rng(0)
 X = rng.standard_normal((N, d))
-op = bl.operators.GramOperator(X, kind=kind)
+op = bl.operators.GramOperator(X, kind=kind, path=os.environ.get("GRAM_PATH", "auto"))
 v = bl.asarray(rng.standard_normal(N).astype(dtype))
 lam = bl.asarray(rng.standard_normal(N).astype(dtype))
 op.bind((rng.standard_normal(d), rng.standard_normal(()), np.asarray(0.1)), dtype)

@@ -1,0 +1,112 @@
+"""GPU parity tests of the tcgen05 (tensor-core) Gram kernel: the contraction itself, and the matvec /
+VJP against the NumPy oracle evaluated in float64 and against the FP32-ALU kernel, on ragged shapes
+(n not a multiple of the 128 x 256 tile, d from 1 to 20).  Tolerances: BASELINE.json north_star fp32
+(1e-5 on values, 1e-4 on gradients); the contraction is checked at the fp32 rounding level of its
+inputs."""
+
+import numpy as np
+import pytest
+from conftest import golden, golden_names, rel_err
+
+import experiments_lanczos_adjoints_b200 as bl
+from oracle import operators
+
+pytestmark = pytest.mark.gpu
+
+
+def scaled_f32(X, raw_ls, kind):
+    """The scaled inputs as the device holds them (fp32), returned in float64."""
+    fac = np.sqrt(3.0) if kind == "matern32" else 1.0  # gp_util.py:84 (Matern-3/2 only)
+    return (fac * X / operators.softplus(raw_ls)).astype(np.float32).astype(np.float64)
+
+
+def problem(n, d, seed, ls_shift=0.5):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d))
+    raw_ls = ls_shift + 0.3 * rng.standard_normal(d)
+    return X, raw_ls, rng.standard_normal(()), np.asarray(0.05), rng.standard_normal(n), rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("n,d", [(300, 9), (129, 1), (1000, 20), (2049, 4)])
+def test_tensor_core_contraction_matches_float64(n, d):
+    """x_i.x_j - |x_j|^2/2 from the TF32 hi/lo split MMA == the float64 value of the same fp32 inputs
+    to a few ulps of the largest term (an fp32 dot product has the same bound)."""
+    X, raw_ls, raw_os, noise, _, _ = problem(n, d, 0)
+    op = bl.operators.GramOperator(X, kind="rbf", path="tensor")
+    op.bind((raw_ls, raw_os, noise), np.float32)
+    Xs = scaled_f32(X, raw_ls, "rbf")
+    for bi, bj in [(0, 0), ((n - 1) // 128, 0)]:
+        acc = op.tile_distances(bi, bj).astype(np.float64)
+        rows = slice(128 * bi, min(n, 128 * bi + 128))
+        cols = slice(256 * bj, min(n, 256 * bj + 256))
+        xi, xj = Xs[rows], Xs[cols]
+        ref = xi @ xj.T - 0.5 * (xj**2).sum(-1)[None, :]
+        scale = np.abs(xi).sum(-1).max() * np.abs(xj).max() + 0.5 * (xj**2).sum(-1).max()
+        assert np.abs(acc[: ref.shape[0], : ref.shape[1]] - ref).max() < 8 * 2.0**-24 * scale
+
+
+@pytest.mark.parametrize("kind", ["matern32", "matern12", "rbf"])
+@pytest.mark.parametrize("n,d", [(1, 3), (127, 9), (300, 9), (777, 2), (2500, 16), (4100, 20)])
+def test_tensor_core_matvec_and_vjp_match_oracle(kind, n, d):
+    X, raw_ls, raw_os, noise, v, lam = problem(n, d, 1)
+    orc = operators.GramOperator(X, kind=kind)
+    # Matern-1/2 is not differentiable at s = 0: sqrt(s2 + eps) makes the fp32 diagonal differ from
+    # the float64 one by sqrt(eps_f32) = 3e-4 (same allowance as tests/test_oracle_golden.py)
+    amp = 100.0 if kind == "matern12" else 1.0
+    y64 = orc.matvec(v, raw_ls, raw_os, noise)
+    z64, (dls64, dos64, dn64) = orc.vjp(v, lam, raw_ls, raw_os, noise)
+    res = {}
+    for path in ("tensor", "alu"):
+        op = bl.operators.GramOperator(X, kind=kind, path=path)
+        op.bind((raw_ls, raw_os, noise), np.float32)
+        y = op.matvec(bl.asarray(v.astype(np.float32))).numpy()
+        op.grad_zero(np.float32)
+        z = op.vjp(bl.asarray(v.astype(np.float32)), bl.asarray(lam.astype(np.float32))).numpy()
+        dls, dos, dn = (a.numpy() for a in op.grad_export(np.float32))
+        res[path] = (y, z, dls, dos)
+        assert rel_err(y, y64) < amp * 1e-5
+        assert rel_err(z, z64) < amp * 1e-5
+        if kind != "matern12" and n > 1:
+            assert rel_err(dls, dls64) < 1e-4
+        assert rel_err(dos, dos64) < amp * 1e-4
+        assert rel_err(dn, dn64) < 1e-4
+    # the two kernels agree with each other to fp32 rounding of the distances
+    assert rel_err(res["tensor"][0], res["alu"][0]) < amp * 1e-5
+    assert rel_err(res["tensor"][1], res["alu"][1]) < amp * 1e-5
+
+
+def test_tensor_core_diagonal_is_exact_for_duplicate_free_inputs():
+    """k(x_i, x_i): s2 = 0 exactly on the diagonal (as the fp32 evaluation of the reference's expanded
+    form gives), so with a tiny lengthscale the Gram matrix is sigma (1 + sqrt(eps)) e^{-sqrt(eps)} I."""
+    n, d = 515, 9
+    rng = np.random.default_rng(2)
+    X = 100.0 * rng.standard_normal((n, d))  # scaled distances >> 1: off-diagonal entries underflow
+    op = bl.operators.GramOperator(X, kind="matern32", path="tensor")
+    raw_os = np.asarray(0.3)
+    v = rng.standard_normal(n).astype(np.float32)
+    y = op(v, np.zeros(d), raw_os, np.asarray(0.0)).numpy()
+    s = np.sqrt(np.float32(np.finfo(np.float32).eps))
+    expect = operators.softplus(raw_os) * (1 + s) * np.exp(-s) * v
+    assert rel_err(y, expect) < 1e-6
+
+
+@pytest.mark.parametrize("name", golden_names("gp_kernels_"))
+def test_tensor_core_path_is_the_default_for_fp32(name):
+    """`path="auto"` == `path="tensor"` bit for bit in fp32 (the golden test above therefore pins the
+    tensor-core kernel); fp64 always takes the FP64-ALU kernel."""
+    g = golden(name)
+    X, v = g["X"], g["v"].astype(np.float32)
+    params = (g["raw_lengthscale"].astype(np.float32), g["raw_outputscale"].astype(np.float32), np.zeros((), np.float32))
+    y_auto = bl.operators.GramOperator(X, kind="matern32")(v, *params).numpy()
+    y_tc = bl.operators.GramOperator(X, kind="matern32", path="tensor")(v, *params).numpy()
+    assert np.array_equal(y_auto, y_tc)
+
+
+def test_tensor_core_path_rejects_large_dimension():
+    X = np.random.default_rng(0).standard_normal((64, 24))
+    with pytest.raises(ValueError):  # BL_EINVAL
+        bl.operators.GramOperator(X, path="tensor")
+    op = bl.operators.GramOperator(X)  # automatic: falls back to the ALU kernel for d > 20
+    y = op(np.ones(64, np.float32), np.zeros(24), np.asarray(0.0), np.asarray(0.1)).numpy()
+    ref = operators.GramOperator(X).matvec(np.ones(64), np.zeros(24), np.asarray(0.0), np.asarray(0.1))
+    assert rel_err(y, ref) < 1e-5
