@@ -51,6 +51,14 @@ SIGNATURES = {
     "bl_profile_begin": (_i32, []),
     "bl_profile_end": (_i32, [C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bl_dist_set_reduce_hook": (_i32, [ALLREDUCE_CB, _vp]),
+    "bl_dist_comm_create": (_i32, [_i32, _i32, _pvp]),
+    "bl_dist_comm_local": (_i32, [_vp, _pvp, _vp]),
+    "bl_dist_comm_connect_ipc": (_i32, [_vp, _vp]),
+    "bl_dist_comm_connect_ptrs": (_i32, [_vp, _pvp]),
+    "bl_dist_comm_activate": (_i32, [_vp]),
+    "bl_dist_comm_error": (_i32, [_vp, C.POINTER(C.c_int)]),
+    "bl_dist_comm_destroy": (_i32, [_vp]),
+    "bl_op_wave_set_comm": (_i32, [_vp, _vp]),
     "bl_op_sparse_create": (_i32, [_i64, _i64, _i64, _vp, _vp, _pvp]),
     "bl_op_sparse_export_csr": (_i32, [_vp, _vp, _vp, _vp]),
     "bl_op_sparse_export_sell": (_i32, [_vp, _i32, _vp, _vp]),

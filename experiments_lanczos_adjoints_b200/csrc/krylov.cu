@@ -13,6 +13,7 @@
 #define BL_DOTS_TILE_BYTES 4096
 #endif
 
+#include "dist.cuh"
 #include "krylov_kernels.cuh"
 #include "stream_kernels.cuh"
 #include "operators.cuh"
@@ -119,14 +120,51 @@ thread_local void* g_reduce_user = nullptr;
 
 // Runs `epi` after the hook: the kernel in front was launched with EPI_NONE and left the local
 // sums in red[0..count).
+bool is_sharded() { return g_reduce_hook != nullptr || dist::active(); }
+
+// cross-rank sum over peer memory fused with the epilogue: one single-block kernel (dist.cuh)
+template <typename T>
+__global__ void __launch_bounds__(256) k_peer_reduce_epilogue(dist::PeerView pv, int count, Epi epi) {
+  dist::peer_allreduce_block(pv, epi.red, count);
+  run_epilogue<T>(epi);
+}
+__global__ void __launch_bounds__(256) k_peer_reduce(dist::PeerView pv, double* values, int count) {
+  dist::peer_allreduce_block(pv, values, count);
+}
+
+// in-place cross-rank SUM of `count` device doubles on `s` (communicator first, then the hook)
+int sharded_sum(double* values, int count, cudaStream_t s) {
+  if (dist::active()) {
+    BL_REQUIRE(count <= dist::kRedSlots, "reduction too large for the peer mailbox");
+    dist::PeerView pv;
+    BL_CHECK(dist::next_reduce(&pv));
+    k_peer_reduce<<<1, 256, 0, s>>>(pv, values, count);
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  if (g_reduce_hook && g_reduce_hook(g_reduce_user, values, count, s) != 0) {
+    set_error("all-reduce hook failed");
+    return BL_ECALLBACK;
+  }
+  return BL_OK;
+}
+
 template <typename T>
 int finish_sharded(const Common& c, Epi epi, int count, cudaStream_t s) {
+  epi.red = c.red;
+  epi.scal = c.scal;
+  if (dist::active()) {
+    BL_REQUIRE(count <= dist::kRedSlots, "reduction too large for the peer mailbox");
+    dist::PeerView pv;
+    BL_CHECK(dist::next_reduce(&pv));
+    k_peer_reduce_epilogue<T><<<1, 256, 0, s>>>(pv, count, epi);
+    BL_LAUNCHED();
+    return BL_OK;
+  }
   if (g_reduce_hook(g_reduce_user, c.red, count, s) != 0) {
     set_error("all-reduce hook failed");
     return BL_ECALLBACK;
   }
-  epi.red = c.red;
-  epi.scal = c.scal;
   k_epilogue_only<T><<<1, 256, 0, s>>>(epi);
   BL_LAUNCHED();
   return BL_OK;
@@ -207,7 +245,7 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
   epi.red = c.red;
   epi.scal = c.scal;
   const Epi full_epi = epi;
-  const bool sharded = g_reduce_hook != nullptr;
+  const bool sharded = is_sharded();
   if (sharded) epi.mode = EPI_NONE;
   {
   ProfScope prof(BL_PROF_DOTS, (double)(blk.nrows + 1) * n * sizeof(T), s);
@@ -236,7 +274,7 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
   a.epi.red = c.red;
   a.epi.scal = c.scal;
   const Epi full_epi = a.epi;
-  const bool sharded = norm && g_reduce_hook != nullptr;
+  const bool sharded = norm && is_sharded();
   if (sharded) a.epi.mode = EPI_NONE;
   const int nrows = a.blk[0].nrows + a.blk[1].nrows;
   {
@@ -372,7 +410,7 @@ int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, int sr, cu
   a.epi.red = c.red;
   a.epi.scal = c.scal;
   const Epi full_epi = a.epi;
-  const bool sharded = g_reduce_hook != nullptr;
+  const bool sharded = is_sharded();
   if (sharded) a.epi.mode = EPI_NONE;
   a.reverse = next_direction();
   const int nrows = f.res.nrows + f.str0.nrows + f.str1.nrows;
@@ -616,10 +654,7 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
     BL_LAUNCHED();
     k_gram_reduce<<<(K * K + 255) / 256, 256, 0, s>>>(K * K, gram_parts, gram_partial, Gmat);
     BL_LAUNCHED();
-    if (g_reduce_hook && g_reduce_hook(g_reduce_user, Gmat, K * K, s) != 0) {
-      set_error("all-reduce hook failed");
-      return BL_ECALLBACK;
-    }
+    BL_CHECK(sharded_sum(Gmat, (int)(K * K), s));
   }
   {
     dim3 grid(K, (K + 127) / 128);

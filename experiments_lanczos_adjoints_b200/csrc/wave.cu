@@ -7,6 +7,7 @@
 //   conv(u)[i,j] = sum_{a,b} st[a,b] * u[clamp(i+1-a), clamp(j+1-b)]     (edge replicate = index clamp)
 // HBM-bound: ~ (3 reads + 2 writes) * g^2 values per matvec; one thread per grid point, rows of
 // the grid are contiguous so every access is coalesced.
+#include "dist.cuh"
 #include "operators.cuh"
 
 // Row-sharded use (one slab of grid rows per GPU): the operator covers `gy` rows x `gx` columns and
@@ -130,6 +131,45 @@ __global__ void k_wave_vjp_b(Field<T> tmp, Stencil st, T* __restrict__ z) {
   }
 }
 
+// Halo exchange over peer memory (dist.cuh): my FIRST row of each field goes to the upper neighbour's
+// "from below" slots (1, 3), my LAST row to the lower neighbour's "from above" slots (0, 2); then wait
+// for the neighbours' rows in my own mailbox.  One block; rows are at most 512 KB.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_wave_halo_exchange(dist::PeerView pv, int64_t gx, const T* __restrict__ first0, const T* __restrict__ last0,
+                     const T* __restrict__ first1, const T* __restrict__ last1, bool has_top, bool has_bot) {
+  const int parity = (int)(pv.seq & 1ull);
+  unsigned char* own = pv.mail[pv.rank];
+  if (has_top) {
+    unsigned char* up = pv.mail[pv.rank - 1];
+    T* d0 = reinterpret_cast<T*>(dist::halo_slot(up, parity, 1));
+    T* d1 = reinterpret_cast<T*>(dist::halo_slot(up, parity, 3));
+    for (int64_t j = threadIdx.x; j < gx; j += blockDim.x) {
+      d0[j] = first0[j];
+      if (first1) d1[j] = first1[j];
+    }
+  }
+  if (has_bot) {
+    unsigned char* down = pv.mail[pv.rank + 1];
+    T* d0 = reinterpret_cast<T*>(dist::halo_slot(down, parity, 0));
+    T* d1 = reinterpret_cast<T*>(dist::halo_slot(down, parity, 2));
+    for (int64_t j = threadIdx.x; j < gx; j += blockDim.x) {
+      d0[j] = last0[j];
+      if (last1) d1[j] = last1[j];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && has_top) {
+    dist::st_release_sys(dist::halo_flag(pv.mail[pv.rank - 1], pv.rank), pv.seq);
+    dist::wait_flag(dist::halo_flag(own, pv.rank - 1), pv.seq, own);
+  }
+  if (threadIdx.x == 32 && has_bot) {
+    dist::st_release_sys(dist::halo_flag(pv.mail[pv.rank + 1], pv.rank), pv.seq);
+    dist::wait_flag(dist::halo_flag(own, pv.rank + 1), pv.seq, own);
+  }
+}
+
 }  // namespace
 
 struct WaveOperator : bl_operator {
@@ -142,6 +182,27 @@ struct WaveOperator : bl_operator {
   // halo rows (gx values each, 8 bytes per value reserved): 0/1 first input top/bottom (u or q_u),
   // 2/3 lam_du top/bottom, 4/5 scale top/bottom, 6/7 tmp top/bottom (internal)
   DevBuf halo[8];
+  bl_comm* comm = nullptr;  // native halo exchange (bl_op_wave_set_comm)
+  // halo rows of the current call: the mailbox slots after an exchange, else the caller-filled buffers
+  const void* cur[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  template <typename T>
+  int exchange(const T* field0, const T* field1, cudaStream_t s) {
+    for (int k = 0; k < 4; ++k) cur[k] = halo[k].p;
+    if (!comm) return BL_OK;
+    BL_REQUIRE((size_t)gx * sizeof(T) <= dist::kHaloRowBytes, "grid row too long for the halo mailbox");
+    dist::PeerView pv;
+    BL_CHECK(dist::view_of(comm, true, &pv));
+    const T* last0 = field0 + (gy - 1) * gx;
+    const T* last1 = field1 ? field1 + (gy - 1) * gx : nullptr;
+    k_wave_halo_exchange<T><<<1, 1024, 0, s>>>(pv, gx, field0, last0, field1, last1, has_top, has_bot);
+    BL_LAUNCHED();
+    const int parity = (int)(pv.seq & 1ull);
+    for (int k = 0; k < 4; ++k) cur[k] = dist::halo_slot(pv.mail[pv.rank], parity, k);
+    return BL_OK;
+  }
+  template <typename T>
+  const T* cur_or_null(int k, bool present) const { return present ? static_cast<const T*>(cur[k]) : nullptr; }
 
   int num_params() const override { return 1; }
   int64_t param_size(int) const override { return gy * gx; }
@@ -159,16 +220,27 @@ struct WaveOperator : bl_operator {
   template <typename T>
   const T* halo_or_null(int k, bool present) const { return present ? halo[k].as<T>() : nullptr; }
 
-  int set_params(int dtype, const void* const* params, int num, cudaStream_t) override {
+  int set_params(int dtype, const void* const* params, int num, cudaStream_t s) override {
     BL_REQUIRE(num == 1 && params && params[0], "wave operator takes one parameter (scale, rows x cols)");
     scale = params[0];
     bound_dtype = dtype;
     BL_CHECK(grad.ensure((size_t)gy * gx * dtype_size(dtype)));
-    return tmp.ensure((size_t)gy * gx * dtype_size(dtype));
+    BL_CHECK(tmp.ensure((size_t)gy * gx * dtype_size(dtype)));
+    if (comm && (has_top || has_bot)) {  // the neighbours' boundary rows of `scale`, kept in halo 4 / 5
+      if (dtype == BL_F32)
+        BL_CHECK(exchange<float>((const float*)scale, nullptr, s));
+      else
+        BL_CHECK(exchange<double>((const double*)scale, nullptr, s));
+      const size_t row = (size_t)gx * dtype_size(dtype);
+      if (has_top) BL_CUDA(cudaMemcpyAsync(halo[4].p, cur[0], row, cudaMemcpyDeviceToDevice, s));
+      if (has_bot) BL_CUDA(cudaMemcpyAsync(halo[5].p, cur[1], row, cudaMemcpyDeviceToDevice, s));
+    }
+    return BL_OK;
   }
   template <typename T>
   int matvec_t(const T* x, T* y, cudaStream_t s) {
-    Field<T> u{x, halo_or_null<T>(0, has_top), halo_or_null<T>(1, has_bot), gy, gx};
+    BL_CHECK(exchange<T>(x, nullptr, s));
+    Field<T> u{x, cur_or_null<T>(0, has_top), cur_or_null<T>(1, has_bot), gy, gx};
     k_wave_matvec<T><<<blocks(), 256, 0, s>>>(u, st, (const T*)scale, x + gy * gx, y);
     BL_LAUNCHED();
     return BL_OK;
@@ -180,10 +252,11 @@ struct WaveOperator : bl_operator {
   }
   template <typename T>
   int vjp_t(const T* q, const T* lam, T* z, cudaStream_t s) {
-    Field<T> qu{q, halo_or_null<T>(0, has_top), halo_or_null<T>(1, has_bot), gy, gx};
+    BL_CHECK(exchange<T>(q, lam + gy * gx, s));  // rows of q_u and of lambda_du
+    Field<T> qu{q, cur_or_null<T>(0, has_top), cur_or_null<T>(1, has_bot), gy, gx};
     k_wave_vjp_a<T><<<blocks(), 256, 0, s>>>(qu, st, (const T*)scale, lam, halo_or_null<T>(4, has_top),
-                                             halo_or_null<T>(5, has_bot), halo_or_null<T>(2, has_top),
-                                             halo_or_null<T>(3, has_bot), tmp.as<T>(),
+                                             halo_or_null<T>(5, has_bot), cur_or_null<T>(2, has_top),
+                                             cur_or_null<T>(3, has_bot), tmp.as<T>(),
                                              has_top ? halo[6].as<T>() : nullptr, has_bot ? halo[7].as<T>() : nullptr,
                                              z, grad.as<T>());
     BL_LAUNCHED();
@@ -240,6 +313,21 @@ int bl_op_wave_slab_create(int64_t rows, int64_t cols, int has_top, int has_bott
 int bl_op_wave_create(int64_t grid, const double* stencil3x3_host, bl_operator_t** op) {
   BL_REQUIRE(grid >= 2, "bad wave operator arguments");
   return bl_op_wave_slab_create(grid, grid, 0, 0, stencil3x3_host, op);
+}
+
+int bl_op_wave_set_comm(bl_operator_t* op, bl_comm_t* comm) {
+  auto* o = dynamic_cast<bl::WaveOperator*>(op);
+  BL_REQUIRE(o != nullptr, "not a wave operator");
+  if (comm) {
+    bl::dist::PeerView pv;
+    BL_CHECK(bl::dist::view_of(comm, true, &pv));  // validates the connection (costs one sequence number on every rank)
+    BL_REQUIRE(o->has_top == (pv.rank > 0) && o->has_bot == (pv.rank < pv.world - 1),
+               "slab neighbours must match the rank order (rank 0 on top)");
+    BL_CHECK(o->init_halos());
+  }
+  o->comm = comm;
+  o->bound_dtype = -1;
+  return BL_OK;
 }
 
 int bl_op_wave_halo(bl_operator_t* op, int which, void** ptr) {

@@ -9,6 +9,7 @@ row stride `ld` (in elements); a Krylov basis is stored as `K` rows of length `l
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import weakref
 
 import numpy as np
@@ -65,14 +66,16 @@ def _destroy_stream(ptr):
         pass
 
 
-_default_stream = None
+_tls = threading.local()
 
 
 def default_stream() -> Stream:
-    global _default_stream
-    if _default_stream is None:
-        _default_stream = Stream()
-    return _default_stream
+    """The stream every call without an explicit `stream=` uses: one per HOST THREAD, so several
+    threads can drive independent work (the C library keeps no global stream either)."""
+    st = getattr(_tls, "stream", None)
+    if st is None:
+        st = _tls.stream = Stream()
+    return st
 
 
 def synchronize():

@@ -154,16 +154,81 @@ def _as_torch(ptr, count, dtype):
     return torch.as_tensor(_RawDeviceBuffer(ptr, count, typestr), device="cuda")
 
 
+class PeerComm:
+    """Peer-memory communicator (`bl_dist_comm_*`): every rank's mailbox is mapped into every other
+    rank's address space (CUDA IPC over NVLink / NVSwitch); reductions and halo exchanges of the
+    row-sharded path are then single-block kernels with no NCCL launch and no host callback.
+    `torch.distributed` is used once, to exchange the 64-byte IPC handles and for the barrier."""
+
+    def __init__(self, group=None, *, rank=None, world=None):
+        import ctypes as C
+
+        from experiments_lanczos_adjoints_b200 import _lib
+
+        self._lib = _lib
+        dist = _dist()
+        self.group = group
+        self.rank = (dist.get_rank(group) if dist else 0) if rank is None else int(rank)
+        self.world = (dist.get_world_size(group) if dist else 1) if world is None else int(world)
+        h = C.c_void_p()
+        _lib.call("bl_dist_comm_create", self.rank, self.world, C.byref(h))
+        self.handle = h.value
+        if rank is None and self.world > 1:  # one process per rank: exchange IPC handles
+            buf = C.create_string_buffer(64)
+            _lib.call("bl_dist_comm_local", self.handle, None, buf)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(buf.raw), group=group)
+            _lib.call("bl_dist_comm_connect_ipc", self.handle, b"".join(handles))
+            dist.barrier(group=group)  # every mailbox is zeroed and mapped before the first store
+
+    @property
+    def mailbox(self) -> int:
+        import ctypes as C
+
+        p = C.c_void_p()
+        self._lib.call("bl_dist_comm_local", self.handle, C.byref(p), None)
+        return p.value
+
+    def connect_local(self, comms):
+        """Same-process ranks (tests: one host thread per rank): connect by mailbox pointer."""
+        import ctypes as C
+
+        ptrs = (C.c_void_p * self.world)(*[c.mailbox for c in comms])
+        self._lib.call("bl_dist_comm_connect_ptrs", self.handle, ptrs)
+
+    def timed_out(self) -> bool:
+        import ctypes as C
+
+        flag = C.c_int(0)
+        self._lib.call("bl_dist_comm_error", self.handle, C.byref(flag))
+        return bool(flag.value)
+
+    def close(self):
+        h, self.handle = self.handle, None
+        if h:
+            self._lib.call("bl_dist_comm_destroy", h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class row_sharded:
     """Context manager: while active, every reduction of the Krylov loops on this thread is
-    summed over the ranks of `group` (bl_dist_set_reduce_hook) — the Arnoldi / Lanczos calls then
-    operate on the LOCAL rows of every vector and produce the same `H`, coefficients and scalars
-    on every rank.  Collectives are enqueued on the library's stream (no host synchronisation)."""
+    summed over the ranks — the Arnoldi / Lanczos calls then operate on the LOCAL rows of every
+    vector and produce the same `H`, coefficients and scalars on every rank.
 
-    def __init__(self, group=None):
+    `comm=PeerComm(...)`: native route, one single-block peer-memory kernel per reduction
+    (`bl_dist_comm_activate`).  Otherwise a hook (`bl_dist_set_reduce_hook`) enqueues an NCCL
+    all-reduce on the library's stream.  Neither synchronises the host."""
+
+    def __init__(self, group=None, comm=None):
         from experiments_lanczos_adjoints_b200 import _lib
 
         self.group = group
+        self.comm = comm
         self._lib = _lib
 
         def hook(_user, values, count, stream):
@@ -185,13 +250,19 @@ class row_sharded:
         self._cb = _lib.ALLREDUCE_CB(hook)
 
     def __enter__(self):
-        self._lib.call("bl_dist_set_reduce_hook", self._cb, None)
+        if self.comm is not None:
+            self._lib.call("bl_dist_comm_activate", self.comm.handle)
+        else:
+            self._lib.call("bl_dist_set_reduce_hook", self._cb, None)
         return self
 
     def __exit__(self, *exc):
         import ctypes as C
 
-        self._lib.call("bl_dist_set_reduce_hook", C.cast(None, self._lib.ALLREDUCE_CB), None)
+        if self.comm is not None:
+            self._lib.call("bl_dist_comm_activate", None)
+        else:
+            self._lib.call("bl_dist_set_reduce_hook", C.cast(None, self._lib.ALLREDUCE_CB), None)
         return False
 
 
@@ -302,17 +373,23 @@ class RowShardedSparseOperator:
 class RowShardedWaveOperator:
     """The wave-stencil operand (BASELINE config 5) with the grid rows sharded over the ranks:
     rank r owns rows `[r*gs, (r+1)*gs)` of `u` and of `du` (local state `[u_slab; du_slab]`).
-    Each matvec exchanges ONE grid row with each neighbour (NCCL send/recv on the library's
-    stream); the VJP exchanges the boundary rows of `q_u` and `lambda_du`.  `d scale` is local to the
-    owner of the row."""
+    Each matvec exchanges ONE grid row with each neighbour; the VJP exchanges the boundary rows of
+    `q_u` and `lambda_du`.  `d scale` is local to the owner of the row.
 
-    def __init__(self, grid, stencil, group=None):
+    Two routes.  `comm=PeerComm(...)` (native): the slab operator pushes its boundary rows into the
+    neighbours' mailboxes itself (`bl_op_wave_set_comm`); `.callback` is then the plain slab operand,
+    its parameter is the LOCAL slab of `scale` (`local_scale`) and its cotangent the local slab of
+    `d scale` — nothing crosses the host.  Without `comm`: NCCL send/recv driven from a host callback,
+    global `scale` in, global `d scale` out (simple, slow)."""
+
+    def __init__(self, grid, stencil, group=None, comm=None):
         from experiments_lanczos_adjoints_b200 import operators as ops
 
         dist = _dist()
         self.group = group
-        self.rank = dist.get_rank(group) if dist else 0
-        self.world = dist.get_world_size(group) if dist else 1
+        self.comm = comm
+        self.rank = comm.rank if comm is not None else (dist.get_rank(group) if dist else 0)
+        self.world = comm.world if comm is not None else (dist.get_world_size(group) if dist else 1)
         self.g = int(grid)
         if self.g % self.world:
             raise ValueError(f"grid rows ({self.g}) must be divisible by the number of ranks ({self.world})")
@@ -320,6 +397,12 @@ class RowShardedWaveOperator:
         self.has_top, self.has_bot = self.rank > 0, self.rank < self.world - 1
         self.local = ops.WaveStencilOperator(self.g, stencil, rows=self.gs, has_top=self.has_top,
                                              has_bottom=self.has_bot)  # fmt: skip
+        if comm is not None:
+            from experiments_lanczos_adjoints_b200 import _lib
+
+            _lib.call("bl_op_wave_set_comm", self.local._handle, comm.handle)
+            self.callback = self.local
+            return
         self.callback = ops.CallbackOperator(self.local.n, self._matvec, self._vjp, num_params=1)
         self.callback.bind = self._bind
         self.callback.grad_zero = lambda dtype, stream=None: self.local.grad_zero(dtype)
@@ -330,6 +413,11 @@ class RowShardedWaveOperator:
         st = np.asarray(state).reshape(2, self.g, self.g)
         lo, hi = self.rank * self.gs, (self.rank + 1) * self.gs
         return np.concatenate([st[0, lo:hi].ravel(), st[1, lo:hi].ravel()])
+
+    def local_scale(self, scale):
+        """Local slab (rows of this rank) of the global parameter field `(g, g)`."""
+        sc = np.asarray(scale).reshape(self.g, self.g)
+        return np.ascontiguousarray(sc[self.rank * self.gs : (self.rank + 1) * self.gs])
 
     def _exchange(self, field_ptr, dtype, slot_top, slot_bot):
         """Send my first / last row of `field` to the neighbours, receive theirs into the halo slots."""

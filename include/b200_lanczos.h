@@ -93,6 +93,31 @@ int bl_profile_end(uint64_t* counts, double* ms, double* bytes); /* arrays of BL
 typedef int (*bl_allreduce_cb)(void* user, double* values_dev, int count, void* stream);
 int bl_dist_set_reduce_hook(bl_allreduce_cb hook, void* user);
 
+/* Peer-memory communicator (NVLink / NVSwitch, one process per GPU of one box; at most 8 ranks):
+ * the native alternative to the hook.  Each rank allocates a mailbox in its own HBM, the ranks
+ * exchange the CUDA-IPC handles out of band (the host layer uses torch.distributed's object
+ * all-gather), map each other's mailboxes and meet at a barrier.  While a communicator is active on
+ * a host thread, every reduction of the Krylov loops on that thread is ONE single-block kernel per
+ * rank: store the local sums into the peers' mailboxes, publish a sequence number, wait for the
+ * peers' numbers, add the contributions in rank order (bit-identical on every rank) and run the
+ * epilogue -- no NCCL launch, no host callback.  Ranks must issue the same sequence of Krylov calls.
+ * A rank that waits ~10 s for a peer gives up, poisons the sums with NaN and sets the error word.
+ * (Several ranks inside ONE process -- host threads, same-process connect -- additionally need every
+ * kernel of the route loaded before the first exchange, because a lazy kernel load may synchronise the
+ * context while the peer spins: run one pass with a one-rank communicator first, or set
+ * CUDA_MODULE_LOADING=EAGER.) */
+typedef struct bl_comm bl_comm_t;
+int bl_dist_comm_create(int rank, int world, bl_comm_t** comm);
+/* own mailbox pointer and / or its 64-byte cudaIpcMemHandle_t (either may be NULL) */
+int bl_dist_comm_local(bl_comm_t* comm, void** mailbox, void* ipc_handle_64);
+/* handles: world x 64 bytes in rank order (the own entry is ignored) */
+int bl_dist_comm_connect_ipc(bl_comm_t* comm, const void* handles);
+/* same-process variant (tests; several ranks driven by several host threads): mailbox pointers */
+int bl_dist_comm_connect_ptrs(bl_comm_t* comm, void* const* mailboxes);
+int bl_dist_comm_activate(bl_comm_t* comm); /* NULL deactivates; per host thread; wins over the hook */
+int bl_dist_comm_error(bl_comm_t* comm, int* timed_out);
+int bl_dist_comm_destroy(bl_comm_t* comm);
+
 /* ---- operators: the `matvec(v, *params)` callback of the reference ------------------
  * An operator owns its index structures and a gradient accumulator for its parameters.
  *   set_params : bind parameter values (device pointers, reference order)
@@ -148,6 +173,11 @@ int bl_op_wave_create(int64_t grid, const double* stencil3x3_host, bl_operator_t
 int bl_op_wave_slab_create(int64_t rows, int64_t cols, int has_top, int has_bottom, const double* stencil3x3_host,
                            bl_operator_t** op);
 int bl_op_wave_halo(bl_operator_t* op, int which, void** ptr);
+/* Native halo exchange: slab `rank` of `world` slabs stacked top to bottom.  With a communicator set,
+ * matvec / vjp / set_params push the boundary rows into the neighbours' mailboxes themselves (one
+ * single-block kernel per exchange, see bl_dist_comm_create) -- the operator is then a plain operand
+ * of the Krylov calls, with no host callback on the path.  NULL returns to caller-filled halos. */
+int bl_op_wave_set_comm(bl_operator_t* op, bl_comm_t* comm);
 
 /* User-supplied matvec: the host layer passes C callbacks that enqueue work on `stream`.
  * matvec_cb(user, dtype, x, y, stream); vjp_cb(user, dtype, q, lam, z_or_null, stream). */

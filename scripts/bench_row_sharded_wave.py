@@ -1,0 +1,113 @@
+"""BASELINE config 5: wave-PDE Arnoldi forward + adjoint on a 4096 x 4096 grid (state n = 33.5M, depth 10),
+grid rows sharded over the ranks.  Launch with torchrun (or plain python for one GPU):
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_row_sharded_wave.py
+
+ROUTE=peer (default; peer-memory reductions + halo pushes, no host callback) or ROUTE=nccl (NCCL all-reduce
+hook + send/recv halo exchange from a host callback).  Inputs are resident on the devices; the timed region
+is REPS forward+adjoint sweeps bracketed by barriers and device synchronisation, max over ranks.  Rank 0
+also times the unsharded operator on its own GPU (when it fits) and checks the sharded H against it."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import experiments_lanczos_adjoints_b200 as bl
+from experiments_lanczos_adjoints_b200 import parallel
+
+rank, world, local_rank = parallel.init_from_env()
+g = int(os.environ.get("GRID", 4096))
+K = int(os.environ.get("DEPTH", 10))
+reps = int(os.environ.get("REPS", 5))
+route = os.environ.get("ROUTE", "peer")
+dtype = np.float64 if os.environ.get("DTYPE", "f32") == "f64" else np.float32
+rng = np.random.default_rng(0)
+dx = 1.0 / (g - 1)
+# dt * Laplacian scaled to O(1) entries (keep expm well conditioned at g = 4096)
+stencil = bl.operators.WaveStencilOperator.stencil_laplacian(dx) * dx * dx
+xs = np.linspace(0, 1, g)
+y0 = np.stack([np.exp(-80 * ((xs[:, None] - 0.4) ** 2 + (xs[None, :] - 0.6) ** 2)),
+               0.1 * np.sin(5 * xs)[:, None] * np.ones(g)[None, :]]).astype(dtype)  # fmt: skip
+scale = (1.0 + 0.1 * np.sin(6 * xs)[:, None] * np.cos(4 * xs)[None, :]).astype(dtype)
+dH = np.eye(K, dtype=dtype) + 0.1 * rng.standard_normal((K, K)).astype(dtype)
+
+dist = None
+if world > 1:
+    import torch
+    import torch.distributed as dist
+
+
+def barrier():
+    bl.synchronize()
+    if dist is not None:
+        dist.barrier()
+
+
+comm = parallel.PeerComm() if route == "peer" else None
+op = parallel.RowShardedWaveOperator(g, stencil, comm=comm)
+alg = bl.arnoldi.hessenberg(op.callback, K, reortho="full")
+v_loc = bl.asarray(op.local_slice(y0))
+sc = bl.asarray(op.local_scale(scale)) if route == "peer" else scale
+
+
+def sweep():
+    with parallel.row_sharded(comm=comm):
+        (Q, H, r, c), pull = bl.vjp(alg, v_loc, sc)
+        dv, ds = pull((None, dH, None, None))
+    return H, dv, ds
+
+
+for _ in range(3):
+    H, dv, ds = sweep()
+barrier()
+e0, e1 = bl.Event(), bl.Event()
+e0.record()
+for _ in range(reps):
+    H, dv, ds = sweep()
+e1.record()
+e1.synchronize()
+ms = e0.elapsed_ms(e1) / reps
+barrier()
+if dist is not None:
+    t = torch.tensor([ms], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+res = {"config": "C5 wave stencil Arnoldi fwd+adjoint", "grid": g, "n": 2 * g * g, "K": K,
+       "dtype": np.dtype(dtype).name, "world": world, "route": route, "sharded_ms": ms,
+       "timed_out": bool(comm.timed_out()) if comm else False}
+Hh = H.numpy()
+if rank == 0 and os.environ.get("SINGLE", "1") == "1":
+    ref = bl.arnoldi.hessenberg(bl.operators.WaveStencilOperator(g, stencil), K, reortho="full")
+    v0, s0 = bl.asarray(y0.ravel()), bl.asarray(scale)
+
+    def single():
+        (Q0, H0, r0, c0), pull0 = bl.vjp(ref, v0, s0)
+        return H0, pull0((None, dH, None, None))
+
+    for _ in range(2):
+        H0, (dv0, ds0) = single()
+    bl.synchronize()
+    e0.record()
+    for _ in range(reps):
+        H0, (dv0, ds0) = single()
+    e1.record()
+    e1.synchronize()
+    res["single_gpu_ms"] = e0.elapsed_ms(e1) / reps
+    res["speedup"] = res["single_gpu_ms"] / ms
+
+    def err(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+    res["err_H"] = err(Hh, H0.numpy())
+    res["err_dv_local"] = err(dv.numpy(), op.local_slice(dv0.numpy().reshape(2, g, g)))
+    ds_h = ds.numpy() if hasattr(ds, "numpy") else ds
+    ds_ref = ds0.numpy()
+    res["err_dscale"] = err(ds_h, op.local_scale(ds_ref) if route == "peer" else ds_ref)
+if rank == 0:
+    print(json.dumps(res))
+if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()

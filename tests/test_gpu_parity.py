@@ -362,3 +362,71 @@ def test_full_size_properties(dtype):
     dv3, dp3 = pull(((None, (c1[0] + 2 * c2[0], c1[1] + 2 * c2[1])), (None, None)))
     assert rel_err(dv3.numpy(), dv1.numpy() + 2 * dv2.numpy()) < 1e-4
     assert rel_err(dp3.numpy(), dp1.numpy() + 2 * dp2.numpy()) < 1e-4
+
+
+def test_peer_memory_route_two_ranks_on_one_gpu_matches_single_operator():
+    """The native row-sharded route (peer-memory reductions fused with the epilogue + halo pushes,
+    `bl_dist_comm_*`) with TWO ranks driven by two host threads on one GPU: each rank owns half of the
+    grid rows; results must equal the single-operator run.  (The cross-process form of the same
+    kernels runs under torchrun: `scripts/run_row_sharded_wave.py`, profiles/.)"""
+    import threading
+
+    from experiments_lanczos_adjoints_b200 import _lib, parallel
+
+    g, K, world = 64, 6, 2
+    rng = np.random.default_rng(0)
+    stencil = bl.operators.WaveStencilOperator.stencil_laplacian(1.0)
+    y0 = rng.standard_normal((2, g, g))
+    scale = 0.3 + 0.05 * rng.standard_normal((g, g))
+    dH = rng.standard_normal((K, K))
+    dr = rng.standard_normal((2, g, g))
+    plain = bl.arnoldi.hessenberg(bl.operators.WaveStencilOperator(g, stencil), K, reortho="full")
+    (Q0, H0, r0, c0), pull0 = bl.vjp(plain, y0.ravel(), scale)
+    dv0, ds0 = pull0((None, dH, dr.ravel(), None))
+    H0, r0, dv0, ds0 = H0.numpy(), r0.numpy().reshape(2, g, g), dv0.numpy().reshape(2, g, g), ds0.numpy()
+    bl.synchronize()
+
+    # CUDA loads kernels lazily and a load may synchronise the context: with both ranks in ONE process a
+    # rank spinning on its peer would block the peer's first launch of a kernel.  Load every kernel of
+    # the sharded route first (same local shape, a one-rank communicator).  Separate processes (the
+    # production set-up) have separate contexts and need none of this.
+    solo = parallel.PeerComm(rank=0, world=1)
+    slab = bl.operators.WaveStencilOperator(g, stencil, rows=g // world)
+    _lib.call("bl_op_wave_set_comm", slab._handle, solo.handle)
+    with parallel.row_sharded(comm=solo):
+        warm = bl.arnoldi.hessenberg(slab, K, reortho="full")
+        _, pull_w = bl.vjp(warm, y0[:, : g // world].ravel(), scale[: g // world])
+        pull_w((None, dH, dr[:, : g // world].ravel(), None))
+    bl.synchronize()
+
+    comms = [parallel.PeerComm(rank=r, world=world) for r in range(world)]
+    for c in comms:
+        c.connect_local(comms)
+    out, errors = {}, []
+
+    def rank_main(r):
+        try:
+            op = parallel.RowShardedWaveOperator(g, stencil, comm=comms[r])
+            alg = bl.arnoldi.hessenberg(op.callback, K, reortho="full")
+            with parallel.row_sharded(comm=comms[r]):
+                (Q, H, rr, c), pull = bl.vjp(alg, op.local_slice(y0), op.local_scale(scale))
+                dv, ds = pull((None, dH, op.local_slice(dr), None))
+            bl.default_stream().synchronize()
+            out[r] = (H.numpy(), rr.numpy(), dv.numpy(), ds.numpy(), op)
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert not errors, errors
+    assert not any(c.timed_out() for c in comms)
+    assert np.array_equal(out[0][0], out[1][0])  # the same H, bit for bit, on both ranks
+    for r in range(world):
+        H, rr, dv, ds, op = out[r]
+        assert rel_err(H, H0) < 1e-12
+        assert rel_err(rr, op.local_slice(r0)) < 1e-11
+        assert rel_err(dv, op.local_slice(dv0)) < 1e-9
+        assert rel_err(ds, op.local_scale(ds0)) < 1e-9
