@@ -65,6 +65,20 @@ def _compile(nvcc, src, obj, verbose):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Build (or reuse) the library.  Safe when several ranks import the package at once: an exclusive
+    file lock serialises the builders and the late-comers find the finished library."""
+    import fcntl
+
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     headers = _headers_digest()
     digests = {src: _file_digest(src, headers) for src in sources()}
     total = hashlib.sha256("".join(digests[s] for s in sorted(digests)).encode()).hexdigest()
@@ -95,8 +109,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     keep = set(objs)
     for f in os.listdir(OBJ):  # drop objects of older source versions
-        if os.path.join(OBJ, f) not in keep:
-            os.remove(os.path.join(OBJ, f))
+        if f.endswith(".o") and os.path.join(OBJ, f) not in keep:
+            try:
+                os.remove(os.path.join(OBJ, f))
+            except FileNotFoundError:
+                pass
     with open(STAMP, "w") as f:
         f.write(total)
     return LIB

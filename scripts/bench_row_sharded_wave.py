@@ -28,8 +28,12 @@ dx = 1.0 / (g - 1)
 # dt * Laplacian scaled to O(1) entries (keep expm well conditioned at g = 4096)
 stencil = bl.operators.WaveStencilOperator.stencil_laplacian(dx) * dx * dx
 xs = np.linspace(0, 1, g)
+# rough initial state (smooth bump + white noise): with a purely smooth state the scaled Laplacian is
+# O(dx^2), the Krylov space is nearly degenerate and the adjoint amplifies rounding by ~1e7 (measured in
+# fp64), which makes an fp32 single-vs-sharded comparison meaningless
 y0 = np.stack([np.exp(-80 * ((xs[:, None] - 0.4) ** 2 + (xs[None, :] - 0.6) ** 2)),
-               0.1 * np.sin(5 * xs)[:, None] * np.ones(g)[None, :]]).astype(dtype)  # fmt: skip
+               0.1 * np.sin(5 * xs)[:, None] * np.ones(g)[None, :]])  # fmt: skip
+y0 = (y0 + rng.standard_normal((2, g, g))).astype(dtype)
 scale = (1.0 + 0.1 * np.sin(6 * xs)[:, None] * np.cos(4 * xs)[None, :]).astype(dtype)
 dH = np.eye(K, dtype=dtype) + 0.1 * rng.standard_normal((K, K)).astype(dtype)
 
