@@ -212,3 +212,27 @@ class finfo:
 
 def dtype(x):
     return x.dtype if isinstance(x, torch.Tensor) else _dtype(x)
+
+
+def argmax(x, axis=None):
+    return torch.argmax(_t(x)) if axis is None else torch.argmax(_t(x), dim=axis)
+
+
+def argsort(x):
+    return torch.argsort(_t(x), stable=True)
+
+
+def logical_and(a, b):
+    return torch.logical_and(torch.as_tensor(a), torch.as_tensor(b))
+
+
+def logical_or(a, b):
+    return torch.logical_or(torch.as_tensor(a), torch.as_tensor(b))
+
+
+def amax(x, axis=None):
+    return torch.amax(_t(x)) if axis is None else torch.amax(_t(x), dim=axis)
+
+
+def minimum(a, b):
+    return torch.minimum(_t(a), _t(b, _t(a).dtype) if not isinstance(b, torch.Tensor) else b)

@@ -175,6 +175,17 @@ def test_wave_operator_and_arnoldi_match_reference_golden():
     dy0, dsc = pull((dQ, dH, None, dc))
     assert rel_err(dy0.numpy(), g["loss_dy0"].ravel()) < 1e-9
     assert rel_err(dsc.numpy(), g["loss_dscale"]) < 1e-9
+    # the same through the drop-in factories (pde_util.py:240-268): solver_expm(expm_arnoldi)
+    field, like = bl.pde.pde_wave_anisotropic(scale, g["stencil"], constrain="square", boundary="neumann")
+    assert like["scale"].shape == scale.shape
+    solve = bl.pde.solver_expm(0.0, t1, field, expm=bl.pde.expm_arnoldi(K))
+    y1, info = solve(g["y0"], scale)
+    assert info == {"num_matvecs": K} and rel_err(y1.numpy(), g["expm_out"].ravel()) < 1e-10
+    (y1, _), pullback = bl.vjp(solve, g["y0"], scale)
+    dy0_f, dsc_f = pullback(g["u"])
+    assert rel_err(y1.numpy(), g["expm_out"].ravel()) < 1e-10
+    assert rel_err(dy0_f.numpy(), g["loss_dy0"].ravel()) < 1e-9
+    assert rel_err(dsc_f.numpy(), g["loss_dscale"]) < 1e-9
 
 
 # ---- seeded random problems against the oracle ---------------------------------------------
