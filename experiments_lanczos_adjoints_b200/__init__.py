@@ -4,7 +4,7 @@ reference's own function API.  All device work goes through libb200lanczos.so (h
 sm_100a CUDA, C ABI in `include/b200_lanczos.h`); there is no CPU fallback.
 """
 
-from experiments_lanczos_adjoints_b200 import arnoldi, hutchinson, lanczos, operators, pde  # noqa: F401
+from experiments_lanczos_adjoints_b200 import arnoldi, cg, gp, hutchinson, lanczos, low_rank, operators, pde  # noqa: F401
 from experiments_lanczos_adjoints_b200._lib import BLError  # noqa: F401
 from experiments_lanczos_adjoints_b200.device import (  # noqa: F401
     DeviceArray,

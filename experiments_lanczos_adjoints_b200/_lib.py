@@ -59,6 +59,16 @@ SIGNATURES = {
     "bl_dist_comm_error": (_i32, [_vp, C.POINTER(C.c_int)]),
     "bl_dist_comm_destroy": (_i32, [_vp]),
     "bl_op_wave_set_comm": (_i32, [_vp, _vp]),
+    "bl_precond_create": (_i32, [_i32, _i64, _i64, _vp, _i64, _vp, _pvp]),
+    "bl_precond_set_shift": (_i32, [_vp, C.c_double, _vp]),
+    "bl_precond_apply": (_i32, [_vp, _i32, _vp, _vp, _vp]),
+    "bl_precond_destroy": (_i32, [_vp]),
+    "bl_pcg_workspace_bytes": (C.c_size_t, [_i64, _i32]),
+    "bl_pcg_solve": (_i32, [_vp, _i32, _i64, _vp, _vp, _i64, _i64, C.c_double, C.c_double, _i32, _vp, _vp,
+                            C.POINTER(C.c_int64), _vp, C.c_size_t, _vp]),
+    "bl_cholesky_workspace_bytes": (C.c_size_t, [_i64, _i64, _i32]),
+    "bl_cholesky_partial": (_i32, [_vp, _i32, _i64, _i64, _i32, _vp, _i64, C.POINTER(C.c_int), C.POINTER(C.c_int64),
+                                   _vp, C.c_size_t, _vp]),
     "bl_op_sparse_create": (_i32, [_i64, _i64, _i64, _vp, _vp, _pvp]),
     "bl_op_sparse_export_csr": (_i32, [_vp, _vp, _vp, _vp]),
     "bl_op_sparse_export_sell": (_i32, [_vp, _i32, _vp, _vp]),

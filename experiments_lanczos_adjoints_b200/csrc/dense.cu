@@ -38,6 +38,16 @@ __global__ void k_dense_outer(int64_t n, int mode, const T* __restrict__ q, cons
   grad[e] += g;
 }
 
+// out[j] = M[j, idx]  /  out[j] = M[j, j]   (M = P, or P + P^T for the symmetrised operand)
+template <typename T>
+__global__ void k_dense_elements(int64_t n, int mode, const T* __restrict__ P, const int64_t* __restrict__ index,
+                                 T* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t c = index ? index[0] : j;
+  out[j] = mode == 1 ? P[j * n + c] + P[c * n + j] : P[j * n + c];
+}
+
 }  // namespace
 
 struct DenseOperator : bl_operator {
@@ -64,6 +74,20 @@ struct DenseOperator : bl_operator {
   int matvec(int dtype, const void* x, void* y, cudaStream_t s) override {
     BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
     return dtype == BL_F32 ? mv<float>(false, x, y, s) : mv<double>(false, x, y, s);
+  }
+  int elements(int dtype, const int64_t* index, void* out, cudaStream_t s) {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    const int blocks = (int)((n + 255) / 256);
+    if (dtype == BL_F32)
+      k_dense_elements<float><<<blocks, 256, 0, s>>>(n, mode, static_cast<const float*>(P), index, static_cast<float*>(out));
+    else
+      k_dense_elements<double><<<blocks, 256, 0, s>>>(n, mode, static_cast<const double*>(P), index, static_cast<double*>(out));
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  int element_diagonal(int dtype, void* out, cudaStream_t s) override { return elements(dtype, nullptr, out, s); }
+  int element_column(int dtype, const int64_t* index, void* out, cudaStream_t s) override {
+    return elements(dtype, index, out, s);
   }
   int vjp(int dtype, const void* q, const void* lam, void* z, cudaStream_t s) override {
     BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");

@@ -292,6 +292,29 @@ k_gram_sweep(int64_t n, int d, const T* __restrict__ xs, const T* __restrict__ x
   }
 }
 
+// out[j] = k(x_j, x_idx) (idx = *index) or k(x_j, x_j) (index == nullptr): the lazy kernel of
+// gp_util.py:257-258, same expanded squared distance as the sweeps
+template <typename T>
+__global__ void k_gram_elements(int64_t n, int dp, int kind, const T* __restrict__ xs, const T* __restrict__ xx,
+                                const T* __restrict__ consts, const int64_t* __restrict__ index, T* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t c = index ? index[0] : j;
+  T dot = T(0);
+  for (int k = 0; k < dp; ++k) dot = fma(xs[j * dp + k], xs[c * dp + k], dot);
+  T s2 = xx[j] + xx[c] - T(2) * dot;
+  s2 = s2 > T(0) ? s2 : T(0);
+  const T sigma = consts[0];
+  T val;
+  if (kind == 2) {
+    val = sigma * exp(-s2 / T(2));
+  } else {
+    const T s = sqrt(s2 + Eps<T>::v());
+    val = kind == 0 ? sigma * (T(1) + s) * exp(-s) : sigma * exp(-s);
+  }
+  out[j] = val;
+}
+
 // y[i] = sum_s part[s][i] + noise * v[i]
 template <typename T>
 __global__ void k_gram_finish(int64_t n, int jsplit, const T* __restrict__ part, const T* __restrict__ noise,
@@ -544,6 +567,23 @@ struct GramOperator : bl_operator {
     BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
     return dtype == BL_F32 ? vjp_t<float>((const float*)q, (const float*)lam, (float*)z, s)
                            : vjp_t<double>((const double*)q, (const double*)lam, (double*)z, s);
+  }
+
+  int elements(int dtype, const int64_t* index, void* out, cudaStream_t s) {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    const int blocks = (int)((n + 255) / 256);
+    if (dtype == BL_F32)
+      k_gram_elements<float><<<blocks, 256, 0, s>>>(n, dp(), kind, xs.as<float>(), xx.as<float>(), consts.as<float>(),
+                                                    index, static_cast<float*>(out));
+    else
+      k_gram_elements<double><<<blocks, 256, 0, s>>>(n, dp(), kind, xs.as<double>(), xx.as<double>(),
+                                                     consts.as<double>(), index, static_cast<double*>(out));
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  int element_diagonal(int dtype, void* out, cudaStream_t s) override { return elements(dtype, nullptr, out, s); }
+  int element_column(int dtype, const int64_t* index, void* out, cudaStream_t s) override {
+    return elements(dtype, index, out, s);
   }
 
   int grad_zero(int dtype, cudaStream_t s) override {

@@ -18,6 +18,17 @@ struct bl_operator {
   // ALGORITHMIC bytes of one matvec / one vjp (roofline report); default: vectors only
   virtual double matvec_bytes(int dtype) const { return 2.0 * n * (dtype == BL_F32 ? 4 : 8); }
   virtual double vjp_bytes(int dtype) const { return 3.0 * n * (dtype == BL_F32 ? 4 : 8); }
+  // Lazily evaluated matrix elements (the `lazy_kernel(i, j)` of gp_util.py:257-258 / the
+  // `matrix_element` callback of low_rank.py): diagonal and one column, for the partial Cholesky.
+  // For the Gram operator these are the KERNEL entries (no noise term), as in the reference.
+  virtual int element_diagonal(int /*dtype*/, void* /*out*/, cudaStream_t) {
+    bl::set_error("this operator does not expose matrix elements");
+    return BL_EINVAL;
+  }
+  virtual int element_column(int /*dtype*/, const int64_t* /*index_dev*/, void* /*out*/, cudaStream_t) {
+    bl::set_error("this operator does not expose matrix elements");
+    return BL_EINVAL;
+  }
 };
 
 namespace bl {

@@ -99,6 +99,25 @@ class Operator:
         return self.matvec(x)
 
 
+class BoundOperator:
+    """`lambda v: matvec(v, *params)` — an operator with its parameters bound: what the reference hands
+    to CG, to the partial Cholesky (`lazy_kernel`) and to the SLQ log-determinant as `A`."""
+
+    def __init__(self, op: Operator, *params):
+        self.op, self.params = op, tuple(params)
+        self.n = op.n
+
+    def bind(self, dtype, stream=None):
+        return self.op.bind(self.params, dtype, stream)
+
+    def __call__(self, v):
+        return self.op(v, *self.params)
+
+
+def bound(op, *params) -> BoundOperator:
+    return BoundOperator(op, *params)
+
+
 class SparseOperator(Operator):
     """`BCOO((params, indices), shape) @ x` with `params` = COO data in COO order
     (`/root/reference/experiments/benchmarks/wall_times_vjp_through_lanczos_arnoldi/suite_sparse/benchmark.py:61-68`).

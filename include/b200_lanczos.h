@@ -228,6 +228,43 @@ int bl_lanczos3_adjoint(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_
                         const void* dalphas, const void* dbetas, const void* vnorm, void* dv,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- linear solves of the GP path (cg.py, low_rank.py) -------------------------------------
+ * Preconditioner of low_rank.py:10-60: v -> (s I + L L^T)^{-1} v (Woodbury).  `L_rows` holds the factor
+ * as `rank` rows of length n (row k = k-th column of the reference's (n, rank) matrix), row stride ld;
+ * the buffer must outlive the object.  create() forms L^T L on the device (synchronises `stream`);
+ * set_shift(s) inverts the rank x rank capacitance matrix on the host (s = the noise); apply() is three
+ * kernels on the stream. */
+typedef struct bl_precond bl_precond_t;
+int bl_precond_create(int dtype, int64_t n, int64_t rank, const void* L_rows, int64_t ld, void* stream,
+                      bl_precond_t** out);
+int bl_precond_set_shift(bl_precond_t* p, double shift, void* stream);
+int bl_precond_apply(bl_precond_t* p, int dtype, const void* v, void* out, void* stream);
+int bl_precond_destroy(bl_precond_t* p);
+
+/* Preconditioned conjugate gradients, x0 = 0 (cg.py:20-131).  precond == NULL: plain CG.
+ *   atol <  0 : pcg_fixed_step(max_steps) -- exactly max_steps iterations, nothing synchronises;
+ *   atol >= 0 : pcg_adaptive(atol, rtol, maxiter = max_steps, miniter = min_steps) -- iterate while
+ *               rms(r / (atol + |x| rtol)) > 1 or fewer than min_steps steps were taken.  The device
+ *               freezes x and r at the iteration where that condition fails; the host reads the flag
+ *               every `check_every` iterations (0 = default 8) and synchronises the stream to do so.
+ * x, r: solution and residual b - A x (n values each); *num_steps_host: iterations taken.
+ * Divisions are cg.py's _safe_divide (a / b where |b| > eps^2, else a). */
+size_t bl_pcg_workspace_bytes(int64_t n, int dtype);
+int bl_pcg_solve(bl_operator_t* op, int dtype, int64_t n, const void* b, bl_precond_t* precond, int64_t max_steps,
+                 int64_t min_steps, double atol, double rtol, int check_every, void* x, void* r,
+                 int64_t* num_steps_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Partial Cholesky factorisation of the lazily evaluated matrix of `op` (dense operand: its matrix; Gram
+ * operand: the kernel matrix WITHOUT the noise term, gp_util.py:257-258).  pivot = 0: low_rank.py:63-118;
+ * pivot = 1: low_rank.py:120-225 (first arg-max of |diag - sum L^2| over the permuted positions; the
+ * factor is returned in the original row order).  L_rows: `rank` rows of length n, stride ld.
+ * success_host / pivots_host (optional; reading them synchronises the stream): low_rank.py:198's flag and
+ * the chosen pivots (original indices).  rank < 1 or rank > n -> BL_EINVAL with the reference's message. */
+size_t bl_cholesky_workspace_bytes(int64_t n, int64_t rank, int dtype);
+int bl_cholesky_partial(bl_operator_t* op, int dtype, int64_t n, int64_t rank, int pivot, void* L_rows, int64_t ld,
+                        int* success_host, int64_t* pivots_host, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* ---- small vector helpers used by the host-side wrappers (lanczos.py:162-167, 24-26) ---- */
 /* out[0] = sum_i x_i y_i  (device scalar, dtype) */
 int bl_vec_dot(int dtype, int64_t n, const void* x, const void* y, void* out, void* workspace,
