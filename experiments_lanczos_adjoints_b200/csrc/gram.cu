@@ -352,6 +352,34 @@ __global__ void k_gram_grad_finish(int d, int nblocks, const double* __restrict_
   }
 }
 
+// batched form: the partial sums come from one k_gram_tc_gradbatch pass over `count` (lam_m, q_m) pairs
+template <typename T>
+__global__ void k_gram_grad_finish_batch(int d, int nblocks, const double* __restrict__ gpart,
+                                         const T* __restrict__ raw_ls, const T* __restrict__ raw_os,
+                                         const T* __restrict__ consts, int64_t n, const T* __restrict__ Lam, int64_t ldl,
+                                         const T* __restrict__ Q, int64_t ldq, int count, T* __restrict__ grad) {
+  __shared__ double red_smem[32];
+  const int k = blockIdx.x;  // 0..d+1
+  double s = 0.0;
+  if (k <= d) {
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += gpart[(size_t)b * (d + 1) + k];
+  } else {
+    for (int m = 0; m < count; ++m)
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+        s += static_cast<double>(Lam[(int64_t)m * ldl + i]) * static_cast<double>(Q[(int64_t)m * ldq + i]);
+  }
+  s = block_sum(s, red_smem);
+  if (threadIdx.x != 0) return;
+  if (k < d) {
+    const double ls = static_cast<double>(softplus_t(raw_ls[k]));
+    grad[k] += static_cast<T>(-2.0 / ls * s * static_cast<double>(softplus_grad_t(raw_ls[k])));
+  } else if (k == d) {
+    grad[d] += static_cast<T>(s / static_cast<double>(consts[0]) * static_cast<double>(softplus_grad_t(raw_os[0])));
+  } else {
+    grad[d + 1] += static_cast<T>(s);
+  }
+}
+
 }  // namespace
 
 struct GramOperator : bl_operator {
@@ -484,6 +512,73 @@ struct GramOperator : bl_operator {
     }
     return BL_OK;
   }
+  // ---- deferred parameter cotangent (operators.cuh) ------------------------------------------
+  bool deferred_grad(int dtype) const override {
+    const char* env = std::getenv("BL_GRAM_DEFER");  // "0": per-step cotangent sweeps (A/B comparisons)
+    return use_tc(dtype) && !(env && env[0] == '0');
+  }
+  int apply_transpose(int dtype, const void* lam, void* z, cudaStream_t s) override {
+    return matvec(dtype, lam, z, s);  // the Gram matrix is symmetric
+  }
+  template <int KIND, int D>
+  int launch_batch(const float* Q, int64_t ldq, const float* Lam, int64_t ldl, int M, cudaStream_t s) {
+    const int slots = gramtc::slots_for((int)d);
+    const gramtc::Plan pl = gramtc::make_plan_batch(slots);
+    auto kernel = gramtc::k_gram_tc_gradbatch<KIND, D>;
+    {
+      static std::mutex mu;
+      static std::map<int, bool> done;
+      int dev = 0;
+      BL_CUDA(cudaGetDevice(&dev));
+      std::lock_guard<std::mutex> lk(mu);
+      if (!done[dev]) {
+        cudaFuncAttributes fa;
+        BL_CUDA(cudaFuncGetAttributes(&fa, kernel));
+        BL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes));
+        done[dev] = true;
+      }
+    }
+    kernel<<<dim3(tc_rowtiles(), tc_split), gramtc::kThreads, pl.total, s>>>(
+        n, npad, (int)d, slots, opA.as<float>(), opB.as<float>(), xt.as<float>(), xx.as<float>(), consts.as<float>(), Q,
+        ldq, Lam, ldl, M, gpart.as<double>());
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  template <int KIND>
+  int launch_batch_d(const float* Q, int64_t ldq, const float* Lam, int64_t ldl, int M, cudaStream_t s) {
+    if (d <= 3) return launch_batch<KIND, 3>(Q, ldq, Lam, ldl, M, s);
+    if (d <= 4) return launch_batch<KIND, 4>(Q, ldq, Lam, ldl, M, s);
+    if (d <= 6) return launch_batch<KIND, 6>(Q, ldq, Lam, ldl, M, s);
+    if (d <= 8) return launch_batch<KIND, 8>(Q, ldq, Lam, ldl, M, s);
+    if (d <= 9) return launch_batch<KIND, 9>(Q, ldq, Lam, ldl, M, s);
+    if (d <= 12) return launch_batch<KIND, 12>(Q, ldq, Lam, ldl, M, s);
+    if (d <= 16) return launch_batch<KIND, 16>(Q, ldq, Lam, ldl, M, s);
+    return launch_batch<KIND, 20>(Q, ldq, Lam, ldl, M, s);
+  }
+  int vjp_batch(int dtype, const void* Q, int64_t ldq, const void* Lam, int64_t ldl, int count,
+                cudaStream_t s) override {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    if (!use_tc(dtype)) return bl_operator::vjp_batch(dtype, Q, ldq, Lam, ldl, count, s);
+    BL_REQUIRE((ldq * 4) % 16 == 0 && (ldl * 4) % 16 == 0 && ldq >= n && ldl >= n, "row strides must be 16-byte multiples");
+    for (int m0 = 0; m0 < count; m0 += gramtc::kBatchMax) {
+      const int M = std::min(gramtc::kBatchMax, count - m0);
+      const float* q = static_cast<const float*>(Q) + (int64_t)m0 * ldq;
+      const float* l = static_cast<const float*>(Lam) + (int64_t)m0 * ldl;
+      if (kind == 0)
+        BL_CHECK((launch_batch_d<0>(q, ldq, l, ldl, M, s)));
+      else if (kind == 1)
+        BL_CHECK((launch_batch_d<1>(q, ldq, l, ldl, M, s)));
+      else
+        BL_CHECK((launch_batch_d<2>(q, ldq, l, ldl, M, s)));
+      k_gram_grad_finish_batch<float><<<(int)d + 2, 256, 0, s>>>(
+          (int)d, tc_gparts(), gpart.as<double>(), static_cast<const float*>(raw_ls), static_cast<const float*>(raw_os),
+          consts.as<float>(), n, l, ldl, q, ldq, M, grad.as<float>());
+      BL_LAUNCHED();
+    }
+    return BL_OK;
+  }
+
   // diagnostic: the tensor-core accumulator (x_i.x_j - |x_j|^2/2) of the tile (rows 128 bi .., columns 256 bj ..)
   int tile_distances(int64_t bi, int64_t bj, float* out_host, cudaStream_t s) {
     BL_REQUIRE(bound_dtype == BL_F32 && use_tc(BL_F32), "tile distances need the fp32 tensor-core path (bind first)");

@@ -162,13 +162,13 @@ struct Plan {
   int stages;   // B-tile ring depth
   uint32_t a_bytes, b_bytes, aux_bytes, stage_bytes, bar_off, total;
 };
-// aux per stage: v [kN] (+ q [kN] + x^T [kXtRows][kN] for the adjoint sweep)
-__host__ __device__ inline Plan make_plan(int slots, bool adj) {
+// aux per stage: `aux_rows` rows of kN floats
+__host__ __device__ inline Plan make_plan_rows(int slots, int aux_rows) {
   Plan p;
   p.ksteps = slots / 8;
   p.a_bytes = (uint32_t)slots * kM * 4;
   p.b_bytes = (uint32_t)slots * kN * 4;
-  p.aux_bytes = (uint32_t)kN * 4 * (adj ? 2 + kXtRows : 1);
+  p.aux_bytes = (uint32_t)kN * 4 * aux_rows;
   p.stage_bytes = p.b_bytes + p.aux_bytes;
   const uint32_t budget = 220 * 1024;
   p.stages = 3;
@@ -178,6 +178,10 @@ __host__ __device__ inline Plan make_plan(int slots, bool adj) {
   if (p.total < 120 * 1024) p.total = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
   return p;
 }
+// sweeps: v [kN] (+ q [kN] + x^T [kXtRows][kN] for the adjoint sweep)
+__host__ __device__ inline Plan make_plan(int slots, bool adj) { return make_plan_rows(slots, adj ? 2 + kXtRows : 1); }
+constexpr int kBatchMax = 16;  // (lambda, q) pairs per pass of the batched parameter-cotangent sweep
+__host__ __device__ inline Plan make_plan_batch(int slots) { return make_plan_rows(slots, kBatchMax + kXtRows); }
 
 // (unscaled) kernel values from the accumulator acc = x.y - |y|^2/2, two entries at a time.
 //   KIND 0: Matern-3/2 (1+s) e^{-s}   KIND 1: Matern-1/2 e^{-s}   KIND 2: RBF e^{-s2/2}
@@ -451,6 +455,228 @@ k_gram_tc_sweep(int64_t n, int64_t npad, int d, int slots, const float* __restri
         else if (lane < d)
           gpart[blk * (d + 1) + lane] = sacc;
       }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// Deferred parameter cotangent of M <= kBatchMax matvec VJPs at once (the adjoint sweep of the Krylov
+// loops defers them: arnoldi.py:207-209 only needs A^T lambda inside the loop):
+//     sum_m d<lam_m, K(theta) q_m>/dtheta = sum_ij W_ij dk_ij/dtheta,   W_ij = sum_m lam_m[i] q_m[j],
+// so the kernel tile (distances on the tensor pipe, sqrt / exp on the MUFU) and the per-dimension
+// (x_ik - x_jk)^2 accumulation are paid ONCE for the M pairs; only the rank-M weight costs M FMAs per
+// kernel entry.  Same warp roles and pipeline as k_gram_tc_sweep; per-CTA partial sums in gpart.
+template <int KIND, int D>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gram_tc_gradbatch(int64_t n, int64_t npad, int d, int slots, const float* __restrict__ opA,
+                    const float* __restrict__ opB, const float* __restrict__ xt, const float* __restrict__ xx,
+                    const float* __restrict__ consts, const float* __restrict__ Qrows, int64_t ldq,
+                    const float* __restrict__ Lrows, int64_t ldl, int M, double* __restrict__ gpart) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Plan pl = make_plan_batch(slots);
+  uint8_t* smA = smem;
+  uint8_t* smS = smem + pl.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 3;
+  uint64_t* acc_full = bars + 6;
+  uint64_t* acc_empty = bars + 8;
+  uint64_t* a_full = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  __shared__ double gred[kEpiWarps][kXtRows + 1];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.x * kM;
+  const int64_t tiles_total = (n + kN - 1) / kN;
+  const int64_t per = (tiles_total + gridDim.y - 1) / gridDim.y;
+  const int64_t t0 = per * blockIdx.y;
+  const int64_t t1 = t0 + per < tiles_total ? t0 + per : tiles_total;
+  const int ntiles = t0 < t1 ? (int)(t1 - t0) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < pl.stages; ++s) {
+      tma::mbar_init(full + s, 1);
+      tma::mbar_init(empty + s, 1 + kEpiWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tma::mbar_init(acc_full + b, 1);
+      tma::mbar_init(acc_empty + b, kEpiWarps);
+    }
+    tma::mbar_init(a_full, 1);
+    tma::fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0 && ntiles > 0) {
+      tma::mbar_arrive_expect_tx(a_full, pl.a_bytes);
+      for (int c = 0; c < 2 * pl.ksteps; ++c)
+        tma::bulk_g2s(smA + (size_t)c * kM * 16, opA + ((int64_t)c * npad + i0) * 4, kM * 16, a_full);
+    }
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % pl.stages;
+      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
+      tma::mbar_wait(empty + s, ph ^ 1u);
+      uint8_t* smB = smS + (size_t)s * pl.stage_bytes;
+      float* smQ = reinterpret_cast<float*>(smB + pl.b_bytes);  // [kBatchMax][kN]
+      float* smX = smQ + kBatchMax * kN;                        // [kXtRows][kN]
+      const int64_t jt = (t0 + it) * kN;
+      // basis rows are zero-padded up to their stride: copy what the row holds, zero the rest of the tile
+      const int w = (int)((ldq - jt) < kN ? (ldq - jt) : kN);
+      const int wv = w & ~3;
+      if (wv < kN) {
+        for (int m = 0; m < M; ++m)
+          for (int c = wv + lane; c < kN; c += 32) smQ[m * kN + c] = (jt + c < n) ? Qrows[(int64_t)m * ldq + jt + c] : 0.f;
+        __syncwarp();
+      }
+      if (lane == 0) {
+        tma::mbar_arrive_expect_tx(full + s, pl.b_bytes + (uint32_t)M * wv * 4 + (uint32_t)D * kN * 4);
+        for (int c = 0; c < 2 * pl.ksteps; ++c)
+          tma::bulk_g2s(smB + (size_t)c * kN * 16, opB + ((int64_t)c * npad + jt) * 4, kN * 16, full + s);
+        if (wv > 0)
+          for (int m = 0; m < M; ++m) tma::bulk_g2s(smQ + (size_t)m * kN, Qrows + (int64_t)m * ldq + jt, (uint32_t)wv * 4, full + s);
+        for (int k = 0; k < D; ++k) tma::bulk_g2s(smX + (size_t)k * kN, xt + (int64_t)k * npad + jt, kN * 4, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issue =====
+    const uint32_t idesc = instr_desc(kM, kN);
+    if (ntiles > 0) tma::mbar_wait(a_full, 0);
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % pl.stages;
+      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
+      const int b = it & 1;
+      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      tma::mbar_wait(full + s, ph);
+      tma::mbar_wait(acc_empty + b, bph ^ 1u);
+      fence_after_sync();
+      if (lane == 0) {
+        const uint32_t sa = tma::smem_u32(smA), sb = tma::smem_u32(smS + (size_t)s * pl.stage_bytes);
+        for (int k = 0; k < pl.ksteps; ++k) {
+          const uint64_t da = smem_desc(sa + (uint32_t)k * 2 * kM * 16, kM * 16, 128);
+          const uint64_t db = smem_desc(sb + (uint32_t)k * 2 * kN * 16, kN * 16, 128);
+          mma_tf32(tmem_base + (uint32_t)b * kN, da, db, idesc, k > 0 ? 1u : 0u);
+        }
+        mma_commit(empty + s);
+        mma_commit(acc_full + b);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue =====
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = qd * 32 + lane;
+    const bool live = i0 + row < n;
+    const float xxi = live ? xx[i0 + row] : 0.f;
+    const float cr = KIND == 2 ? -0.5f * xxi : xxi + 1.1920928955078125e-07f;
+    const float2 crow = make_float2(cr, cr);
+    const uint32_t acc_diag = __float_as_uint(0.5f * xxi);
+    double uacc = 0.0, dacc[D];
+    float2 nxi[D], lam2[kBatchMax];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const float x = xt[(int64_t)k * npad + i0 + row];
+      nxi[k] = make_float2(-x, -x);
+      dacc[k] = 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < kBatchMax; ++m) {
+      const float l = (live && m < M) ? Lrows[(int64_t)m * ldl + i0 + row] : 0.f;
+      lam2[m] = make_float2(l, l);
+    }
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % pl.stages;
+      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
+      const int b = it & 1;
+      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      const float* smQ = reinterpret_cast<const float*>(smS + (size_t)s * pl.stage_bytes + pl.b_bytes);
+      const float* smX = smQ + kBatchMax * kN;
+      tma::mbar_wait(full + s, ph);
+      tma::mbar_wait(acc_full + b, bph);
+      fence_after_sync();
+      const int64_t jt = (t0 + it) * kN;
+      const bool diag_tile = jt < i0 + kM && i0 < jt + kN;
+      float2 u0 = make_float2(0.f, 0.f), u1 = u0, dl[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) dl[k] = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int col0 = half * 128 + cc * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * kN + col0), r);
+        if (diag_tile) {
+          const int jd = (int)(i0 + row - jt) - col0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = c == jd ? acc_diag : r[c];
+        }
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const float2 a01 = make_float2(__uint_as_float(r[4 * p]), __uint_as_float(r[4 * p + 1]));
+          const float2 a23 = make_float2(__uint_as_float(r[4 * p + 2]), __uint_as_float(r[4 * p + 3]));
+          const Eval2 e01 = kernel_from_acc<KIND>(a01, crow), e23 = kernel_from_acc<KIND>(a23, crow);
+          float2 w01 = make_float2(0.f, 0.f), w23 = w01;  // W_ij = sum_m lam_m[i] q_m[j]
+#pragma unroll
+          for (int m = 0; m < kBatchMax; ++m) {
+            if (m < M) {
+              const float4 q4 = *reinterpret_cast<const float4*>(smQ + (size_t)m * kN + col0 + 4 * p);
+              w01 = __ffma2_rn(lam2[m], make_float2(q4.x, q4.y), w01);
+              w23 = __ffma2_rn(lam2[m], make_float2(q4.z, q4.w), w23);
+            }
+          }
+          u0 = __ffma2_rn(e01.k, w01, u0);
+          u1 = __ffma2_rn(e23.k, w23, u1);
+          const float2 g01 = __fmul2_rn(dkernel_from_eval<KIND>(e01), w01);
+          const float2 g23 = __fmul2_rn(dkernel_from_eval<KIND>(e23), w23);
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            const float4 x4 = *reinterpret_cast<const float4*>(smX + (size_t)k * kN + col0 + 4 * p);
+            const float2 d01 = __fadd2_rn(make_float2(x4.x, x4.y), nxi[k]);
+            const float2 d23 = __fadd2_rn(make_float2(x4.z, x4.w), nxi[k]);
+            dl[k] = __ffma2_rn(g01, __fmul2_rn(d01, d01), dl[k]);
+            dl[k] = __ffma2_rn(g23, __fmul2_rn(d23, d23), dl[k]);
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        tma::mbar_arrive(acc_empty + b);
+        tma::mbar_arrive(empty + s);
+      }
+      uacc += (double)(u0.x + u0.y) + (double)(u1.x + u1.y);
+#pragma unroll
+      for (int k = 0; k < D; ++k) dacc[k] += (double)(dl[k].x + dl[k].y);
+    }
+    const double sigma = (double)consts[0];
+    const int ew = warp - 2;
+    double t = warp_sum(sigma * uacc);
+    if (lane == 0) gred[ew][D] = t;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      t = warp_sum(sigma * dacc[k]);
+      if (lane == 0) gred[ew][k] = t;
+    }
+    tma::named_bar_sync(1, kEpiWarps * 32);
+    if (warp == 2 && lane <= D) {
+      double sacc = 0.0;
+      for (int e = 0; e < kEpiWarps; ++e) sacc += gred[e][lane];
+      const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      if (lane == D)
+        gpart[blk * (d + 1) + d] = sacc;
+      else if (lane < d)
+        gpart[blk * (d + 1) + lane] = sacc;
     }
   }
   fence_before_sync();

@@ -610,6 +610,7 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
   T* lam = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
   BL_REQUIRE(w.ok(), "workspace too small (bl_arnoldi_workspace_bytes)");
   const Grid g = pick_grid<T>(n);
+  const bool defer_grad = op->deferred_grad(dtype);
 
   BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
   BL_CUDA(cudaMemsetAsync(Gamma, 0, (size_t)K * K * 8, s));
@@ -691,7 +692,10 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
     // (A^T lambda, dparams += ...) = vjp of matvec at (q_idx, params)            arnoldi.py:207-209
     {
       ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
-      BL_CHECK(op->vjp(dtype, Q + (int64_t)idx * ld, Lrow, z, s));
+      if (defer_grad)  // A^T lambda only; the parameter cotangent of all K steps follows in one batched pass
+        BL_CHECK(op->apply_transpose(dtype, Lrow, z, s));
+      else
+        BL_CHECK(op->vjp(dtype, Q + (int64_t)idx * ld, Lrow, z, s));
     }
     {  // Gamma[idx, :] and the coefficients of the back-substitution             arnoldi.py:212-218
       Epi e;
@@ -750,6 +754,10 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
       a.out_div_ptr = c.scal + S_BETA_MINUS;
       BL_CHECK(launch_combine<T>(g, c, a, false, s));
     }
+  }
+  if (defer_grad) {  // dparams = sum_idx d<Lambda[idx], A(Q[idx]; params)>/dparams   arnoldi.py:207-209, 168
+    ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
+    BL_CHECK(op->vjp_batch(dtype, Q, ld, Lambda, ld, K, s));
   }
   // dv = lambda * c                                                              arnoldi.py:166
   k_load_scalar<T><<<1, 1, 0, s>>>(c_in, c.scal + S_C);

@@ -18,6 +18,25 @@ struct bl_operator {
   // ALGORITHMIC bytes of one matvec / one vjp (roofline report); default: vectors only
   virtual double matvec_bytes(int dtype) const { return 2.0 * n * (dtype == BL_F32 ? 4 : 8); }
   virtual double vjp_bytes(int dtype) const { return 3.0 * n * (dtype == BL_F32 ? 4 : 8); }
+  // Deferred parameter cotangent (the adjoint sweeps only need A^T lam inside the loop): operators that
+  // return true provide `apply_transpose` (z = A^T lam, no gradient work) and `vjp_batch`
+  // (grad += sum_m d<lam_m, A(q_m)>/dparams for `count` rows of two row-strided arrays) -- for the Gram
+  // operator one batched sweep costs about as much as ONE per-step cotangent sweep.
+  virtual bool deferred_grad(int /*dtype*/) const { return false; }
+  virtual int apply_transpose(int /*dtype*/, const void* /*lam*/, void* /*z*/, cudaStream_t) {
+    bl::set_error("apply_transpose is not implemented for this operator");
+    return BL_EINVAL;
+  }
+  virtual int vjp_batch(int dtype, const void* Q, int64_t ldq, const void* Lam, int64_t ldl, int count,
+                        cudaStream_t s) {
+    const size_t w = dtype == BL_F32 ? 4 : 8;
+    for (int m = 0; m < count; ++m) {
+      const int rc = vjp(dtype, static_cast<const char*>(Q) + (size_t)m * ldq * w,
+                         static_cast<const char*>(Lam) + (size_t)m * ldl * w, nullptr, s);
+      if (rc != BL_OK) return rc;
+    }
+    return BL_OK;
+  }
   // Lazily evaluated matrix elements (the `lazy_kernel(i, j)` of gp_util.py:257-258 / the
   // `matrix_element` callback of low_rank.py): diagonal and one column, for the partial Cholesky.
   // For the Gram operator these are the KERNEL entries (no noise term), as in the reference.
