@@ -352,6 +352,20 @@ __global__ void k_gram_grad_finish(int d, int nblocks, const double* __restrict_
   }
 }
 
+// y_p[i] = sum_s part[s][p][i] + noise * v_p[i]   (P vectors of one k_gram_tc_multi pass)
+struct OutPtrs {
+  float* p[gramtc::kBatchMax];
+};
+__global__ void k_gram_finish_multi(int64_t n, int jsplit, int P, const float* __restrict__ part,
+                                    const float* __restrict__ noise, gramtc::VecPtrs v, OutPtrs y) {
+  const int p = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int sp = 0; sp < jsplit; ++sp) s += part[((int64_t)sp * P + p) * n + i];
+    y.p[p][i] = fmaf(noise[0], v.p[p][i], s);
+  }
+}
+
 // batched form: the partial sums come from one k_gram_tc_gradbatch pass over `count` (lam_m, q_m) pairs
 template <typename T>
 __global__ void k_gram_grad_finish_batch(int d, int nblocks, const double* __restrict__ gpart,
@@ -520,6 +534,55 @@ struct GramOperator : bl_operator {
   int apply_transpose(int dtype, const void* lam, void* z, cudaStream_t s) override {
     return matvec(dtype, lam, z, s);  // the Gram matrix is symmetric
   }
+  template <int KIND>
+  int launch_multi(const gramtc::VecPtrs& vp, int P, cudaStream_t s) {
+    const int slots = gramtc::slots_for((int)d);
+    const gramtc::Plan pl = gramtc::make_plan_multi(slots);
+    auto kernel = gramtc::k_gram_tc_multi<KIND>;
+    {
+      static std::mutex mu;
+      static std::map<int, bool> done;
+      int dev = 0;
+      BL_CUDA(cudaGetDevice(&dev));
+      std::lock_guard<std::mutex> lk(mu);
+      if (!done[dev]) {
+        cudaFuncAttributes fa;
+        BL_CUDA(cudaFuncGetAttributes(&fa, kernel));
+        BL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes));
+        done[dev] = true;
+      }
+    }
+    kernel<<<dim3(tc_rowtiles(), tc_split), gramtc::kThreads, pl.total, s>>>(
+        n, npad, slots, opA.as<float>(), opB.as<float>(), xx.as<float>(), consts.as<float>(), vp, P, part.as<float>());
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  int matvec_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) override {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    if (!use_tc(dtype) || count == 1) return bl_operator::matvec_batch(dtype, count, in, out, s);
+    BL_CHECK(part.ensure((size_t)tc_split * gramtc::kBatchMax * n * sizeof(float)));
+    for (int p0 = 0; p0 < count; p0 += gramtc::kBatchMax) {
+      const int P = std::min(gramtc::kBatchMax, count - p0);
+      gramtc::VecPtrs vp{};
+      OutPtrs op_{};
+      for (int p = 0; p < P; ++p) vp.p[p] = static_cast<const float*>(in[p0 + p]), op_.p[p] = static_cast<float*>(out[p0 + p]);
+      if (kind == 0)
+        BL_CHECK(launch_multi<0>(vp, P, s));
+      else if (kind == 1)
+        BL_CHECK(launch_multi<1>(vp, P, s));
+      else
+        BL_CHECK(launch_multi<2>(vp, P, s));
+      k_gram_finish_multi<<<dim3(std::min<int>(256, (int)((n + 255) / 256)), P), 256, 0, s>>>(
+          n, tc_split, P, part.as<float>(), static_cast<const float*>(noise), vp, op_);
+      BL_LAUNCHED();
+    }
+    return BL_OK;
+  }
+  int apply_transpose_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) override {
+    return matvec_batch(dtype, count, in, out, s);  // symmetric
+  }
+
   template <int KIND, int D>
   int launch_batch(const float* Q, int64_t ldq, const float* Lam, int64_t ldl, int M, cudaStream_t s) {
     const int slots = gramtc::slots_for((int)d);

@@ -687,5 +687,193 @@ k_gram_tc_gradbatch(int64_t n, int64_t npad, int d, int slots, const float* __re
   }
 }
 
+
+// Matvec of P <= kBatchMax vectors at once (lockstep Krylov runs over probes): every kernel tile --
+// distances on the tensor pipe, sqrt / exp on the MUFU -- is evaluated ONCE and applied to the P
+// vectors (P extra FMAs per entry), so P matvecs cost about as much as one.
+//   part[split][p][i] = sigma sum_{j in split} k_ij v_p[j]
+struct VecPtrs {
+  const float* p[kBatchMax];
+};
+__host__ __device__ inline Plan make_plan_multi(int slots) { return make_plan_rows(slots, kBatchMax); }
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gram_tc_multi(int64_t n, int64_t npad, int slots, const float* __restrict__ opA, const float* __restrict__ opB,
+                const float* __restrict__ xx, const float* __restrict__ consts, VecPtrs vecs, int P,
+                float* __restrict__ part) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Plan pl = make_plan_multi(slots);
+  uint8_t* smA = smem;
+  uint8_t* smS = smem + pl.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 3;
+  uint64_t* acc_full = bars + 6;
+  uint64_t* acc_empty = bars + 8;
+  uint64_t* a_full = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  __shared__ double ycomb[kBatchMax][kM];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.x * kM;
+  const int64_t tiles_total = (n + kN - 1) / kN;
+  const int64_t per = (tiles_total + gridDim.y - 1) / gridDim.y;
+  const int64_t t0 = per * blockIdx.y;
+  const int64_t t1 = t0 + per < tiles_total ? t0 + per : tiles_total;
+  const int ntiles = t0 < t1 ? (int)(t1 - t0) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < pl.stages; ++s) {
+      tma::mbar_init(full + s, 1);
+      tma::mbar_init(empty + s, 1 + kEpiWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tma::mbar_init(acc_full + b, 1);
+      tma::mbar_init(acc_empty + b, kEpiWarps);
+    }
+    tma::mbar_init(a_full, 1);
+    tma::fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0 && ntiles > 0) {
+      tma::mbar_arrive_expect_tx(a_full, pl.a_bytes);
+      for (int c = 0; c < 2 * pl.ksteps; ++c)
+        tma::bulk_g2s(smA + (size_t)c * kM * 16, opA + ((int64_t)c * npad + i0) * 4, kM * 16, a_full);
+    }
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % pl.stages;
+      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
+      tma::mbar_wait(empty + s, ph ^ 1u);
+      uint8_t* smB = smS + (size_t)s * pl.stage_bytes;
+      float* smV = reinterpret_cast<float*>(smB + pl.b_bytes);  // [kBatchMax][kN]
+      const int64_t jt = (t0 + it) * kN;
+      const int w = (int)((n - jt) < kN ? (n - jt) : kN);
+      const int wv = w & ~3;
+      if (w < kN) {
+        for (int p = 0; p < P; ++p)
+          for (int c = wv + lane; c < kN; c += 32) smV[p * kN + c] = c < w ? vecs.p[p][jt + c] : 0.f;
+        __syncwarp();
+      }
+      if (lane == 0) {
+        tma::mbar_arrive_expect_tx(full + s, pl.b_bytes + (uint32_t)P * wv * 4);
+        for (int c = 0; c < 2 * pl.ksteps; ++c)
+          tma::bulk_g2s(smB + (size_t)c * kN * 16, opB + ((int64_t)c * npad + jt) * 4, kN * 16, full + s);
+        if (wv > 0)
+          for (int p = 0; p < P; ++p) tma::bulk_g2s(smV + (size_t)p * kN, vecs.p[p] + jt, (uint32_t)wv * 4, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issue =====
+    const uint32_t idesc = instr_desc(kM, kN);
+    if (ntiles > 0) tma::mbar_wait(a_full, 0);
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % pl.stages;
+      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
+      const int b = it & 1;
+      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      tma::mbar_wait(full + s, ph);
+      tma::mbar_wait(acc_empty + b, bph ^ 1u);
+      fence_after_sync();
+      if (lane == 0) {
+        const uint32_t sa = tma::smem_u32(smA), sb = tma::smem_u32(smS + (size_t)s * pl.stage_bytes);
+        for (int k = 0; k < pl.ksteps; ++k) {
+          const uint64_t da = smem_desc(sa + (uint32_t)k * 2 * kM * 16, kM * 16, 128);
+          const uint64_t db = smem_desc(sb + (uint32_t)k * 2 * kN * 16, kN * 16, 128);
+          mma_tf32(tmem_base + (uint32_t)b * kN, da, db, idesc, k > 0 ? 1u : 0u);
+        }
+        mma_commit(empty + s);
+        mma_commit(acc_full + b);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue =====
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = qd * 32 + lane;
+    const bool live = i0 + row < n;
+    const float xxi = live ? xx[i0 + row] : 0.f;
+    const float cr = KIND == 2 ? -0.5f * xxi : xxi + 1.1920928955078125e-07f;
+    const float2 crow = make_float2(cr, cr);
+    const uint32_t acc_diag = __float_as_uint(0.5f * xxi);
+    double yacc[kBatchMax];
+#pragma unroll
+    for (int p = 0; p < kBatchMax; ++p) yacc[p] = 0.0;
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % pl.stages;
+      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
+      const int b = it & 1;
+      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      const float* smV = reinterpret_cast<const float*>(smS + (size_t)s * pl.stage_bytes + pl.b_bytes);
+      tma::mbar_wait(full + s, ph);
+      tma::mbar_wait(acc_full + b, bph);
+      fence_after_sync();
+      const int64_t jt = (t0 + it) * kN;
+      const bool diag_tile = jt < i0 + kM && i0 < jt + kN;
+      float2 y[kBatchMax];
+#pragma unroll
+      for (int p = 0; p < kBatchMax; ++p) y[p] = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int col0 = half * 128 + cc * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * kN + col0), r);
+        if (diag_tile) {
+          const int jd = (int)(i0 + row - jt) - col0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = c == jd ? acc_diag : r[c];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float2 a01 = make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]));
+          const float2 a23 = make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          const Eval2 e01 = kernel_from_acc<KIND>(a01, crow), e23 = kernel_from_acc<KIND>(a23, crow);
+#pragma unroll
+          for (int p = 0; p < kBatchMax; ++p) {
+            if (p < P) {
+              const float4 v4 = *reinterpret_cast<const float4*>(smV + (size_t)p * kN + col0 + 4 * q);
+              y[p] = __ffma2_rn(e01.k, make_float2(v4.x, v4.y), y[p]);
+              y[p] = __ffma2_rn(e23.k, make_float2(v4.z, v4.w), y[p]);
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        tma::mbar_arrive(acc_empty + b);
+        tma::mbar_arrive(empty + s);
+      }
+#pragma unroll
+      for (int p = 0; p < kBatchMax; ++p) yacc[p] += (double)(y[p].x + y[p].y);
+    }
+    const double sigma = (double)consts[0];
+    if (half == 1) {
+#pragma unroll
+      for (int p = 0; p < kBatchMax; ++p) ycomb[p][row] = yacc[p];
+    }
+    tma::named_bar_sync(1, kEpiWarps * 32);
+    if (half == 0 && live) {
+#pragma unroll
+      for (int p = 0; p < kBatchMax; ++p)
+        if (p < P) part[((int64_t)blockIdx.y * P + p) * n + i0 + row] = (float)((yacc[p] + ycomb[p][row]) * sigma);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace gramtc
 }  // namespace bl

@@ -6,6 +6,7 @@
 #include <mutex>
 #include <set>
 #include <utility>
+#include <vector>
 #include <type_traits>
 
 #include <cstdlib>
@@ -498,14 +499,35 @@ int check_basis(int dtype, int64_t n, int64_t K, int64_t ld, const void* Q) {
 }
 
 // ---------------------------------------------------------------------------------------
+// One Arnoldi forward run, split at the matvec so that several runs (probes) can advance in lockstep
+// and share ONE batched matvec per step (arnoldi_forward_batch_t): begin(), then per step
+// pre(i) -> [r = A q_i] -> post(i).
 template <typename T>
-int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool second_pass, const T* v, T* Q,
-                      int64_t ld, T* H, T* r, T* c_out, void* workspace, size_t wbytes, cudaStream_t s) {
-  Workspace w(workspace, wbytes);
+struct FwdRun {
+  bl_operator_t* op;
+  int dtype;
+  int64_t n;
+  int K;
+  bool second_pass;
+  const T* v;
+  T* Q;
+  int64_t ld;
+  T* H;
+  T* r;
+  T* c_out;
+  void* workspace;
+  size_t wbytes;
+  cudaStream_t s;
   Common c;
+  Grid g;
+
+  T* q_row(int i) const { return Q + (int64_t)i * ld; }
+
+  int begin() {
+  Workspace w(workspace, wbytes);
   carve_common(w, K, c);
   BL_REQUIRE(w.ok(), "workspace too small (bl_arnoldi_workspace_bytes)");
-  const Grid g = pick_grid<T>(n);
+  g = pick_grid<T>(n);
 
   BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
   BL_CUDA(cudaMemsetAsync(H, 0, (size_t)K * K * sizeof(T), s));
@@ -518,15 +540,15 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool secon
     e.out_t = c_out;
     BL_CHECK(launch_dots<T>(g, c, rows(r, n, 0, 1), r, n, e, s));
   }
-  for (int i = 0; i < K; ++i) {
+    return BL_OK;
+  }
+  int pre(int i) {
     T* qi = Q + (int64_t)i * ld;
     // v /= length; Q[:, i] = v                                                 arnoldi.py:80-81
     BL_CHECK(launch_scale_copy<T>(n, r, 1.0, c.scal + S_LEN, qi, ld, s));
-    // v = matvec(v, *params)                                                   arnoldi.py:84
-    {
-      ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype), s);
-      BL_CHECK(op->matvec(dtype, qi, r, s));
-    }
+    return BL_OK;
+  }
+  int post(int i) {
     const int m = i + 1;
     {  // h = Q^H v (active columns only)                                       arnoldi.py:87
       Epi e;
@@ -587,30 +609,106 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool secon
       a.epi = norm_epi;
       BL_CHECK(launch_combine<T>(g, c, a, true, s));
     }
+    return BL_OK;
+  }
+};
+
+template <typename T>
+int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool second_pass, const T* v, T* Q,
+                      int64_t ld, T* H, T* r, T* c_out, void* workspace, size_t wbytes, cudaStream_t s) {
+  FwdRun<T> run{op, dtype, n, K, second_pass, v, Q, ld, H, r, c_out, workspace, wbytes, s, {}, {}};
+  BL_CHECK(run.begin());
+  for (int i = 0; i < K; ++i) {
+    BL_CHECK(run.pre(i));
+    // v = matvec(v, *params)                                                   arnoldi.py:84
+    {
+      ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype), s);
+      BL_CHECK(op->matvec(dtype, run.q_row(i), r, s));
+    }
+    BL_CHECK(run.post(i));
+  }
+  return BL_OK;
+}
+
+// P independent runs in lockstep: per step one batched matvec for all of them.
+template <typename T>
+int arnoldi_forward_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, bool second_pass, int P, const T* v,
+                            int64_t ldv, T* Q, int64_t ld, T* H, T* r, T* c_out, void* workspace, size_t wbytes,
+                            cudaStream_t s) {
+  const size_t per = bl_arnoldi_workspace_bytes(n, K, dtype);
+  BL_REQUIRE(wbytes >= per * (size_t)P, "workspace too small (P * bl_arnoldi_workspace_bytes)");
+  std::vector<FwdRun<T>> runs;
+  std::vector<const void*> in(P);
+  std::vector<void*> out(P);
+  for (int p = 0; p < P; ++p) {
+    runs.push_back(FwdRun<T>{op, dtype, n, K, second_pass, v + (int64_t)p * ldv, Q + (int64_t)p * K * ld, ld,
+                             H + (int64_t)p * K * K, r + (int64_t)p * ld, c_out + p,
+                             static_cast<char*>(workspace) + per * p, per, s, {}, {}});
+    BL_CHECK(runs.back().begin());
+    out[p] = runs[p].r;
+  }
+  for (int i = 0; i < K; ++i) {
+    for (int p = 0; p < P; ++p) {
+      BL_CHECK(runs[p].pre(i));
+      in[p] = runs[p].q_row(i);
+    }
+    {
+      ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype) * P, s);
+      BL_CHECK(op->matvec_batch(dtype, P, in.data(), out.data(), s));
+    }
+    for (int p = 0; p < P; ++p) BL_CHECK(runs[p].post(i));
   }
   return BL_OK;
 }
 
 // ---------------------------------------------------------------------------------------
+// One Arnoldi adjoint run, split at the operator call (see FwdRun): begin(), then for idx = K-1..0
+// pre(idx) -> [z = A^T Lambda[idx] (+ parameter cotangent)] -> post(idx), then end().
 template <typename T>
-int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reortho_full, const T* Q,
-                      int64_t ld, const T* H, const T* r, const T* c_in, const T* dQ, const T* dH,
-                      const T* dr, const T* dc, T* dv, T* Lambda, void* workspace, size_t wbytes,
-                      cudaStream_t s) {
-  Workspace w(workspace, wbytes);
+struct AdjRun {
+  bl_operator_t* op;
+  int dtype;
+  int64_t n;
+  int K;
+  bool reortho_full;
+  const T* Q;
+  int64_t ld;
+  const T* H;
+  const T* r;
+  const T* c_in;
+  const T* dQ;
+  const T* dH;
+  const T* dr;
+  const T* dc;
+  T* dv;
+  T* Lambda;
+  void* workspace;
+  size_t wbytes;
+  cudaStream_t s;
   Common c;
+  Grid g;
+  double *eta = nullptr, *Gamma = nullptr, *PiGamma = nullptr, *Gmat = nullptr, *gram_partial = nullptr;
+  int gram_parts = 0;
+  T *z = nullptr, *lam = nullptr;
+  bool defer_grad = false, have_reproj = false;
+
+  const T* q_row(int idx) const { return Q + (int64_t)idx * ld; }
+  T* lam_row(int idx) const { return Lambda + (int64_t)idx * ld; }
+
+  int begin() {
+  Workspace w(workspace, wbytes);
   carve_common(w, K, c);
-  double* eta = static_cast<double*>(w.take((size_t)K * 8));
-  double* Gamma = static_cast<double*>(w.take((size_t)K * K * 8));
-  double* PiGamma = static_cast<double*>(w.take((size_t)K * K * 8));
-  double* Gmat = static_cast<double*>(w.take((size_t)K * K * 8));
-  const int gram_parts = (int)gram_parts_for(n, K);
-  double* gram_partial = static_cast<double*>(w.take((size_t)gram_parts * K * K * 8));
-  T* z = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
-  T* lam = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  eta = static_cast<double*>(w.take((size_t)K * 8));
+  Gamma = static_cast<double*>(w.take((size_t)K * K * 8));
+  PiGamma = static_cast<double*>(w.take((size_t)K * K * 8));
+  Gmat = static_cast<double*>(w.take((size_t)K * K * 8));
+  gram_parts = (int)gram_parts_for(n, K);
+  gram_partial = static_cast<double*>(w.take((size_t)gram_parts * K * K * 8));
+  z = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  lam = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
   BL_REQUIRE(w.ok(), "workspace too small (bl_arnoldi_workspace_bytes)");
-  const Grid g = pick_grid<T>(n);
-  const bool defer_grad = op->deferred_grad(dtype);
+  g = pick_grid<T>(n);
+  defer_grad = op->deferred_grad(dtype);
 
   BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
   BL_CUDA(cudaMemsetAsync(Gamma, 0, (size_t)K * K * 8, s));
@@ -663,8 +761,10 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
     BL_LAUNCHED();
   }
 
-  bool have_reproj = false;  // coefA already holds p - P lambda for this idx (fused into the previous step)
-  for (int idx = K - 1; idx >= 0; --idx) {
+    have_reproj = false;  // coefA already holds p - P lambda for this idx (fused into the previous step)
+    return BL_OK;
+  }
+  int pre(int idx) {
     T* Lrow = Lambda + (int64_t)idx * ld;
     if (reortho_full) {
       // lambda -= P^T (P lambda) - P^T p, rows <= idx+1 of P = Q^T              arnoldi.py:201-204
@@ -689,14 +789,10 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
     } else {
       BL_CHECK(launch_scale_copy<T>(n, lam, 1.0, nullptr, Lrow, n, s));
     }
-    // (A^T lambda, dparams += ...) = vjp of matvec at (q_idx, params)            arnoldi.py:207-209
-    {
-      ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
-      if (defer_grad)  // A^T lambda only; the parameter cotangent of all K steps follows in one batched pass
-        BL_CHECK(op->apply_transpose(dtype, Lrow, z, s));
-      else
-        BL_CHECK(op->vjp(dtype, Q + (int64_t)idx * ld, Lrow, z, s));
-    }
+    return BL_OK;
+  }
+  int post(int idx) {
+    T* Lrow = Lambda + (int64_t)idx * ld;
     {  // Gamma[idx, :] and the coefficients of the back-substitution             arnoldi.py:212-218
       Epi e;
       e.mode = EPI_ADJ_GAMMA;
@@ -754,11 +850,9 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
       a.out_div_ptr = c.scal + S_BETA_MINUS;
       BL_CHECK(launch_combine<T>(g, c, a, false, s));
     }
+    return BL_OK;
   }
-  if (defer_grad) {  // dparams = sum_idx d<Lambda[idx], A(Q[idx]; params)>/dparams   arnoldi.py:207-209, 168
-    ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
-    BL_CHECK(op->vjp_batch(dtype, Q, ld, Lambda, ld, K, s));
-  }
+  int end() {
   // dv = lambda * c                                                              arnoldi.py:166
   k_load_scalar<T><<<1, 1, 0, s>>>(c_in, c.scal + S_C);
   BL_LAUNCHED();
@@ -770,6 +864,72 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
     a.vec[0] = term(lam, 1.0, c.scal + S_C);
     BL_CHECK(launch_combine<T>(g, c, a, false, s));
   }
+    return BL_OK;
+  }
+};
+
+template <typename T>
+int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reortho_full, const T* Q,
+                      int64_t ld, const T* H, const T* r, const T* c_in, const T* dQ, const T* dH,
+                      const T* dr, const T* dc, T* dv, T* Lambda, void* workspace, size_t wbytes,
+                      cudaStream_t s) {
+  AdjRun<T> run{op, dtype, n, K, reortho_full, Q, ld, H, r, c_in, dQ, dH, dr, dc, dv, Lambda, workspace, wbytes, s, {}, {}};
+  BL_CHECK(run.begin());
+  for (int idx = K - 1; idx >= 0; --idx) {
+    BL_CHECK(run.pre(idx));
+    // (A^T lambda, dparams += ...) = vjp of matvec at (q_idx, params)            arnoldi.py:207-209
+    {
+      ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
+      if (run.defer_grad)  // A^T lambda only; the parameter cotangent of all K steps follows in one batched pass
+        BL_CHECK(op->apply_transpose(dtype, run.lam_row(idx), run.z, s));
+      else
+        BL_CHECK(op->vjp(dtype, run.q_row(idx), run.lam_row(idx), run.z, s));
+    }
+    BL_CHECK(run.post(idx));
+  }
+  if (run.defer_grad) {  // dparams = sum_idx d<Lambda[idx], A(Q[idx]; params)>/dparams   arnoldi.py:207-209, 168
+    ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
+    BL_CHECK(op->vjp_batch(dtype, Q, ld, Lambda, ld, K, s));
+  }
+  return run.end();
+}
+
+// P independent adjoint runs in lockstep (bases of the P forward runs are contiguous: Q[p][K][ld]): one
+// batched A^T Lambda per step, and ONE batched parameter-cotangent pass over all P*K (lambda, q) pairs.
+template <typename T>
+int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reortho_full, int P, const T* Q,
+                            int64_t ld, const T* H, const T* r, const T* c_in, const T* dH, T* dv, int64_t lddv,
+                            T* Lambda, void* workspace, size_t wbytes, cudaStream_t s) {
+  const size_t per = bl_arnoldi_workspace_bytes(n, K, dtype);
+  BL_REQUIRE(wbytes >= per * (size_t)P, "workspace too small (P * bl_arnoldi_workspace_bytes)");
+  BL_REQUIRE(op->deferred_grad(dtype), "the batched adjoint needs an operator with a deferred parameter cotangent");
+  std::vector<AdjRun<T>> runs;
+  std::vector<const void*> in(P);
+  std::vector<void*> out(P);
+  for (int p = 0; p < P; ++p) {
+    runs.push_back(AdjRun<T>{op, dtype, n, K, reortho_full, Q + (int64_t)p * K * ld, ld, H + (int64_t)p * K * K,
+                             r + (int64_t)p * ld, c_in + p, nullptr, dH + (int64_t)p * K * K, nullptr, nullptr,
+                             dv + (int64_t)p * lddv, Lambda + (int64_t)p * K * ld,
+                             static_cast<char*>(workspace) + per * p, per, s, {}, {}});
+    BL_CHECK(runs.back().begin());
+    out[p] = runs[p].z;
+  }
+  for (int idx = K - 1; idx >= 0; --idx) {
+    for (int p = 0; p < P; ++p) {
+      BL_CHECK(runs[p].pre(idx));
+      in[p] = runs[p].lam_row(idx);
+    }
+    {
+      ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype) * P, s);
+      BL_CHECK(op->apply_transpose_batch(dtype, P, in.data(), out.data(), s));
+    }
+    for (int p = 0; p < P; ++p) BL_CHECK(runs[p].post(idx));
+  }
+  {
+    ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
+    BL_CHECK(op->vjp_batch(dtype, Q, ld, Lambda, ld, P * K, s));
+  }
+  for (int p = 0; p < P; ++p) BL_CHECK(runs[p].end());
   return BL_OK;
 }
 
@@ -967,6 +1127,46 @@ int bl_arnoldi_adjoint(bl_operator_t* op, int dtype, int64_t n, int64_t K, int r
                                    (const double*)r, (const double*)c, (const double*)dQ, (const double*)dH,
                                    (const double*)dr, (const double*)dc, (double*)dv, (double*)Lambda, workspace,
                                    workspace_bytes, s);
+}
+
+int bl_arnoldi_forward_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K, int second_pass, int64_t count,
+                             const void* v, int64_t ldv, void* Q, int64_t ld, void* H, void* r, void* c,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  BL_REQUIRE(op && v && Q && H && r && c && workspace && count >= 1 && count <= 4096 && ldv >= n, "bad batch arguments");
+  BL_CHECK(check_basis(dtype, n, K, ld, Q));
+  BL_REQUIRE(op->n == n, "operator size does not match n");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    return arnoldi_forward_batch_t<float>(op, dtype, n, (int)K, second_pass != 0, (int)count, (const float*)v, ldv,
+                                          (float*)Q, ld, (float*)H, (float*)r, (float*)c, workspace, workspace_bytes, s);
+  return arnoldi_forward_batch_t<double>(op, dtype, n, (int)K, second_pass != 0, (int)count, (const double*)v, ldv,
+                                         (double*)Q, ld, (double*)H, (double*)r, (double*)c, workspace, workspace_bytes, s);
+}
+
+int bl_arnoldi_adjoint_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K, int reortho_full, int64_t count,
+                             const void* Q, int64_t ld, const void* H, const void* r, const void* c, const void* dH,
+                             void* dv, int64_t lddv, void* Lambda, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  BL_REQUIRE(op && Q && H && r && c && dH && dv && Lambda && workspace && count >= 1 && count <= 4096 && lddv >= n,
+             "bad batch arguments");
+  BL_CHECK(check_basis(dtype, n, K, ld, Q));
+  BL_REQUIRE(reinterpret_cast<uintptr_t>(Lambda) % 16 == 0, "Lambda must be 16-byte aligned");
+  BL_REQUIRE(op->n == n, "operator size does not match n");
+  BL_REQUIRE(ld <= (int64_t)align_up((size_t)n, 64), "ld must be at most n rounded up to 64");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == BL_F32)
+    return arnoldi_adjoint_batch_t<float>(op, dtype, n, (int)K, reortho_full != 0, (int)count, (const float*)Q, ld,
+                                          (const float*)H, (const float*)r, (const float*)c, (const float*)dH,
+                                          (float*)dv, lddv, (float*)Lambda, workspace, workspace_bytes, s);
+  return arnoldi_adjoint_batch_t<double>(op, dtype, n, (int)K, reortho_full != 0, (int)count, (const double*)Q, ld,
+                                         (const double*)H, (const double*)r, (const double*)c, (const double*)dH,
+                                         (double*)dv, lddv, (double*)Lambda, workspace, workspace_bytes, s);
+}
+
+int bl_op_deferred_grad(bl_operator_t* op, int dtype, int* yes) {
+  BL_REQUIRE(op && yes, "NULL argument");
+  *yes = op->deferred_grad(dtype) ? 1 : 0;
+  return BL_OK;
 }
 
 size_t bl_lanczos3_workspace_bytes(int64_t n, int64_t K, int dtype) {

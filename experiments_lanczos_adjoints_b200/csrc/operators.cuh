@@ -37,6 +37,22 @@ struct bl_operator {
     }
     return BL_OK;
   }
+  // Several independent vectors at once (lockstep Krylov runs over probes): out[p] = A in[p].  The
+  // default loops; the Gram operator evaluates each kernel tile once for all of them.
+  virtual int matvec_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) {
+    for (int p = 0; p < count; ++p) {
+      const int rc = matvec(dtype, in[p], out[p], s);
+      if (rc != BL_OK) return rc;
+    }
+    return BL_OK;
+  }
+  virtual int apply_transpose_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) {
+    for (int p = 0; p < count; ++p) {
+      const int rc = apply_transpose(dtype, in[p], out[p], s);
+      if (rc != BL_OK) return rc;
+    }
+    return BL_OK;
+  }
   // Lazily evaluated matrix elements (the `lazy_kernel(i, j)` of gp_util.py:257-258 / the
   // `matrix_element` callback of low_rank.py): diagonal and one column, for the partial Cholesky.
   // For the Gram operator these are the KERNEL entries (no noise term), as in the reference.

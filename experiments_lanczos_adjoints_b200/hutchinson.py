@@ -87,6 +87,11 @@ def _resident(parameters, like):
 
 def probe_sum(integrand_fun, samples, parameters, *, with_grad=False):
     """Sum (not mean) of the integrand over probes; gradients stay on the device."""
+    if isinstance(samples, np.ndarray) and samples.ndim == 2 and len(samples) > 1 and hasattr(integrand_fun, "alg"):
+        from experiments_lanczos_adjoints_b200 import lanczos
+
+        if samples.dtype in (np.float32, np.float64) and lanczos._batch_eligible(integrand_fun, samples.dtype):
+            return lanczos.probe_batch_sum(integrand_fun, samples, parameters, with_grad=with_grad)
     total, grads, count = 0.0, None, 0
     rows = _probe_rows(samples)
     if len(rows):

@@ -251,6 +251,82 @@ class _IntegrandSPD:
         return diag.dtype.type(s2 * g), (dv0, *dparams)
 
 
+def _batch_eligible(integrand, dtype) -> bool:
+    """Lockstep batching applies to the full-reorthogonalisation adjoint path on operators that defer
+    their parameter cotangent (the Gram operator on the tensor-core path)."""
+    import ctypes as C
+
+    alg = integrand.alg
+    if not isinstance(alg, _TridiagFull) or not alg.alg.custom_vjp:
+        return False
+    op = alg.alg.op
+    if not hasattr(op, "_handle") or type(op).__name__ == "CallbackOperator":
+        return False
+    yes = C.c_int(0)
+    try:
+        _lib.call("bl_op_deferred_grad", op._handle, dev.dtype_code(dtype), C.byref(yes))
+    except Exception:
+        return False
+    return bool(yes.value)
+
+
+def probe_batch_sum(integrand, probes, parameters, *, with_grad, stream=None, chunk=16):
+    """Sum over the rows of `probes (P, n)` of the SLQ integrand (and of its parameter gradient), with the P
+    Lanczos runs advancing in lockstep (`bl_arnoldi_{forward,adjoint}_batch`): one batched matvec per step
+    for all probes and one batched parameter-cotangent pass per chunk.  Same numbers as P calls of
+    `integrand.value_and_grad` (`jax.vmap(integrand)`, hutchinson.py:14)."""
+    stream = stream or dev.default_stream()
+    probes = np.asarray(probes)
+    P, n = probes.shape
+    dtype = probes.dtype
+    hess = integrand.alg.alg  # HessenbergEstimate
+    op, K = hess.op, hess.K
+    if not isinstance(K, (int, np.integer)) or K < 1 or K > n:
+        raise ValueError(f"Parameter depth {K} is outside the expected range")
+    bound = op.bind(parameters, dtype, stream)
+    ld = dev.basis_ld(n, dtype)
+    code = dev.dtype_code(dtype)
+    per = _lib.load().bl_arnoldi_workspace_bytes(n, K, code)
+    total, grads = 0.0, None
+    if with_grad:
+        op.grad_zero(dtype, stream)
+    for p0 in range(0, P, chunk):
+        vs = probes[p0 : p0 + chunk]
+        B = len(vs)
+        scale = np.linalg.norm(vs.astype(np.float64), axis=1)  # lanczos.py:25
+        U = dev.asarray(np.ascontiguousarray((vs / scale[:, None]).astype(dtype)))
+        Q = dev.DeviceArray((B * K, n), dtype, ld=ld)
+        H = dev.DeviceArray((B, K * K), dtype)
+        r = dev.DeviceArray((B, n), dtype, ld=ld)
+        c = dev.DeviceArray((B,), dtype)
+        ws = dev.DeviceArray(((per * B + 7) // 8,), np.float64)
+        _lib.call("bl_arnoldi_forward_batch", op._handle, code, n, K, 1, B, U.ptr, n, Q.ptr, ld, H.ptr, r.ptr, c.ptr,
+                  ws.ptr, per * B, stream.ptr)  # fmt: skip
+        Hh = H.numpy(stream).reshape(B, K, K)
+        dH = np.zeros((B, K, K), dtype=dtype)
+        for b in range(B):
+            T = 0.5 * (Hh[b] + Hh[b].T)  # lanczos.py:162
+            diag, off = np.diag(T, 0), np.diag(T, 1)
+            g, dalpha, dbeta, _ = _quadform_and_cotangents(integrand.matfun, integrand.matfun_grad, diag, off, with_grad)
+            s2 = scale[b] ** 2
+            total += s2 * g
+            if with_grad:
+                dH[b] = np.diag(s2 * dalpha)
+                if K > 1:
+                    dH[b] += 0.5 * (np.diag(s2 * dbeta, 1) + np.diag(s2 * dbeta, -1))
+        if with_grad:
+            dHd = dev.asarray(dH.reshape(B, K * K))
+            dv = dev.DeviceArray((B, n), dtype, ld=ld)
+            Lam = dev.DeviceArray((B * K, n), dtype, ld=ld)
+            _lib.call("bl_arnoldi_adjoint_batch", op._handle, code, n, K, 1, B, Q.ptr, ld, H.ptr, r.ptr, c.ptr, dHd.ptr,
+                      dv.ptr, ld, Lam.ptr, ws.ptr, per * B, stream.ptr)  # fmt: skip
+            stream.synchronize()  # the buffers of this chunk go back to the pool
+    if with_grad:
+        grads = op.grad_export(dtype, stream=stream)
+    del bound
+    return total, grads, P
+
+
 def _flat(v0):
     v0 = dev.asarray(v0)
     if v0.ndim != 1:  # ravel_pytree of a single array (lanczos.py:24)

@@ -141,3 +141,33 @@ def test_deferred_batched_parameter_cotangent_matches_per_step_sweeps(kind, n, d
     amp = 50.0 if kind == "matern12" else 1.0
     for a, b in zip(out["1"], g_r):
         assert rel_err(a, np.asarray(b).ravel()) < amp * 1e-4
+
+
+@pytest.mark.parametrize("kind,n,d,K,P", [("matern32", 900, 9, 8, 5), ("rbf", 300, 3, 6, 19), ("matern32", 2100, 4, 10, 16)])
+def test_lockstep_probe_batch_matches_sequential_probes(kind, n, d, K, P, monkeypatch):
+    """Hutchinson over P probes with the Lanczos runs in lockstep (`bl_arnoldi_*_batch`: one batched Gram
+    sweep per step for all probes, one batched cotangent pass) == P sequential runs == the float64 oracle."""
+    from oracle import krylov
+
+    X, raw_ls, raw_os, noise, _, _ = problem(n, d, 7, ls_shift=1.0)
+    rng = np.random.default_rng(8)
+    probes = (rng.integers(0, 2, size=(P, n)) * 2 - 1).astype(np.float32)
+    params = (raw_ls.astype(np.float32), np.float32(raw_os), np.float32(0.3))
+    out = {}
+    for mode in ("batch", "sequential"):
+        monkeypatch.setenv("BL_GRAM_DEFER", "1" if mode == "batch" else "0")
+        op = bl.operators.GramOperator(X, kind=kind)
+        est = bl.hutchinson.hutchinson(bl.lanczos.integrand_spd(np.log, K, op), lambda key: probes)
+        launches = bl.launch_count()
+        value, grads = est.value_and_grad(None, *params)
+        out[mode] = (float(value), [np.asarray(g.numpy(), np.float64).ravel() for g in grads], bl.launch_count() - launches)
+        assert abs(float(est(None, *params)) - float(value)) < 1e-5 * abs(float(value))
+    assert out["batch"][2] < out["sequential"][2]  # fewer launches: the probes share their Gram sweeps
+    assert abs(out["batch"][0] - out["sequential"][0]) < 1e-5 * abs(out["sequential"][0])
+    for a, b in zip(out["batch"][1], out["sequential"][1]):
+        assert rel_err(a, b) < 2e-4
+    integrand = krylov.IntegrandSPD(np.log, lambda x: 1.0 / x, K, operators.GramOperator(X, kind=kind))
+    v_r, g_r = krylov.hutchinson_value_and_grad(integrand, probes.astype(np.float64), raw_ls, raw_os, 0.3)
+    assert abs(out["batch"][0] - v_r) < 1e-5 * abs(v_r)
+    for a, b in zip(out["batch"][1], g_r):
+        assert rel_err(a, np.asarray(b).ravel()) < 1e-4
