@@ -40,7 +40,7 @@ class constraint_greater_than:
     def __call__(self, x):
         x = np.asarray(x, dtype=np.float64)
         safe = np.where(x < 20.0, x, 1.0)
-        return self.minval + np.where(x < 20.0, np.log1p(np.exp(safe)), x)
+        return self.minval + np.where(x < 20.0, np.log(1.0 + np.exp(safe)), x)  # log(1 + exp), as gp_util.py:196
 
     def grad(self, x):
         x = np.asarray(x, dtype=np.float64)
