@@ -68,8 +68,8 @@ class _Solver:
         return x, r, steps.value
 
     def __call__(self, A, b, P=None, *, stream=None):
+        A = _as_bound(A)  # argument errors first, before any device work
         stream = stream or dev.default_stream()
-        A = _as_bound(A)
         b = dev.asarray(b)
         x, r, steps = self._solve(A, b, P, stream)
         info = _Info(x, residual_abs=r)
@@ -78,8 +78,8 @@ class _Solver:
         return x, info
 
     def vjp(self, A, b, P=None, *, stream=None):
-        stream = stream or dev.default_stream()
         A = _as_bound(A)
+        stream = stream or dev.default_stream()
         b = dev.asarray(b)
         x, info = self(A, b, P, stream=stream)
 

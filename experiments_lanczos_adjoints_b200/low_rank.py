@@ -45,6 +45,8 @@ def _factorise(lazy_kernel, n, rank, pivot, dtype, stream):
 
 
 def _dtype_of(lazy_kernel, dtype):
+    if not isinstance(lazy_kernel, BoundOperator):
+        raise TypeError("lazy_kernel must be operators.bound(op, *params) with an element-providing operator")
     if dtype is not None:
         return np.dtype(dtype)
     for p in lazy_kernel.params:
