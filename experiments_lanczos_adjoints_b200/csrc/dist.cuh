@@ -65,10 +65,14 @@ __device__ __forceinline__ double ld_volatile(const double* p) {
 // spin until *flag >= seq; false after the timeout (and the mailbox's error word is set)
 __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq,
                                           unsigned char* own_mail) {
+  // once a wait has timed out the communicator is dead: later exchanges fail at once instead of
+  // stalling ~10 s each
+  volatile unsigned long long* err = error_flag(own_mail);
+  if (*err != 0ull) return ld_acquire_sys(flag) >= seq;
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < seq) {
     if (clock64() - t0 > kSpinTimeout) {
-      *error_flag(own_mail) = 1ull;
+      *err = 1ull;
       return false;
     }
   }

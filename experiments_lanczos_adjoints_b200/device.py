@@ -110,17 +110,23 @@ def _destroy_event(ptr):
 
 # --- a small caching allocator: cudaMalloc/cudaFree synchronise, the loops must not -----
 class _Pool:
+    """One pool per HOST THREAD: a returned buffer is reused without synchronisation, which is safe only
+    for work on the same stream (stream order) -- and every thread has its own default stream.  A buffer
+    finalised from another thread (garbage collection) still goes back to its owner's pool."""
+
     def __init__(self, max_cached_bytes=24 << 30):
         self.free = {}
         self.cached = 0
         self.max_cached = max_cached_bytes
+        self.lock = threading.Lock()
 
     def alloc(self, nbytes: int) -> tuple[int, int]:
         size = max(256, (int(nbytes) + 255) // 256 * 256)
-        bucket = self.free.get(size)
-        if bucket:
-            self.cached -= size
-            return bucket.pop(), size
+        with self.lock:
+            bucket = self.free.get(size)
+            if bucket:
+                self.cached -= size
+                return bucket.pop(), size
         p = C.c_void_p()
         try:
             _lib.call("bl_malloc", C.byref(p), size)
@@ -130,37 +136,52 @@ class _Pool:
         return p.value, size
 
     def give_back(self, ptr: int, size: int):
-        if self.cached + size > self.max_cached:
-            try:
-                _lib.load().bl_free(ptr)
-            except Exception:
-                pass
-            return
-        self.free.setdefault(size, []).append(ptr)
-        self.cached += size
+        with self.lock:
+            if self.cached + size <= self.max_cached:
+                self.free.setdefault(size, []).append(ptr)
+                self.cached += size
+                return
+        try:
+            _lib.load().bl_free(ptr)
+        except Exception:
+            pass
 
     def release_all(self):
-        for bucket in self.free.values():
+        with self.lock:
+            buckets, self.free, self.cached = self.free, {}, 0
+        for bucket in buckets.values():
             for ptr in bucket:
                 _lib.load().bl_free(ptr)
-        self.free.clear()
-        self.cached = 0
 
 
-_pool = _Pool()
+_pools = []
+_pools_lock = threading.Lock()
+
+
+def _thread_pool() -> _Pool:
+    pool = getattr(_tls, "pool", None)
+    if pool is None:
+        pool = _tls.pool = _Pool()
+        with _pools_lock:
+            _pools.append(pool)
+    return pool
 
 
 def empty_cache():
     synchronize()
-    _pool.release_all()
+    with _pools_lock:
+        pools = list(_pools)
+    for pool in pools:
+        pool.release_all()
 
 
 class _Owner:
     """Owns one pool allocation; shared by every view of it."""
 
     def __init__(self, nbytes):
-        self.ptr, self.size = _pool.alloc(nbytes)
-        self._fin = weakref.finalize(self, _pool.give_back, self.ptr, self.size)
+        pool = _thread_pool()
+        self.ptr, self.size = pool.alloc(nbytes)
+        self._fin = weakref.finalize(self, pool.give_back, self.ptr, self.size)
 
 
 class DeviceArray:
