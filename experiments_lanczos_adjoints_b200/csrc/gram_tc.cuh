@@ -180,8 +180,12 @@ __host__ __device__ inline Plan make_plan_rows(int slots, int aux_rows) {
 }
 // sweeps: v [kN] (+ q [kN] + x^T [kXtRows][kN] for the adjoint sweep)
 __host__ __device__ inline Plan make_plan(int slots, bool adj) { return make_plan_rows(slots, adj ? 2 + kXtRows : 1); }
-constexpr int kBatchMax = 16;  // (lambda, q) pairs per pass of the batched parameter-cotangent sweep
+constexpr int kBatchMax = 16;  // vectors / (lambda, q) pairs per pass of the batched sweeps
 __host__ __device__ inline Plan make_plan_batch(int slots) { return make_plan_rows(slots, kBatchMax + kXtRows); }
+__host__ __device__ inline Plan make_plan_multi(int slots) { return make_plan_rows(slots, kBatchMax); }
+struct VecPtrs {
+  const float* p[kBatchMax];
+};
 
 // (unscaled) kernel values from the accumulator acc = x.y - |y|^2/2, two entries at a time.
 //   KIND 0: Matern-3/2 (1+s) e^{-s}   KIND 1: Matern-1/2 e^{-s}   KIND 2: RBF e^{-s2/2}
@@ -226,7 +230,267 @@ __device__ __forceinline__ float2 dkernel_from_eval(const Eval2& o) {
   return dk;
 }
 
-// grid = (row tiles of 128, column splits).
+// ---- the pipeline shared by every sweep ---------------------------------------------------------
+// One CTA per SM; grid = (row tiles of 128, column splits).  warp 0 = TMA producer, warp 1 = MMA issue,
+// warps 2..9 = epilogue.  A stage of the ring holds the B operand tile (kN points) followed by the
+// kernel-specific auxiliary rows (vectors, transposed coordinates); the accumulator is double-buffered in
+// TMEM.  The kernels below differ in their auxiliary loader and in their epilogue only.
+struct Pipe {
+  Plan pl;
+  uint8_t* smA;
+  uint8_t* smS;
+  uint64_t *full, *empty, *acc_full, *acc_empty, *a_full;  // see pipe_setup
+  uint32_t tmem_base;
+  int64_t i0, t0;  // first row of this CTA, first column tile of its split
+  int ntiles;
+
+  __device__ __forceinline__ uint8_t* stage(int s) const { return smS + (size_t)s * pl.stage_bytes; }
+  __device__ __forceinline__ float* aux(int s) const { return reinterpret_cast<float*>(stage(s) + pl.b_bytes); }
+};
+struct Slot {  // ring stage / accumulator buffer and their mbarrier parities for tile `it`
+  int s, b;
+  uint32_t ph, bph;
+};
+__device__ __forceinline__ Slot slot_of(const Pipe& p, int it) {
+  return Slot{it % p.pl.stages, it & 1, (uint32_t)(it / p.pl.stages) & 1u, (uint32_t)(it >> 1) & 1u};
+}
+
+// barriers, TMEM allocation, tile range; ends with a block-wide sync.  `full`: TMA -> MMA and epilogue;
+// `empty`: MMA commit + 8 epilogue warps -> TMA; `acc_full`: MMA commit -> epilogue; `acc_empty`: 8 epilogue
+// warps -> MMA; `a_full`: the A tile (loaded once).
+__device__ __forceinline__ Pipe pipe_setup(uint8_t* smem, const Plan& pl, int64_t n) {
+  Pipe p;
+  p.pl = pl;
+  p.smA = smem;
+  p.smS = smem + pl.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
+  p.full = bars, p.empty = bars + 3, p.acc_full = bars + 6, p.acc_empty = bars + 8, p.a_full = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  p.i0 = (int64_t)blockIdx.x * kM;
+  const int64_t tiles_total = (n + kN - 1) / kN;
+  const int64_t per = (tiles_total + gridDim.y - 1) / gridDim.y;
+  p.t0 = per * blockIdx.y;
+  const int64_t t1 = p.t0 + per < tiles_total ? p.t0 + per : tiles_total;
+  p.ntiles = p.t0 < t1 ? (int)(t1 - p.t0) : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < pl.stages; ++s) {
+      tma::mbar_init(p.full + s, 1);
+      tma::mbar_init(p.empty + s, 1 + kEpiWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tma::mbar_init(p.acc_full + b, 1);
+      tma::mbar_init(p.acc_empty + b, kEpiWarps);
+    }
+    tma::mbar_init(p.a_full, 1);
+    tma::fence_barrier_init();
+  }
+  if ((threadIdx.x >> 5) == 1) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  p.tmem_base = *tmem_slot;
+  return p;
+}
+__device__ __forceinline__ void pipe_teardown(const Pipe& p) {
+  fence_before_sync();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    fence_after_sync();
+    tmem_dealloc(p.tmem_base, kTmemCols);
+  }
+}
+
+// A row of `kN` floats of a stage's auxiliary area filled from a global vector of `len` valid entries
+// starting at column jt: whole 16-byte granules by TMA (`issue`), the ragged end and the zero padding by the
+// producer warp (`fill`, generic stores that the arrive.expect_tx of lane 0 publishes).
+struct RaggedRow {
+  const float* src;  // element 0 of the vector
+  int64_t len;       // entries that may be read (the rest of the tile is zero)
+  __device__ __forceinline__ int granules(int64_t jt) const {
+    const int64_t w = len - jt < kN ? len - jt : kN;
+    return (int)(w > 0 ? w : 0) & ~3;
+  }
+  __device__ __forceinline__ void fill(float* dst, int64_t jt, int lane) const {
+    for (int c = granules(jt) + lane; c < kN; c += 32) dst[c] = jt + c < len ? src[jt + c] : 0.f;
+  }
+  __device__ __forceinline__ uint32_t issue(float* dst, int64_t jt, uint64_t* bar) const {
+    const uint32_t bytes = (uint32_t)granules(jt) * 4;
+    if (bytes) tma::bulk_g2s(dst, src + jt, bytes, bar);
+    return bytes;
+  }
+};
+
+// warp 0.  Aux: `bool ragged(jt)`, `void fill(float* aux, jt, lane)`, `uint32_t bytes(jt)`,
+// `void issue(float* aux, jt, bar)` for the auxiliary rows of one stage.
+template <class Aux>
+__device__ __forceinline__ void producer_warp(const Pipe& p, const float* __restrict__ opA,
+                                              const float* __restrict__ opB, int64_t npad, const Aux& aux) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0 && p.ntiles > 0) {
+    tma::mbar_arrive_expect_tx(p.a_full, p.pl.a_bytes);
+    for (int c = 0; c < 2 * p.pl.ksteps; ++c)
+      tma::bulk_g2s(p.smA + (size_t)c * kM * 16, opA + ((int64_t)c * npad + p.i0) * 4, kM * 16, p.a_full);
+  }
+  for (int it = 0; it < p.ntiles; ++it) {
+    const Slot sl = slot_of(p, it);
+    tma::mbar_wait(p.empty + sl.s, sl.ph ^ 1u);
+    const int64_t jt = (p.t0 + it) * kN;
+    if (aux.ragged(jt)) {
+      aux.fill(p.aux(sl.s), jt, lane);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      tma::mbar_arrive_expect_tx(p.full + sl.s, p.pl.b_bytes + aux.bytes(jt));
+      uint8_t* smB = p.stage(sl.s);
+      for (int c = 0; c < 2 * p.pl.ksteps; ++c)
+        tma::bulk_g2s(smB + (size_t)c * kN * 16, opB + ((int64_t)c * npad + jt) * 4, kN * 16, p.full + sl.s);
+      aux.issue(p.aux(sl.s), jt, p.full + sl.s);
+    }
+  }
+}
+
+// warp 1: one group of `ksteps` TF32 MMAs (128 x 256 x 8 each) per tile, issued by lane 0
+__device__ __forceinline__ void mma_warp(const Pipe& p) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t idesc = instr_desc(kM, kN);
+  if (p.ntiles > 0) tma::mbar_wait(p.a_full, 0);
+  for (int it = 0; it < p.ntiles; ++it) {
+    const Slot sl = slot_of(p, it);
+    tma::mbar_wait(p.full + sl.s, sl.ph);
+    tma::mbar_wait(p.acc_empty + sl.b, sl.bph ^ 1u);
+    fence_after_sync();
+    if (lane == 0) {
+      const uint32_t sa = tma::smem_u32(p.smA), sb = tma::smem_u32(p.stage(sl.s));
+      for (int k = 0; k < p.pl.ksteps; ++k) {
+        const uint64_t da = smem_desc(sa + (uint32_t)k * 2 * kM * 16, kM * 16, 128);
+        const uint64_t db = smem_desc(sb + (uint32_t)k * 2 * kN * 16, kN * 16, 128);
+        mma_tf32(p.tmem_base + (uint32_t)sl.b * kN, da, db, idesc, k > 0 ? 1u : 0u);
+      }
+      mma_commit(p.empty + sl.s);
+      mma_commit(p.acc_full + sl.b);
+    }
+    __syncwarp();
+  }
+}
+
+// Epilogue warps 2..9: thread = row (TMEM lane `qd*32 + lane`), the two warpgroups split the kN columns.
+struct EpiThread {
+  int qd, half, row;
+  bool live;
+  float2 crow;        // per-row constant of kernel_from_acc
+  uint32_t acc_diag;  // accumulator value that makes s2 exactly zero (the diagonal i == j)
+};
+template <int KIND>
+__device__ __forceinline__ EpiThread epi_thread(const Pipe& p, int64_t n, const float* __restrict__ xx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  EpiThread e;
+  e.qd = warp & 3;            // TMEM lane quadrant this warp may access
+  e.half = (warp - 2) >> 2;   // column half of the tile
+  e.row = e.qd * 32 + lane;
+  e.live = p.i0 + e.row < n;
+  const float xxi = e.live ? xx[p.i0 + e.row] : 0.f;
+  const float cr = KIND == 2 ? -0.5f * xxi : xxi + 1.1920928955078125e-07f;
+  e.crow = make_float2(cr, cr);
+  e.acc_diag = __float_as_uint(0.5f * xxi);
+  return e;
+}
+__device__ __forceinline__ void epi_wait(const Pipe& p, const Slot& sl) {
+  tma::mbar_wait(p.full + sl.s, sl.ph);
+  tma::mbar_wait(p.acc_full + sl.b, sl.bph);
+  fence_after_sync();
+}
+__device__ __forceinline__ void epi_release(const Pipe& p, const Slot& sl) {
+  fence_before_sync();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    tma::mbar_arrive(p.acc_empty + sl.b);
+    tma::mbar_arrive(p.empty + sl.s);
+  }
+}
+// 32 accumulator columns (col0 ..) of this thread's row; on tiles that hold pairs with i == j the
+// diagonal entry is replaced by the value that makes s2 exactly zero
+__device__ __forceinline__ void epi_load(const Pipe& p, const EpiThread& e, const Slot& sl, int it, int col0,
+                                         uint32_t (&r)[32]) {
+  tmem_ld32(p.tmem_base + ((uint32_t)(e.qd * 32) << 16) + (uint32_t)(sl.b * kN + col0), r);
+  const int64_t jt = (p.t0 + it) * kN;
+  if (jt < p.i0 + kM && p.i0 < jt + kN) {
+    const int jd = (int)(p.i0 + e.row - jt) - col0;  // column of this chunk with j == i (if any)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) r[c] = c == jd ? e.acc_diag : r[c];
+  }
+}
+// block-wide sums of the epilogue threads' `count` doubles -> gpart[cta][0..d) and gpart[cta][d] (slot `last`)
+template <int D>
+__device__ __forceinline__ void epi_reduce_grad(const double (&dacc)[D], double uacc, int d, double* __restrict__ gpart) {
+  __shared__ double gred[kEpiWarps][kXtRows + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ew = warp - 2;
+  double t = warp_sum(uacc);
+  if (lane == 0) gred[ew][D] = t;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    t = warp_sum(dacc[k]);
+    if (lane == 0) gred[ew][k] = t;
+  }
+  tma::named_bar_sync(1, kEpiWarps * 32);
+  if (warp == 2 && lane <= D) {
+    double sacc = 0.0;
+    for (int e = 0; e < kEpiWarps; ++e) sacc += gred[e][lane];
+    const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (lane == D)
+      gpart[blk * (d + 1) + d] = sacc;
+    else if (lane < d)
+      gpart[blk * (d + 1) + lane] = sacc;
+  }
+}
+
+// ---- auxiliary loaders --------------------------------------------------------------------------
+// sweep: v [kN] (+ q [kN] + x^T [D][kN] for the adjoint sweep)
+template <bool ADJ, int D>
+struct SweepAux {
+  RaggedRow v, q;
+  const float* xt;
+  int64_t npad;
+  __device__ __forceinline__ bool ragged(int64_t jt) const { return v.granules(jt) < kN; }
+  __device__ __forceinline__ void fill(float* aux, int64_t jt, int lane) const {
+    v.fill(aux, jt, lane);
+    if (ADJ) q.fill(aux + kN, jt, lane);
+  }
+  __device__ __forceinline__ uint32_t bytes(int64_t jt) const {
+    return (uint32_t)v.granules(jt) * 4 * (ADJ ? 2 : 1) + (ADJ ? D * kN * 4 : 0);
+  }
+  __device__ __forceinline__ void issue(float* aux, int64_t jt, uint64_t* bar) const {
+    v.issue(aux, jt, bar);
+    if (ADJ) {
+      q.issue(aux + kN, jt, bar);
+      for (int k = 0; k < D; ++k) tma::bulk_g2s(aux + (size_t)(2 + k) * kN, xt + (int64_t)k * npad + jt, kN * 4, bar);
+    }
+  }
+};
+// batched sweeps: M rows (vectors, or the q rows of (lambda, q) pairs) [+ x^T [D][kN] after kBatchMax rows]
+template <int D>
+struct RowsAux {
+  VecPtrs rows;
+  int M;
+  int64_t len;       // readable entries per row
+  const float* xt;   // nullptr: no coordinate rows
+  int64_t npad;
+  __device__ __forceinline__ RaggedRow row(int m) const { return RaggedRow{rows.p[m], len}; }
+  __device__ __forceinline__ bool ragged(int64_t jt) const { return row(0).granules(jt) < kN; }
+  __device__ __forceinline__ void fill(float* aux, int64_t jt, int lane) const {
+    for (int m = 0; m < M; ++m) row(m).fill(aux + (size_t)m * kN, jt, lane);
+  }
+  __device__ __forceinline__ uint32_t bytes(int64_t jt) const {
+    return (uint32_t)row(0).granules(jt) * 4 * M + (xt ? D * kN * 4 : 0);
+  }
+  __device__ __forceinline__ void issue(float* aux, int64_t jt, uint64_t* bar) const {
+    for (int m = 0; m < M; ++m) row(m).issue(aux + (size_t)m * kN, jt, bar);
+    if (xt)
+      for (int k = 0; k < D; ++k)
+        tma::bulk_g2s(aux + (size_t)(kBatchMax + k) * kN, xt + (int64_t)k * npad + jt, kN * 4, bar);
+  }
+};
+
+// ---- the sweeps -----------------------------------------------------------------------------------
 //   ADJ == false: part[split][i] = sigma sum_{j in split} k_ij v_j
 //   ADJ == true : the same with v = lam, plus per-CTA partial sums (layout of the ALU kernel)
 //                 gpart[cta][d]  = sum lam_i q_j k_ij               (k includes sigma)
@@ -236,171 +500,55 @@ template <int KIND, bool ADJ, int D>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_sweep(int64_t n, int64_t npad, int d, int slots, const float* __restrict__ opA,
                 const float* __restrict__ opB, const float* __restrict__ xt, const float* __restrict__ xx,
-                const float* __restrict__ consts,
-                const float* __restrict__ v, const float* __restrict__ q, float* __restrict__ part,
-                double* __restrict__ gpart, float* __restrict__ dbg, int dbg_bx, int dbg_by) {
+                const float* __restrict__ consts, const float* __restrict__ v, const float* __restrict__ q,
+                float* __restrict__ part, double* __restrict__ gpart, float* __restrict__ dbg, int dbg_bx, int dbg_by) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const Plan pl = make_plan(slots, ADJ);
-  uint8_t* smA = smem;
-  uint8_t* smS = smem + pl.a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
-  uint64_t* full = bars;            // [stages]  TMA -> MMA, epilogue
-  uint64_t* empty = bars + 3;       // [stages]  MMA commit + 8 epilogue warps -> TMA
-  uint64_t* acc_full = bars + 6;    // [2]       MMA commit -> epilogue
-  uint64_t* acc_empty = bars + 8;   // [2]       8 epilogue warps -> MMA
-  uint64_t* a_full = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   __shared__ double ycomb[kM];
-  __shared__ double gred[kEpiWarps][kXtRows + 1];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i0 = (int64_t)blockIdx.x * kM;
-  const int64_t tiles_total = (n + kN - 1) / kN;
-  const int64_t per = (tiles_total + gridDim.y - 1) / gridDim.y;
-  const int64_t t0 = per * blockIdx.y;
-  const int64_t t1 = t0 + per < tiles_total ? t0 + per : tiles_total;
-  const int ntiles = t0 < t1 ? (int)(t1 - t0) : 0;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < pl.stages; ++s) {
-      tma::mbar_init(full + s, 1);
-      tma::mbar_init(empty + s, 1 + kEpiWarps);
-    }
-    for (int b = 0; b < 2; ++b) {
-      tma::mbar_init(acc_full + b, 1);
-      tma::mbar_init(acc_empty + b, kEpiWarps);
-    }
-    tma::mbar_init(a_full, 1);
-    tma::fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
+  const Pipe p = pipe_setup(smem, make_plan(slots, ADJ), n);
+  const int warp = threadIdx.x >> 5;
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0 && ntiles > 0) {
-      tma::mbar_arrive_expect_tx(a_full, pl.a_bytes);
-      for (int c = 0; c < 2 * pl.ksteps; ++c)
-        tma::bulk_g2s(smA + (size_t)c * kM * 16, opA + ((int64_t)c * npad + i0) * 4, kM * 16, a_full);
-    }
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      tma::mbar_wait(empty + s, ph ^ 1u);
-      uint8_t* smB = smS + (size_t)s * pl.stage_bytes;
-      float* smV = reinterpret_cast<float*>(smB + pl.b_bytes);
-      float* smQ = smV + kN;
-      float* smX = smV + 2 * kN;
-      const int64_t jt = (t0 + it) * kN;
-      const int w = (int)((n - jt) < kN ? (n - jt) : kN);
-      const int wv = w & ~3;  // whole 16-byte granules by TMA, the ragged end by this warp
-      if (w < kN) {
-        for (int c = wv + lane; c < kN; c += 32) {
-          smV[c] = c < w ? v[jt + c] : 0.f;
-          if (ADJ) smQ[c] = c < w ? q[jt + c] : 0.f;
-        }
-        __syncwarp();
-      }
-      if (lane == 0) {
-        tma::mbar_arrive_expect_tx(full + s, pl.b_bytes + (uint32_t)wv * 4 * (ADJ ? 2 : 1) + (ADJ ? D * kN * 4 : 0));
-        for (int c = 0; c < 2 * pl.ksteps; ++c)
-          tma::bulk_g2s(smB + (size_t)c * kN * 16, opB + ((int64_t)c * npad + jt) * 4, kN * 16, full + s);
-        if (wv > 0) tma::bulk_g2s(smV, v + jt, (uint32_t)wv * 4, full + s);
-        if (ADJ) {
-          if (wv > 0) tma::bulk_g2s(smQ, q + jt, (uint32_t)wv * 4, full + s);
-          for (int k = 0; k < D; ++k) tma::bulk_g2s(smX + (size_t)k * kN, xt + (int64_t)k * npad + jt, kN * 4, full + s);
-        }
-      }
-    }
+    producer_warp(p, opA, opB, npad, SweepAux<ADJ, D>{RaggedRow{v, n}, RaggedRow{q, n}, xt, npad});
   } else if (warp == 1) {
-    // ===== MMA issue =====
-    const uint32_t idesc = instr_desc(kM, kN);
-    if (ntiles > 0) tma::mbar_wait(a_full, 0);
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      const int b = it & 1;
-      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-      tma::mbar_wait(full + s, ph);
-      tma::mbar_wait(acc_empty + b, bph ^ 1u);
-      fence_after_sync();
-      if (lane == 0) {
-        const uint32_t sa = tma::smem_u32(smA), sb = tma::smem_u32(smS + (size_t)s * pl.stage_bytes);
-        for (int k = 0; k < pl.ksteps; ++k) {
-          const uint64_t da = smem_desc(sa + (uint32_t)k * 2 * kM * 16, kM * 16, 128);
-          const uint64_t db = smem_desc(sb + (uint32_t)k * 2 * kN * 16, kN * 16, 128);
-          mma_tf32(tmem_base + (uint32_t)b * kN, da, db, idesc, k > 0 ? 1u : 0u);
-        }
-        mma_commit(empty + s);
-        mma_commit(acc_full + b);
-      }
-      __syncwarp();
-    }
+    mma_warp(p);
   } else {
-    // ===== epilogue: thread = row (TMEM lane), registers = columns =====
-    const int qd = warp & 3;           // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;  // column half of the tile
-    const int row = qd * 32 + lane;
-    const bool live = i0 + row < n;
-    const float xxi = live ? xx[i0 + row] : 0.f;
-    const float cr = KIND == 2 ? -0.5f * xxi : xxi + 1.1920928955078125e-07f;
-    const float2 crow = make_float2(cr, cr);
-    const uint32_t acc_diag = __float_as_uint(0.5f * xxi);  // accumulator value that makes s2 exactly zero
+    const EpiThread e = epi_thread<KIND>(p, n, xx);
     double yacc = 0.0, uacc = 0.0, dacc[ADJ ? D : 1];
     float2 nxi[ADJ ? D : 1];  // (-x_ik, -x_ik)
-    if (ADJ) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        const float x = xt[(int64_t)k * npad + i0 + row];
-        nxi[k] = make_float2(-x, -x);
-        dacc[k] = 0.0;
-      }
+    for (int k = 0; k < (ADJ ? D : 1); ++k) {
+      const float x = ADJ ? xt[(int64_t)k * npad + p.i0 + e.row] : 0.f;
+      nxi[k] = make_float2(-x, -x);
+      dacc[k] = 0.0;
     }
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      const int b = it & 1;
-      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-      const float* smV = reinterpret_cast<const float*>(smS + (size_t)s * pl.stage_bytes + pl.b_bytes);
+    for (int it = 0; it < p.ntiles; ++it) {
+      const Slot sl = slot_of(p, it);
+      const float* smV = p.aux(sl.s);
       const float* smQ = smV + kN;
       const float* smX = smV + 2 * kN;
-      tma::mbar_wait(full + s, ph);
-      tma::mbar_wait(acc_full + b, bph);
-      fence_after_sync();
-      const int64_t jt = (t0 + it) * kN;
-      const bool diag_tile = jt < i0 + kM && i0 < jt + kN;  // the tile holds pairs with i == j
+      epi_wait(p, sl);
       float2 y0 = make_float2(0.f, 0.f), y1 = y0, u0 = y0, u1 = y0, dl[ADJ ? D : 1];
-      if (ADJ) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) dl[k] = make_float2(0.f, 0.f);
-      }
+      for (int k = 0; k < (ADJ ? D : 1); ++k) dl[k] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = half * 128 + cc * 32;
+        const int col0 = e.half * 128 + cc * 32;
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * kN + col0), r);
         if (dbg != nullptr && it == 0 && (int)blockIdx.x == dbg_bx && (int)blockIdx.y == dbg_by) {
+          tmem_ld32(p.tmem_base + ((uint32_t)(e.qd * 32) << 16) + (uint32_t)(sl.b * kN + col0), r);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) dbg[(size_t)row * kN + col0 + c] = __uint_as_float(r[c]);
+          for (int c = 0; c < 32; ++c) dbg[(size_t)e.row * kN + col0 + c] = __uint_as_float(r[c]);
         }
-        if (diag_tile) {
-          const int jd = (int)(i0 + row - jt) - col0;  // column of this chunk with j == i (if any)
+        epi_load(p, e, sl, it, col0, r);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = c == jd ? acc_diag : r[c];
-        }
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const float4 v4 = *reinterpret_cast<const float4*>(smV + col0 + 4 * p);
-          const float2 a01 = make_float2(__uint_as_float(r[4 * p]), __uint_as_float(r[4 * p + 1]));
-          const float2 a23 = make_float2(__uint_as_float(r[4 * p + 2]), __uint_as_float(r[4 * p + 3]));
-          const Eval2 e01 = kernel_from_acc<KIND>(a01, crow), e23 = kernel_from_acc<KIND>(a23, crow);
+        for (int pp = 0; pp < 8; ++pp) {
+          const float4 v4 = *reinterpret_cast<const float4*>(smV + col0 + 4 * pp);
+          const float2 a01 = make_float2(__uint_as_float(r[4 * pp]), __uint_as_float(r[4 * pp + 1]));
+          const float2 a23 = make_float2(__uint_as_float(r[4 * pp + 2]), __uint_as_float(r[4 * pp + 3]));
+          const Eval2 e01 = kernel_from_acc<KIND>(a01, e.crow), e23 = kernel_from_acc<KIND>(a23, e.crow);
           y0 = __ffma2_rn(e01.k, make_float2(v4.x, v4.y), y0);
           y1 = __ffma2_rn(e23.k, make_float2(v4.z, v4.w), y1);
           if (ADJ) {
-            const float4 q4 = *reinterpret_cast<const float4*>(smQ + col0 + 4 * p);
+            const float4 q4 = *reinterpret_cast<const float4*>(smQ + col0 + 4 * pp);
             const float2 q01 = make_float2(q4.x, q4.y), q23 = make_float2(q4.z, q4.w);
             u0 = __ffma2_rn(e01.k, q01, u0);
             u1 = __ffma2_rn(e23.k, q23, u1);
@@ -408,7 +556,7 @@ k_gram_tc_sweep(int64_t n, int64_t npad, int d, int slots, const float* __restri
             const float2 g23 = __fmul2_rn(dkernel_from_eval<KIND>(e23), q23);
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-              const float4 x4 = *reinterpret_cast<const float4*>(smX + (size_t)k * kN + col0 + 4 * p);
+              const float4 x4 = *reinterpret_cast<const float4*>(smX + (size_t)k * kN + col0 + 4 * pp);
               const float2 d01 = __fadd2_rn(make_float2(x4.x, x4.y), nxi[k]);
               const float2 d23 = __fadd2_rn(make_float2(x4.z, x4.w), nxi[k]);
               dl[k] = __ffma2_rn(g01, __fmul2_rn(d01, d01), dl[k]);
@@ -417,12 +565,7 @@ k_gram_tc_sweep(int64_t n, int64_t npad, int d, int slots, const float* __restri
           }
         }
       }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        tma::mbar_arrive(acc_empty + b);
-        tma::mbar_arrive(empty + s);
-      }
+      epi_release(p, sl);
       yacc += (double)(y0.x + y0.y) + (double)(y1.x + y1.y);
       if (ADJ) {
         uacc += (double)(u0.x + u0.y) + (double)(u1.x + u1.y);
@@ -432,46 +575,25 @@ k_gram_tc_sweep(int64_t n, int64_t npad, int d, int slots, const float* __restri
     }
     // combine the two column halves, scale, store
     const double sigma = (double)consts[0];
-    if (half == 1) ycomb[row] = yacc;
+    if (e.half == 1) ycomb[e.row] = yacc;
     tma::named_bar_sync(1, kEpiWarps * 32);
-    if (half == 0 && live) part[(int64_t)blockIdx.y * n + i0 + row] = (float)((yacc + ycomb[row]) * sigma);
+    if (e.half == 0 && e.live) part[(int64_t)blockIdx.y * n + p.i0 + e.row] = (float)((yacc + ycomb[e.row]) * sigma);
     if (ADJ) {
-      const double li = live ? (double)v[i0 + row] * sigma : 0.0;
-      const int ew = warp - 2;
-      double t = warp_sum(li * uacc);
-      if (lane == 0) gred[ew][D] = t;
+      const double li = e.live ? (double)v[p.i0 + e.row] * sigma : 0.0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        t = warp_sum(li * dacc[k]);
-        if (lane == 0) gred[ew][k] = t;
-      }
-      tma::named_bar_sync(1, kEpiWarps * 32);
-      if (warp == 2 && lane <= D) {
-        double sacc = 0.0;
-        for (int e = 0; e < kEpiWarps; ++e) sacc += gred[e][lane];
-        const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-        if (lane == D)
-          gpart[blk * (d + 1) + d] = sacc;
-        else if (lane < d)
-          gpart[blk * (d + 1) + lane] = sacc;
-      }
+      for (int k = 0; k < D; ++k) dacc[k] *= li;
+      epi_reduce_grad<ADJ ? D : 1>(dacc, li * uacc, d, gpart);
     }
   }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
+  pipe_teardown(p);
 }
-
 
 // Deferred parameter cotangent of M <= kBatchMax matvec VJPs at once (the adjoint sweep of the Krylov
 // loops defers them: arnoldi.py:207-209 only needs A^T lambda inside the loop):
 //     sum_m d<lam_m, K(theta) q_m>/dtheta = sum_ij W_ij dk_ij/dtheta,   W_ij = sum_m lam_m[i] q_m[j],
 // so the kernel tile (distances on the tensor pipe, sqrt / exp on the MUFU) and the per-dimension
 // (x_ik - x_jk)^2 accumulation are paid ONCE for the M pairs; only the rank-M weight costs M FMAs per
-// kernel entry.  Same warp roles and pipeline as k_gram_tc_sweep; per-CTA partial sums in gpart.
+// kernel entry.  Per-CTA partial sums in gpart (layout of the adjoint sweep).
 template <int KIND, int D>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_gradbatch(int64_t n, int64_t npad, int d, int slots, const float* __restrict__ opA,
@@ -479,158 +601,52 @@ k_gram_tc_gradbatch(int64_t n, int64_t npad, int d, int slots, const float* __re
                     const float* __restrict__ consts, const float* __restrict__ Qrows, int64_t ldq,
                     const float* __restrict__ Lrows, int64_t ldl, int M, double* __restrict__ gpart) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const Plan pl = make_plan_batch(slots);
-  uint8_t* smA = smem;
-  uint8_t* smS = smem + pl.a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 3;
-  uint64_t* acc_full = bars + 6;
-  uint64_t* acc_empty = bars + 8;
-  uint64_t* a_full = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-  __shared__ double gred[kEpiWarps][kXtRows + 1];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i0 = (int64_t)blockIdx.x * kM;
-  const int64_t tiles_total = (n + kN - 1) / kN;
-  const int64_t per = (tiles_total + gridDim.y - 1) / gridDim.y;
-  const int64_t t0 = per * blockIdx.y;
-  const int64_t t1 = t0 + per < tiles_total ? t0 + per : tiles_total;
-  const int ntiles = t0 < t1 ? (int)(t1 - t0) : 0;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < pl.stages; ++s) {
-      tma::mbar_init(full + s, 1);
-      tma::mbar_init(empty + s, 1 + kEpiWarps);
-    }
-    for (int b = 0; b < 2; ++b) {
-      tma::mbar_init(acc_full + b, 1);
-      tma::mbar_init(acc_empty + b, kEpiWarps);
-    }
-    tma::mbar_init(a_full, 1);
-    tma::fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
+  const Pipe p = pipe_setup(smem, make_plan_batch(slots), n);
+  const int warp = threadIdx.x >> 5;
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0 && ntiles > 0) {
-      tma::mbar_arrive_expect_tx(a_full, pl.a_bytes);
-      for (int c = 0; c < 2 * pl.ksteps; ++c)
-        tma::bulk_g2s(smA + (size_t)c * kM * 16, opA + ((int64_t)c * npad + i0) * 4, kM * 16, a_full);
-    }
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      tma::mbar_wait(empty + s, ph ^ 1u);
-      uint8_t* smB = smS + (size_t)s * pl.stage_bytes;
-      float* smQ = reinterpret_cast<float*>(smB + pl.b_bytes);  // [kBatchMax][kN]
-      float* smX = smQ + kBatchMax * kN;                        // [kXtRows][kN]
-      const int64_t jt = (t0 + it) * kN;
-      // basis rows are zero-padded up to their stride: copy what the row holds, zero the rest of the tile
-      const int w = (int)((ldq - jt) < kN ? (ldq - jt) : kN);
-      const int wv = w & ~3;
-      if (wv < kN) {
-        for (int m = 0; m < M; ++m)
-          for (int c = wv + lane; c < kN; c += 32) smQ[m * kN + c] = (jt + c < n) ? Qrows[(int64_t)m * ldq + jt + c] : 0.f;
-        __syncwarp();
-      }
-      if (lane == 0) {
-        tma::mbar_arrive_expect_tx(full + s, pl.b_bytes + (uint32_t)M * wv * 4 + (uint32_t)D * kN * 4);
-        for (int c = 0; c < 2 * pl.ksteps; ++c)
-          tma::bulk_g2s(smB + (size_t)c * kN * 16, opB + ((int64_t)c * npad + jt) * 4, kN * 16, full + s);
-        if (wv > 0)
-          for (int m = 0; m < M; ++m) tma::bulk_g2s(smQ + (size_t)m * kN, Qrows + (int64_t)m * ldq + jt, (uint32_t)wv * 4, full + s);
-        for (int k = 0; k < D; ++k) tma::bulk_g2s(smX + (size_t)k * kN, xt + (int64_t)k * npad + jt, kN * 4, full + s);
-      }
-    }
+    RowsAux<D> aux{{}, M, n, xt, npad};
+    for (int m = 0; m < M; ++m) aux.rows.p[m] = Qrows + (int64_t)m * ldq;
+    producer_warp(p, opA, opB, npad, aux);
   } else if (warp == 1) {
-    // ===== MMA issue =====
-    const uint32_t idesc = instr_desc(kM, kN);
-    if (ntiles > 0) tma::mbar_wait(a_full, 0);
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      const int b = it & 1;
-      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-      tma::mbar_wait(full + s, ph);
-      tma::mbar_wait(acc_empty + b, bph ^ 1u);
-      fence_after_sync();
-      if (lane == 0) {
-        const uint32_t sa = tma::smem_u32(smA), sb = tma::smem_u32(smS + (size_t)s * pl.stage_bytes);
-        for (int k = 0; k < pl.ksteps; ++k) {
-          const uint64_t da = smem_desc(sa + (uint32_t)k * 2 * kM * 16, kM * 16, 128);
-          const uint64_t db = smem_desc(sb + (uint32_t)k * 2 * kN * 16, kN * 16, 128);
-          mma_tf32(tmem_base + (uint32_t)b * kN, da, db, idesc, k > 0 ? 1u : 0u);
-        }
-        mma_commit(empty + s);
-        mma_commit(acc_full + b);
-      }
-      __syncwarp();
-    }
+    mma_warp(p);
   } else {
-    // ===== epilogue =====
-    const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = qd * 32 + lane;
-    const bool live = i0 + row < n;
-    const float xxi = live ? xx[i0 + row] : 0.f;
-    const float cr = KIND == 2 ? -0.5f * xxi : xxi + 1.1920928955078125e-07f;
-    const float2 crow = make_float2(cr, cr);
-    const uint32_t acc_diag = __float_as_uint(0.5f * xxi);
+    const EpiThread e = epi_thread<KIND>(p, n, xx);
     double uacc = 0.0, dacc[D];
     float2 nxi[D], lam2[kBatchMax];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const float x = xt[(int64_t)k * npad + i0 + row];
+      const float x = xt[(int64_t)k * npad + p.i0 + e.row];
       nxi[k] = make_float2(-x, -x);
       dacc[k] = 0.0;
     }
 #pragma unroll
     for (int m = 0; m < kBatchMax; ++m) {
-      const float l = (live && m < M) ? Lrows[(int64_t)m * ldl + i0 + row] : 0.f;
+      const float l = (e.live && m < M) ? Lrows[(int64_t)m * ldl + p.i0 + e.row] : 0.f;
       lam2[m] = make_float2(l, l);
     }
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      const int b = it & 1;
-      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-      const float* smQ = reinterpret_cast<const float*>(smS + (size_t)s * pl.stage_bytes + pl.b_bytes);
+    for (int it = 0; it < p.ntiles; ++it) {
+      const Slot sl = slot_of(p, it);
+      const float* smQ = p.aux(sl.s);
       const float* smX = smQ + kBatchMax * kN;
-      tma::mbar_wait(full + s, ph);
-      tma::mbar_wait(acc_full + b, bph);
-      fence_after_sync();
-      const int64_t jt = (t0 + it) * kN;
-      const bool diag_tile = jt < i0 + kM && i0 < jt + kN;
+      epi_wait(p, sl);
       float2 u0 = make_float2(0.f, 0.f), u1 = u0, dl[D];
 #pragma unroll
       for (int k = 0; k < D; ++k) dl[k] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = half * 128 + cc * 32;
+        const int col0 = e.half * 128 + cc * 32;
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * kN + col0), r);
-        if (diag_tile) {
-          const int jd = (int)(i0 + row - jt) - col0;
+        epi_load(p, e, sl, it, col0, r);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = c == jd ? acc_diag : r[c];
-        }
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const float2 a01 = make_float2(__uint_as_float(r[4 * p]), __uint_as_float(r[4 * p + 1]));
-          const float2 a23 = make_float2(__uint_as_float(r[4 * p + 2]), __uint_as_float(r[4 * p + 3]));
-          const Eval2 e01 = kernel_from_acc<KIND>(a01, crow), e23 = kernel_from_acc<KIND>(a23, crow);
+        for (int pp = 0; pp < 8; ++pp) {
+          const float2 a01 = make_float2(__uint_as_float(r[4 * pp]), __uint_as_float(r[4 * pp + 1]));
+          const float2 a23 = make_float2(__uint_as_float(r[4 * pp + 2]), __uint_as_float(r[4 * pp + 3]));
+          const Eval2 e01 = kernel_from_acc<KIND>(a01, e.crow), e23 = kernel_from_acc<KIND>(a23, e.crow);
           float2 w01 = make_float2(0.f, 0.f), w23 = w01;  // W_ij = sum_m lam_m[i] q_m[j]
 #pragma unroll
           for (int m = 0; m < kBatchMax; ++m) {
             if (m < M) {
-              const float4 q4 = *reinterpret_cast<const float4*>(smQ + (size_t)m * kN + col0 + 4 * p);
+              const float4 q4 = *reinterpret_cast<const float4*>(smQ + (size_t)m * kN + col0 + 4 * pp);
               w01 = __ffma2_rn(lam2[m], make_float2(q4.x, q4.y), w01);
               w23 = __ffma2_rn(lam2[m], make_float2(q4.z, q4.w), w23);
             }
@@ -641,7 +657,7 @@ k_gram_tc_gradbatch(int64_t n, int64_t npad, int d, int slots, const float* __re
           const float2 g23 = __fmul2_rn(dkernel_from_eval<KIND>(e23), w23);
 #pragma unroll
           for (int k = 0; k < D; ++k) {
-            const float4 x4 = *reinterpret_cast<const float4*>(smX + (size_t)k * kN + col0 + 4 * p);
+            const float4 x4 = *reinterpret_cast<const float4*>(smX + (size_t)k * kN + col0 + 4 * pp);
             const float2 d01 = __fadd2_rn(make_float2(x4.x, x4.y), nxi[k]);
             const float2 d23 = __fadd2_rn(make_float2(x4.z, x4.w), nxi[k]);
             dl[k] = __ffma2_rn(g01, __fmul2_rn(d01, d01), dl[k]);
@@ -649,230 +665,85 @@ k_gram_tc_gradbatch(int64_t n, int64_t npad, int d, int slots, const float* __re
           }
         }
       }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        tma::mbar_arrive(acc_empty + b);
-        tma::mbar_arrive(empty + s);
-      }
+      epi_release(p, sl);
       uacc += (double)(u0.x + u0.y) + (double)(u1.x + u1.y);
 #pragma unroll
       for (int k = 0; k < D; ++k) dacc[k] += (double)(dl[k].x + dl[k].y);
     }
     const double sigma = (double)consts[0];
-    const int ew = warp - 2;
-    double t = warp_sum(sigma * uacc);
-    if (lane == 0) gred[ew][D] = t;
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-      t = warp_sum(sigma * dacc[k]);
-      if (lane == 0) gred[ew][k] = t;
-    }
-    tma::named_bar_sync(1, kEpiWarps * 32);
-    if (warp == 2 && lane <= D) {
-      double sacc = 0.0;
-      for (int e = 0; e < kEpiWarps; ++e) sacc += gred[e][lane];
-      const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-      if (lane == D)
-        gpart[blk * (d + 1) + d] = sacc;
-      else if (lane < d)
-        gpart[blk * (d + 1) + lane] = sacc;
-    }
+    for (int k = 0; k < D; ++k) dacc[k] *= sigma;
+    epi_reduce_grad<D>(dacc, sigma * uacc, d, gpart);
   }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
+  pipe_teardown(p);
 }
-
 
 // Matvec of P <= kBatchMax vectors at once (lockstep Krylov runs over probes): every kernel tile --
 // distances on the tensor pipe, sqrt / exp on the MUFU -- is evaluated ONCE and applied to the P
-// vectors (P extra FMAs per entry), so P matvecs cost about as much as one.
+// vectors (P extra FMAs per entry), so P matvecs cost about as much as two.
 //   part[split][p][i] = sigma sum_{j in split} k_ij v_p[j]
-struct VecPtrs {
-  const float* p[kBatchMax];
-};
-__host__ __device__ inline Plan make_plan_multi(int slots) { return make_plan_rows(slots, kBatchMax); }
-
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_multi(int64_t n, int64_t npad, int slots, const float* __restrict__ opA, const float* __restrict__ opB,
                 const float* __restrict__ xx, const float* __restrict__ consts, VecPtrs vecs, int P,
                 float* __restrict__ part) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const Plan pl = make_plan_multi(slots);
-  uint8_t* smA = smem;
-  uint8_t* smS = smem + pl.a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 3;
-  uint64_t* acc_full = bars + 6;
-  uint64_t* acc_empty = bars + 8;
-  uint64_t* a_full = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   __shared__ double ycomb[kBatchMax][kM];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i0 = (int64_t)blockIdx.x * kM;
-  const int64_t tiles_total = (n + kN - 1) / kN;
-  const int64_t per = (tiles_total + gridDim.y - 1) / gridDim.y;
-  const int64_t t0 = per * blockIdx.y;
-  const int64_t t1 = t0 + per < tiles_total ? t0 + per : tiles_total;
-  const int ntiles = t0 < t1 ? (int)(t1 - t0) : 0;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < pl.stages; ++s) {
-      tma::mbar_init(full + s, 1);
-      tma::mbar_init(empty + s, 1 + kEpiWarps);
-    }
-    for (int b = 0; b < 2; ++b) {
-      tma::mbar_init(acc_full + b, 1);
-      tma::mbar_init(acc_empty + b, kEpiWarps);
-    }
-    tma::mbar_init(a_full, 1);
-    tma::fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
+  const Pipe p = pipe_setup(smem, make_plan_multi(slots), n);
+  const int warp = threadIdx.x >> 5;
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0 && ntiles > 0) {
-      tma::mbar_arrive_expect_tx(a_full, pl.a_bytes);
-      for (int c = 0; c < 2 * pl.ksteps; ++c)
-        tma::bulk_g2s(smA + (size_t)c * kM * 16, opA + ((int64_t)c * npad + i0) * 4, kM * 16, a_full);
-    }
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      tma::mbar_wait(empty + s, ph ^ 1u);
-      uint8_t* smB = smS + (size_t)s * pl.stage_bytes;
-      float* smV = reinterpret_cast<float*>(smB + pl.b_bytes);  // [kBatchMax][kN]
-      const int64_t jt = (t0 + it) * kN;
-      const int w = (int)((n - jt) < kN ? (n - jt) : kN);
-      const int wv = w & ~3;
-      if (w < kN) {
-        for (int p = 0; p < P; ++p)
-          for (int c = wv + lane; c < kN; c += 32) smV[p * kN + c] = c < w ? vecs.p[p][jt + c] : 0.f;
-        __syncwarp();
-      }
-      if (lane == 0) {
-        tma::mbar_arrive_expect_tx(full + s, pl.b_bytes + (uint32_t)P * wv * 4);
-        for (int c = 0; c < 2 * pl.ksteps; ++c)
-          tma::bulk_g2s(smB + (size_t)c * kN * 16, opB + ((int64_t)c * npad + jt) * 4, kN * 16, full + s);
-        if (wv > 0)
-          for (int p = 0; p < P; ++p) tma::bulk_g2s(smV + (size_t)p * kN, vecs.p[p] + jt, (uint32_t)wv * 4, full + s);
-      }
-    }
+    producer_warp(p, opA, opB, npad, RowsAux<1>{vecs, P, n, nullptr, npad});
   } else if (warp == 1) {
-    // ===== MMA issue =====
-    const uint32_t idesc = instr_desc(kM, kN);
-    if (ntiles > 0) tma::mbar_wait(a_full, 0);
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      const int b = it & 1;
-      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-      tma::mbar_wait(full + s, ph);
-      tma::mbar_wait(acc_empty + b, bph ^ 1u);
-      fence_after_sync();
-      if (lane == 0) {
-        const uint32_t sa = tma::smem_u32(smA), sb = tma::smem_u32(smS + (size_t)s * pl.stage_bytes);
-        for (int k = 0; k < pl.ksteps; ++k) {
-          const uint64_t da = smem_desc(sa + (uint32_t)k * 2 * kM * 16, kM * 16, 128);
-          const uint64_t db = smem_desc(sb + (uint32_t)k * 2 * kN * 16, kN * 16, 128);
-          mma_tf32(tmem_base + (uint32_t)b * kN, da, db, idesc, k > 0 ? 1u : 0u);
-        }
-        mma_commit(empty + s);
-        mma_commit(acc_full + b);
-      }
-      __syncwarp();
-    }
+    mma_warp(p);
   } else {
-    // ===== epilogue =====
-    const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = qd * 32 + lane;
-    const bool live = i0 + row < n;
-    const float xxi = live ? xx[i0 + row] : 0.f;
-    const float cr = KIND == 2 ? -0.5f * xxi : xxi + 1.1920928955078125e-07f;
-    const float2 crow = make_float2(cr, cr);
-    const uint32_t acc_diag = __float_as_uint(0.5f * xxi);
+    const EpiThread e = epi_thread<KIND>(p, n, xx);
     double yacc[kBatchMax];
 #pragma unroll
-    for (int p = 0; p < kBatchMax; ++p) yacc[p] = 0.0;
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % pl.stages;
-      const uint32_t ph = (uint32_t)(it / pl.stages) & 1u;
-      const int b = it & 1;
-      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-      const float* smV = reinterpret_cast<const float*>(smS + (size_t)s * pl.stage_bytes + pl.b_bytes);
-      tma::mbar_wait(full + s, ph);
-      tma::mbar_wait(acc_full + b, bph);
-      fence_after_sync();
-      const int64_t jt = (t0 + it) * kN;
-      const bool diag_tile = jt < i0 + kM && i0 < jt + kN;
+    for (int q = 0; q < kBatchMax; ++q) yacc[q] = 0.0;
+    for (int it = 0; it < p.ntiles; ++it) {
+      const Slot sl = slot_of(p, it);
+      const float* smV = p.aux(sl.s);
+      epi_wait(p, sl);
       float2 y[kBatchMax];
 #pragma unroll
-      for (int p = 0; p < kBatchMax; ++p) y[p] = make_float2(0.f, 0.f);
+      for (int q = 0; q < kBatchMax; ++q) y[q] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = half * 128 + cc * 32;
+        const int col0 = e.half * 128 + cc * 32;
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * kN + col0), r);
-        if (diag_tile) {
-          const int jd = (int)(i0 + row - jt) - col0;
+        epi_load(p, e, sl, it, col0, r);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = c == jd ? acc_diag : r[c];
-        }
+        for (int pp = 0; pp < 8; ++pp) {
+          const float2 a01 = make_float2(__uint_as_float(r[4 * pp]), __uint_as_float(r[4 * pp + 1]));
+          const float2 a23 = make_float2(__uint_as_float(r[4 * pp + 2]), __uint_as_float(r[4 * pp + 3]));
+          const Eval2 e01 = kernel_from_acc<KIND>(a01, e.crow), e23 = kernel_from_acc<KIND>(a23, e.crow);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float2 a01 = make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]));
-          const float2 a23 = make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-          const Eval2 e01 = kernel_from_acc<KIND>(a01, crow), e23 = kernel_from_acc<KIND>(a23, crow);
-#pragma unroll
-          for (int p = 0; p < kBatchMax; ++p) {
-            if (p < P) {
-              const float4 v4 = *reinterpret_cast<const float4*>(smV + (size_t)p * kN + col0 + 4 * q);
-              y[p] = __ffma2_rn(e01.k, make_float2(v4.x, v4.y), y[p]);
-              y[p] = __ffma2_rn(e23.k, make_float2(v4.z, v4.w), y[p]);
+          for (int q = 0; q < kBatchMax; ++q) {
+            if (q < P) {
+              const float4 v4 = *reinterpret_cast<const float4*>(smV + (size_t)q * kN + col0 + 4 * pp);
+              y[q] = __ffma2_rn(e01.k, make_float2(v4.x, v4.y), y[q]);
+              y[q] = __ffma2_rn(e23.k, make_float2(v4.z, v4.w), y[q]);
             }
           }
         }
       }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        tma::mbar_arrive(acc_empty + b);
-        tma::mbar_arrive(empty + s);
-      }
+      epi_release(p, sl);
 #pragma unroll
-      for (int p = 0; p < kBatchMax; ++p) yacc[p] += (double)(y[p].x + y[p].y);
+      for (int q = 0; q < kBatchMax; ++q) yacc[q] += (double)(y[q].x + y[q].y);
     }
     const double sigma = (double)consts[0];
-    if (half == 1) {
+    if (e.half == 1) {
 #pragma unroll
-      for (int p = 0; p < kBatchMax; ++p) ycomb[p][row] = yacc[p];
+      for (int q = 0; q < kBatchMax; ++q) ycomb[q][e.row] = yacc[q];
     }
     tma::named_bar_sync(1, kEpiWarps * 32);
-    if (half == 0 && live) {
+    if (e.half == 0 && e.live) {
 #pragma unroll
-      for (int p = 0; p < kBatchMax; ++p)
-        if (p < P) part[((int64_t)blockIdx.y * P + p) * n + i0 + row] = (float)((yacc[p] + ycomb[p][row]) * sigma);
+      for (int q = 0; q < kBatchMax; ++q)
+        if (q < P) part[((int64_t)blockIdx.y * P + q) * n + p.i0 + e.row] = (float)((yacc[q] + ycomb[q][e.row]) * sigma);
     }
   }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
+  pipe_teardown(p);
 }
 
 }  // namespace gramtc
