@@ -306,7 +306,7 @@ def main():
     d = prof[dom]
     dom_gbs = d["algorithmic_bytes"] / max(d["ms"], 1e-9) / 1e6
     prof_total = sum(c["ms"] for c in prof.values())
-    KERNEL_OF = {"dots": "k_dots_tma", "combine": "k_combine_tma", "matvec": "k_sell_spmv", "vjp": "k_sell_vjp",
+    KERNEL_OF = {"dots": "k_dots_tma", "combine": "k_combine_tma", "matvec": "k_sell_spmv_normalised", "vjp": "k_sell_vjp",
                  "other": "k_scale_copy", "fused": "k_fused_tma"}
     roofline = {
         "bound": "hbm", "kernel": KERNEL_OF[dom],

@@ -520,12 +520,39 @@ struct FwdRun {
   cudaStream_t s;
   Common c;
   Grid g;
+  T* alt = nullptr;    // spare vector: the fused normalise + matvec cannot run in place
+  T* r_out = nullptr;  // the caller's remainder buffer (`r` is the CURRENT vector and may be `alt`)
 
   T* q_row(int i) const { return Q + (int64_t)i * ld; }
+
+  // q_i = v / length, v = A q_i                                               arnoldi.py:80-84
+  int advance(int i) {
+    {
+      ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype) + 2.0 * n * sizeof(T), s);
+      const int rc = op->matvec_normalised(dtype, r, c.scal + S_LEN, q_row(i), ld, alt, s);
+      if (rc == BL_OK) {
+        std::swap(r, alt);
+        return BL_OK;
+      }
+      if (rc != -1) return rc;
+    }
+    BL_CHECK(pre(i));
+    ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype), s);
+    return op->matvec(dtype, q_row(i), r, s);
+  }
+  int finish() {
+    if (r != r_out) {
+      BL_CUDA(cudaMemcpyAsync(r_out, r, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+      std::swap(r, alt);
+    }
+    return BL_OK;
+  }
 
   int begin() {
   Workspace w(workspace, wbytes);
   carve_common(w, K, c);
+  alt = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
+  r_out = r;
   BL_REQUIRE(w.ok(), "workspace too small (bl_arnoldi_workspace_bytes)");
   g = pick_grid<T>(n);
 
@@ -619,15 +646,10 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool secon
   FwdRun<T> run{op, dtype, n, K, second_pass, v, Q, ld, H, r, c_out, workspace, wbytes, s, {}, {}};
   BL_CHECK(run.begin());
   for (int i = 0; i < K; ++i) {
-    BL_CHECK(run.pre(i));
-    // v = matvec(v, *params)                                                   arnoldi.py:84
-    {
-      ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype), s);
-      BL_CHECK(op->matvec(dtype, run.q_row(i), r, s));
-    }
+    BL_CHECK(run.advance(i));
     BL_CHECK(run.post(i));
   }
-  return BL_OK;
+  return run.finish();
 }
 
 // P independent runs in lockstep: per step one batched matvec for all of them.

@@ -18,6 +18,14 @@ struct bl_operator {
   // ALGORITHMIC bytes of one matvec / one vjp (roofline report); default: vectors only
   virtual double matvec_bytes(int dtype) const { return 2.0 * n * (dtype == BL_F32 ? 4 : 8); }
   virtual double vjp_bytes(int dtype) const { return 3.0 * n * (dtype == BL_F32 ? 4 : 8); }
+  // Forward step of the Krylov loops: q = v / *len (true division, arnoldi.py:80-81; the row is written up
+  // to n_pad entries with zero padding) followed by y = A q.  Operators that can normalise on the fly
+  // return BL_OK and save one pass over the vector; the default returns BL_EUNSUPPORTED (-1) and the
+  // caller runs the two steps separately.
+  virtual int matvec_normalised(int /*dtype*/, const void* /*v*/, const double* /*len*/, void* /*q_out*/,
+                                int64_t /*n_pad*/, void* /*y*/, cudaStream_t) {
+    return -1;
+  }
   // Deferred parameter cotangent (the adjoint sweeps only need A^T lam inside the loop): operators that
   // return true provide `apply_transpose` (z = A^T lam, no gradient work) and `vjp_batch`
   // (grad += sum_m d<lam_m, A(q_m)>/dparams for `count` rows of two row-strided arrays) -- for the Gram

@@ -147,6 +147,35 @@ k_sell_spmv(int64_t nrows, const int64_t* __restrict__ slice_ptr, const int32_t*
   if (r < nrows) y[r] = acc0 + acc1;
 }
 
+// The forward Krylov step's normalisation fused into the matvec: q = v / len (true division as in
+// arnoldi.py:80, written once per row, zero padded up to n_pad) and y = A q, one pass over the vector
+// less.  The gathered entries are scaled with the reciprocal (a division per non-zero makes the kernel
+// ALU-bound): they can differ from the stored q by one ulp, the size of the matvec's own rounding.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_sell_spmv_normalised(int64_t nrows, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+                       const T* __restrict__ val, const T* __restrict__ v, const double* __restrict__ len,
+                       T* __restrict__ q_out, int64_t n_pad, T* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = slice * kSlice + lane;
+  if (slice * kSlice >= nrows) return;
+  const T d = static_cast<T>(*len);
+  const T inv = T(1) / d;
+  if (r < n_pad) q_out[r] = r < nrows ? v[r] * T(1) / d : T(0);
+  const int64_t s0 = slice_ptr[slice], s1 = slice_ptr[slice + 1];
+  T acc0 = T(0), acc1 = T(0);
+  int64_t p = s0 + lane;
+  for (; p + kSlice < s1; p += 2 * kSlice) {
+    const int c0 = ld_stream_i32(col + p), c1 = ld_stream_i32(col + p + kSlice);
+    const T v0 = ld_stream_t(val + p), v1 = ld_stream_t(val + p + kSlice);
+    acc0 = fma(v0, __ldg(v + c0) * inv, acc0);
+    acc1 = fma(v1, __ldg(v + c1) * inv, acc1);
+  }
+  if (p < s1) acc0 = fma(ld_stream_t(val + p), __ldg(v + ld_stream_i32(col + p)) * inv, acc0);
+  if (r < nrows) y[r] = acc0 + acc1;
+}
+
 // Adjoint of the sparse matvec in one launch:
 //   z[r]       = sum_k valT[slot] * lam[colT[slot]]      (A^T lam, via SELL of A^T; optional)
 //   grad[slot] += lam[r] * q[col[slot]]                   (d<lam, A q>/dparams, SELL of A)
@@ -281,6 +310,27 @@ struct SparseOperator : bl_operator {
     BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
     return dtype == BL_F32 ? matvec_t<float>(static_cast<const float*>(x), static_cast<float*>(y), s)
                            : matvec_t<double>(static_cast<const double*>(x), static_cast<double*>(y), s);
+  }
+
+  template <typename T>
+  int matvec_normalised_t(const T* v, const double* len, T* q_out, int64_t n_pad, T* y, cudaStream_t s) {
+    const int64_t threads = sell.nslices * kSlice;
+    const int blocks = (int)((threads + 255) / 256);
+    k_sell_spmv_normalised<T><<<blocks, 256, 0, s>>>(n_rows, sell.slice_ptr.as<int64_t>(), sell.col.as<int32_t>(),
+                                                     sell.val.as<T>(), v, len, q_out, n_pad, y);
+    BL_LAUNCHED();
+    return BL_OK;
+  }
+  int matvec_normalised(int dtype, const void* v, const double* len, void* q_out, int64_t n_pad, void* y,
+                        cudaStream_t s) override {
+    // the fused kernel writes the padded row from its own threads: it needs a square operand whose slices
+    // cover the padding, and in-place use (y aliasing v) is not possible
+    if (dtype != bound_dtype || n_rows != n_cols || n_pad > sell.nslices * kSlice || v == y || n_rows == 0) return -1;
+    return dtype == BL_F32
+               ? matvec_normalised_t<float>(static_cast<const float*>(v), len, static_cast<float*>(q_out), n_pad,
+                                            static_cast<float*>(y), s)
+               : matvec_normalised_t<double>(static_cast<const double*>(v), len, static_cast<double*>(q_out), n_pad,
+                                             static_cast<double*>(y), s);
   }
 
   template <typename T>
