@@ -56,6 +56,11 @@ SIGNATURES = {
     "bl_dist_comm_connect_ipc": (_i32, [_vp, _vp]),
     "bl_dist_comm_connect_ptrs": (_i32, [_vp, _pvp]),
     "bl_dist_comm_activate": (_i32, [_vp]),
+    "bl_dist_comm_window_create": (_i32, [_vp, C.c_size_t, _vp]),
+    "bl_dist_comm_window_local": (_i32, [_vp, _pvp]),
+    "bl_dist_comm_window_connect_ipc": (_i32, [_vp, _vp]),
+    "bl_dist_comm_window_connect_ptrs": (_i32, [_vp, _pvp]),
+    "bl_op_sharded_sparse_create": (_i32, [_vp, _vp, _vp, _i64, _i64, _pvp]),
     "bl_dist_comm_error": (_i32, [_vp, C.POINTER(C.c_int)]),
     "bl_dist_comm_destroy": (_i32, [_vp]),
     "bl_op_wave_set_comm": (_i32, [_vp, _vp]),

@@ -21,7 +21,7 @@ constexpr int kMaxRanks = 8;
 constexpr int kRedSlots = 16384;           // doubles per reduction (K*K of the dense-cotangent set-up, K <= 128)
 constexpr size_t kHaloRowBytes = 512 * 1024;  // one halo row (<= 65536 doubles)
 constexpr int kHaloSlots = 4;              // field 0 from above / below, field 1 from above / below
-constexpr size_t kFlagBytes = 1024;        // [0..8) reduce flags by source, [8..16) halo flags, [64] error
+constexpr size_t kFlagBytes = 1024;        // [0..8) reduce flags by source, [8..16) halo, [16..32) gather slots 0/1, [64] error
 constexpr size_t kRedOff = kFlagBytes;
 constexpr size_t kHaloOff = kRedOff + 2ull * kMaxRanks * kRedSlots * 8;
 constexpr size_t kMailboxBytes = kHaloOff + 2ull * kHaloSlots * kHaloRowBytes;
@@ -38,6 +38,9 @@ __device__ __forceinline__ unsigned long long* red_flag(unsigned char* mail, int
 }
 __device__ __forceinline__ unsigned long long* halo_flag(unsigned char* mail, int src) {
   return reinterpret_cast<unsigned long long*>(mail) + 8 + src;
+}
+__device__ __forceinline__ unsigned long long* gather_flag(unsigned char* mail, int slot, int src) {
+  return reinterpret_cast<unsigned long long*>(mail) + 16 + slot * 8 + src;
 }
 __device__ __forceinline__ unsigned long long* error_flag(unsigned char* mail) {
   return reinterpret_cast<unsigned long long*>(mail) + 64;
@@ -112,6 +115,16 @@ __device__ __forceinline__ void peer_allreduce_block(const PeerView& pv, double*
   __syncthreads();
 }
 
+// All-gather window (optional, bl_dist_comm_window_*): every rank owns [2 parities][2 slots][slot_bytes] in
+// its HBM, mapped by the peers; a rank pushes its chunk of a vector into every peer's window.
+struct WindowView {
+  size_t slot_bytes = 0;
+  unsigned char* win[kMaxRanks] = {};
+  __host__ __device__ __forceinline__ unsigned char* slot(int rank, int parity, int slot_index) const {
+    return win[rank] + ((size_t)parity * 2 + slot_index) * slot_bytes;
+  }
+};
+
 // host side (dist.cu)
 bool active();
 int world();
@@ -125,5 +138,6 @@ struct bl_comm;  // opaque (include/b200_lanczos.h: bl_comm_t)
 namespace bl {
 namespace dist {
 int view_of(bl_comm* comm, bool halo, PeerView* pv);  // advances the sequence number of `comm`
+int gather_view_of(bl_comm* comm, PeerView* pv, WindowView* wv);  // advances the gather sequence number
 }
 }  // namespace bl

@@ -173,6 +173,8 @@ class PeerComm:
         h = C.c_void_p()
         _lib.call("bl_dist_comm_create", self.rank, self.world, C.byref(h))
         self.handle = h.value
+        self._window_bytes = 0
+        self._multi_process = rank is None
         if rank is None and self.world > 1:  # one process per rank: exchange IPC handles
             buf = C.create_string_buffer(64)
             _lib.call("bl_dist_comm_local", self.handle, None, buf)
@@ -195,6 +197,39 @@ class PeerComm:
 
         ptrs = (C.c_void_p * self.world)(*[c.mailbox for c in comms])
         self._lib.call("bl_dist_comm_connect_ptrs", self.handle, ptrs)
+
+    def create_window(self, slot_bytes: int):
+        """All-gather window (`bl_dist_comm_window_*`): call on every rank with the same size; with one
+        process per rank the IPC handles are exchanged here, same-process ranks call `connect_windows`."""
+        import ctypes as C
+
+        if self._window_bytes:
+            if slot_bytes > self._window_bytes:
+                raise ValueError("the communicator's all-gather window is smaller than requested")
+            return
+        buf = C.create_string_buffer(64)
+        self._lib.call("bl_dist_comm_window_create", self.handle, int(slot_bytes), buf)
+        self._window_bytes = int(slot_bytes)
+        dist = _dist()
+        if self._multi_process and self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(buf.raw), group=self.group)
+            self._lib.call("bl_dist_comm_window_connect_ipc", self.handle, b"".join(handles))
+            dist.barrier(group=self.group)
+
+    @property
+    def window(self) -> int:
+        import ctypes as C
+
+        p = C.c_void_p()
+        self._lib.call("bl_dist_comm_window_local", self.handle, C.byref(p))
+        return p.value
+
+    def connect_windows(self, comms):
+        import ctypes as C
+
+        ptrs = (C.c_void_p * self.world)(*[c.window for c in comms])
+        self._lib.call("bl_dist_comm_window_connect_ptrs", self.handle, ptrs)
 
     def timed_out(self) -> bool:
         import ctypes as C
@@ -266,7 +301,20 @@ class row_sharded:
         return False
 
 
-def shard_coo_rows(row, col, n, rank, world):
+class _NativeShardedSparse:
+    """Host handle of `bl_op_sharded_sparse_create` (a plain operand of the Krylov calls)."""
+
+    def __new__(cls, handle, chunk, nnz_a, nnz_b):
+        from experiments_lanczos_adjoints_b200 import operators as ops
+
+        class Native(ops.Operator):
+            def param_shapes(self_inner):
+                return [(nnz_a,), (nnz_b,)]
+
+        return Native(handle, chunk)
+
+
+def shard_coo_rows(row, col, n, rank, world, align=1):
     """Index work of the row-sharded sparse operand (pure host, bit-exact, testable on CPU).
 
     Uniform chunks of `chunk = ceil(n / world)` rows; rank r owns global rows
@@ -277,7 +325,8 @@ def shard_coo_rows(row, col, n, rank, world):
     row = np.asarray(row, dtype=np.int64)
     col = np.asarray(col, dtype=np.int64)
     chunk = -(-int(n) // world)
-    lo, hi = rank * chunk, min(int(n), (rank + 1) * chunk)
+    chunk = -(-chunk // align) * align  # the peer-memory all-gather moves whole 128-byte lines
+    lo, hi = min(int(n), rank * chunk), min(int(n), (rank + 1) * chunk)
     idx_a = np.nonzero((row >= lo) & (row < hi))[0]
     idx_b = np.nonzero((col >= lo) & (col < hi))[0]
     return (chunk, idx_a, (row[idx_a] - lo).astype(np.int32), col[idx_a].astype(np.int32),
@@ -292,24 +341,52 @@ class RowShardedSparseOperator:
     parameter cotangent (`d theta_e` is local to the owner of row_e).  Built on two rectangular
     `SparseOperator`s; plugs into the Krylov loops as a `CallbackOperator`."""
 
-    def __init__(self, row, col, n, group=None):
+    def __init__(self, row, col, n, group=None, comm=None):
+        """`comm=PeerComm(...)`: native route — the all-gathers are single kernels over the communicator's
+        peer-memory window (`bl_op_sharded_sparse_create`), `.callback` is a plain operand whose parameters
+        are `local_params(data)` and whose cotangent is the local part (`assemble_grad` puts it back in COO
+        order).  Without `comm`: NCCL all-gathers from a host callback."""
         from experiments_lanczos_adjoints_b200 import operators as ops
 
         dist = _dist()
         self.group = group
-        self.rank = dist.get_rank(group) if dist else 0
-        self.world = dist.get_world_size(group) if dist else 1
+        self.comm = comm
+        self.rank = comm.rank if comm is not None else (dist.get_rank(group) if dist else 0)
+        self.world = comm.world if comm is not None else (dist.get_world_size(group) if dist else 1)
         self.n_global, self.nnz = int(n), len(row)
         (self.chunk, self.idx_a, row_a, col_a, self.idx_b, row_b, col_b) = shard_coo_rows(
-            row, col, n, self.rank, self.world)  # fmt: skip
+            row, col, n, self.rank, self.world, align=32 if comm is not None else 1)  # fmt: skip
         width = self.chunk * self.world
         self.A = ops.SparseOperator(row_a, col_a, (self.chunk, width))
         self.B = ops.SparseOperator(row_b, col_b, (self.chunk, width))
         self._gathered = {}
+        if comm is not None:
+            import ctypes as C
+
+            from experiments_lanczos_adjoints_b200 import _lib
+
+            comm.create_window(width * 8)
+            h = C.c_void_p()
+            _lib.call("bl_op_sharded_sparse_create", self.A._handle, self.B._handle, comm.handle, self.chunk, width,
+                      C.byref(h))  # fmt: skip
+            self.callback = _NativeShardedSparse(h.value, self.chunk, len(self.idx_a), len(self.idx_b))
+            return
         self.callback = ops.CallbackOperator(self.chunk, self._matvec, self._vjp, num_params=1)
         self.callback.bind = self._bind
         self.callback.grad_zero = self._grad_zero
         self.callback.grad_export = self._grad_export
+
+    def local_params(self, data):
+        """The two parameter arrays of the native operand: values of the local rows of A and of A^T."""
+        data = np.asarray(data)
+        return data[self.idx_a], data[self.idx_b]
+
+    def assemble_grad(self, g_local, dtype=np.float64):
+        """Local cotangent (entries of the local rows, operand order) -> global COO order, summed over ranks."""
+        full = np.zeros(self.nnz, dtype=np.float64)
+        full[self.idx_a] = np.asarray(g_local.numpy() if isinstance(g_local, dev.DeviceArray) else g_local)
+        (full,) = all_reduce_sum([full], self.group)
+        return full.astype(dtype)
 
     # vectors ------------------------------------------------------------------------------
     def local_slice(self, x_global):

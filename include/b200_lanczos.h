@@ -114,6 +114,12 @@ int bl_dist_comm_local(bl_comm_t* comm, void** mailbox, void* ipc_handle_64);
 int bl_dist_comm_connect_ipc(bl_comm_t* comm, const void* handles);
 /* same-process variant (tests; several ranks driven by several host threads): mailbox pointers */
 int bl_dist_comm_connect_ptrs(bl_comm_t* comm, void* const* mailboxes);
+/* All-gather window: 4 * slot_bytes of this rank's HBM ([2 parities][2 slots][slot_bytes]) that the peers
+ * map like the mailbox; needed by operands that all-gather a sharded vector (bl_op_sharded_sparse_create). */
+int bl_dist_comm_window_create(bl_comm_t* comm, size_t slot_bytes, void* ipc_handle_64);
+int bl_dist_comm_window_local(bl_comm_t* comm, void** window);
+int bl_dist_comm_window_connect_ipc(bl_comm_t* comm, const void* handles);
+int bl_dist_comm_window_connect_ptrs(bl_comm_t* comm, void* const* windows);
 int bl_dist_comm_activate(bl_comm_t* comm); /* NULL deactivates; per host thread; wins over the hook */
 int bl_dist_comm_error(bl_comm_t* comm, int* timed_out);
 int bl_dist_comm_destroy(bl_comm_t* comm);
@@ -142,6 +148,16 @@ int bl_op_sparse_export_csr(const bl_operator_t* op, int32_t* row_ptr_host, int3
 /* SELL-32 view: slice_ptr[n_slices+1] (int64), slot_of_csr[nnz] (int64). */
 int bl_op_sparse_export_sell(const bl_operator_t* op, int transpose, int64_t* slice_ptr_host,
                              int64_t* slot_of_csr_host);
+
+/* Row-sharded sparse operand over peer memory ("one large operator"): rank r owns rows [r*chunk, (r+1)*chunk)
+ * of every vector (chunk a multiple of 32; width = world * chunk).  A_local / B_local are rectangular
+ * chunk x width sparse operands holding the local rows of A and of A^T (they must outlive this object).
+ * matvec: all-gather of the vector through the communicator's window (one kernel: NVLink stores into every
+ * peer's window, sequence-number handshake), then the local rows of A.  vjp: gathers q and lambda, applies
+ * the local rows of A^T, accumulates the cotangent of the entries of the local rows.  Two parameters:
+ * the values of A_local and of B_local; the second gradient is zero (every entry is owned by its row). */
+int bl_op_sharded_sparse_create(bl_operator_t* A_local, bl_operator_t* B_local, bl_comm_t* comm, int64_t chunk,
+                                int64_t width, bl_operator_t** op);
 
 /* Dense operand of the reference's tests: mode 0 `p @ s` (test_hessenberg_forward.py:20),
  * mode 1 `(p + p.T) @ s` (test_tridiag_adjoint.py:20-21).  One parameter: p (n x n row-major). */

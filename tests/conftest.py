@@ -17,6 +17,10 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
+# Two tests drive two ranks from two host threads of THIS process; a lazily loaded kernel may synchronise
+# the context while the peer rank spins on it, so load every kernel up front (must be set before CUDA starts).
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200) and the built library")

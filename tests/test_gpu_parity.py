@@ -460,3 +460,72 @@ def test_peer_memory_route_two_ranks_on_one_gpu_matches_single_operator():
         assert rel_err(rr, op.local_slice(r0)) < 1e-11
         assert rel_err(dv, op.local_slice(dv0)) < 1e-9
         assert rel_err(ds, op.local_scale(ds0)) < 1e-9
+
+
+def test_peer_memory_sharded_sparse_two_ranks_on_one_gpu_matches_single_operator():
+    """Row-sharded SPARSE operand on the native route (`bl_op_sharded_sparse_create`: all-gather of the
+    Lanczos vector through the communicator's peer-memory window, reductions fused with their epilogue),
+    two ranks as two host threads on one GPU, against the unsharded operand: tridiagonal coefficients,
+    dv and the parameter cotangent in COO order.  n is not a multiple of the chunk alignment."""
+    import threading
+
+    from experiments_lanczos_adjoints_b200 import parallel
+
+    n, K, world = 20_011, 12, 2
+    row, col, data = banded_spd(n, 4, seed=5, max_off=300)
+    rng = np.random.default_rng(6)
+    v = rng.standard_normal(n)
+    dalpha, dbeta = rng.standard_normal(K), rng.standard_normal(K - 1)
+    full = bl.lanczos.tridiag(bl.operators.SparseOperator(row, col, (n, n)), K, reortho="full")
+    ((_, (a0, b0)), _), pull0 = bl.vjp(full, v, data)
+    dv0, dp0 = pull0(((None, (dalpha, dbeta)), (None, None)))
+    dv0, dp0 = dv0.numpy(), dp0.numpy()
+    bl.synchronize()
+
+    def attempt():
+        comms = [parallel.PeerComm(rank=r, world=world) for r in range(world)]
+        for c in comms:
+            c.connect_local(comms)
+        ops = [parallel.RowShardedSparseOperator(row, col, n, comm=comms[r]) for r in range(world)]
+        for c in comms:
+            c.connect_windows(comms)
+        out, errors = {}, []
+        ready = threading.Barrier(world)
+
+        def rank_main(r):
+            try:
+                bl.default_stream()
+                op = ops[r]
+                alg = bl.lanczos.tridiag(op.callback, K, reortho="full")
+                v_loc, params = op.local_slice(v), op.local_params(data)
+                ready.wait(30)
+                with parallel.row_sharded(comm=comms[r]):
+                    ((_, (alpha, beta)), _), pull = bl.vjp(alg, v_loc, *params)
+                    dv, dpa, _dpb = pull(((None, (dalpha, dbeta)), (None, None)))
+                bl.default_stream().synchronize()
+                out[r] = (np.asarray(alpha), np.asarray(beta), dv.numpy(), dpa.numpy())
+            except Exception as exc:  # pragma: no cover
+                errors.append(exc)
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(90)
+        return ops, out, errors, any(c.timed_out() for c in comms)
+
+    ops, out, errors, timed_out = attempt()
+    if timed_out and not errors:
+        ops, out, errors, timed_out = attempt()
+    assert not errors, errors
+    assert not timed_out
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    grad = np.zeros(len(data))
+    for r in range(world):
+        alpha, beta, dv, dpa = out[r]
+        assert rel_err(alpha, a0) < 1e-12 and rel_err(beta, b0) < 1e-12
+        lo = r * ops[r].chunk
+        hi = min(n, lo + ops[r].chunk)
+        assert rel_err(dv[: hi - lo], dv0[lo:hi]) < 1e-10
+        grad[ops[r].idx_a] = dpa
+    assert rel_err(grad, dp0) < 1e-10
