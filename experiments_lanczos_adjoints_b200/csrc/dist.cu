@@ -6,6 +6,7 @@ struct bl_comm {
   unsigned char* mail[bl::dist::kMaxRanks] = {};
   bool ipc[bl::dist::kMaxRanks] = {};
   unsigned long long red_seq = 0, halo_seq = 0, gather_seq = 0;
+  bool header_written = false;
   size_t slot_bytes = 0;  // all-gather window: [2][2][slot_bytes] per rank
   unsigned char* win[bl::dist::kMaxRanks] = {};
   bool win_ipc[bl::dist::kMaxRanks] = {};
@@ -150,6 +151,17 @@ int bl_dist_comm_window_connect_ptrs(bl_comm_t* comm, void* const* windows) {
 }
 
 int bl_dist_comm_activate(bl_comm_t* comm) {
+  if (comm && !comm->header_written) {  // publish the peer table in the own mailbox (kernels rebuild their PeerView from it)
+    dist::MailHeader h{};
+    h.rank = comm->rank;
+    h.world = comm->world;
+    for (int p = 0; p < comm->world; ++p) {
+      BL_REQUIRE(comm->mail[p] != nullptr, "communicator is not connected to every rank");
+      h.mail[p] = comm->mail[p];
+    }
+    BL_CUDA(cudaMemcpy(comm->mail[comm->rank] + dist::kHeaderOff, &h, sizeof(h), cudaMemcpyHostToDevice));
+    comm->header_written = true;
+  }
   dist::t_comm = comm;
   return BL_OK;
 }

@@ -42,6 +42,13 @@ __device__ __forceinline__ unsigned long long* halo_flag(unsigned char* mail, in
 __device__ __forceinline__ unsigned long long* gather_flag(unsigned char* mail, int slot, int src) {
   return reinterpret_cast<unsigned long long*>(mail) + 16 + slot * 8 + src;
 }
+// header of the own mailbox (written at connect time): rank, world and the mapped mailbox of every rank, so
+// that kernels which only carry the own mailbox pointer and a sequence number can rebuild the PeerView
+constexpr size_t kHeaderOff = 768;
+struct MailHeader {
+  int rank, world;
+  unsigned char* mail[kMaxRanks];
+};
 __device__ __forceinline__ unsigned long long* error_flag(unsigned char* mail) {
   return reinterpret_cast<unsigned long long*>(mail) + 64;
 }
@@ -124,6 +131,17 @@ struct WindowView {
     return win[rank] + ((size_t)parity * 2 + slot_index) * slot_bytes;
   }
 };
+
+__device__ __forceinline__ PeerView view_from_mailbox(unsigned char* own_mail, unsigned long long seq) {
+  const MailHeader* h = reinterpret_cast<const MailHeader*>(own_mail + kHeaderOff);
+  PeerView pv;
+  pv.rank = h->rank;
+  pv.world = h->world;
+  pv.seq = seq;
+#pragma unroll
+  for (int p = 0; p < kMaxRanks; ++p) pv.mail[p] = h->mail[p];
+  return pv;
+}
 
 // host side (dist.cu)
 bool active();

@@ -150,6 +150,27 @@ int sharded_sum(double* values, int count, cudaStream_t s) {
   return BL_OK;
 }
 
+// Peer-memory route: the cross-rank sum rides in the last block of the streaming kernel itself (its
+// epilogue carries the peer view), so a sharded reduction costs no extra launch.  Returns true when the
+// epilogue was armed; the NCCL-hook route still splits the kernel (EPI_NONE + finish_sharded).
+bool arm_peer_epilogue(Epi& epi, int count, int* rc) {
+  *rc = BL_OK;
+  if (!dist::active()) return false;
+  if (count > dist::kRedSlots) {
+    set_error("reduction too large for the peer mailbox");
+    *rc = BL_EINVAL;
+    return true;
+  }
+  dist::PeerView pv;
+  *rc = dist::next_reduce(&pv);
+  if (pv.world > 1) {  // one rank: the local sums are the global sums
+    epi.peer_mail = pv.mail[pv.rank];
+    epi.peer_seq = pv.seq;
+    epi.peer_count = count;
+  }
+  return true;
+}
+
 template <typename T>
 int finish_sharded(const Common& c, Epi epi, int count, cudaStream_t s) {
   epi.red = c.red;
@@ -246,7 +267,10 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
   epi.red = c.red;
   epi.scal = c.scal;
   const Epi full_epi = epi;
-  const bool sharded = is_sharded();
+  int prc = BL_OK;
+  const bool peer = arm_peer_epilogue(epi, blk.nrows, &prc);
+  BL_CHECK(prc);
+  const bool sharded = !peer && is_sharded();
   if (sharded) epi.mode = EPI_NONE;
   {
   ProfScope prof(BL_PROF_DOTS, (double)(blk.nrows + 1) * n * sizeof(T), s);
@@ -275,7 +299,10 @@ int launch_combine(const Grid& g, const Common& c, CombineArgs a, bool norm, cud
   a.epi.red = c.red;
   a.epi.scal = c.scal;
   const Epi full_epi = a.epi;
-  const bool sharded = norm && is_sharded();
+  int prc = BL_OK;
+  const bool peer = norm && arm_peer_epilogue(a.epi, 1, &prc);
+  BL_CHECK(prc);
+  const bool sharded = norm && !peer && is_sharded();
   if (sharded) a.epi.mode = EPI_NONE;
   const int nrows = a.blk[0].nrows + a.blk[1].nrows;
   {
@@ -411,7 +438,10 @@ int launch_fused_tile(const Common& c, const FusedSpec& f, int dtype, int sr, cu
   a.epi.red = c.red;
   a.epi.scal = c.scal;
   const Epi full_epi = a.epi;
-  const bool sharded = is_sharded();
+  int prc = BL_OK;
+  const bool peer = arm_peer_epilogue(a.epi, f.res.nrows, &prc);
+  BL_CHECK(prc);
+  const bool sharded = !peer && is_sharded();
   if (sharded) a.epi.mode = EPI_NONE;
   a.reverse = next_direction();
   const int nrows = f.res.nrows + f.str0.nrows + f.str1.nrows;

@@ -10,6 +10,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "dist.cuh"
 
 namespace bl {
 
@@ -63,12 +64,20 @@ struct Epi {
   const void* in_t3 = nullptr; // (alphas)
   const void* in_t4 = nullptr; // (betas)
   int slot = 0;
+  // row sharding over peer memory: the `peer_count` values of red[] are summed over the ranks (dist.cuh) by
+  // the block that runs the epilogue, before the epilogue consumes them.  Only the own mailbox and the
+  // sequence number travel with the kernel; the peer table sits in the mailbox header.
+  unsigned char* peer_mail = nullptr;
+  unsigned long long peer_seq = 0;
+  int peer_count = 0;
 };
 
 // Runs in the last block, after `red[0..m)` has been written by that same block and a
 // __syncthreads().
 template <typename T>
 __device__ void run_epilogue(const Epi& e) {
+  if (e.peer_mail != nullptr && e.peer_count > 0)
+    dist::peer_allreduce_block(dist::view_from_mailbox(e.peer_mail, e.peer_seq), e.red, e.peer_count);
   const int t = threadIdx.x, nt = blockDim.x;
   const int K = e.K, i = e.i;
   switch (e.mode) {
