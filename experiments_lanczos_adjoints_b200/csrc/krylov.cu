@@ -105,9 +105,18 @@ bool use_tma(int64_t n) { return stream_mode() != 0 && n >= 8192; }
 template <typename T>
 constexpr int dots_tile() { return BL_DOTS_TILE_BYTES / (int)sizeof(T); }  // row segment per copy
 
+// Blocks per SM of the TMA-staged kernels (BL_BLOCKS_PER_SM = 1 or 2, default 2).  Two fill the shared memory
+// of an SM; one leaves room for the successor's blocks to become resident and prefetch under the tail.
+int blocks_per_sm() {
+  static int v = [] {
+    const char* e = std::getenv("BL_BLOCKS_PER_SM");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return v;
+}
 template <typename T>
 int tma_grid(int64_t n, int tile) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(2 * sm_count(), kMaxDotsGrid), (n + tile - 1) / tile));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(blocks_per_sm() * sm_count(), kMaxDotsGrid), (n + tile - 1) / tile));
 }
 
 // Launch with the programmatic-dependent-launch attribute (BL_PDL=0 disables it): the kernel's
