@@ -35,6 +35,14 @@ def _run(op, name, *args):
         raise
 
 
+BL_ADJ_REORTHO_FULL, BL_ADJ_SYMMETRIC = 1, 2  # include/b200_lanczos.h
+
+
+def adjoint_flags(reortho_full: bool, symmetric: bool) -> int:
+    """The `reortho_full` argument of `bl_arnoldi_adjoint(_batch)`."""
+    return (BL_ADJ_REORTHO_FULL if reortho_full else 0) | (BL_ADJ_SYMMETRIC if reortho_full and symmetric else 0)
+
+
 def _ptr(a):
     return a.ptr if a is not None else None
 
@@ -97,12 +105,19 @@ class HessenbergEstimate:
     def __init__(self, op, krylov_depth, *, reortho, custom_vjp, reortho_vjp):
         self.op, self.K = op, krylov_depth
         self.reortho, self.custom_vjp, self.reortho_vjp = reortho, custom_vjp, reortho_vjp
+        # set by `lanczos.tridiag(reortho="full")`, whose operand is symmetric by contract: the adjoint may
+        # treat H as tridiagonal (BL_ADJ_SYMMETRIC in include/b200_lanczos.h)
+        self.symmetric = False
         self._ws = _Workspace()
 
     # arnoldi.py:26 — `reortho_` is always `reortho_vjp`; only "none" switches the 2nd pass off
     @property
     def _second_pass(self) -> bool:
         return self.reortho_vjp != "none"
+
+    @property
+    def _adjoint_flags(self) -> int:
+        return adjoint_flags(self.reortho == "full", self.symmetric and self._second_pass)
 
     def _forward(self, v, params, stream):
         op, K = self.op, self.K
@@ -151,7 +166,7 @@ class HessenbergEstimate:
             dv = dev.DeviceArray((n,), dtype)
             Lam = dev.DeviceArray((K, n), dtype, ld=ld)
             _run(op, "bl_arnoldi_adjoint", op._handle, dev.dtype_code(dtype), n, K,
-                 int(self.reortho == "full"), Q.ptr, ld, H.ptr, r.ptr, c.ptr, _ptr(dQb), dHd.ptr,
+                 self._adjoint_flags, Q.ptr, ld, H.ptr, r.ptr, c.ptr, _ptr(dQb), dHd.ptr,
                  _ptr(drd), _ptr(dcd), dv.ptr, Lam.ptr, ws.ptr, nbytes, stream.ptr)  # fmt: skip
             grads = op.grad_export(dtype, stream=stream)
             return (dv, *grads)

@@ -722,6 +722,16 @@ int arnoldi_forward_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, bool
   return BL_OK;
 }
 
+// BL_ADJ_SYMMETRIC of the caller's flags; BL_SYMMETRIC_ADJOINT=0 in the environment switches the
+// shortcut off (A/B measurements, debugging).
+bool symmetric_shortcut(int flags) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("BL_SYMMETRIC_ADJOINT");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && (flags & BL_ADJ_SYMMETRIC) != 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // One Arnoldi adjoint run, split at the operator call (see FwdRun): begin(), then for idx = K-1..0
 // pre(idx) -> [z = A^T Lambda[idx] (+ parameter cotangent)] -> post(idx), then end().
@@ -752,9 +762,20 @@ struct AdjRun {
   int gram_parts = 0;
   T *z = nullptr, *lam = nullptr;
   bool defer_grad = false, have_reproj = false;
+  // BL_ADJ_SYMMETRIC: the operand is symmetric, so H is tridiagonal up to rounding (full
+  // re-orthogonalisation keeps |H[idx, j]| = O(eps |A|) for j > idx+1) and `Lambda beta_plus`
+  // (arnoldi.py:218) reduces to its one O(1) term, -H[idx, idx+1] Lambda[idx+1]: K-idx-2 basis rows
+  // per step are not read.  SURVEY Appendix B7; off unless the caller says the operand is symmetric.
+  bool symmetric = false;
 
   const T* q_row(int idx) const { return Q + (int64_t)idx * ld; }
   T* lam_row(int idx) const { return Lambda + (int64_t)idx * ld; }
+  // terms of `- Lambda beta_plus`: every later row of Lambda, or (symmetric) row idx+1 as a vector term
+  int lam_rows_streamed(int idx) const { return symmetric ? 0 : K - idx - 1; }
+  template <typename Terms>
+  void add_symmetric_term(int idx, Terms& vec, int& nv) const {
+    if (symmetric && idx + 1 < K) vec[nv++] = term(lam_row(idx + 1), 1.0, c.coefC + idx + 1);
+  }
 
   int begin() {
   Workspace w(workspace, wbytes);
@@ -881,10 +902,11 @@ struct AdjRun {
       f.vec[nv++] = term(r, 1.0, c.scal + S_ETA_IDX);
       f.vec[nv++] = term(Lrow, 1.0, c.scal + S_NEG_ALPHA);
       f.vec[nv++] = term(z);
+      add_symmetric_term(idx, f.vec, nv);
       f.nvec = nv;
       f.res = rows(Q, ld, 0, idx + 1, c.coefB, 1.0);
       f.str0 = rows(Q, ld, idx + 1, K - idx - 1, c.coefB, 1.0, idx + 1);
-      f.str1 = rows(Lambda, ld, idx + 1, K - idx - 1, c.coefC, 1.0, idx + 1);
+      f.str1 = rows(Lambda, ld, idx + 1, lam_rows_streamed(idx), c.coefC, 1.0, idx + 1);
       f.rows_total0 = K;
       f.rows_total1 = K;
       f.out_div_ptr = c.scal + S_BETA_MINUS;
@@ -905,9 +927,10 @@ struct AdjRun {
       a.vec[nv++] = term(r, 1.0, c.scal + S_ETA_IDX);
       a.vec[nv++] = term(Lrow, 1.0, c.scal + S_NEG_ALPHA);
       a.vec[nv++] = term(z);
+      add_symmetric_term(idx, a.vec, nv);
       a.nvec = nv;
       a.blk[0] = rows(Q, ld, 0, K, c.coefB, 1.0);
-      a.blk[1] = rows(Lambda, ld, idx + 1, K - idx - 1, c.coefC, 1.0, idx + 1);
+      a.blk[1] = rows(Lambda, ld, idx + 1, lam_rows_streamed(idx), c.coefC, 1.0, idx + 1);
       a.out_div_ptr = c.scal + S_BETA_MINUS;
       BL_CHECK(launch_combine<T>(g, c, a, false, s));
     }
@@ -930,11 +953,12 @@ struct AdjRun {
 };
 
 template <typename T>
-int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reortho_full, const T* Q,
+int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags, const T* Q,
                       int64_t ld, const T* H, const T* r, const T* c_in, const T* dQ, const T* dH,
                       const T* dr, const T* dc, T* dv, T* Lambda, void* workspace, size_t wbytes,
                       cudaStream_t s) {
-  AdjRun<T> run{op, dtype, n, K, reortho_full, Q, ld, H, r, c_in, dQ, dH, dr, dc, dv, Lambda, workspace, wbytes, s, {}, {}};
+  AdjRun<T> run{op, dtype, n, K, (flags & BL_ADJ_REORTHO_FULL) != 0, Q, ld, H, r, c_in, dQ, dH, dr, dc, dv, Lambda, workspace, wbytes, s, {}, {}};
+  run.symmetric = symmetric_shortcut(flags);
   BL_CHECK(run.begin());
   for (int idx = K - 1; idx >= 0; --idx) {
     BL_CHECK(run.pre(idx));
@@ -958,7 +982,7 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reort
 // P independent adjoint runs in lockstep (bases of the P forward runs are contiguous: Q[p][K][ld]): one
 // batched A^T Lambda per step, and ONE batched parameter-cotangent pass over all P*K (lambda, q) pairs.
 template <typename T>
-int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, bool reortho_full, int P, const T* Q,
+int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags, int P, const T* Q,
                             int64_t ld, const T* H, const T* r, const T* c_in, const T* dH, T* dv, int64_t lddv,
                             T* Lambda, void* workspace, size_t wbytes, cudaStream_t s) {
   const size_t per = bl_arnoldi_workspace_bytes(n, K, dtype);
@@ -968,10 +992,11 @@ int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, bool
   std::vector<const void*> in(P);
   std::vector<void*> out(P);
   for (int p = 0; p < P; ++p) {
-    runs.push_back(AdjRun<T>{op, dtype, n, K, reortho_full, Q + (int64_t)p * K * ld, ld, H + (int64_t)p * K * K,
+    runs.push_back(AdjRun<T>{op, dtype, n, K, (flags & BL_ADJ_REORTHO_FULL) != 0, Q + (int64_t)p * K * ld, ld, H + (int64_t)p * K * K,
                              r + (int64_t)p * ld, c_in + p, nullptr, dH + (int64_t)p * K * K, nullptr, nullptr,
                              dv + (int64_t)p * lddv, Lambda + (int64_t)p * K * ld,
                              static_cast<char*>(workspace) + per * p, per, s, {}, {}});
+    runs.back().symmetric = symmetric_shortcut(flags);
     BL_CHECK(runs.back().begin());
     out[p] = runs[p].z;
   }
@@ -1180,11 +1205,11 @@ int bl_arnoldi_adjoint(bl_operator_t* op, int dtype, int64_t n, int64_t K, int r
   BL_REQUIRE(ld <= (int64_t)align_up((size_t)n, 64), "ld must be at most n rounded up to 64");
   cudaStream_t s = as_stream(stream);
   if (dtype == BL_F32)
-    return arnoldi_adjoint_t<float>(op, dtype, n, (int)K, reortho_full != 0, (const float*)Q, ld, (const float*)H,
+    return arnoldi_adjoint_t<float>(op, dtype, n, (int)K, reortho_full, (const float*)Q, ld, (const float*)H,
                                     (const float*)r, (const float*)c, (const float*)dQ, (const float*)dH,
                                     (const float*)dr, (const float*)dc, (float*)dv, (float*)Lambda, workspace,
                                     workspace_bytes, s);
-  return arnoldi_adjoint_t<double>(op, dtype, n, (int)K, reortho_full != 0, (const double*)Q, ld, (const double*)H,
+  return arnoldi_adjoint_t<double>(op, dtype, n, (int)K, reortho_full, (const double*)Q, ld, (const double*)H,
                                    (const double*)r, (const double*)c, (const double*)dQ, (const double*)dH,
                                    (const double*)dr, (const double*)dc, (double*)dv, (double*)Lambda, workspace,
                                    workspace_bytes, s);
@@ -1216,10 +1241,10 @@ int bl_arnoldi_adjoint_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K,
   BL_REQUIRE(ld <= (int64_t)align_up((size_t)n, 64), "ld must be at most n rounded up to 64");
   cudaStream_t s = as_stream(stream);
   if (dtype == BL_F32)
-    return arnoldi_adjoint_batch_t<float>(op, dtype, n, (int)K, reortho_full != 0, (int)count, (const float*)Q, ld,
+    return arnoldi_adjoint_batch_t<float>(op, dtype, n, (int)K, reortho_full, (int)count, (const float*)Q, ld,
                                           (const float*)H, (const float*)r, (const float*)c, (const float*)dH,
                                           (float*)dv, lddv, (float*)Lambda, workspace, workspace_bytes, s);
-  return arnoldi_adjoint_batch_t<double>(op, dtype, n, (int)K, reortho_full != 0, (int)count, (const double*)Q, ld,
+  return arnoldi_adjoint_batch_t<double>(op, dtype, n, (int)K, reortho_full, (int)count, (const double*)Q, ld,
                                          (const double*)H, (const double*)r, (const double*)c, (const double*)dH,
                                          (double*)dv, lddv, (double*)Lambda, workspace, workspace_bytes, s);
 }

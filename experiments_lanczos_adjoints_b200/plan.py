@@ -16,6 +16,7 @@ import numpy as np
 
 from experiments_lanczos_adjoints_b200 import _lib
 from experiments_lanczos_adjoints_b200 import device as dev
+from experiments_lanczos_adjoints_b200.arnoldi import adjoint_flags
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:
@@ -45,6 +46,8 @@ class TridiagAdjointPlan:
         if K < 1 or K > n:
             raise ValueError(f"Parameter depth {K} is outside the expected range")
         self.code = dev.dtype_code(self.dtype)
+        # `tridiag` is defined for symmetric operands: the adjoint treats H as tridiagonal (BL_ADJ_SYMMETRIC)
+        self.adjoint_flags = adjoint_flags(True, True)
         self.ld = dev.basis_ld(n, self.dtype)
         self.Q = dev.DeviceArray((K, n), self.dtype, ld=self.ld)
         self.Lam = dev.DeviceArray((K, n), self.dtype, ld=self.ld)
@@ -86,7 +89,7 @@ class TridiagAdjointPlan:
     def adjoint(self, dQ=None, dr=None):
         s = self.stream.ptr
         _lib.call("bl_op_grad_zero", self.op._handle, self.code, s)
-        _lib.call("bl_arnoldi_adjoint", self.op._handle, self.code, self.n, self.K, 1, self.Q.ptr, self.ld,
+        _lib.call("bl_arnoldi_adjoint", self.op._handle, self.code, self.n, self.K, self.adjoint_flags, self.Q.ptr, self.ld,
                   self.H.ptr, self.r.ptr, self.c.ptr, dQ.ptr if dQ is not None else None, self.dH.ptr,
                   dr.ptr if dr is not None else None, None, self.dv.ptr, self.Lam.ptr, self.ws.ptr,
                   self.ws_bytes, s)  # fmt: skip

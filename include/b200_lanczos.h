@@ -222,7 +222,16 @@ int bl_arnoldi_forward(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_d
                        const void* v, void* Q, int64_t ld, void* H, void* r, void* c,
                        void* workspace, size_t workspace_bytes, void* stream);
 
-/* arnoldi._adjoint (arnoldi.py:104-220).  reortho_full != 0 re-projects lambda
+/* Bits of the `reortho_full` argument of the adjoint entry points (0 / 1 keep their meaning). */
+#define BL_ADJ_REORTHO_FULL 1 /* `reortho == "full"`: re-project lambda, arnoldi.py:201-204 */
+#define BL_ADJ_SYMMETRIC 2    /* the operand is symmetric and the forward ran with second_pass (what
+                               * lanczos.tridiag(reortho="full") guarantees, lanczos.py:152-169): H is
+                               * tridiagonal up to rounding, and `Lambda beta_plus` (arnoldi.py:218) keeps
+                               * only its O(1) term H[idx, idx+1] Lambda[idx+1].  Results change by
+                               * O(eps K |Lambda|); K^2/2 fewer basis rows are read per sweep.
+                               * BL_SYMMETRIC_ADJOINT=0 in the environment ignores the bit. */
+
+/* arnoldi._adjoint (arnoldi.py:104-220).  reortho_full & BL_ADJ_REORTHO_FULL re-projects lambda
  * (`reortho == "full"`, arnoldi.py:201-204).  dQ (K rows, ld), dr, dc may be NULL (= zero
  * cotangent, the SLQ case of SURVEY 3.3).  Lambda is a K x ld scratch basis supplied by the
  * caller.  Output dv (n); parameter gradients accumulate in `op`. */

@@ -240,6 +240,35 @@ def test_sparse_tridiag_and_adjoint_match_oracle(dtype, n, K):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_symmetric_adjoint_shortcut_matches_general_adjoint(dtype):
+    """`BL_ADJ_SYMMETRIC` (what `tridiag(reortho="full")` passes: `Lambda beta_plus`, arnoldi.py:218, keeps only
+    its super-diagonal term) against the general adjoint, which multiplies the O(eps) entries of `H` above the
+    first super-diagonal into `Lambda` like the reference.  Same operand, same cotangent."""
+    n, K = 30011, 64
+    row, col, data = banded_spd(n, 4, seed=11)
+    rng = np.random.default_rng(12)
+    v = rng.standard_normal(n)
+    op = bl.operators.SparseOperator(row, col, (n, n))
+    alg = bl.arnoldi.hessenberg(op, K, reortho="full")
+    dalpha, dbeta = rng.standard_normal(K), rng.standard_normal(K - 1)
+    dH = np.diag(dalpha) + 0.5 * (np.diag(dbeta, 1) + np.diag(dbeta, -1))
+    cots = [(None, dH, None, None),
+            (rng.standard_normal((n, K)), dH, rng.standard_normal(n), rng.standard_normal())]  # fmt: skip
+    results = {}
+    for symmetric in (False, True):
+        alg.symmetric = symmetric
+        assert alg._adjoint_flags == (3 if symmetric else 1)
+        (_, H, _, _), pull = bl.vjp(alg, v.astype(dtype), data.astype(dtype))
+        results[symmetric] = [tuple(x.numpy() for x in pull(c)) for c in cots]
+    Hh = H.numpy()
+    assert np.abs(np.triu(Hh, 2)).max() < 100 * np.finfo(dtype).eps * np.abs(Hh).max()  # why the shortcut is legal
+    t = F64 if dtype == np.float64 else F32_GRAD
+    for general, short in zip(results[False], results[True]):
+        for a, b in zip(general, short):
+            assert rel_err(b, a) < t
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_lanczos3_matches_oracle(dtype):
     n, K = 3001, 12
     row, col, data = banded_spd(n, 3, seed=5)
