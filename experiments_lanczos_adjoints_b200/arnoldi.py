@@ -35,12 +35,17 @@ def _run(op, name, *args):
         raise
 
 
-BL_ADJ_REORTHO_FULL, BL_ADJ_SYMMETRIC = 1, 2  # include/b200_lanczos.h
+BL_ADJ_REORTHO_FULL, BL_ADJ_SYMMETRIC, BL_ADJ_TRIDIAG_COTANGENT = 1, 2, 4  # include/b200_lanczos.h
 
 
-def adjoint_flags(reortho_full: bool, symmetric: bool) -> int:
+def adjoint_flags(reortho_full: bool, symmetric: bool, tridiagonal_cotangent: bool = False) -> int:
     """The `reortho_full` argument of `bl_arnoldi_adjoint(_batch)`."""
-    return (BL_ADJ_REORTHO_FULL if reortho_full else 0) | (BL_ADJ_SYMMETRIC if reortho_full and symmetric else 0)
+    flags = BL_ADJ_REORTHO_FULL if reortho_full else 0
+    if reortho_full and symmetric:
+        flags |= BL_ADJ_SYMMETRIC
+        if tridiagonal_cotangent:
+            flags |= BL_ADJ_TRIDIAG_COTANGENT
+    return flags
 
 
 def _ptr(a):
@@ -108,6 +113,7 @@ class HessenbergEstimate:
         # set by `lanczos.tridiag(reortho="full")`, whose operand is symmetric by contract: the adjoint may
         # treat H as tridiagonal (BL_ADJ_SYMMETRIC in include/b200_lanczos.h)
         self.symmetric = False
+        self.tridiagonal_cotangent = False  # dH handed to the pullback is tridiagonal (BL_ADJ_TRIDIAG_COTANGENT)
         self._ws = _Workspace()
 
     # arnoldi.py:26 — `reortho_` is always `reortho_vjp`; only "none" switches the 2nd pass off
@@ -117,7 +123,7 @@ class HessenbergEstimate:
 
     @property
     def _adjoint_flags(self) -> int:
-        return adjoint_flags(self.reortho == "full", self.symmetric and self._second_pass)
+        return adjoint_flags(self.reortho == "full", self.symmetric and self._second_pass, self.tridiagonal_cotangent)
 
     def _forward(self, v, params, stream):
         op, K = self.op, self.K

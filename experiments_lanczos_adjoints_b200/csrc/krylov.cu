@@ -767,6 +767,15 @@ struct AdjRun {
   // (arnoldi.py:218) reduces to its one O(1) term, -H[idx, idx+1] Lambda[idx+1]: K-idx-2 basis rows
   // per step are not read.  SURVEY Appendix B7; off unless the caller says the operand is symmetric.
   bool symmetric = false;
+  // BL_ADJ_TRIDIAG_COTANGENT on top of it, no dQ: Gamma is banded.  After the re-projection
+  // Q_{<=idx+1}^T lambda = dH[:idx+2, idx] exactly (arnoldi.py:201-204), and A q_j = Q H[:, j], so
+  // Gamma[idx, j] = (H dH^T - dH^T H)[idx, j] up to rounding -- zero for j < idx-2 when H and dH are
+  // tridiagonal.  The dots `Q^T (A^T lambda)` (arnoldi.py:213) then need rows idx-2..idx only and
+  // `Q (Gamma + Gamma^T)[idx]` (arnoldi.py:217) rows idx-2..idx+2: the sweep reads the active basis
+  // twice per step (the re-projection itself), like the forward's Gram-Schmidt passes.
+  bool tridiag_cot = false, banded = false;
+  int band_lo(int idx) const { return banded ? std::max(0, idx - 2) : 0; }
+  int band_hi(int idx) const { return banded ? std::min(idx + 3, K) : K; }  // exclusive
 
   const T* q_row(int idx) const { return Q + (int64_t)idx * ld; }
   T* lam_row(int idx) const { return Lambda + (int64_t)idx * ld; }
@@ -791,6 +800,7 @@ struct AdjRun {
   BL_REQUIRE(w.ok(), "workspace too small (bl_arnoldi_workspace_bytes)");
   g = pick_grid<T>(n);
   defer_grad = op->deferred_grad(dtype);
+  banded = symmetric && tridiag_cot && reortho_full && dQ == nullptr;
 
   BL_CUDA(cudaMemsetAsync(c.counters, 0, 256, s));
   BL_CUDA(cudaMemsetAsync(Gamma, 0, (size_t)K * K * 8, s));
@@ -880,14 +890,15 @@ struct AdjRun {
       e.mode = EPI_ADJ_GAMMA;
       e.i = idx;
       e.K = K;
-      e.m = idx + 1;
+      e.j0 = band_lo(idx);
+      e.m = idx + 1 - e.j0;
       e.Hc = H;
       e.Gamma = Gamma;
       e.PiGamma = PiGamma;
       e.eta = eta;
       e.coef = c.coefB;
       e.coef2 = c.coefC;
-      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, idx + 1), z, n, e, s));
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, e.j0, e.m), z, n, e, s));
     }
     // lambda = (Pi_xi[idx] + Q gamma_row - alpha lambda + A^T lambda - Lambda beta_plus) / beta_minus
     have_reproj = false;
@@ -904,8 +915,10 @@ struct AdjRun {
       f.vec[nv++] = term(z);
       add_symmetric_term(idx, f.vec, nv);
       f.nvec = nv;
-      f.res = rows(Q, ld, 0, idx + 1, c.coefB, 1.0);
-      f.str0 = rows(Q, ld, idx + 1, K - idx - 1, c.coefB, 1.0, idx + 1);
+      // banded: rows idx+1, idx+2 ride as resident rows (their two extra dots are not read by the epilogue)
+      const int nres = banded ? band_hi(idx) : idx + 1;
+      f.res = rows(Q, ld, 0, nres, c.coefB, 1.0);
+      f.str0 = rows(Q, ld, nres, K - nres, c.coefB, 1.0, nres);
       f.str1 = rows(Lambda, ld, idx + 1, lam_rows_streamed(idx), c.coefC, 1.0, idx + 1);
       f.rows_total0 = K;
       f.rows_total1 = K;
@@ -929,7 +942,7 @@ struct AdjRun {
       a.vec[nv++] = term(z);
       add_symmetric_term(idx, a.vec, nv);
       a.nvec = nv;
-      a.blk[0] = rows(Q, ld, 0, K, c.coefB, 1.0);
+      a.blk[0] = rows(Q, ld, band_lo(idx), band_hi(idx) - band_lo(idx), c.coefB, 1.0, band_lo(idx));
       a.blk[1] = rows(Lambda, ld, idx + 1, lam_rows_streamed(idx), c.coefC, 1.0, idx + 1);
       a.out_div_ptr = c.scal + S_BETA_MINUS;
       BL_CHECK(launch_combine<T>(g, c, a, false, s));
@@ -959,6 +972,7 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
                       cudaStream_t s) {
   AdjRun<T> run{op, dtype, n, K, (flags & BL_ADJ_REORTHO_FULL) != 0, Q, ld, H, r, c_in, dQ, dH, dr, dc, dv, Lambda, workspace, wbytes, s, {}, {}};
   run.symmetric = symmetric_shortcut(flags);
+  run.tridiag_cot = (flags & BL_ADJ_TRIDIAG_COTANGENT) != 0;
   BL_CHECK(run.begin());
   for (int idx = K - 1; idx >= 0; --idx) {
     BL_CHECK(run.pre(idx));
@@ -997,6 +1011,7 @@ int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int 
                              dv + (int64_t)p * lddv, Lambda + (int64_t)p * K * ld,
                              static_cast<char*>(workspace) + per * p, per, s, {}, {}});
     runs.back().symmetric = symmetric_shortcut(flags);
+    runs.back().tridiag_cot = (flags & BL_ADJ_TRIDIAG_COTANGENT) != 0;
     BL_CHECK(runs.back().begin());
     out[p] = runs[p].z;
   }

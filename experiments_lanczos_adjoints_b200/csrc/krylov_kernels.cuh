@@ -64,6 +64,7 @@ struct Epi {
   const void* in_t3 = nullptr; // (alphas)
   const void* in_t4 = nullptr; // (betas)
   int slot = 0;
+  int j0 = 0;  // EPI_ADJ_GAMMA: red[] holds the dots with rows j0..idx only; Gamma[idx, j < j0] = 0
   // row sharding over peer memory: the `peer_count` values of red[] are summed over the ranks (dist.cuh) by
   // the block that runs the epilogue, before the epilogue consumes them.  Only the own mailbox and the
   // sequence number travel with the kernel; the peer table sits in the mailbox header.
@@ -135,8 +136,8 @@ __device__ void run_epilogue(const Epi& e) {
       // Gamma[idx, j] = lower_mask[idx, j] * (Pi_gamma[idx, j] - (A^T lam)^T q_j),  j <= idx
       for (int j = t; j < K; j += nt) {
         double g = 0.0;
-        if (j <= idx) {
-          g = e.PiGamma[(size_t)idx * K + j] - e.red[j];
+        if (j <= idx && j >= e.j0) {
+          g = e.PiGamma[(size_t)idx * K + j] - e.red[j - e.j0];
           if (j == idx) g *= 0.5;
           g = static_cast<double>(static_cast<T>(g));
         }

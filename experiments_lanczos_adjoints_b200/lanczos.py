@@ -47,6 +47,7 @@ class _TridiagFull:
     def __init__(self, op, krylov_depth, custom_vjp):
         self.alg = arnoldi.hessenberg(op, krylov_depth, custom_vjp=custom_vjp, reortho="full")
         self.alg.symmetric = True  # tridiagonalisation is defined for symmetric operands (lanczos.py:152-169)
+        self.alg.tridiagonal_cotangent = True  # `pullback` below builds dH from (dalpha, dbeta)
 
     @staticmethod
     def _wrap(Qn, H, r, stream):
@@ -319,7 +320,7 @@ def probe_batch_sum(integrand, probes, parameters, *, with_grad, stream=None, ch
             dHd = dev.asarray(dH.reshape(B, K * K))
             dv = dev.DeviceArray((B, n), dtype, ld=ld)
             Lam = dev.DeviceArray((B * K, n), dtype, ld=ld)
-            _lib.call("bl_arnoldi_adjoint_batch", op._handle, code, n, K, arnoldi.adjoint_flags(True, True), B, Q.ptr, ld, H.ptr, r.ptr, c.ptr, dHd.ptr,
+            _lib.call("bl_arnoldi_adjoint_batch", op._handle, code, n, K, arnoldi.adjoint_flags(True, True, True), B, Q.ptr, ld, H.ptr, r.ptr, c.ptr, dHd.ptr,
                       dv.ptr, ld, Lam.ptr, ws.ptr, per * B, stream.ptr)  # fmt: skip
             stream.synchronize()  # the buffers of this chunk go back to the pool
     if with_grad:

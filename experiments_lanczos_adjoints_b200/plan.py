@@ -38,7 +38,7 @@ class TridiagAdjointPlan:
     """`(Q^T, alpha, beta), r = tridiag(op, K, reortho="full")(v, params)` followed by the adjoint
     for cotangents on `(alpha, beta)` (the SLQ case) or on every output."""
 
-    def __init__(self, op, krylov_depth: int, dtype, stream: dev.Stream | None = None):
+    def __init__(self, op, krylov_depth: int, dtype, stream: dev.Stream | None = None, tridiagonal_cotangent: bool = True):
         self.op, self.K, self.dtype = op, int(krylov_depth), np.dtype(dtype)
         self.n = op.n
         self.stream = stream or dev.default_stream()
@@ -46,8 +46,9 @@ class TridiagAdjointPlan:
         if K < 1 or K > n:
             raise ValueError(f"Parameter depth {K} is outside the expected range")
         self.code = dev.dtype_code(self.dtype)
-        # `tridiag` is defined for symmetric operands: the adjoint treats H as tridiagonal (BL_ADJ_SYMMETRIC)
-        self.adjoint_flags = adjoint_flags(True, True)
+        # `tridiag` is defined for symmetric operands and its cotangent dH is tridiagonal: the adjoint treats H as
+        # tridiagonal and Gamma as banded (BL_ADJ_SYMMETRIC | BL_ADJ_TRIDIAG_COTANGENT, include/b200_lanczos.h)
+        self.adjoint_flags = adjoint_flags(True, True, tridiagonal_cotangent)
         self.ld = dev.basis_ld(n, self.dtype)
         self.Q = dev.DeviceArray((K, n), self.dtype, ld=self.ld)
         self.Lam = dev.DeviceArray((K, n), self.dtype, ld=self.ld)

@@ -230,6 +230,11 @@ int bl_arnoldi_forward(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_d
                                * only its O(1) term H[idx, idx+1] Lambda[idx+1].  Results change by
                                * O(eps K |Lambda|); K^2/2 fewer basis rows are read per sweep.
                                * BL_SYMMETRIC_ADJOINT=0 in the environment ignores the bit. */
+#define BL_ADJ_TRIDIAG_COTANGENT 4 /* with BL_ADJ_SYMMETRIC | BL_ADJ_REORTHO_FULL and dQ == NULL: dH is
+                               * tridiagonal (the cotangent of lanczos.tridiag's (alpha, beta), lanczos.py:162-164).
+                               * Gamma (arnoldi.py:213) is then banded up to rounding, because the re-projected
+                               * lambda satisfies Q^T lambda = dH[:, idx] exactly: the dots Q^T(A^T lambda) are
+                               * taken with rows idx-2..idx and Q (Gamma+Gamma^T)[idx] with rows idx-2..idx+2. */
 
 /* arnoldi._adjoint (arnoldi.py:104-220).  reortho_full & BL_ADJ_REORTHO_FULL re-projects lambda
  * (`reortho == "full"`, arnoldi.py:201-204).  dQ (K rows, ld), dr, dc may be NULL (= zero

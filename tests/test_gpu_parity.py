@@ -240,10 +240,11 @@ def test_sparse_tridiag_and_adjoint_match_oracle(dtype, n, K):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_symmetric_adjoint_shortcut_matches_general_adjoint(dtype):
-    """`BL_ADJ_SYMMETRIC` (what `tridiag(reortho="full")` passes: `Lambda beta_plus`, arnoldi.py:218, keeps only
-    its super-diagonal term) against the general adjoint, which multiplies the O(eps) entries of `H` above the
-    first super-diagonal into `Lambda` like the reference.  Same operand, same cotangent."""
+def test_symmetric_adjoint_shortcuts_match_general_adjoint(dtype):
+    """What `tridiag(reortho="full")` passes to the adjoint -- `BL_ADJ_SYMMETRIC` (`Lambda beta_plus`, arnoldi.py:218,
+    keeps only its super-diagonal term) and `BL_ADJ_TRIDIAG_COTANGENT` (banded `Gamma`, arnoldi.py:213-217) --
+    against the general adjoint, which carries the O(eps) entries of `H` and `Gamma` outside the bands like the
+    reference.  Same operand, same cotangents."""
     n, K = 30011, 64
     row, col, data = banded_spd(n, 4, seed=11)
     rng = np.random.default_rng(12)
@@ -253,19 +254,21 @@ def test_symmetric_adjoint_shortcut_matches_general_adjoint(dtype):
     dalpha, dbeta = rng.standard_normal(K), rng.standard_normal(K - 1)
     dH = np.diag(dalpha) + 0.5 * (np.diag(dbeta, 1) + np.diag(dbeta, -1))
     cots = [(None, dH, None, None),
+            (None, dH, rng.standard_normal(n), rng.standard_normal()),
             (rng.standard_normal((n, K)), dH, rng.standard_normal(n), rng.standard_normal())]  # fmt: skip
     results = {}
-    for symmetric in (False, True):
-        alg.symmetric = symmetric
-        assert alg._adjoint_flags == (3 if symmetric else 1)
+    for flags, (symmetric, tridiagonal) in {1: (False, False), 3: (True, False), 7: (True, True)}.items():
+        alg.symmetric, alg.tridiagonal_cotangent = symmetric, tridiagonal
+        assert alg._adjoint_flags == flags
         (_, H, _, _), pull = bl.vjp(alg, v.astype(dtype), data.astype(dtype))
-        results[symmetric] = [tuple(x.numpy() for x in pull(c)) for c in cots]
+        results[flags] = [tuple(x.numpy() for x in pull(c)) for c in cots]
     Hh = H.numpy()
     assert np.abs(np.triu(Hh, 2)).max() < 100 * np.finfo(dtype).eps * np.abs(Hh).max()  # why the shortcut is legal
     t = F64 if dtype == np.float64 else F32_GRAD
-    for general, short in zip(results[False], results[True]):
-        for a, b in zip(general, short):
-            assert rel_err(b, a) < t
+    for flags in (3, 7):
+        for general, short in zip(results[1], results[flags]):
+            for a, b in zip(general, short):
+                assert rel_err(b, a) < t, flags
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -402,6 +405,12 @@ def test_full_size_properties(dtype):
     dv3, dp3 = pull(((None, (c1[0] + 2 * c2[0], c1[1] + 2 * c2[1])), (None, None)))
     assert rel_err(dv3.numpy(), dv1.numpy() + 2 * dv2.numpy()) < 1e-4
     assert rel_err(dp3.numpy(), dp1.numpy() + 2 * dp2.numpy()) < 1e-4
+    # the symmetric / banded shortcuts of the adjoint (BL_ADJ_SYMMETRIC | BL_ADJ_TRIDIAG_COTANGENT, what `tridiag`
+    # passes) against the general adjoint that carries every entry of H and Gamma, at the headline size
+    alg.alg.symmetric = alg.alg.tridiagonal_cotangent = False
+    dv1_general, dp1_general = pull(((None, c1), (None, None)))
+    assert rel_err(dv1.numpy(), dv1_general.numpy()) < 1e-4
+    assert rel_err(dp1.numpy(), dp1_general.numpy()) < 1e-4
 
 
 def test_peer_memory_route_two_ranks_on_one_gpu_matches_single_operator():
