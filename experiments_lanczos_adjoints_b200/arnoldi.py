@@ -38,6 +38,11 @@ def _run(op, name, *args):
 BL_ADJ_REORTHO_FULL, BL_ADJ_SYMMETRIC, BL_ADJ_TRIDIAG_COTANGENT = 1, 2, 4  # include/b200_lanczos.h
 
 
+def forward_flags(second_pass: bool, symmetric: bool) -> int:
+    """The `second_pass` argument of `bl_arnoldi_forward(_batch)`."""
+    return (1 if second_pass else 0) | (2 if second_pass and symmetric else 0)
+
+
 def adjoint_flags(reortho_full: bool, symmetric: bool, tridiagonal_cotangent: bool = False) -> int:
     """The `reortho_full` argument of `bl_arnoldi_adjoint(_batch)`."""
     flags = BL_ADJ_REORTHO_FULL if reortho_full else 0
@@ -122,6 +127,10 @@ class HessenbergEstimate:
         return self.reortho_vjp != "none"
 
     @property
+    def _forward_flags(self) -> int:  # BL_FWD_SECOND_PASS | BL_FWD_SYMMETRIC (include/b200_lanczos.h)
+        return forward_flags(self._second_pass, self.symmetric)
+
+    @property
     def _adjoint_flags(self) -> int:
         return adjoint_flags(self.reortho == "full", self.symmetric and self._second_pass, self.tridiagonal_cotangent)
 
@@ -143,7 +152,7 @@ class HessenbergEstimate:
         c = dev.DeviceArray((), dtype)
         nbytes = _lib.load().bl_arnoldi_workspace_bytes(n, K, dev.dtype_code(dtype))
         ws = self._ws.get(("arnoldi", n, K, dtype.str), nbytes)
-        _run(op, "bl_arnoldi_forward", op._handle, dev.dtype_code(dtype), n, K, int(self._second_pass),
+        _run(op, "bl_arnoldi_forward", op._handle, dev.dtype_code(dtype), n, K, self._forward_flags,
              v.ptr, Q.ptr, ld, H.ptr, r.ptr, c.ptr, ws.ptr, nbytes, stream.ptr)  # fmt: skip
         return (Q, H, r, c), (n, dtype, ld, nbytes, ws, bound)
 

@@ -537,6 +537,16 @@ int check_basis(int dtype, int64_t n, int64_t K, int64_t ld, const void* Q) {
   return BL_OK;
 }
 
+// BL_FWD_SYMMETRIC of the caller's flags (needs the second pass); BL_SYMMETRIC_FORWARD=0 in the
+// environment switches it off (A/B measurements, debugging).
+bool symmetric_forward(int flags) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("BL_SYMMETRIC_FORWARD");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && (flags & BL_FWD_SYMMETRIC) != 0 && (flags & BL_FWD_SECOND_PASS) != 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // One Arnoldi forward run, split at the matvec so that several runs (probes) can advance in lockstep
 // and share ONE batched matvec per step (arnoldi_forward_batch_t): begin(), then per step
@@ -560,6 +570,11 @@ struct FwdRun {
   Common c;
   Grid g;
   T* alt = nullptr;    // spare vector: the fused normalise + matvec cannot run in place
+  // BL_FWD_SYMMETRIC: the first Gram-Schmidt pass (arnoldi.py:87-88) takes rows i-1 and i only -- for a
+  // symmetric operand the other entries of h = Q^H (A q_i) are O(eps |A|) while Q stays orthonormal, and the
+  // second pass (arnoldi.py:91-92) removes what they would have removed: v'' = (I - Q Q^H) v' either way.
+  bool local_first = false;
+  int first_lo(int i) const { return local_first ? std::max(0, i - 1) : 0; }
   T* r_out = nullptr;  // the caller's remainder buffer (`r` is the CURRENT vector and may be `alt`)
 
   T* q_row(int i) const { return Q + (int64_t)i * ld; }
@@ -621,10 +636,11 @@ struct FwdRun {
       e.mode = EPI_FWD_A;
       e.i = i;
       e.K = K;
-      e.m = m;
+      e.j0 = first_lo(i);
+      e.m = m - e.j0;
       e.H = H;
       e.coef = c.coefA;
-      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, m), r, n, e, s));
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, e.j0, e.m), r, n, e, s));
     }
     Epi norm_epi;  // length = sqrt(v . v); h[i+1] = length                      arnoldi.py:95-98
     norm_epi.mode = EPI_FWD_NORM;
@@ -654,7 +670,7 @@ struct FwdRun {
       a.out = r;
       a.nvec = 1;
       a.vec[0] = term(r);
-      a.blk[0] = rows(Q, ld, 0, m, c.coefA, -1.0);
+      a.blk[0] = rows(Q, ld, first_lo(i), m - first_lo(i), c.coefA, -1.0, first_lo(i));
       a.epi = norm_epi;
       BL_CHECK(launch_combine<T>(g, c, a, !second_pass, s));
       if (second_pass) {
@@ -680,9 +696,10 @@ struct FwdRun {
 };
 
 template <typename T>
-int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool second_pass, const T* v, T* Q,
+int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags, const T* v, T* Q,
                       int64_t ld, T* H, T* r, T* c_out, void* workspace, size_t wbytes, cudaStream_t s) {
-  FwdRun<T> run{op, dtype, n, K, second_pass, v, Q, ld, H, r, c_out, workspace, wbytes, s, {}, {}};
+  FwdRun<T> run{op, dtype, n, K, (flags & BL_FWD_SECOND_PASS) != 0, v, Q, ld, H, r, c_out, workspace, wbytes, s, {}, {}};
+  run.local_first = symmetric_forward(flags);
   BL_CHECK(run.begin());
   for (int i = 0; i < K; ++i) {
     BL_CHECK(run.advance(i));
@@ -693,7 +710,7 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, bool secon
 
 // P independent runs in lockstep: per step one batched matvec for all of them.
 template <typename T>
-int arnoldi_forward_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, bool second_pass, int P, const T* v,
+int arnoldi_forward_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags, int P, const T* v,
                             int64_t ldv, T* Q, int64_t ld, T* H, T* r, T* c_out, void* workspace, size_t wbytes,
                             cudaStream_t s) {
   const size_t per = bl_arnoldi_workspace_bytes(n, K, dtype);
@@ -702,9 +719,10 @@ int arnoldi_forward_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, bool
   std::vector<const void*> in(P);
   std::vector<void*> out(P);
   for (int p = 0; p < P; ++p) {
-    runs.push_back(FwdRun<T>{op, dtype, n, K, second_pass, v + (int64_t)p * ldv, Q + (int64_t)p * K * ld, ld,
+    runs.push_back(FwdRun<T>{op, dtype, n, K, (flags & BL_FWD_SECOND_PASS) != 0, v + (int64_t)p * ldv, Q + (int64_t)p * K * ld, ld,
                              H + (int64_t)p * K * K, r + (int64_t)p * ld, c_out + p,
                              static_cast<char*>(workspace) + per * p, per, s, {}, {}});
+    runs.back().local_first = symmetric_forward(flags);
     BL_CHECK(runs.back().begin());
     out[p] = runs[p].r;
   }
@@ -1202,9 +1220,9 @@ int bl_arnoldi_forward(bl_operator_t* op, int dtype, int64_t n, int64_t K, int s
   BL_REQUIRE(op->n == n, "operator size does not match n");
   cudaStream_t s = as_stream(stream);
   if (dtype == BL_F32)
-    return arnoldi_forward_t<float>(op, dtype, n, (int)K, second_pass != 0, (const float*)v, (float*)Q, ld,
+    return arnoldi_forward_t<float>(op, dtype, n, (int)K, second_pass, (const float*)v, (float*)Q, ld,
                                     (float*)H, (float*)r, (float*)c, workspace, workspace_bytes, s);
-  return arnoldi_forward_t<double>(op, dtype, n, (int)K, second_pass != 0, (const double*)v, (double*)Q, ld,
+  return arnoldi_forward_t<double>(op, dtype, n, (int)K, second_pass, (const double*)v, (double*)Q, ld,
                                    (double*)H, (double*)r, (double*)c, workspace, workspace_bytes, s);
 }
 
@@ -1238,9 +1256,9 @@ int bl_arnoldi_forward_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K,
   BL_REQUIRE(op->n == n, "operator size does not match n");
   cudaStream_t s = as_stream(stream);
   if (dtype == BL_F32)
-    return arnoldi_forward_batch_t<float>(op, dtype, n, (int)K, second_pass != 0, (int)count, (const float*)v, ldv,
+    return arnoldi_forward_batch_t<float>(op, dtype, n, (int)K, second_pass, (int)count, (const float*)v, ldv,
                                           (float*)Q, ld, (float*)H, (float*)r, (float*)c, workspace, workspace_bytes, s);
-  return arnoldi_forward_batch_t<double>(op, dtype, n, (int)K, second_pass != 0, (int)count, (const double*)v, ldv,
+  return arnoldi_forward_batch_t<double>(op, dtype, n, (int)K, second_pass, (int)count, (const double*)v, ldv,
                                          (double*)Q, ld, (double*)H, (double*)r, (double*)c, workspace, workspace_bytes, s);
 }
 

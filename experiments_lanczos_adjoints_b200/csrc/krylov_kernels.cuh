@@ -64,7 +64,7 @@ struct Epi {
   const void* in_t3 = nullptr; // (alphas)
   const void* in_t4 = nullptr; // (betas)
   int slot = 0;
-  int j0 = 0;  // EPI_ADJ_GAMMA: red[] holds the dots with rows j0..idx only; Gamma[idx, j < j0] = 0
+  int j0 = 0;  // EPI_ADJ_GAMMA / EPI_FWD_A: red[] holds the dots with rows j0.. only; Gamma[idx, j < j0] = 0, h[j < j0] = 0
   // row sharding over peer memory: the `peer_count` values of red[] are summed over the ranks (dist.cuh) by
   // the block that runs the epilogue, before the epilogue consumes them.  Only the own mailbox and the
   // sequence number travel with the kernel; the peer table sits in the mailbox header.
@@ -98,10 +98,10 @@ __device__ void run_epilogue(const Epi& e) {
       }
     } break;
     case EPI_FWD_A: {
-      T* H = static_cast<T*>(e.H);
-      for (int j = t; j < e.m; j += nt) {
-        T h = static_cast<T>(e.red[j]);
-        H[(size_t)j * K + i] = h;
+      T* H = static_cast<T*>(e.H);  // red[] holds the dots with rows j0..i; h[j < j0] = 0 (H starts as zeros)
+      for (int j = t; j < e.j0 + e.m; j += nt) {
+        T h = j >= e.j0 ? static_cast<T>(e.red[j - e.j0]) : T(0);
+        if (j >= e.j0) H[(size_t)j * K + i] = h;
         e.coef[j] = static_cast<double>(h);
       }
     } break;

@@ -302,7 +302,7 @@ def probe_batch_sum(integrand, probes, parameters, *, with_grad, stream=None, ch
         r = dev.DeviceArray((B, n), dtype, ld=ld)
         c = dev.DeviceArray((B,), dtype)
         ws = dev.DeviceArray(((per * B + 7) // 8,), np.float64)
-        _lib.call("bl_arnoldi_forward_batch", op._handle, code, n, K, 1, B, U.ptr, n, Q.ptr, ld, H.ptr, r.ptr, c.ptr,
+        _lib.call("bl_arnoldi_forward_batch", op._handle, code, n, K, arnoldi.forward_flags(True, True), B, U.ptr, n, Q.ptr, ld, H.ptr, r.ptr, c.ptr,
                   ws.ptr, per * B, stream.ptr)  # fmt: skip
         Hh = H.numpy(stream).reshape(B, K, K)
         dH = np.zeros((B, K, K), dtype=dtype)

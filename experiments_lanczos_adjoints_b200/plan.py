@@ -16,7 +16,7 @@ import numpy as np
 
 from experiments_lanczos_adjoints_b200 import _lib
 from experiments_lanczos_adjoints_b200 import device as dev
-from experiments_lanczos_adjoints_b200.arnoldi import adjoint_flags
+from experiments_lanczos_adjoints_b200.arnoldi import adjoint_flags, forward_flags
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:
@@ -84,7 +84,7 @@ class TridiagAdjointPlan:
     def forward(self):
         s = self.stream.ptr
         _lib.call("bl_op_set_params", self.op._handle, self.code, self._pptr, len(self.params), s)
-        _lib.call("bl_arnoldi_forward", self.op._handle, self.code, self.n, self.K, 1, self.v.ptr, self.Q.ptr,
+        _lib.call("bl_arnoldi_forward", self.op._handle, self.code, self.n, self.K, forward_flags(True, True), self.v.ptr, self.Q.ptr,
                   self.ld, self.H.ptr, self.r.ptr, self.c.ptr, self.ws.ptr, self.ws_bytes, s)  # fmt: skip
 
     def adjoint(self, dQ=None, dr=None):

@@ -215,7 +215,16 @@ int bl_op_grad_export(bl_operator_t* op, int dtype, void* const* grads, int num,
 /* ---- Arnoldi with CGS2 re-orthogonalisation and its adjoint (arnoldi.py) --------------- */
 size_t bl_arnoldi_workspace_bytes(int64_t n, int64_t krylov_depth, int dtype);
 
-/* arnoldi._forward (arnoldi.py:57-101).  second_pass != 0 performs the second
+/* Bits of the `second_pass` argument of the forward entry points (0 / 1 keep their meaning). */
+#define BL_FWD_SECOND_PASS 1 /* second Gram-Schmidt pass, arnoldi.py:91-92 */
+#define BL_FWD_SYMMETRIC 2   /* with BL_FWD_SECOND_PASS, symmetric operand (lanczos.tridiag(reortho="full")):
+                              * the first pass (arnoldi.py:87-88) takes h = Q^H v with rows i-1, i only -- the
+                              * other entries are O(eps |A|) and H[j < i-1, i] is stored as zero; the second
+                              * pass still projects against every row, so Q stays orthonormal to rounding.
+                              * The basis is read twice per step instead of three times.
+                              * BL_SYMMETRIC_FORWARD=0 in the environment ignores the bit. */
+
+/* arnoldi._forward (arnoldi.py:57-101).  second_pass & BL_FWD_SECOND_PASS performs the second
  * Gram-Schmidt pass (`reortho_ != "none"`, arnoldi.py:91; the reference's default always
  * does, arnoldi.py:26).  Outputs: Q (K rows, ld), H (K x K), r (n), c (1 element = 1/||v||). */
 int bl_arnoldi_forward(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_depth, int second_pass,

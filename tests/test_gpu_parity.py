@@ -256,14 +256,23 @@ def test_symmetric_adjoint_shortcuts_match_general_adjoint(dtype):
     cots = [(None, dH, None, None),
             (None, dH, rng.standard_normal(n), rng.standard_normal()),
             (rng.standard_normal((n, K)), dH, rng.standard_normal(n), rng.standard_normal())]  # fmt: skip
-    results = {}
+    results, Hs, Qs = {}, {}, {}
     for flags, (symmetric, tridiagonal) in {1: (False, False), 3: (True, False), 7: (True, True)}.items():
         alg.symmetric, alg.tridiagonal_cotangent = symmetric, tridiagonal
-        assert alg._adjoint_flags == flags
-        (_, H, _, _), pull = bl.vjp(alg, v.astype(dtype), data.astype(dtype))
+        assert alg._adjoint_flags == flags and alg._forward_flags == (3 if symmetric else 1)
+        (Q, H, _, _), pull = bl.vjp(alg, v.astype(dtype), data.astype(dtype))
+        Hs[flags], Qs[flags] = H.numpy(), Q.numpy()
         results[flags] = [tuple(x.numpy() for x in pull(c)) for c in cots]
-    Hh = H.numpy()
-    assert np.abs(np.triu(Hh, 2)).max() < 100 * np.finfo(dtype).eps * np.abs(Hh).max()  # why the shortcut is legal
+    eps = np.finfo(dtype).eps
+    # why the shortcuts are legal: the general forward's H is tridiagonal up to rounding
+    assert np.abs(np.triu(Hs[1], 2)).max() < 100 * eps * np.abs(Hs[1]).max()
+    # the symmetric forward (first Gram-Schmidt pass on rows i-1, i; BL_FWD_SYMMETRIC) against the general one
+    t_val = F64 if dtype == np.float64 else F32_VAL
+    assert np.all(np.triu(Hs[7], 2) == 0)
+    assert rel_err(np.diag(Hs[7]), np.diag(Hs[1])) < t_val and rel_err(np.diag(Hs[7], 1), np.diag(Hs[1], 1)) < t_val
+    assert rel_err(Qs[7], Qs[1]) < 10 * t_val
+    gram = Qs[7].astype(np.float64).T @ Qs[7].astype(np.float64)
+    assert np.abs(gram - np.eye(K)).max() < 50 * eps
     t = F64 if dtype == np.float64 else F32_GRAD
     for flags in (3, 7):
         for general, short in zip(results[1], results[flags]):
