@@ -258,6 +258,15 @@ int set_smem(F* kernel, size_t bytes) {
   return BL_OK;
 }
 
+// BL_DOTS_FEW=0 sends dots with <= 4 rows through the TMA pipeline like the wide ones (A/B measurements).
+bool few_rows_enabled() {
+  static const bool enabled = [] {
+    const char* e = std::getenv("BL_DOTS_FEW");
+    return !(e && e[0] == '0');
+  }();
+  return enabled;
+}
+
 RowSource row_source(const RowBlock& b0, const RowBlock* b1, size_t w) {
   RowSource r;
   r.base0 = static_cast<const char*>(b0.base) + (long long)b0.row0 * b0.ld * (long long)w;
@@ -283,7 +292,21 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
   if (sharded) epi.mode = EPI_NONE;
   {
   ProfScope prof(BL_PROF_DOTS, (double)(blk.nrows + 1) * n * sizeof(T), s);
-  if (use_tma(n)) {
+  if (use_tma(n) && blk.nrows <= 4 && few_rows_enabled()) {
+    FewRows fr;
+    for (int j = 0; j < blk.nrows; ++j)
+      fr.row[j] = static_cast<const char*>(blk.base) + (long long)(blk.row0 + j) * blk.ld * (long long)sizeof(T);
+    // about two 16-byte vectors per thread and stream; the partials buffer holds (K+2) x kMaxDotsGrid doubles
+    const long long vecs = n / Vec<T>::N;
+    const int grid = (int)std::max<long long>(1, std::min<long long>({4LL * sm_count(), (vecs + 511) / 512,
+                                                                      (long long)kMaxDotsGrid * 3 / blk.nrows}));
+    switch (blk.nrows) {
+      case 1: BL_CUDA(launch_pdl(k_dots_few<T, 1>, grid, 256, 0, s, fr, x, (long long)n, c.partials_dots, c.counters + 0, epi)); break;
+      case 2: BL_CUDA(launch_pdl(k_dots_few<T, 2>, grid, 256, 0, s, fr, x, (long long)n, c.partials_dots, c.counters + 0, epi)); break;
+      case 3: BL_CUDA(launch_pdl(k_dots_few<T, 3>, grid, 256, 0, s, fr, x, (long long)n, c.partials_dots, c.counters + 0, epi)); break;
+      default: BL_CUDA(launch_pdl(k_dots_few<T, 4>, grid, 256, 0, s, fr, x, (long long)n, c.partials_dots, c.counters + 0, epi)); break;
+    }
+  } else if (use_tma(n)) {
     constexpr int TILE = dots_tile<T>();
     const size_t smem = (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 4) * 8 +
                         (size_t)blk.nrows * 8 + 16;

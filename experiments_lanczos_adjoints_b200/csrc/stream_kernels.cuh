@@ -526,6 +526,67 @@ __host__ __device__ inline FusedLayout fused_layout(int nres, int nstr0, int nst
   return L;
 }
 
+// ---------------------------------------------------------------------------------------------
+// red[j] = <row_j, x> for R <= 4 rows (the neighbouring-row dots of the symmetric loops, norms, single dots):
+// two to five streams saturate nothing and need no staging -- every thread reads 16-byte vectors of x and of the
+// rows straight into registers, one block-wide sum per row, last block reduces and runs the epilogue.  A launch
+// is a few microseconds where the TMA pipeline's ramp costs more than the data.
+struct FewRows {
+  const void* row[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+template <typename T, int R>
+__global__ void __launch_bounds__(256)
+k_dots_few(FewRows rows, const T* __restrict__ x, long long n, double* __restrict__ partials, unsigned int* counter,
+           Epi epi) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  __shared__ double red_smem[32];
+  tma::griddep_launch_dependents();
+  tma::griddep_wait();  // x (and possibly the newest row) are the predecessor's output
+  const long long ngroups = n / VN;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const V* xv = reinterpret_cast<const V*>(x);
+  T acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = T(0);
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    V q[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) q[r] = ld_stream(static_cast<const V*>(rows.row[r]) + g);
+    const V xx = ld_stream(xv + g);
+    T b[VN];
+    vec_unpack(xx, b);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      T a[VN];
+      vec_unpack(q[r], a);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[r] = fma(a[k], b[k], acc[r]);
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {  // scalar tail (n not a multiple of the vector width)
+    for (long long c = ngroups * VN; c < n; ++c)
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fma(static_cast<const T*>(rows.row[r])[c], x[c], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double bs = block_sum(static_cast<double>(acc[r]), red_smem);
+    if (threadIdx.x == 0) partials[(size_t)r * gridDim.x + blockIdx.x] = bs;
+  }
+  if (!last_block_done(counter)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < R) {  // fixed-order reduction over blocks: warp r owns row r
+    double s = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(partials + (size_t)warp * gridDim.x + b);
+    s = warp_sum(s);
+    if (lane == 0) epi.red[warp] = s;
+  }
+  __syncthreads();
+  run_epilogue<T>(epi);
+}
+
 template <typename T, int TILE>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 k_fused_tma(const __grid_constant__ FusedArgs a) {
