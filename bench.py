@@ -40,8 +40,9 @@ UNIT = "krylov_steps/s"
 # DRAM traffic of the dominant kernel from one `ncu --set full` capture (profiles/r1_prof_r1_fused.md):
 # k_fused_tma<float,128>, adjoint step idx = 14 (15 resident + 170 streamed basis rows + 4 vectors + out),
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, next to the algorithmic bytes of that launch.
-NCU_TRAFFIC = {"k_fused_tma": {"traffic": 815.0e6 + 7.0e6, "algorithmic": 190 * 4.0e6,
-                               "launch": "adjoint idx=14, fp32, n=1M", "source": "profiles/r1_prof_r1_fused.md"}}
+NCU_TRAFFIC = {"k_fused_tma": {"traffic": 395.3e6 + 6.8e6, "algorithmic": 98 * 4.0e6,
+                               "launch": "forward pass B, i=95 (96 resident rows), fp32, n=1M",
+                               "source": "profiles/r1b_prof_sym_fused.md"}}
 
 
 def algorithmic_bytes(n, nnz, K, w):
@@ -343,8 +344,10 @@ def main():
                 "workload": f"sparse SPD COO operator n={N_ROWS} nnz={nnz} ({2 * BANDS + 1}/row), Lanczos full "
                             f"reortho depth {DEPTH}, forward + adjoint (cotangents on alpha/beta)",
                 "per_gpu": "one probe vector per GPU per step; parameter cotangent all-reduced once per step",
-                "adjoint": "symmetric operand: Lambda beta_plus keeps its super-diagonal term (BL_ADJ_SYMMETRIC)"
-                           if os.environ.get("BL_SYMMETRIC_ADJOINT", "1")[:1] != "0" else "general (all rows of Lambda)",
+                "loops": ("symmetric loops of tridiag(reortho=full): BL_FWD_SYMMETRIC, BL_ADJ_SYMMETRIC, "
+                          "BL_ADJ_TRIDIAG_COTANGENT (include/b200_lanczos.h); switched off by BL_SYMMETRIC_FORWARD=0 / "
+                          "BL_SYMMETRIC_ADJOINT=0: " + ",".join(
+                              f"{k}={os.environ[k]}" for k in ("BL_SYMMETRIC_FORWARD", "BL_SYMMETRIC_ADJOINT") if k in os.environ)),
                 "l2": f"inputs larger than L2 (basis Q {DEPTH * N_ROWS * w / 1e6:.0f} MB + adjoint basis, 126 MB L2)",
             },
             "clocks": clocks, "gpu_launches": launches,
