@@ -142,3 +142,30 @@ def test_quadform_cotangents_match_finite_differences():
         fd = (_quadform_and_cotangents(np.log, None, a, b + e, False)[0]
               - _quadform_and_cotangents(np.log, None, a, b - e, False)[0]) / (2 * eps)  # fmt: skip
         assert abs(fd - db[i]) < 1e-8
+
+
+def test_loop_flags_match_the_header_and_only_tridiag_sets_the_symmetric_bits():
+    """`second_pass` / `reortho_full` of the Krylov entry points are bit masks (include/b200_lanczos.h):
+    the general loops of `arnoldi.hessenberg` pass 0/1, `lanczos.tridiag(reortho="full")` -- symmetric operand,
+    tridiagonal cotangent (lanczos.py:152-169) -- adds the symmetric bits."""
+    import re
+
+    from experiments_lanczos_adjoints_b200 import arnoldi
+
+    header = open(os.path.join(ROOT, "include", "b200_lanczos.h")).read()
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (BL_(?:FWD|ADJ)_\w+) (\d+)", header)}
+    assert consts == {"BL_FWD_SECOND_PASS": 1, "BL_FWD_SYMMETRIC": 2, "BL_ADJ_REORTHO_FULL": 1,
+                      "BL_ADJ_SYMMETRIC": 2, "BL_ADJ_TRIDIAG_COTANGENT": 4}  # fmt: skip
+    assert (arnoldi.BL_ADJ_REORTHO_FULL, arnoldi.BL_ADJ_SYMMETRIC, arnoldi.BL_ADJ_TRIDIAG_COTANGENT) == (1, 2, 4)
+    assert [arnoldi.forward_flags(*a) for a in ((False, False), (True, False), (True, True), (False, True))] == [0, 1, 3, 0]
+    assert arnoldi.adjoint_flags(False, True, True) == 0  # the shortcuts need the re-projection
+    assert arnoldi.adjoint_flags(True, False, True) == 1
+    assert arnoldi.adjoint_flags(True, True) == 3 and arnoldi.adjoint_flags(True, True, True) == 7
+
+    op = bl.operators.DenseOperator(4)
+    general = bl.arnoldi.hessenberg(op, 2, reortho="full")
+    assert (general._forward_flags, general._adjoint_flags) == (1, 1)
+    assert bl.arnoldi.hessenberg(op, 2, reortho="none")._adjoint_flags == 0
+    assert bl.arnoldi.hessenberg(op, 2, reortho="full", reortho_vjp="none")._forward_flags == 0
+    tri = bl.lanczos.tridiag(op, 2, reortho="full")
+    assert (tri.alg._forward_flags, tri.alg._adjoint_flags) == (3, 7)
