@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--probes", type=int, default=int(os.environ.get("BL_BENCH_PROBES", 4)),
+                    help="independent probe vectors in flight per GPU, each on its own stream (one step = all of them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-timed steps only (profiling runs)")
     args = ap.parse_args()
@@ -214,35 +216,49 @@ def main():
     w = np.dtype(dtype).itemsize
     row, col, data, dalpha, dbeta = build_workload()
     nnz = len(data)
-    op = bl.operators.SparseOperator(row, col, (N_ROWS, N_ROWS))
-    plan = bl_plan.TridiagAdjointPlan(op, DEPTH, dtype)
-    stream = plan.stream
+    # P independent probes per GPU (the Hutchinson / SLQ workload: probes are independent runs), each with its own
+    # operator handle, plan and stream: while one run sits in a kernel's ramp or grid-wide reduction tail, the other
+    # runs' kernels keep the memory system busy.  One "step" = one forward + adjoint of every probe.
+    from experiments_lanczos_adjoints_b200 import device as bl_dev
 
-    # pinned host buffers for the end-to-end path; one probe vector per rank
-    v_host = bl_plan.pinned_empty((N_ROWS,), dtype)
-    v_host[:] = np.random.default_rng(100 + rank).standard_normal(N_ROWS)
+    P = max(1, args.probes)
+    plans = []
+    for p in range(P):
+        op = bl.operators.SparseOperator(row, col, (N_ROWS, N_ROWS))
+        plans.append(bl_plan.TridiagAdjointPlan(op, DEPTH, dtype, stream=bl_dev.Stream()))
+    plan = plans[0]
+
+    # pinned host buffers for the end-to-end path; P probe vectors per rank
     p_host = bl_plan.pinned_empty((nnz,), dtype)
     p_host[:] = data
     dH_host = bl_plan.pinned_empty((DEPTH, DEPTH), dtype)
     dH_host[:] = synthetic.slq_cotangent_dH(dalpha, dbeta, dtype)
-    out_H = bl_plan.pinned_empty((DEPTH, DEPTH), dtype)
-    out_dv = bl_plan.pinned_empty((N_ROWS,), dtype)
-    out_g = [bl_plan.pinned_empty((nnz,), dtype)]
-
-    plan.set_vector(v_host)
-    plan.set_params(p_host)
-    plan.set_cotangent(dH_host)
-    grad_t = None
+    v_hosts, outs = [], []
+    for p, pl in enumerate(plans):
+        v_host = bl_plan.pinned_empty((N_ROWS,), dtype)
+        v_host[:] = np.random.default_rng(100 + rank * P + p).standard_normal(N_ROWS)
+        v_hosts.append(v_host)
+        outs.append((bl_plan.pinned_empty((DEPTH, DEPTH), dtype), bl_plan.pinned_empty((N_ROWS,), dtype),
+                     [bl_plan.pinned_empty((nnz,), dtype)]))  # fmt: skip
+        pl.set_vector(v_host)
+        pl.set_params(p_host)
+        pl.set_cotangent(dH_host)
+    grad_ts = []
     if dist is not None:
         import torch
 
-        grad_t = torch.as_tensor(plan.grads[0], device=f"cuda:{local_rank}")
+        grad_ts = [torch.as_tensor(pl.grads[0], device=f"cuda:{local_rank}") for pl in plans]
 
-    def step_device():
-        plan.run()
-        if dist is not None:  # probe sharding: one all-reduce of the parameter cotangent per step
-            stream.synchronize()
-            dist.all_reduce(grad_t)
+    def reduce_grads():  # probe sharding: the parameter cotangents of all probes are all-reduced every step
+        for pl, g in zip(plans, grad_ts):
+            pl.stream.synchronize()
+            dist.all_reduce(g)
+
+    def step_device(active=None):
+        for pl in active or plans:
+            pl.run()
+        if dist is not None:
+            reduce_grads()
 
     def barrier():
         if dist is not None:
@@ -252,21 +268,24 @@ def main():
             dist.barrier()
         bl.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, active=None):
+        active = active or plans
         barrier()
-        e0, e1 = bl.Event(), bl.Event()
+        e0, ends = bl.Event(), [bl.Event() for _ in active]
         launches0 = bl.launch_count()
-        e0.record(stream)
+        e0.record(active[0].stream)
         for _ in range(steps):
             fn()
         if dist is not None:
             import torch
 
             torch.cuda.synchronize()
-        e1.record(stream)
-        e1.synchronize()
+        for pl, e1 in zip(active, ends):
+            e1.record(pl.stream)
+        for e1 in ends:
+            e1.synchronize()
         barrier()
-        ms = e0.elapsed_ms(e1)
+        ms = max(e0.elapsed_ms(e1) for e1 in ends)  # first stream's start -> last stream's end
         if dist is not None:
             import torch
 
@@ -282,46 +301,56 @@ def main():
     ms_total, launches = timed(step_device, args.steps)
     clocks = sampler.stop()
     ms_per_step = ms_total / args.steps
-    value = world * DEPTH / (ms_per_step * 1e-3)
+    value = world * P * DEPTH / (ms_per_step * 1e-3)
 
     if args.quick:
         if rank == 0:
             sys.stdout.flush()
             os.dup2(stdout_fd, 1)
-            print(json.dumps({"value": value, "ms_per_step": ms_per_step, "gpu_launches": launches, "quick": True}),
+            print(json.dumps({"value": value, "ms_per_step": ms_per_step, "gpu_launches": launches, "probes": P, "quick": True}),
                   flush=True)
         return
     # end-to-end through the host-buffer entry point: H2D (v, params, dH) + fwd + adjoint + D2H
     io = {}
 
     def step_host():
-        io["h2d"], io["d2h"] = plan.run_host(v_host, [p_host], dH_host, out_H, out_dv, out_g)
+        h2d = d2h = 0
+        for pl, v_host, (out_H, out_dv, out_g) in zip(plans, v_hosts, outs):
+            a, b = pl.run_host(v_host, [p_host], dH_host, out_H, out_dv, out_g, sync=False)
+            h2d, d2h = h2d + a, d2h + b
+        for pl in plans:
+            pl.stream.synchronize()  # the step's results (H, dv, dparams of every probe) are on the host
+        io["h2d"], io["d2h"] = h2d, d2h
         if dist is not None:
-            dist.all_reduce(grad_t)
+            reduce_grads()
 
     for _ in range(2):
         step_host()
     e2e_steps = max(2, args.steps // 2)
     ms_e2e, _ = timed(step_host, e2e_steps)
-    e2e_value = world * DEPTH / (ms_e2e / e2e_steps * 1e-3)
+    e2e_value = world * P * DEPTH / (ms_e2e / e2e_steps * 1e-3)
+
+    # one probe alone (the latency of a single forward + adjoint), for transparency next to the P-probe throughput
+    ms_single, _ = timed(lambda: step_device(plans[:1]), 3, plans[:1])
+    ms_single /= 3
 
     # per-kernel-class timing of one more step (events around every launch)
     prof = bl_plan.profile(plan.run)
     peak, peak_src = measured_peaks()
-    fwd_b, adj_b = algorithmic_bytes(N_ROWS, nnz, DEPTH, w)
+    fwd_b, adj_b = (P * b for b in algorithmic_bytes(N_ROWS, nnz, DEPTH, w))
     step_gbs = (fwd_b + adj_b) / (ms_per_step * 1e-3) / 1e9
     dom = max(prof, key=lambda k: prof[k]["ms"])
     d = prof[dom]
     dom_gbs = d["algorithmic_bytes"] / max(d["ms"], 1e-9) / 1e6
     prof_total = sum(c["ms"] for c in prof.values())
-    streamed_b = sum(c["algorithmic_bytes"] for c in prof.values())
+    streamed_b = P * sum(c["algorithmic_bytes"] for c in prof.values())  # per step = P probes
     KERNEL_OF = {"dots": "k_dots_tma", "combine": "k_combine_tma", "matvec": "k_sell_spmv_normalised", "vjp": "k_sell_vjp",
                  "other": "k_scale_copy", "fused": "k_fused_tma"}
     roofline = {
         "bound": "hbm", "kernel": KERNEL_OF[dom],
         "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "peak_source": peak_src,
         "traffic": NCU_TRAFFIC.get(KERNEL_OF[dom], {}).get("traffic"),
-        "traffic_capture": NCU_TRAFFIC.get(KERNEL_OF[dom]), "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / max(1, d["launches"]),
+        "traffic_capture": NCU_TRAFFIC.get(KERNEL_OF[dom]), "launches_per_step": P * d["launches"], "avg_launch_ms": d["ms"] / max(1, d["launches"]),
         "share_of_step": d["ms"] / max(prof_total, 1e-9),
         # streamed = the bytes this build's kernels account for; contract = SURVEY 8(d)'s figure for the general
         # (non-symmetric) loops.  The symmetric loops of tridiag(reortho="full") skip part of the contract's traffic
@@ -343,7 +372,10 @@ def main():
             "config": {
                 "workload": f"sparse SPD COO operator n={N_ROWS} nnz={nnz} ({2 * BANDS + 1}/row), Lanczos full "
                             f"reortho depth {DEPTH}, forward + adjoint (cotangents on alpha/beta)",
-                "per_gpu": "one probe vector per GPU per step; parameter cotangent all-reduced once per step",
+                "per_gpu": f"{P} independent probe vectors per GPU per step, each on its own stream (one step = forward + "
+                           f"adjoint of all {P}); parameter cotangents all-reduced every step",
+                "probes_in_flight": P,
+                "single_probe": {"ms_per_forward_adjoint": ms_single, "krylov_steps_per_s": DEPTH / (ms_single * 1e-3)},
                 "loops": ("symmetric loops of tridiag(reortho=full): BL_FWD_SYMMETRIC, BL_ADJ_SYMMETRIC, "
                           "BL_ADJ_TRIDIAG_COTANGENT (include/b200_lanczos.h); switched off by BL_SYMMETRIC_FORWARD=0 / "
                           "BL_SYMMETRIC_ADJOINT=0: " + ",".join(

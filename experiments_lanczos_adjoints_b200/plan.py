@@ -102,16 +102,19 @@ class TridiagAdjointPlan:
         self.adjoint()
 
     # -- host-buffer entry point (the e2e path of bench.py) -----------------------------------
-    def run_host(self, v_host, params_host, dH_host, out_H, out_dv, out_grads):
+    def run_host(self, v_host, params_host, dH_host, out_H, out_dv, out_grads, sync=True):
         """Host buffers in, host buffers out: H2D of `(v, params, dH)`, forward + adjoint, D2H of
-        `(H, dv, dparams)`; synchronises once at the end.  Returns (h2d_bytes, d2h_bytes)."""
+        `(H, dv, dparams)`; synchronises once at the end (`sync=False`: the caller synchronises the plan's
+        stream -- several plans on several streams overlap one probe's copies with another's kernels).
+        Returns (h2d_bytes, d2h_bytes)."""
         h2d = self.set_vector(v_host) + self.set_params(*params_host) + self.set_cotangent(dH_host)
         self.run()
         d2h = 0
         for src, dst in [(self.H, out_H), (self.dv, out_dv), *zip(self.grads, out_grads)]:
             _lib.call("bl_memcpy_d2h", dst.ctypes.data, src.ptr, dst.nbytes, self.stream.ptr)
             d2h += dst.nbytes
-        self.stream.synchronize()
+        if sync:
+            self.stream.synchronize()
         return h2d, d2h
 
     def coefficients(self):
