@@ -249,10 +249,11 @@ def main():
 
         grad_ts = [torch.as_tensor(pl.grads[0], device=f"cuda:{local_rank}") for pl in plans]
 
-    def reduce_grads():  # probe sharding: the parameter cotangents of all probes are all-reduced every step
-        for pl, g in zip(plans, grad_ts):
+    def reduce_grads():  # probe sharding: the rank's probes are summed, then ONE all-reduce per step (hutchinson.py:54)
+        for pl in plans:
             pl.stream.synchronize()
-            dist.all_reduce(g)
+        total = grad_ts[0] if P == 1 else torch.stack(grad_ts).sum(0)
+        dist.all_reduce(total)
 
     def step_device(active=None):
         for pl in active or plans:
@@ -373,7 +374,7 @@ def main():
                 "workload": f"sparse SPD COO operator n={N_ROWS} nnz={nnz} ({2 * BANDS + 1}/row), Lanczos full "
                             f"reortho depth {DEPTH}, forward + adjoint (cotangents on alpha/beta)",
                 "per_gpu": f"{P} independent probe vectors per GPU per step, each on its own stream (one step = forward + "
-                           f"adjoint of all {P}); parameter cotangents all-reduced every step",
+                           f"adjoint of all {P}); their parameter cotangents are summed and all-reduced once per step",
                 "probes_in_flight": P,
                 "single_probe": {"ms_per_forward_adjoint": ms_single, "krylov_steps_per_s": DEPTH / (ms_single * 1e-3)},
                 "loops": ("symmetric loops of tridiag(reortho=full): BL_FWD_SYMMETRIC, BL_ADJ_SYMMETRIC, "
