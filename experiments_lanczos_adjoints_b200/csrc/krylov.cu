@@ -518,6 +518,67 @@ int launch_fused(const Common& c, const FusedSpec& f, int dtype, cudaStream_t s,
   return BL_OK;
 }
 
+// out = (sum of <= kXTerms vector terms) / div and red[j] = <row_j, out> over a block of basis rows: the symmetric
+// loops' replacement for the fused kernel (k_xdots_tma, stream_kernels.cuh).  `*done` stays false when the TMA
+// path is off or the shape does not fit; the caller then runs its general kernels.  BL_XDOTS=0 disables it.
+struct XDotsSpec {
+  int64_t n = 0;
+  void* out = nullptr;
+  int nvec = 0;
+  VecTerm vec[kXTerms];
+  RowBlock rows;
+  const double* out_div_ptr = nullptr;
+  Epi epi;
+};
+
+bool xdots_enabled() {
+  static const bool enabled = [] {
+    const char* e = std::getenv("BL_XDOTS");
+    return !(e && e[0] == '0');
+  }();
+  return enabled;
+}
+
+template <typename T>
+int launch_xdots(const Common& c, const XDotsSpec& f, cudaStream_t s, bool* done) {
+  *done = false;
+  constexpr int TILE = kConsumerThreads * Vec<T>::N;  // 4 KB row segments
+  const size_t smem = (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 4) * 8 +
+                      (size_t)f.rows.nrows * 8 + 16;
+  if (!xdots_enabled() || !use_tma(f.n) || stream_mode() == 2 || f.nvec > kXTerms || f.rows.nrows < 1 ||
+      smem > 112 * 1024)
+    return BL_OK;
+  *done = true;
+  XDotsArgs a;
+  a.src = row_source(f.rows, nullptr, sizeof(T));
+  a.nrows = f.rows.nrows;
+  a.n = f.n;
+  a.out = f.out;
+  a.nvec = f.nvec;
+  for (int k = 0; k < f.nvec; ++k) a.vec[k] = f.vec[k];
+  a.out_div_ptr = f.out_div_ptr;
+  a.partials = c.partials_dots;
+  a.counter = c.counters + 0;
+  a.epi = f.epi;
+  a.epi.red = c.red;
+  a.epi.scal = c.scal;
+  const Epi full_epi = a.epi;
+  int prc = BL_OK;
+  const bool peer = arm_peer_epilogue(a.epi, f.rows.nrows, &prc);
+  BL_CHECK(prc);
+  const bool sharded = !peer && is_sharded();
+  if (sharded) a.epi.mode = EPI_NONE;
+  a.reverse = next_direction();
+  BL_CHECK(set_smem(k_xdots_tma<T, TILE>, 112 * 1024));
+  {
+    ProfScope prof(BL_PROF_FUSED, (double)(f.rows.nrows + f.nvec + 1) * f.n * sizeof(T), s);
+    BL_CUDA(launch_pdl(k_xdots_tma<T, TILE>, tma_grid<T>(f.n, TILE), kStreamThreads, smem, s, a));
+    BL_LAUNCHED();
+  }
+  if (sharded) return finish_sharded<T>(c, full_epi, f.rows.nrows, s);
+  return BL_OK;
+}
+
 template <typename T>
 int launch_scale_copy(int64_t n, const T* x, double mul, const double* div_ptr, T* out, int64_t n_pad, cudaStream_t s) {
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(16 * sm_count(), (n_pad + 255) / 256));
@@ -671,7 +732,21 @@ struct FwdRun {
     norm_epi.K = K;
     norm_epi.H = H;
     bool fused = false;
-    if (second_pass) {
+    if (second_pass && local_first) {
+      // symmetric loop: v = v - h_{i-1} q_{i-1} - h_i q_i is a three-vector combination, and h2 = Q^H v streams
+      // every active row once (no row is needed twice: nothing stays resident)   arnoldi.py:88,92
+      XDotsSpec f;
+      f.n = n;
+      f.out = r;
+      f.vec[f.nvec++] = term(r);
+      for (int j = first_lo(i); j < m; ++j) f.vec[f.nvec++] = term(q_row(j), -1.0, c.coefA + j);
+      f.rows = rows(Q, ld, 0, m);
+      f.epi.mode = EPI_FWD_B;
+      f.epi.m = m;
+      f.epi.coef = c.coefB;
+      BL_CHECK(launch_xdots<T>(c, f, s, &fused));
+    }
+    if (second_pass && !fused) {
       // v = v - Q h and, from the same read of Q, h2 = Q^H v (the second pass's coefficients;
       // h itself is not updated, arnoldi.py:92)
       Epi e;
@@ -943,7 +1018,28 @@ struct AdjRun {
     }
     // lambda = (Pi_xi[idx] + Q gamma_row - alpha lambda + A^T lambda - Lambda beta_plus) / beta_minus
     have_reproj = false;
-    if (reortho_full && idx > 0) {
+    if (banded && idx > 0) {
+      // banded Gamma: the back-substitution combines nine vectors at most, and the NEXT step's re-projection dots
+      // t = P lambda stream rows 0..idx once                                    arnoldi.py:202,217-219
+      XDotsSpec f;
+      f.n = n;
+      f.out = lam;
+      f.vec[f.nvec++] = term(r, 1.0, c.scal + S_ETA_IDX);
+      f.vec[f.nvec++] = term(Lrow, 1.0, c.scal + S_NEG_ALPHA);
+      f.vec[f.nvec++] = term(z);
+      add_symmetric_term(idx, f.vec, f.nvec);
+      for (int j = band_lo(idx); j < band_hi(idx); ++j) f.vec[f.nvec++] = term(q_row(j), 1.0, c.coefB + j);
+      f.rows = rows(Q, ld, 0, idx + 1);
+      f.out_div_ptr = c.scal + S_BETA_MINUS;
+      f.epi.mode = EPI_ADJ_REPROJ;
+      f.epi.i = idx - 1;
+      f.epi.K = K;
+      f.epi.m = idx + 1;
+      f.epi.dH = dH;
+      f.epi.coef = c.coefA;
+      BL_CHECK(launch_xdots<T>(c, f, s, &have_reproj));
+    }
+    if (!have_reproj && reortho_full && idx > 0) {
       // ... fused with the NEXT step's re-projection dots t = P lambda (rows 0..idx of Q are the
       // active rows of P at idx-1): one read of those rows serves both          arnoldi.py:202,217-219
       FusedSpec f;
