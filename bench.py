@@ -40,8 +40,11 @@ UNIT = "krylov_steps/s"
 # DRAM traffic of the dominant kernel from one `ncu --set full` capture (profiles/r1_prof_r1_fused.md):
 # k_fused_tma<float,128>, adjoint step idx = 14 (15 resident + 170 streamed basis rows + 4 vectors + out),
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, next to the algorithmic bytes of that launch.
-NCU_TRAFFIC = {"k_fused_tma": {"traffic": 395.3e6 + 6.8e6, "algorithmic": 98 * 4.0e6,
-                               "launch": "forward pass B, i=95 (96 resident rows), fp32, n=1M",
+NCU_TRAFFIC = {"k_xdots_tma": {"traffic": 396.5e6 + 11.7e6, "algorithmic": 100 * 4.0e6,
+                               "launch": "forward pass B, i=95 (96 streamed rows + 3 terms + out), fp32, n=1M",
+                               "source": "profiles/r1c_prof_xdots.md"},
+               "k_fused_tma": {"traffic": 395.3e6 + 6.8e6, "algorithmic": 98 * 4.0e6,
+                               "launch": "forward pass B, i=95 (96 resident rows), fp32, n=1M (before k_xdots_tma)",
                                "source": "profiles/r1b_prof_sym_fused.md"}}
 
 
@@ -345,8 +348,10 @@ def main():
     dom_gbs = d["algorithmic_bytes"] / max(d["ms"], 1e-9) / 1e6
     prof_total = sum(c["ms"] for c in prof.values())
     streamed_b = P * sum(c["algorithmic_bytes"] for c in prof.values())  # per step = P probes
-    KERNEL_OF = {"dots": "k_dots_tma", "combine": "k_combine_tma", "matvec": "k_sell_spmv_normalised", "vjp": "k_sell_vjp",
-                 "other": "k_scale_copy", "fused": "k_fused_tma"}
+    symmetric = all(os.environ.get(k, "1")[:1] != "0" for k in ("BL_SYMMETRIC_FORWARD", "BL_SYMMETRIC_ADJOINT", "BL_XDOTS"))
+    KERNEL_OF = {"dots": "k_dots_few" if symmetric else "k_dots_tma", "combine": "k_combine_tma",
+                 "matvec": "k_sell_spmv_normalised", "vjp": "k_sell_vjp", "other": "k_scale_copy",
+                 "fused": "k_xdots_tma" if symmetric else "k_fused_tma"}  # fmt: skip
     roofline = {
         "bound": "hbm", "kernel": KERNEL_OF[dom],
         "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "peak_source": peak_src,
