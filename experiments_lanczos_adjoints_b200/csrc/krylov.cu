@@ -68,6 +68,7 @@ struct Common {
   double* coefC;
   double* partials_dots;
   double* partials_comb;
+  long long partials_dots_count = 0;  // doubles behind partials_dots
 };
 
 size_t common_bytes(int64_t n, int64_t K) {
@@ -89,6 +90,7 @@ void carve_common(Workspace& w, int64_t K, Common& c) {
   c.coefB = static_cast<double*>(w.take((K + 2) * 8));
   c.coefC = static_cast<double*>(w.take((K + 2) * 8));
   c.partials_dots = static_cast<double*>(w.take((size_t)(K + 2) * kMaxDotsGrid * 8));
+  c.partials_dots_count = (long long)(K + 2) * kMaxDotsGrid;
   c.partials_comb = static_cast<double*>(w.take((size_t)kMaxCombineGrid * 8));
 }
 
@@ -299,7 +301,7 @@ int launch_dots(const Grid& g, const Common& c, RowBlock blk, const T* x, int64_
     // about two 16-byte vectors per thread and stream; the partials buffer holds (K+2) x kMaxDotsGrid doubles
     const long long vecs = n / Vec<T>::N;
     const int grid = (int)std::max<long long>(1, std::min<long long>({4LL * sm_count(), (vecs + 511) / 512,
-                                                                      (long long)kMaxDotsGrid * 3 / blk.nrows}));
+                                                                      c.partials_dots_count / blk.nrows}));
     switch (blk.nrows) {
       case 1: BL_CUDA(launch_pdl(k_dots_few<T, 1>, grid, 256, 0, s, fr, x, (long long)n, c.partials_dots, c.counters + 0, epi)); break;
       case 2: BL_CUDA(launch_pdl(k_dots_few<T, 2>, grid, 256, 0, s, fr, x, (long long)n, c.partials_dots, c.counters + 0, epi)); break;

@@ -739,19 +739,31 @@ k_dots_few(FewRows rows, const T* __restrict__ x, long long n, double* __restric
   T acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = T(0);
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-    V q[R];
+  // U grid strides at a time: all (R + 1) * U loads are issued before the first FMA (the kernel is latency-bound)
+  constexpr int U = R <= 2 ? 4 : 3;
+  for (long long g0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; g0 < ngroups; g0 += U * stride) {
+    V q[U][R], xx[U];
 #pragma unroll
-    for (int r = 0; r < R; ++r) q[r] = ld_stream(static_cast<const V*>(rows.row[r]) + g);
-    const V xx = ld_stream(xv + g);
-    T b[VN];
-    vec_unpack(xx, b);
+    for (int u = 0; u < U; ++u) {
+      const long long g = g0 + u * stride;
+      const long long gc = g < ngroups ? g : g0;  // clamped: a valid address, the product is masked below
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      T a[VN];
-      vec_unpack(q[r], a);
+      for (int r = 0; r < R; ++r) q[u][r] = ld_stream(static_cast<const V*>(rows.row[r]) + gc);
+      xx[u] = ld_stream(xv + gc);
+    }
 #pragma unroll
-      for (int k = 0; k < VN; ++k) acc[r] = fma(a[k], b[k], acc[r]);
+    for (int u = 0; u < U; ++u) {
+      if (g0 + u * stride < ngroups) {
+        T b[VN];
+        vec_unpack(xx[u], b);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          T a[VN];
+          vec_unpack(q[u][r], a);
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[r] = fma(a[k], b[k], acc[r]);
+        }
+      }
     }
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {  // scalar tail (n not a multiple of the vector width)
