@@ -92,6 +92,8 @@ def probe_sum(integrand_fun, samples, parameters, *, with_grad=False):
 
         if samples.dtype in (np.float32, np.float64) and lanczos._batch_eligible(integrand_fun, samples.dtype):
             return lanczos.probe_batch_sum(integrand_fun, samples, parameters, with_grad=with_grad)
+        if lanczos._pipeline_eligible(integrand_fun, samples):
+            return lanczos.probe_pipelined_sum(integrand_fun, samples, parameters, with_grad=with_grad)
     total, grads, count = 0.0, None, 0
     rows = _probe_rows(samples)
     if len(rows):

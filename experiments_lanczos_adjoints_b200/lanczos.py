@@ -272,6 +272,89 @@ def _batch_eligible(integrand, dtype) -> bool:
     return bool(yes.value)
 
 
+PROBE_LANES = 4  # independent probes in flight per GPU in `probe_pipelined_sum`
+
+
+def _pipeline_eligible(integrand, probes) -> bool:
+    """Probes in flight apply to the full-reorthogonalisation adjoint path on a sparse operand (an operator that
+    can be cloned: every lane needs its own values and cotangent accumulator)."""
+    alg = getattr(integrand, "alg", None)
+    if not isinstance(alg, _TridiagFull) or not alg.alg.custom_vjp or PROBE_LANES < 2:
+        return False
+    op = alg.alg.op
+    return (type(op).__name__ == "SparseOperator" and op.shape[0] == op.shape[1] and len(probes) >= 2 * PROBE_LANES
+            and probes.dtype in (np.float32, np.float64))  # fmt: skip
+
+
+def probe_pipelined_sum(integrand, probes, parameters, *, with_grad, lanes=None):
+    """Sum over the rows of `probes (P, n)` of the SLQ integrand (and of its parameter gradient) with several
+    probes IN FLIGHT: every lane owns an operator handle, a `TridiagAdjointPlan` (basis, adjoint basis, workspace)
+    and a stream.  The forward runs of a group of probes are enqueued back to back; while the host does the
+    K x K `eigh` of one lane (`lanczos.py:48-59`), the other lanes' kernels run, and one run's per-launch fixed
+    costs are filled by the others' kernels.  The parameter cotangent accumulates inside each lane's operator over
+    all its probes and is exported once.  Same numbers as a loop of `integrand.value_and_grad`
+    (`jax.vmap(integrand)`, hutchinson.py:14) up to summation order."""
+    from experiments_lanczos_adjoints_b200 import plan as _plan
+
+    probes = np.asarray(probes)
+    P, n = probes.shape
+    dtype = probes.dtype
+    hess = integrand.alg.alg
+    K = hess.K
+    if not isinstance(K, (int, np.integer)) or K < 1 or K > n:
+        raise ValueError(f"Parameter depth {K} is outside the expected range")
+    L = max(1, min(lanes or PROBE_LANES, P))
+    cache = integrand.__dict__.setdefault("_lane_plans", {})
+    key = (L, dtype.str, n, K)
+    if key not in cache:
+        ops = [hess.op] + [hess.op.clone() for _ in range(L - 1)]
+        cache[key] = [_plan.TridiagAdjointPlan(o, K, dtype, stream=dev.Stream()) for o in ops]
+    plans = cache[key]
+    host_params = [p.numpy() if isinstance(p, dev.DeviceArray) else np.asarray(p) for p in parameters]
+    dev.synchronize()  # the lanes' streams start after whatever the caller enqueued
+    for pl in plans:
+        pl.set_params(*host_params)
+    total = 0.0
+    used = [False] * L
+    for p0 in range(0, P, L):
+        group = probes[p0 : p0 + L]
+        scales = np.linalg.norm(group.astype(np.float64), axis=1)  # lanczos.py:25
+        for pl, v, sc in zip(plans, group, scales):
+            pl.set_vector((v / sc).astype(dtype))
+            pl.forward()
+        for li, (pl, sc) in enumerate(zip(plans, scales)):
+            diag, off = pl.coefficients()  # synchronises this lane only
+            g, dalpha, dbeta, _ = _quadform_and_cotangents(integrand.matfun, integrand.matfun_grad, diag, off, with_grad)
+            s2 = sc**2
+            total += s2 * g
+            if with_grad:
+                dH = np.diag(s2 * dalpha)
+                if K > 1:
+                    dH = dH + 0.5 * (np.diag(s2 * dbeta, 1) + np.diag(s2 * dbeta, -1))
+                pl.set_cotangent(dH.astype(dtype))
+                pl.adjoint(zero=not used[li], export=False)
+                used[li] = True
+    grads = None
+    if with_grad:
+        active = [pl for pl, u in zip(plans, used) if u]
+        for pl in active:
+            pl.export_grads()
+            pl.stream.synchronize()
+        stream = dev.default_stream()
+        grads = []
+        for gi in range(len(active[0].grads)):
+            acc = dev.DeviceArray(active[0].grads[gi].shape, dtype)
+            _lib.call("bl_vec_axpby", dev.dtype_code(dtype), acc.size, 1.0, active[0].grads[gi].ptr, 0.0, None, acc.ptr, stream.ptr)
+            for pl in active[1:]:
+                _lib.call("bl_vec_axpby", dev.dtype_code(dtype), acc.size, 1.0, acc.ptr, 1.0, pl.grads[gi].ptr, acc.ptr, stream.ptr)
+            grads.append(acc)
+        stream.synchronize()
+    else:
+        for pl in plans:
+            pl.stream.synchronize()
+    return total, grads, P
+
+
 def probe_batch_sum(integrand, probes, parameters, *, with_grad, stream=None, chunk=16):
     """Sum over the rows of `probes (P, n)` of the SLQ integrand (and of its parameter gradient), with the P
     Lanczos runs advancing in lockstep (`bl_arnoldi_{forward,adjoint}_batch`): one batched matvec per step

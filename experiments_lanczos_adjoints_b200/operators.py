@@ -130,10 +130,16 @@ class SparseOperator(Operator):
             raise ValueError("row and col must be 1-D arrays of equal length")
         self.shape = (int(shape[0]), int(shape[1]))
         self.nnz = int(row.size)
+        self._coo = (row, col)  # kept for `clone()`
         h = C.c_void_p()
         _lib.call("bl_op_sparse_create", self.shape[0], self.shape[1], self.nnz, row.ctypes.data,
                   col.ctypes.data, C.byref(h))  # fmt: skip
         super().__init__(h.value, self.shape[0])
+
+    def clone(self):
+        """A second handle on the same sparsity pattern with its own values and cotangent accumulator: independent
+        Krylov runs (probes) on different streams need one operator each."""
+        return SparseOperator(self._coo[0], self._coo[1], self.shape)
 
     @classmethod
     def from_matrix_market(cls, path):

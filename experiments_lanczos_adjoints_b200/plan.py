@@ -87,14 +87,21 @@ class TridiagAdjointPlan:
         _lib.call("bl_arnoldi_forward", self.op._handle, self.code, self.n, self.K, forward_flags(True, True), self.v.ptr, self.Q.ptr,
                   self.ld, self.H.ptr, self.r.ptr, self.c.ptr, self.ws.ptr, self.ws_bytes, s)  # fmt: skip
 
-    def adjoint(self, dQ=None, dr=None):
+    def adjoint(self, dQ=None, dr=None, zero=True, export=True):
+        """`zero=False` keeps accumulating the parameter cotangent inside the operator (a sum over probes),
+        `export=False` leaves it there; `export_grads()` brings the sum out once."""
         s = self.stream.ptr
-        _lib.call("bl_op_grad_zero", self.op._handle, self.code, s)
+        if zero:
+            _lib.call("bl_op_grad_zero", self.op._handle, self.code, s)
         _lib.call("bl_arnoldi_adjoint", self.op._handle, self.code, self.n, self.K, self.adjoint_flags, self.Q.ptr, self.ld,
                   self.H.ptr, self.r.ptr, self.c.ptr, dQ.ptr if dQ is not None else None, self.dH.ptr,
                   dr.ptr if dr is not None else None, None, self.dv.ptr, self.Lam.ptr, self.ws.ptr,
                   self.ws_bytes, s)  # fmt: skip
-        _lib.call("bl_op_grad_export", self.op._handle, self.code, self._gptr, len(self.grads), s)
+        if export:
+            self.export_grads()
+
+    def export_grads(self):
+        _lib.call("bl_op_grad_export", self.op._handle, self.code, self._gptr, len(self.grads), self.stream.ptr)
 
     def run(self):
         """One forward + adjoint, enqueued back to back (no host sync)."""

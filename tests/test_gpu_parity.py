@@ -457,6 +457,39 @@ def test_concurrent_plans_on_separate_streams_match_their_solo_runs():
     assert rel_err(solo[0][0], solo[1][0]) > 1e-3  # different probes: the comparison above is not vacuous
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_slq_estimator_with_probes_in_flight_matches_the_sequential_loop(dtype):
+    """`hutchinson(integrand_spd(log, K, sparse_op), sampler)`: with >= 8 probes the estimator keeps four Lanczos
+    runs in flight (own operator handle, plan and stream per lane, `lanczos.probe_pipelined_sum`); value and gradient
+    must equal the one-probe-at-a-time loop (`jax.vmap(integrand)` + mean, hutchinson.py:14,54)."""
+    from experiments_lanczos_adjoints_b200 import lanczos
+
+    n, K, num = 20_000, 12, 9  # 9 = 4 + 4 + 1: the last group is ragged
+    row, col, data = banded_spd(n, 4, seed=31)
+    probes = (np.random.default_rng(32).integers(0, 2, size=(num, n)) * 2 - 1).astype(dtype)
+    results = {}
+    for lanes in (1, 4):
+        lanczos.PROBE_LANES = lanes
+        try:
+            op = bl.operators.SparseOperator(row, col, (n, n))
+            integrand = bl.lanczos.integrand_spd(np.log, K, op)
+            estimate = bl.hutchinson.hutchinson(integrand, lambda key: probes)
+            assert lanczos._pipeline_eligible(integrand, probes) == (lanes > 1)
+            value, (grad,) = estimate.value_and_grad(None, data.astype(dtype))
+            results[lanes] = (float(value), grad.numpy(), float(estimate(None, data.astype(dtype))))
+        finally:
+            lanczos.PROBE_LANES = 4
+    t_val, t_grad = (F64, F64) if dtype == np.float64 else (F32_VAL, F32_GRAD)
+    assert abs(results[4][0] - results[1][0]) < t_val * abs(results[1][0])
+    assert abs(results[4][2] - results[1][2]) < t_val * abs(results[1][2])
+    assert rel_err(results[4][1], results[1][1]) < t_grad
+    # and against the float64 oracle on the same probes
+    ref = krylov.IntegrandSPD(np.log, lambda x: 1.0 / x, K, operators.CsrFastOperator(row, col, (n, n)))
+    val_ref, (grad_ref,) = krylov.hutchinson_value_and_grad(ref, probes.astype(np.float64), data)
+    assert abs(results[4][0] - val_ref) < 10 * t_val * abs(val_ref)
+    assert rel_err(results[4][1], grad_ref) < 10 * t_grad
+
+
 def test_peer_memory_route_two_ranks_on_one_gpu_matches_single_operator():
     """The native row-sharded route (peer-memory reductions fused with the epilogue + halo pushes,
     `bl_dist_comm_*`) with TWO ranks driven by two host threads on one GPU: each rank owns half of the
