@@ -4,8 +4,10 @@ Host-side mirror of `/root/reference/src/matfree_extensions/hutchinson.py` plus 
 `matfree.hutchinson.hutchinson` / `sampler_rademacher` pair the reference imports
 (`/root/reference/src/matfree_extensions/util/gp_util.py:8,557`).  An estimator is
 `sample(key, *parameters)`; `sample_fun(key)` returns the `(num, n)` probe matrix.  Probe
-vectors are independent Lanczos runs, executed one after the other on this GPU and sharded
-over GPUs by `parallel.shard_probes`.
+vectors are independent Lanczos runs: in lockstep batches on operators that share work between
+vectors (the Gram operator, `lanczos.probe_batch_sum`), four in flight on separate streams on a
+sparse operand (`lanczos.probe_pipelined_sum`), one after the other otherwise; sharded over GPUs
+by `parallel.shard_probes`.
 
 PRNG note: JAX's threefry stream cannot be reproduced without JAX.  `sampler_rademacher` /
 `sampler_normal` / `split` here are NumPy-based; parity tests always pass probes explicitly.

@@ -169,3 +169,18 @@ def test_loop_flags_match_the_header_and_only_tridiag_sets_the_symmetric_bits():
     assert bl.arnoldi.hessenberg(op, 2, reortho="full", reortho_vjp="none")._forward_flags == 0
     tri = bl.lanczos.tridiag(op, 2, reortho="full")
     assert (tri.alg._forward_flags, tri.alg._adjoint_flags) == (3, 7)
+
+
+def test_sparse_operator_clone_shares_the_pattern_not_the_handle():
+    """Probes in flight need one operator handle per lane (`SparseOperator.clone`): same index work, own handle."""
+    rng = np.random.default_rng(5)
+    n, nnz = 97, 400
+    row, col = rng.integers(0, n, nnz).astype(np.int32), rng.integers(0, n, nnz).astype(np.int32)
+    op = bl.operators.SparseOperator(row, col, (n, n))
+    twin = op.clone()
+    assert twin._handle != op._handle and twin.shape == op.shape and twin.nnz == op.nnz
+    for a, b in zip(op.export_csr(), twin.export_csr()):
+        assert np.array_equal(a, b)
+    for t in (False, True):
+        for a, b in zip(op.export_sell(t), twin.export_sell(t)):
+            assert np.array_equal(a, b)
