@@ -1117,7 +1117,7 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
     BL_CHECK(run.pre(idx));
     // (A^T lambda, dparams += ...) = vjp of matvec at (q_idx, params)            arnoldi.py:207-209
     {
-      ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
+      ProfScope prof(BL_PROF_VJP, run.defer_grad ? op->apply_transpose_bytes(dtype) : op->vjp_bytes(dtype), s);
       if (run.defer_grad)  // A^T lambda only; the parameter cotangent of all K steps follows in one batched pass
         BL_CHECK(op->apply_transpose(dtype, run.lam_row(idx), run.z, s));
       else
@@ -1126,7 +1126,7 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
     BL_CHECK(run.post(idx));
   }
   if (run.defer_grad) {  // dparams = sum_idx d<Lambda[idx], A(Q[idx]; params)>/dparams   arnoldi.py:207-209, 168
-    ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
+    ProfScope prof(BL_PROF_VJP, op->vjp_batch_bytes(dtype, K), s);
     BL_CHECK(op->vjp_batch(dtype, Q, ld, Lambda, ld, K, s));
   }
   return run.end();

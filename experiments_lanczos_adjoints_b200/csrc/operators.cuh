@@ -31,6 +31,9 @@ struct bl_operator {
   // (grad += sum_m d<lam_m, A(q_m)>/dparams for `count` rows of two row-strided arrays) -- for the Gram
   // operator one batched sweep costs about as much as ONE per-step cotangent sweep.
   virtual bool deferred_grad(int /*dtype*/) const { return false; }
+  // ALGORITHMIC bytes of the two halves of a deferred cotangent (roofline report)
+  virtual double apply_transpose_bytes(int dtype) const { return vjp_bytes(dtype); }
+  virtual double vjp_batch_bytes(int dtype, int /*count*/) const { return vjp_bytes(dtype); }
   virtual int apply_transpose(int /*dtype*/, const void* /*lam*/, void* /*z*/, cudaStream_t) {
     bl::set_error("apply_transpose is not implemented for this operator");
     return BL_EINVAL;

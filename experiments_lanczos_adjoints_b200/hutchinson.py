@@ -92,10 +92,10 @@ def probe_sum(integrand_fun, samples, parameters, *, with_grad=False):
     if isinstance(samples, np.ndarray) and samples.ndim == 2 and len(samples) > 1 and hasattr(integrand_fun, "alg"):
         from experiments_lanczos_adjoints_b200 import lanczos
 
+        if lanczos._pipeline_eligible(integrand_fun, samples):  # sparse operand: probes in flight on separate streams
+            return lanczos.probe_pipelined_sum(integrand_fun, samples, parameters, with_grad=with_grad)
         if samples.dtype in (np.float32, np.float64) and lanczos._batch_eligible(integrand_fun, samples.dtype):
             return lanczos.probe_batch_sum(integrand_fun, samples, parameters, with_grad=with_grad)
-        if lanczos._pipeline_eligible(integrand_fun, samples):
-            return lanczos.probe_pipelined_sum(integrand_fun, samples, parameters, with_grad=with_grad)
     total, grads, count = 0.0, None, 0
     rows = _probe_rows(samples)
     if len(rows):

@@ -262,8 +262,8 @@ def _batch_eligible(integrand, dtype) -> bool:
     if not isinstance(alg, _TridiagFull) or not alg.alg.custom_vjp:
         return False
     op = alg.alg.op
-    if not hasattr(op, "_handle") or type(op).__name__ == "CallbackOperator":
-        return False
+    if not hasattr(op, "_handle") or type(op).__name__ in ("CallbackOperator", "SparseOperator"):
+        return False  # (the sparse operand defers its cotangent too, but shares no work between probes)
     yes = C.c_int(0)
     try:
         _lib.call("bl_op_deferred_grad", op._handle, dev.dtype_code(dtype), C.byref(yes))
