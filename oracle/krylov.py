@@ -13,6 +13,11 @@ any object with `matvec(x, *params)` and `vjp(x, lam, *params)` (see
 (the cheap wrappers around the custom VJP, `eigh`), the oracle uses the closed form
 and the golden vectors in `tests/golden/` (made by running the reference sources)
 pin it.
+
+The keyword arguments `symmetric=` / `tridiagonal_cotangent=` of `arnoldi_forward` / `arnoldi_adjoint` are the one
+thing here that is NOT the reference: they restate the library's symmetric loops (default off), so that
+the shortcut can be checked against the reference restatement and the goldens without a GPU.  Every parity test
+of the CUDA path compares with the reference restatement (the defaults).
 """
 
 from __future__ import annotations
@@ -31,11 +36,15 @@ def check_reortho_arnoldi(reortho):
         raise TypeError(f"Unexpected input for {reortho}: either of {expected} expected.")
 
 
-def arnoldi_forward(op, krylov_depth, v, *params, reortho_fwd="match"):
+def arnoldi_forward(op, krylov_depth, v, *params, reortho_fwd="match", symmetric=False):
     """`arnoldi.py:57-101`.  `reortho_fwd` is what the reference calls `reortho_` inside
     `estimate_backend` (`arnoldi.py:26`): it always equals `reortho_vjp`, whose default
     "match" is != "none", so the second Gram-Schmidt pass runs unless the caller passed
-    `reortho_vjp="none"`."""
+    `reortho_vjp="none"`.
+
+    `symmetric=True` is NOT the reference: it restates the library's `BL_FWD_SYMMETRIC` loop -- the first
+    pass takes `h` with columns i-1, i only -- so that the shortcut can be checked against the reference
+    restatement (`symmetric=False`) and the goldens on the CPU (tests/test_oracle_golden.py)."""
     v = np.asarray(v)
     n = len(v)
     K = krylov_depth
@@ -50,6 +59,8 @@ def arnoldi_forward(op, krylov_depth, v, *params, reortho_fwd="match"):
         Q[:, i] = v  # :81
         v = op.matvec(v, *params)  # :84
         h = Q.T.conj() @ v  # :87   (columns > i of Q are zero)
+        if symmetric and reortho_fwd != "none":
+            h[: max(0, i - 1)] = 0.0  # BL_FWD_SYMMETRIC: q_j^H A q_i = O(eps |A|) for j < i-1
         v = v - Q @ h  # :88
         if reortho_fwd != "none":  # :91
             v = v - Q @ (Q.T.conj() @ v)  # :92  -- h is NOT updated
@@ -65,8 +76,12 @@ def _lower(m):
     return t - 0.5 * np.diag(np.diag(t))
 
 
-def arnoldi_adjoint(op, params, *, Q, H, r, c, dQ, dH, dr, dc, reortho):
-    """`arnoldi.py:104-220`.  Returns `(dv, dparams_tuple)`."""
+def arnoldi_adjoint(op, params, *, Q, H, r, c, dQ, dH, dr, dc, reortho, symmetric=False, tridiagonal_cotangent=False):
+    """`arnoldi.py:104-220`.  Returns `(dv, dparams_tuple)`.
+
+    `symmetric` / `tridiagonal_cotangent` are NOT the reference: they restate the library's `BL_ADJ_SYMMETRIC`
+    (`Lambda beta_plus` keeps its super-diagonal term) and `BL_ADJ_TRIDIAG_COTANGENT` (no dQ: `Gamma[idx, j] = 0` for
+    `j < idx-2`) loops for CPU checks against the reference restatement."""
     n, K = Q.shape
     dt = Q.dtype
     e1 = np.zeros(K, dtype=dt)
@@ -89,6 +104,10 @@ def arnoldi_adjoint(op, params, *, Q, H, r, c, dQ, dH, dr, dc, reortho):
     beta_minuses = np.concatenate([np.ones(1, dtype=dt), np.diag(H, -1)])  # :136
     alphas = np.diag(H)
     beta_pluses = H - np.diag(np.diag(H)) - np.diag(np.diag(H, -1), -1)  # :138
+    symmetric = symmetric and reortho == "full"
+    banded = symmetric and tridiagonal_cotangent and not np.any(dQ)
+    if symmetric:
+        beta_pluses = np.diag(np.diag(H, 1), 1)
 
     for idx in range(K - 1, -1, -1):  # scan(reverse=True), :162
         p = ps[idx]
@@ -99,6 +118,8 @@ def arnoldi_adjoint(op, params, *, Q, H, r, c, dQ, dH, dr, dc, reortho):
         vecmat, dp_inc = op.vjp(Q[:, idx], lam, *params)  # :207-208
         dp = [g + h for g, h in zip(dp, dp_inc)]
         Gamma[idx, :] = lower_mask[idx] * (Pi_gamma[idx] - vecmat @ Q)  # :212-213
+        if banded:
+            Gamma[idx, : max(0, idx - 2)] = 0.0
         Lambda[:, idx] = lam  # :216
         xi = Pi_xi[idx] + (Gamma + Gamma.T)[idx, :] @ Q.T  # :217
         lam = xi - (alphas[idx] * lam - vecmat) - beta_pluses[idx] @ Lambda.T  # :218

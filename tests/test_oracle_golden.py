@@ -194,3 +194,74 @@ def test_oracle_error_conventions():
             krylov.Hessenberg(operators.DenseOperator(), depth, reortho="none")(np.ones(2), np.eye(2))
     with pytest.raises(ValueError, match="unsupported"):
         krylov.tridiag(operators.DenseOperator(), 1, reortho="partial")
+
+
+# ---- the library's symmetric loops, restated in the oracle, against the reference restatement ---------
+def _symmetric_tridiag_vjp(op, K, v, params, cot_alpha_beta, dr=None, dQ=None):
+    """`tridiag(reortho="full")` through `arnoldi_forward(symmetric=True)` and the banded adjoint."""
+    Q, H, r, c = krylov.arnoldi_forward(op, K, v, *params, symmetric=True)
+    dalpha, dbeta = cot_alpha_beta
+    dH = np.diag(dalpha) + 0.5 * (np.diag(dbeta, 1) + np.diag(dbeta, -1))
+    n = len(v)
+    dv, dp = krylov.arnoldi_adjoint(
+        op, params, Q=Q, H=H, r=r, c=c, dQ=np.zeros((n, K)) if dQ is None else dQ, dH=dH,
+        dr=np.zeros(n) if dr is None else dr, dc=0.0, reortho="full", symmetric=True, tridiagonal_cotangent=True,
+    )  # fmt: skip
+    return (Q, H, r, c), (dv, dp)
+
+
+def test_symmetric_loops_match_the_reference_loops_on_a_sparse_spd_operand():
+    """Why the shortcuts are legal, checked in float64 without a GPU: with a symmetric operand and full
+    re-orthogonalisation `H` is tridiagonal up to rounding, and so is everything the three flag bits drop."""
+    rng = np.random.default_rng(0)
+    n, K = 600, 40
+    offs = [1, 7, 31]
+    row = np.concatenate([np.arange(n)] + [np.arange(o, n) for o in offs] + [np.arange(0, n - o) for o in offs])
+    col = np.concatenate([np.arange(n)] + [np.arange(0, n - o) for o in offs] + [np.arange(o, n) for o in offs])
+    vals = [-rng.uniform(0, 1, n - o) for o in offs]
+    data = np.concatenate([np.full(n, 8.0)] + vals + vals)
+    op = operators.CsrFastOperator(row.astype(np.int32), col.astype(np.int32), (n, n))
+    v = rng.standard_normal(n)
+    dalpha, dbeta, dr = rng.standard_normal(K), rng.standard_normal(K - 1), rng.standard_normal(n)
+
+    Q0, H0, r0, c0 = krylov.arnoldi_forward(op, K, v, data)
+    assert np.abs(np.triu(H0, 2)).max() < 1e-13 * np.abs(H0).max()
+    dH = np.diag(dalpha) + 0.5 * (np.diag(dbeta, 1) + np.diag(dbeta, -1))
+    for with_dr in (False, True):
+        dr_ = dr if with_dr else np.zeros(n)
+        dv0, dp0 = krylov.arnoldi_adjoint(op, (data,), Q=Q0, H=H0, r=r0, c=c0, dQ=np.zeros((n, K)), dH=dH, dr=dr_,
+                                          dc=0.0, reortho="full")  # fmt: skip
+        (Q1, H1, r1, c1), (dv1, dp1) = _symmetric_tridiag_vjp(op, K, v, (data,), (dalpha, dbeta), dr=dr_)
+        assert np.all(np.triu(H1, 2) == 0)
+        assert rel_err(np.diag(H1), np.diag(H0)) < 1e-13 and rel_err(np.diag(H1, 1), np.diag(H0, 1)) < 1e-13
+        assert rel_err(Q1, Q0) < 1e-12 and rel_err(r1, r0) < 1e-11
+        assert np.abs(Q1.T @ Q1 - np.eye(K)).max() < 1e-14
+        assert rel_err(dv1, dv0) < 1e-11 and rel_err(dp1[0], dp0[0]) < 1e-11
+    # a dense dQ keeps the general Gamma (only `Lambda beta_plus` is shortened)
+    dQ = rng.standard_normal((n, K))
+    dv0, dp0 = krylov.arnoldi_adjoint(op, (data,), Q=Q0, H=H0, r=r0, c=c0, dQ=dQ, dH=dH, dr=dr, dc=0.3, reortho="full")
+    dv1, dp1 = krylov.arnoldi_adjoint(op, (data,), Q=Q0, H=H0, r=r0, c=c0, dQ=dQ, dH=dH, dr=dr, dc=0.3, reortho="full",
+                                      symmetric=True, tridiagonal_cotangent=True)  # fmt: skip
+    assert rel_err(dv1, dv0) < 1e-11 and rel_err(dp1[0], dp0[0]) < 1e-11
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("tridiag_") if "_full_" in n and "k12" not in n])
+def test_symmetric_loops_reproduce_the_reference_goldens(name):
+    """The same restatement against the outputs of the reference's own sources (tests/golden)."""
+    g = golden(name)
+    A, v = cast(g, "A", "v")
+    K = int(g["K"])
+    dQt, dalpha, dbeta, dq_rem, db_rem = cast(g, "dQt", "dalpha", "dbeta", "dq_rem", "db_rem")
+    op = OPS[str(g["matvec"])]()
+    Q, H, r, c = krylov.arnoldi_forward(op, K, v, A, symmetric=True)
+    T = 0.5 * (H + H.T)
+    assert rel_err(np.diag(T), g["alpha"]) < tol(g) and rel_err(np.diag(T, 1), g["beta"]) < tol(g)
+    assert rel_err(Q.T, g["Qt"]) < tol(g)
+    # cotangent of (r/||r||, ||r||) -> dr (lanczos.py:166), then the symmetric adjoint
+    norm = np.linalg.norm(r)
+    dr = dq_rem / norm + (db_rem / norm - np.dot(r, dq_rem) / norm**3) * r
+    dH = np.diag(dalpha) + 0.5 * (np.diag(dbeta, 1) + np.diag(dbeta, -1))
+    dv, dp = krylov.arnoldi_adjoint(op, (A,), Q=Q, H=H, r=r, c=c, dQ=dQt.T, dH=dH, dr=dr, dc=np.zeros((), A.dtype),
+                                    reortho="full", symmetric=True, tridiagonal_cotangent=True)  # fmt: skip
+    assert rel_err(dv, g["dv_adjoint"]) < tol(g, True)
+    assert rel_err(dp[0], g["dp_adjoint"]) < tol(g, True)
