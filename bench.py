@@ -225,6 +225,10 @@ def main():
     from experiments_lanczos_adjoints_b200 import device as bl_dev
 
     P = max(1, args.probes)
+    # three or more runs in flight: one block per SM and kernel, so that kernels of different runs share an SM and
+    # fill each other's ramps and reduction tails (4 probes: 4.8k -> 5.15k steps/s); one run alone wants two
+    blocks_in_flight = 1 if P >= 3 and "BL_BLOCKS_PER_SM" not in os.environ else 0
+    bl.set_blocks_per_sm(blocks_in_flight)
     plans = []
     for p in range(P):
         op = bl.operators.SparseOperator(row, col, (N_ROWS, N_ROWS))
@@ -335,6 +339,8 @@ def main():
     e2e_value = world * P * DEPTH / (ms_e2e / e2e_steps * 1e-3)
 
     # one probe alone (the latency of a single forward + adjoint), for transparency next to the P-probe throughput
+    bl.set_blocks_per_sm(0)  # a run alone: the default two blocks per SM
+    step_device(plans[:1])
     ms_single, _ = timed(lambda: step_device(plans[:1]), 3, plans[:1])
     ms_single /= 3
 
@@ -381,6 +387,7 @@ def main():
                 "per_gpu": f"{P} independent probe vectors per GPU per step, each on its own stream (one step = forward + "
                            f"adjoint of all {P}); their parameter cotangents are summed and all-reduced once per step",
                 "probes_in_flight": P,
+                "blocks_per_sm": {"timed_region": blocks_in_flight or 2, "single_probe_and_kernel_profile": 2},
                 "single_probe": {"ms_per_forward_adjoint": ms_single, "krylov_steps_per_s": DEPTH / (ms_single * 1e-3)},
                 "loops": ("symmetric loops of tridiag(reortho=full): BL_FWD_SYMMETRIC, BL_ADJ_SYMMETRIC, "
                           "BL_ADJ_TRIDIAG_COTANGENT (include/b200_lanczos.h); switched off by BL_SYMMETRIC_FORWARD=0 / "

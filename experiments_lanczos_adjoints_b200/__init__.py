@@ -16,6 +16,7 @@ from experiments_lanczos_adjoints_b200.device import (  # noqa: F401
     empty,
     empty_cache,
     launch_count,
+    set_blocks_per_sm,
     set_device,
     sm_count,
     synchronize,

@@ -109,12 +109,14 @@ constexpr int dots_tile() { return BL_DOTS_TILE_BYTES / (int)sizeof(T); }  // ro
 
 // Blocks per SM of the TMA-staged kernels (BL_BLOCKS_PER_SM = 1 or 2, default 2).  Two fill the shared memory
 // of an SM; one leaves room for the successor's blocks to become resident and prefetch under the tail.
+std::atomic<int> g_blocks_per_sm{0};  // bl_set_blocks_per_sm; 0 = environment / default
 int blocks_per_sm() {
   static int v = [] {
     const char* e = std::getenv("BL_BLOCKS_PER_SM");
     return (e && e[0] == '1') ? 1 : 2;
   }();
-  return v;
+  const int set = g_blocks_per_sm.load(std::memory_order_relaxed);
+  return set ? set : v;
 }
 template <typename T>
 int tma_grid(int64_t n, int tile) {
@@ -1401,6 +1403,12 @@ int bl_arnoldi_adjoint_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K,
   return arnoldi_adjoint_batch_t<double>(op, dtype, n, (int)K, reortho_full, (int)count, (const double*)Q, ld,
                                          (const double*)H, (const double*)r, (const double*)c, (const double*)dH,
                                          (double*)dv, lddv, (double*)Lambda, workspace, workspace_bytes, s);
+}
+
+int bl_set_blocks_per_sm(int blocks) {
+  BL_REQUIRE(blocks >= 0 && blocks <= 2, "blocks per SM must be 0 (default), 1 or 2");
+  g_blocks_per_sm.store(blocks, std::memory_order_relaxed);
+  return BL_OK;
 }
 
 int bl_op_deferred_grad(bl_operator_t* op, int dtype, int* yes) {

@@ -42,6 +42,12 @@ def sm_count() -> int:
     return n.value
 
 
+def set_blocks_per_sm(blocks: int):
+    """Blocks per SM of the basis-streaming kernels from now on: 2 (default), 1 (several runs in flight on separate
+    streams), 0 = back to the default (`bl_set_blocks_per_sm`)."""
+    _lib.call("bl_set_blocks_per_sm", int(blocks))
+
+
 def launch_count() -> int:
     n = C.c_uint64(0)
     _lib.call("bl_launch_count", C.byref(n))

@@ -316,6 +316,20 @@ def probe_pipelined_sum(integrand, probes, parameters, *, with_grad, lanes=None)
         pl.set_params(*host_params)
     total = 0.0
     used = [False] * L
+    if L >= 3:  # kernels of different lanes share an SM (one block per SM and kernel), see bl_set_blocks_per_sm
+        dev.set_blocks_per_sm(1)
+    try:
+        total = _pipelined_groups(integrand, plans, probes, L, K, dtype, with_grad, used)
+    finally:
+        dev.set_blocks_per_sm(0)
+        for pl in plans:
+            pl.stream.synchronize()
+    return _pipelined_finish(plans, used, dtype, total, P, with_grad)
+
+
+def _pipelined_groups(integrand, plans, probes, L, K, dtype, with_grad, used):
+    total = 0.0
+    P = len(probes)
     for p0 in range(0, P, L):
         group = probes[p0 : p0 + L]
         scales = np.linalg.norm(group.astype(np.float64), axis=1)  # lanczos.py:25
@@ -334,6 +348,10 @@ def probe_pipelined_sum(integrand, probes, parameters, *, with_grad, lanes=None)
                 pl.set_cotangent(dH.astype(dtype))
                 pl.adjoint(zero=not used[li], export=False)
                 used[li] = True
+    return total
+
+
+def _pipelined_finish(plans, used, dtype, total, P, with_grad):
     grads = None
     if with_grad:
         active = [pl for pl, u in zip(plans, used) if u]
@@ -349,9 +367,6 @@ def probe_pipelined_sum(integrand, probes, parameters, *, with_grad, lanes=None)
                 _lib.call("bl_vec_axpby", dev.dtype_code(dtype), acc.size, 1.0, acc.ptr, 1.0, pl.grads[gi].ptr, acc.ptr, stream.ptr)
             grads.append(acc)
         stream.synchronize()
-    else:
-        for pl in plans:
-            pl.stream.synchronize()
     return total, grads, P
 
 

@@ -70,6 +70,10 @@ int bl_event_sync(void* event);
 int bl_event_elapsed_ms(void* start, void* stop, float* ms);
 /* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
 int bl_launch_count(uint64_t* count);
+/* Blocks per SM of the basis-streaming kernels for launches from now on: 2 (default: one run alone fills the
+ * memory system), 1 (several independent runs in flight on separate streams: kernels of different runs share an
+ * SM and fill each other's ramps and reduction tails), 0 = back to the default / BL_BLOCKS_PER_SM. */
+int bl_set_blocks_per_sm(int blocks);
 
 /* Per-kernel-class device timing for the roofline report.  Between begin and end every
  * streaming launch of the Krylov loops is bracketed by CUDA events on its own stream; end
