@@ -67,8 +67,8 @@ SIGNATURES = {
     "bl_op_wave_set_comm": (_i32, [_vp, _vp]),
     "bl_arnoldi_forward_batch": (_i32, [_vp, _i32, _i64, _i64, _i32, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp,
                                         C.c_size_t, _vp]),
-    "bl_arnoldi_adjoint_batch": (_i32, [_vp, _i32, _i64, _i64, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp,
-                                        _vp, C.c_size_t, _vp]),
+    "bl_arnoldi_adjoint_batch": (_i32, [_vp, _i32, _i64, _i64, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
     "bl_op_deferred_grad": (_i32, [_vp, _i32, C.POINTER(C.c_int)]),
     "bl_precond_create": (_i32, [_i32, _i64, _i64, _vp, _i64, _vp, _pvp]),
     "bl_precond_set_shift": (_i32, [_vp, C.c_double, _vp]),

@@ -17,6 +17,7 @@
 #include "dist.cuh"
 #include "krylov_kernels.cuh"
 #include "stream_kernels.cuh"
+#include "step_kernel.cuh"
 #include "operators.cuh"
 
 namespace bl {
@@ -583,6 +584,110 @@ int launch_xdots(const Common& c, const XDotsSpec& f, cudaStream_t s, bool* done
   return BL_OK;
 }
 
+// One launch for the three basis-streaming phases of a symmetric-loop step (k_step_tma, step_kernel.cuh).
+// BL_STEP=0 disables it (A/B measurements); BL_STEP_PDL=0 launches it without the programmatic-dependent-launch
+// attribute.  The kernel's blocks wait for one another, so the launch is cooperative (the driver starts the
+// grid only when all of it is resident: kernels of other streams cannot wedge it) and the grid is capped at
+// what fits the device.
+int step_mode() {
+  static const int mode = [] {
+    const char* e = std::getenv("BL_STEP");
+    return e ? std::atoi(e) : 1;
+  }();
+  return mode;
+}
+bool step_pdl() {
+  static const bool on = [] {
+    const char* e = std::getenv("BL_STEP_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+std::atomic<int> g_step_pdl_ok{1};  // cleared when the driver refuses cooperative + programmatic launch together
+
+template <typename T>
+size_t step_smem_bytes(int nrows1, int nrows2) {
+  constexpr int TILE = kConsumerThreads * Vec<T>::N;
+  const int nacc = std::max(nrows1, kFewMax * kConsumerWarps);
+  return (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 2) * 8 + (size_t)nacc * 8 +
+         (size_t)std::max(nrows1, kFewMax) * 8 + (size_t)((nrows2 + kGroup - 1) / kGroup * kGroup) * sizeof(T) + 16;
+}
+
+// whether `blocks` blocks per SM of k_step_tma are co-resident on this device (cached per dtype and device)
+template <typename T>
+bool step_fits(size_t smem, int blocks) {
+  constexpr int TILE = kConsumerThreads * Vec<T>::N;
+  static std::mutex mu;
+  static std::set<std::pair<int, int>> ok, bad;  // (device, blocks per SM), for the 112 KB opt-in size
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_pair(dev, blocks);
+  if (ok.count(key)) return true;
+  if (bad.count(key)) return false;
+  int coop = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_tma<T, TILE>, kStreamThreads, 112 * 1024) ==
+                  cudaSuccess && per_sm >= blocks) {
+    ok.insert(key);
+    return true;
+  }
+  (void)smem;
+  (void)cudaGetLastError();
+  bad.insert(key);
+  return false;
+}
+
+template <typename T>
+int launch_step(const Common& c, StepArgs a, double bytes, cudaStream_t s, bool* done) {
+  *done = false;
+  constexpr int TILE = kConsumerThreads * Vec<T>::N;
+  const size_t smem = step_smem_bytes<T>(a.nrows1, a.nrows2);
+  if (step_mode() == 0 || !xdots_enabled() || !use_tma(a.n) || stream_mode() == 2 || is_sharded() ||
+      a.nvec > kXTerms || a.few_n > kFewMax || a.nrows1 < 1 || a.nrows2 < 1 || smem > 112 * 1024)
+    return BL_OK;
+  BL_CHECK(set_smem(k_step_tma<T, TILE>, 112 * 1024));
+  const int bps = blocks_per_sm();
+  if (!step_fits<T>(smem, bps)) return BL_OK;
+  *done = true;
+  a.partials = c.partials_dots;
+  a.red_g = c.red;
+  a.partials_norm = c.partials_comb;
+  a.bar = c.counters + 8;
+  a.exit_counter = c.counters + 9;
+  for (Epi* e : {&a.epi0, &a.epi1, &a.epi2}) {
+    e->red = c.red;
+    e->scal = c.scal;
+  }
+  a.reverse = next_direction();
+  (void)next_direction();  // phase 2 walks the other way: the next streaming kernel starts where it ended
+  const int grid = tma_grid<T>(a.n, TILE);
+  ProfScope prof(BL_PROF_FUSED, bytes, s);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kStreamThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const bool pdl = pdl_enabled() && step_pdl() && g_step_pdl_ok.load(std::memory_order_relaxed) != 0;
+  cfg.numAttrs = pdl ? 2 : 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, k_step_tma<T, TILE>, a);
+  if (err != cudaSuccess && pdl) {  // cooperative + programmatic launch refused together: cooperative alone
+    (void)cudaGetLastError();
+    g_step_pdl_ok.store(0, std::memory_order_relaxed);
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, k_step_tma<T, TILE>, a);
+  }
+  BL_CUDA(err);
+  BL_LAUNCHED();
+  return BL_OK;
+}
+
 template <typename T>
 int launch_scale_copy(int64_t n, const T* x, double mul, const double* div_ptr, T* out, int64_t n_pad, cudaStream_t s) {
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(16 * sm_count(), (n_pad + 255) / 256));
@@ -711,6 +816,18 @@ struct FwdRun {
   }
     return BL_OK;
   }
+  // epilogue of the second pass's dots: coefB = Q^H v'; with the local first pass also H[j < i-1, i]
+  Epi pass_b_epi(int i) const {
+    Epi e;
+    e.mode = EPI_FWD_B;
+    e.m = i + 1;
+    e.coef = c.coefB;
+    e.i = i;
+    e.K = K;
+    e.j0 = first_lo(i);
+    e.H = local_first ? H : nullptr;
+    return e;
+  }
   int pre(int i) {
     T* qi = Q + (int64_t)i * ld;
     // v /= length; Q[:, i] = v                                                 arnoldi.py:80-81
@@ -737,6 +854,40 @@ struct FwdRun {
     norm_epi.H = H;
     bool fused = false;
     if (second_pass && local_first) {
+      // symmetric loop, ONE launch: h = (q_{i-1}, q_i)^H v | v' = v - h_{i-1} q_{i-1} - h_i q_i, h2 = Q^H v' |
+      // v'' = v' - Q h2, ||v''||                                                 arnoldi.py:87-98
+      const int j0 = first_lo(i);
+      StepArgs a;
+      a.n = n;
+      a.few_n = m - j0;
+      for (int j = j0; j < m; ++j) a.few_row[j - j0] = q_row(j);
+      a.few_x = r;
+      a.epi0.mode = EPI_FWD_A;
+      a.epi0.i = i;
+      a.epi0.K = K;
+      a.epi0.j0 = j0;
+      a.epi0.m = m - j0;
+      a.epi0.H = H;
+      a.epi0.coef = c.coefA;
+      a.out1 = r;
+      a.vec[a.nvec++] = term(r);
+      for (int j = j0; j < m; ++j) a.vec[a.nvec++] = term(q_row(j), -1.0, c.coefA + j);
+      a.src1 = row_source(rows(Q, ld, 0, m), nullptr, sizeof(T));
+      a.nrows1 = m;
+      a.epi1 = pass_b_epi(i);
+      a.src2 = a.src1;
+      a.nrows2 = m;
+      a.coef2 = c.coefB;
+      a.sign2 = -1.0;
+      a.out2 = r;
+      a.norm = 1;
+      a.epi2 = norm_epi;
+      a.wait_row = i;  // row i is the operator kernel's output (fused normalise + matvec)
+      bool stepped = false;
+      BL_CHECK(launch_step<T>(c, a, (double)((m - j0 + 1) + (m + a.nvec + 1) + (m + 2)) * n * sizeof(T), s, &stepped));
+      if (stepped) return BL_OK;
+    }
+    if (second_pass && local_first) {
       // symmetric loop: v = v - h_{i-1} q_{i-1} - h_i q_i is a three-vector combination, and h2 = Q^H v streams
       // every active row once (no row is needed twice: nothing stays resident)   arnoldi.py:88,92
       XDotsSpec f;
@@ -745,18 +896,13 @@ struct FwdRun {
       f.vec[f.nvec++] = term(r);
       for (int j = first_lo(i); j < m; ++j) f.vec[f.nvec++] = term(q_row(j), -1.0, c.coefA + j);
       f.rows = rows(Q, ld, 0, m);
-      f.epi.mode = EPI_FWD_B;
-      f.epi.m = m;
-      f.epi.coef = c.coefB;
+      f.epi = pass_b_epi(i);
       BL_CHECK(launch_xdots<T>(c, f, s, &fused));
     }
     if (second_pass && !fused) {
       // v = v - Q h and, from the same read of Q, h2 = Q^H v (the second pass's coefficients;
       // h itself is not updated, arnoldi.py:92)
-      Epi e;
-      e.mode = EPI_FWD_B;
-      e.m = m;
-      e.coef = c.coefB;
+      Epi e = pass_b_epi(i);
       FusedSpec f;
       f.n = n;
       f.out = r;
@@ -776,11 +922,7 @@ struct FwdRun {
       a.epi = norm_epi;
       BL_CHECK(launch_combine<T>(g, c, a, !second_pass, s));
       if (second_pass) {
-        Epi e;
-        e.mode = EPI_FWD_B;
-        e.m = m;
-        e.coef = c.coefB;
-        BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, m), r, n, e, s));
+        BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, 0, m), r, n, pass_b_epi(i), s));
       }
     }
     if (second_pass) {  // v = v - Q (Q^H v)                                    arnoldi.py:91-92
@@ -976,8 +1118,10 @@ struct AdjRun {
     have_reproj = false;  // coefA already holds p - P lambda for this idx (fused into the previous step)
     return BL_OK;
   }
+  int pre_done = -1;  // the step kernel of idx+1 already wrote Lambda[idx] (its phase 2)
   int pre(int idx) {
     T* Lrow = Lambda + (int64_t)idx * ld;
+    if (pre_done == idx) return BL_OK;
     if (reortho_full) {
       // lambda -= P^T (P lambda) - P^T p, rows <= idx+1 of P = Q^T              arnoldi.py:201-204
       const int mact = std::min(idx + 2, K);
@@ -1003,8 +1147,63 @@ struct AdjRun {
     }
     return BL_OK;
   }
+  // banded Gamma, ONE launch: Gamma row from the dots of z with rows idx-2..idx | back-substitution and the
+  // next step's re-projection dots | Lambda[idx-1] = lambda + Q (p - P lambda)   arnoldi.py:212-219, 201-204, 216
+  int post_step(int idx, bool* stepped) {
+    T* Lrow = Lambda + (int64_t)idx * ld;
+    StepArgs a;
+    a.n = n;
+    const int j0 = band_lo(idx);
+    a.few_n = idx + 1 - j0;
+    for (int j = j0; j <= idx; ++j) a.few_row[j - j0] = q_row(j);
+    a.few_x = z;
+    a.epi0.mode = EPI_ADJ_GAMMA;
+    a.epi0.i = idx;
+    a.epi0.K = K;
+    a.epi0.j0 = j0;
+    a.epi0.m = idx + 1 - j0;
+    a.epi0.Hc = H;
+    a.epi0.Gamma = Gamma;
+    a.epi0.PiGamma = PiGamma;
+    a.epi0.eta = eta;
+    a.epi0.coef = c.coefB;
+    a.epi0.coef2 = c.coefC;
+    a.out1 = lam;
+    a.vec[a.nvec++] = term(r, 1.0, c.scal + S_ETA_IDX);
+    a.vec[a.nvec++] = term(Lrow, 1.0, c.scal + S_NEG_ALPHA);
+    a.vec[a.nvec++] = term(z);
+    add_symmetric_term(idx, a.vec, a.nvec);
+    for (int j = band_lo(idx); j < band_hi(idx); ++j) a.vec[a.nvec++] = term(q_row(j), 1.0, c.coefB + j);
+    a.out_div_ptr = c.scal + S_BETA_MINUS;
+    a.src1 = row_source(rows(Q, ld, 0, idx + 1), nullptr, sizeof(T));
+    a.nrows1 = idx + 1;
+    a.epi1.mode = EPI_ADJ_REPROJ;
+    a.epi1.i = idx - 1;
+    a.epi1.K = K;
+    a.epi1.m = idx + 1;
+    a.epi1.dH = dH;
+    a.epi1.coef = c.coefA;
+    a.src2 = a.src1;  // rows <= (idx-1)+1 of P = Q^T
+    a.nrows2 = idx + 1;
+    a.coef2 = c.coefA;
+    a.sign2 = 1.0;
+    a.out2 = Lambda + (int64_t)(idx - 1) * ld;
+    a.norm = 0;
+    BL_CHECK(launch_step<T>(c, a, (double)((a.few_n + 1) + (idx + 1 + a.nvec + 1) + (idx + 1 + 2)) * n * sizeof(T), s,
+                            stepped));
+    if (*stepped) {
+      pre_done = idx - 1;
+      have_reproj = false;
+    }
+    return BL_OK;
+  }
   int post(int idx) {
     T* Lrow = Lambda + (int64_t)idx * ld;
+    if (banded && idx > 0 && reortho_full) {
+      bool stepped = false;
+      BL_CHECK(post_step(idx, &stepped));
+      if (stepped) return BL_OK;
+    }
     {  // Gamma[idx, :] and the coefficients of the back-substitution             arnoldi.py:212-218
       Epi e;
       e.mode = EPI_ADJ_GAMMA;
@@ -1138,17 +1337,19 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
 // batched A^T Lambda per step, and ONE batched parameter-cotangent pass over all P*K (lambda, q) pairs.
 template <typename T>
 int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags, int P, const T* Q,
-                            int64_t ld, const T* H, const T* r, const T* c_in, const T* dH, T* dv, int64_t lddv,
-                            T* Lambda, void* workspace, size_t wbytes, cudaStream_t s) {
+                            int64_t ld, const T* H, const T* r, const T* c_in, const T* dQ, const T* dH, const T* dr,
+                            const T* dc, T* dv, int64_t lddv, T* Lambda, void* workspace, size_t wbytes,
+                            cudaStream_t s) {
   const size_t per = bl_arnoldi_workspace_bytes(n, K, dtype);
   BL_REQUIRE(wbytes >= per * (size_t)P, "workspace too small (P * bl_arnoldi_workspace_bytes)");
-  BL_REQUIRE(op->deferred_grad(dtype), "the batched adjoint needs an operator with a deferred parameter cotangent");
+  const bool deferred = op->deferred_grad(dtype);
   std::vector<AdjRun<T>> runs;
   std::vector<const void*> in(P);
   std::vector<void*> out(P);
   for (int p = 0; p < P; ++p) {
     runs.push_back(AdjRun<T>{op, dtype, n, K, (flags & BL_ADJ_REORTHO_FULL) != 0, Q + (int64_t)p * K * ld, ld, H + (int64_t)p * K * K,
-                             r + (int64_t)p * ld, c_in + p, nullptr, dH + (int64_t)p * K * K, nullptr, nullptr,
+                             r + (int64_t)p * ld, c_in + p, dQ ? dQ + (int64_t)p * K * ld : nullptr,
+                             dH + (int64_t)p * K * K, dr ? dr + (int64_t)p * ld : nullptr, dc ? dc + p : nullptr,
                              dv + (int64_t)p * lddv, Lambda + (int64_t)p * K * ld,
                              static_cast<char*>(workspace) + per * p, per, s, {}, {}});
     runs.back().symmetric = symmetric_shortcut(flags);
@@ -1163,11 +1364,15 @@ int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int 
     }
     {
       ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype) * P, s);
-      BL_CHECK(op->apply_transpose_batch(dtype, P, in.data(), out.data(), s));
+      if (deferred) {
+        BL_CHECK(op->apply_transpose_batch(dtype, P, in.data(), out.data(), s));
+      } else {  // the parameter cotangent accumulates in the operator over steps and runs (a sum over the batch)
+        for (int p = 0; p < P; ++p) BL_CHECK(op->vjp(dtype, runs[p].q_row(idx), in[p], out[p], s));
+      }
     }
     for (int p = 0; p < P; ++p) BL_CHECK(runs[p].post(idx));
   }
-  {
+  if (deferred) {
     ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
     BL_CHECK(op->vjp_batch(dtype, Q, ld, Lambda, ld, P * K, s));
   }
@@ -1386,23 +1591,26 @@ int bl_arnoldi_forward_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K,
 }
 
 int bl_arnoldi_adjoint_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K, int reortho_full, int64_t count,
-                             const void* Q, int64_t ld, const void* H, const void* r, const void* c, const void* dH,
-                             void* dv, int64_t lddv, void* Lambda, void* workspace, size_t workspace_bytes,
-                             void* stream) {
+                             const void* Q, int64_t ld, const void* H, const void* r, const void* c, const void* dQ,
+                             const void* dH, const void* dr, const void* dc, void* dv, int64_t lddv, void* Lambda,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   BL_REQUIRE(op && Q && H && r && c && dH && dv && Lambda && workspace && count >= 1 && count <= 4096 && lddv >= n,
              "bad batch arguments");
   BL_CHECK(check_basis(dtype, n, K, ld, Q));
   BL_REQUIRE(reinterpret_cast<uintptr_t>(Lambda) % 16 == 0, "Lambda must be 16-byte aligned");
+  BL_REQUIRE(dQ == nullptr || reinterpret_cast<uintptr_t>(dQ) % 16 == 0, "dQ must be 16-byte aligned");
   BL_REQUIRE(op->n == n, "operator size does not match n");
   BL_REQUIRE(ld <= (int64_t)align_up((size_t)n, 64), "ld must be at most n rounded up to 64");
   cudaStream_t s = as_stream(stream);
   if (dtype == BL_F32)
     return arnoldi_adjoint_batch_t<float>(op, dtype, n, (int)K, reortho_full, (int)count, (const float*)Q, ld,
-                                          (const float*)H, (const float*)r, (const float*)c, (const float*)dH,
-                                          (float*)dv, lddv, (float*)Lambda, workspace, workspace_bytes, s);
+                                          (const float*)H, (const float*)r, (const float*)c, (const float*)dQ,
+                                          (const float*)dH, (const float*)dr, (const float*)dc, (float*)dv, lddv,
+                                          (float*)Lambda, workspace, workspace_bytes, s);
   return arnoldi_adjoint_batch_t<double>(op, dtype, n, (int)K, reortho_full, (int)count, (const double*)Q, ld,
-                                         (const double*)H, (const double*)r, (const double*)c, (const double*)dH,
-                                         (double*)dv, lddv, (double*)Lambda, workspace, workspace_bytes, s);
+                                         (const double*)H, (const double*)r, (const double*)c, (const double*)dQ,
+                                         (const double*)dH, (const double*)dr, (const double*)dc, (double*)dv, lddv,
+                                         (double*)Lambda, workspace, workspace_bytes, s);
 }
 
 int bl_set_blocks_per_sm(int blocks) {

@@ -24,7 +24,7 @@ enum EpiMode : int {
   EPI_STORE,        // out_t[j] = red[j]                          (plain helper calls)
   EPI_INIT_NORM,    // len0 = sqrt(red[0]); inv_len = 1/len0; c = 1/len0
   EPI_FWD_A,        // H[j,i] = red[j]; coef[j] = H[j,i]                      arnoldi.py:87,99
-  EPI_FWD_B,        // coef[j] = red[j]                                       arnoldi.py:92
+  EPI_FWD_B,        // coef[j] = red[j] (+ H[j,i] = red[j] for the rows j < j0 the first pass skipped)  arnoldi.py:92
   EPI_FWD_NORM,     // len = sqrt(red[0]); H[i+1,i] = len; inv_len = 1/len    arnoldi.py:95-98
   EPI_ADJ_ETA,      // eta[j] = dH[j,K-1] - red[j]                            arnoldi.py:119
   EPI_ADJ_REPROJ,   // coef[j] = dH[j,idx] - red[j]   (j <= idx+1)            arnoldi.py:202-204
@@ -73,13 +73,14 @@ struct Epi {
   int peer_count = 0;
 };
 
-// Runs in the last block, after `red[0..m)` has been written by that same block and a
-// __syncthreads().
-template <typename T>
-__device__ void run_epilogue(const Epi& e) {
-  if (e.peer_mail != nullptr && e.peer_count > 0)
-    dist::peer_allreduce_block(dist::view_from_mailbox(e.peer_mail, e.peer_seq), e.red, e.peer_count);
-  const int t = threadIdx.x, nt = blockDim.x;
+// Runs after `red[0..m)` has been written and the `nt` participating threads (index t) have synchronised;
+// `sync()` is their barrier (the whole block for the last-block pattern, the consumer threads of k_step_tma).
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+template <typename T, typename Sync>
+__device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync sync) {
   const int K = e.K, i = e.i;
   switch (e.mode) {
     case EPI_NONE:
@@ -107,6 +108,11 @@ __device__ void run_epilogue(const Epi& e) {
     } break;
     case EPI_FWD_B: {
       for (int j = t; j < e.m; j += nt) e.coef[j] = static_cast<double>(static_cast<T>(e.red[j]));
+      // BL_FWD_SYMMETRIC: the first pass skipped rows j < j0, so the second pass's coefficient q_j . v' IS
+      // q_j . (A q_i) up to rounding (v' differs from A q_i along q_{i-1}, q_i only): it completes column i of H.
+      // O(eps |A|) for a symmetric operand; the host reads these entries to detect a non-symmetric one.
+      if (e.H != nullptr)
+        for (int j = t; j < e.j0; j += nt) static_cast<T*>(e.H)[(size_t)j * K + i] = static_cast<T>(e.red[j]);
     } break;
     case EPI_FWD_NORM: {
       if (t == 0) {
@@ -143,7 +149,7 @@ __device__ void run_epilogue(const Epi& e) {
         }
         e.Gamma[(size_t)idx * K + j] = g;
       }
-      __syncthreads();
+      sync();
       for (int j = t; j < K; j += nt) {
         // (Gamma + Gamma^T)[idx, j]
         e.coef[j] = static_cast<double>(
@@ -218,6 +224,14 @@ __device__ void run_epilogue(const Epi& e) {
       }
     } break;
   }
+}
+
+// Runs in the last block, after `red[0..m)` has been written by that same block and a __syncthreads().
+template <typename T>
+__device__ void run_epilogue(const Epi& e) {
+  if (e.peer_mail != nullptr && e.peer_count > 0)
+    dist::peer_allreduce_block(dist::view_from_mailbox(e.peer_mail, e.peer_seq), e.red, e.peer_count);
+  run_epilogue_impl<T>(e, (int)threadIdx.x, (int)blockDim.x, BlockSync());
 }
 
 // ---- dots ---------------------------------------------------------------------------------

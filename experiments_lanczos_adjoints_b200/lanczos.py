@@ -41,17 +41,50 @@ def device_axpby(a, x, b, y, stream=None) -> dev.DeviceArray:
     return out
 
 
-class _TridiagFull:
-    """`_tridiag_reortho_full` (`lanczos.py:152-169`)."""
+def hessenberg_is_tridiagonal(H: np.ndarray) -> bool:
+    """Whether the Arnoldi matrix of a run is tridiagonal and symmetric up to rounding -- i.e. whether the operand
+    behaved like a symmetric one on this Krylov space.  The symmetric loops complete `H` with the
+    second pass's coefficients above the band (`EPI_FWD_B`), so every entry the adjoint shortcuts would drop is
+    visible here: `|H[j, i]|, j < i-1` and `|H[i, i+1] - H[i+1, i]|` are `O(eps |H|)` for a symmetric operand and
+    `O(|H|)` otherwise."""
+    H = np.asarray(H)
+    K = H.shape[0]
+    if K < 2:
+        return True
+    scale = float(np.abs(H).max())
+    bound = 1e3 * np.finfo(H.dtype).eps * scale
+    asym = float(np.abs(np.diag(H, 1) - np.diag(H, -1)).max())
+    above = float(np.abs(np.triu(H, 2)).max()) if K > 2 else 0.0
+    return bool(np.isfinite(scale) and asym <= bound and above <= bound)
 
-    def __init__(self, op, krylov_depth, custom_vjp):
+
+class _TridiagFull:
+    """`_tridiag_reortho_full` (`lanczos.py:152-169`).
+
+    The reference runs general Arnoldi and symmetrises `H`.  `assume_symmetric=None` (default) runs the symmetric
+    loops and CHECKS the assumption on the `H` of every run (`hessenberg_is_tridiagonal`): an operand that is not
+    symmetric gets the general adjoint loops (what the reference computes) and a warning.  `True` skips the check,
+    `False` always runs the general loops."""
+
+    def __init__(self, op, krylov_depth, custom_vjp, assume_symmetric=None):
         self.alg = arnoldi.hessenberg(op, krylov_depth, custom_vjp=custom_vjp, reortho="full")
-        self.alg.symmetric = True  # tridiagonalisation is defined for symmetric operands (lanczos.py:152-169)
-        self.alg.tridiagonal_cotangent = True  # `pullback` below builds dH from (dalpha, dbeta)
+        self.assume_symmetric = assume_symmetric
+        # tridiagonalisation is defined for symmetric operands (lanczos.py:152-169)
+        self.alg.symmetric = assume_symmetric is not False
+        self.alg.tridiagonal_cotangent = self.alg.symmetric  # `pullback` below builds dH from (dalpha, dbeta)
+
+    def _general_adjoint_needed(self, Hh) -> bool:
+        if self.assume_symmetric is not None or hessenberg_is_tridiagonal(Hh):
+            return False
+        warnings.warn(
+            "tridiag(reortho='full'): the operand is not symmetric on this Krylov space (H is not tridiagonal "
+            "up to rounding); the adjoint runs the general Arnoldi loops, as the reference does.",
+            stacklevel=3,
+        )
+        return True
 
     @staticmethod
-    def _wrap(Qn, H, r, stream):
-        Hh = H.numpy(stream)
+    def _wrap(Qn, Hh, r, stream):
         T = 0.5 * (Hh + Hh.T)  # lanczos.py:162
         diags, offdiags = np.diag(T, 0).copy(), np.diag(T, 1).copy()
         norm = np.sqrt(device_dot(r, r, stream)).astype(Hh.dtype)
@@ -61,14 +94,16 @@ class _TridiagFull:
     def __call__(self, vec, *params, stream=None):
         stream = stream or dev.default_stream()
         Qn, H, r, _c = self.alg(vec, *params, stream=stream)
-        return self._wrap(Qn, H, r, stream)
+        return self._wrap(Qn, H.numpy(stream), r, stream)
 
     def vjp(self, vec, *params, stream=None):
         stream = stream or dev.default_stream()
         (Qn, H, r, _c), pull = self.alg.vjp(vec, *params, stream=stream)
-        out = self._wrap(Qn, H, r, stream)
+        Hh = H.numpy(stream)
+        out = self._wrap(Qn, Hh, r, stream)
         K, dtype = H.shape[0], H.dtype
         norm = float(out[1][1])
+        general = self._general_adjoint_needed(Hh)
 
         def pullback(cot):
             (dQt, (dalpha, dbeta)), (dq_rem, dnorm) = cot
@@ -89,7 +124,14 @@ class _TridiagFull:
                 else:
                     dr = device_axpby(coef_r, r, 0.0, None, stream)
             dQ = None if dQt is None else _as_kn(dQt, K, r.size, dtype)
-            return pull((dQ, dH, dr, None))
+            if not general:
+                return pull((dQ, dH, dr, None))
+            saved = self.alg.symmetric, self.alg.tridiagonal_cotangent
+            self.alg.symmetric = self.alg.tridiagonal_cotangent = False  # H is complete: general loops on it
+            try:
+                return pull((dQ, dH, dr, None))
+            finally:
+                self.alg.symmetric, self.alg.tridiagonal_cotangent = saved
 
         return out, pullback
 
@@ -178,11 +220,12 @@ class _TridiagNone:
         return out, pullback
 
 
-def tridiag(matvec, krylov_depth, /, *, reortho: str, custom_vjp: bool = True):
+def tridiag(matvec, krylov_depth, /, *, reortho: str, custom_vjp: bool = True, assume_symmetric=None):
     """Drop-in for `lanczos.tridiag` (`/root/reference/src/matfree_extensions/lanczos.py:142-149`):
-    returns `estimate(vec, *params) -> ((Q.T (K,n), (diags, offdiags)), (r/||r||, ||r||))`."""
+    returns `estimate(vec, *params) -> ((Q.T (K,n), (diags, offdiags)), (r/||r||, ||r||))`.
+    `assume_symmetric` (not in the reference) controls the symmetric loops of `reortho="full"`, see `_TridiagFull`."""
     if reortho == "full":
-        return _TridiagFull(matvec, krylov_depth, custom_vjp)
+        return _TridiagFull(matvec, krylov_depth, custom_vjp, assume_symmetric)
     if reortho == "none":
         return _TridiagNone(matvec, krylov_depth, custom_vjp)
     msg = f"reortho={reortho} unsupported. Choose eiter {'full', 'none'}."
@@ -418,8 +461,8 @@ def probe_batch_sum(integrand, probes, parameters, *, with_grad, stream=None, ch
             dHd = dev.asarray(dH.reshape(B, K * K))
             dv = dev.DeviceArray((B, n), dtype, ld=ld)
             Lam = dev.DeviceArray((B * K, n), dtype, ld=ld)
-            _lib.call("bl_arnoldi_adjoint_batch", op._handle, code, n, K, arnoldi.adjoint_flags(True, True, True), B, Q.ptr, ld, H.ptr, r.ptr, c.ptr, dHd.ptr,
-                      dv.ptr, ld, Lam.ptr, ws.ptr, per * B, stream.ptr)  # fmt: skip
+            _lib.call("bl_arnoldi_adjoint_batch", op._handle, code, n, K, arnoldi.adjoint_flags(True, True, True), B, Q.ptr, ld, H.ptr, r.ptr, c.ptr, None, dHd.ptr,
+                      None, None, dv.ptr, ld, Lam.ptr, ws.ptr, per * B, stream.ptr)  # fmt: skip
             stream.synchronize()  # the buffers of this chunk go back to the pool
     if with_grad:
         grads = op.grad_export(dtype, stream=stream)

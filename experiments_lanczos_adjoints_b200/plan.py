@@ -49,6 +49,7 @@ class TridiagAdjointPlan:
         # `tridiag` is defined for symmetric operands and its cotangent dH is tridiagonal: the adjoint treats H as
         # tridiagonal and Gamma as banded (BL_ADJ_SYMMETRIC | BL_ADJ_TRIDIAG_COTANGENT, include/b200_lanczos.h)
         self.adjoint_flags = adjoint_flags(True, True, tridiagonal_cotangent)
+        self._symmetric_flags = self.adjoint_flags
         self.ld = dev.basis_ld(n, self.dtype)
         self.Q = dev.DeviceArray((K, n), self.dtype, ld=self.ld)
         self.Lam = dev.DeviceArray((K, n), self.dtype, ld=self.ld)
@@ -125,8 +126,21 @@ class TridiagAdjointPlan:
         return h2d, d2h
 
     def coefficients(self):
-        """`(alpha, beta)` of the last forward (`lanczos.py:162-164`); synchronises."""
+        """`(alpha, beta)` of the last forward (`lanczos.py:162-164`); synchronises.  Also checks on this `H` that
+        the operand behaved like a symmetric one (`lanczos.hessenberg_is_tridiagonal`): if not, the next `adjoint()`
+        runs the general Arnoldi loops (what the reference computes for any operand).  `run()` -- forward and
+        adjoint without a host read in between -- cannot check and is for operands known to be symmetric."""
+        import warnings
+
+        from experiments_lanczos_adjoints_b200.lanczos import hessenberg_is_tridiagonal
+
         H = self.H.numpy(self.stream)
+        if hessenberg_is_tridiagonal(H):
+            self.adjoint_flags = self._symmetric_flags
+        else:
+            warnings.warn("TridiagAdjointPlan: operand is not symmetric on this Krylov space; general adjoint loops",
+                          stacklevel=2)  # fmt: skip
+            self.adjoint_flags = adjoint_flags(True, False, False)
         T = 0.5 * (H + H.T)
         return np.diag(T, 0).copy(), np.diag(T, 1).copy()
 

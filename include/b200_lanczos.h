@@ -263,16 +263,19 @@ int bl_arnoldi_adjoint(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_d
  * matvec (operators that share work between vectors -- the Gram operator evaluates each kernel tile once
  * for all of them -- make `count` runs cost little more than one).  Layouts: v (count, ldv), Q (count, K, ld),
  * H (count, K, K), r (count, ld), c (count); workspace = count * bl_arnoldi_workspace_bytes.  The adjoint
- * takes the cotangent of H only (what the SLQ integrand produces), writes dv (count, lddv) and Lambda
- * (count, K, ld), and needs an operator with a deferred parameter cotangent (bl_op_deferred_grad): all
- * count*K (lambda, q) pairs go through one batched cotangent pass at the end. */
+ * takes per-run cotangents dH (count, K, K) and, each optional (NULL = zero, the SLQ case), dQ (count, K, ld),
+ * dr (count, ld), dc (count) -- the general cotangent of `jax.vmap(solve)` over initial conditions
+ * (experiments/applications/partial_differential_equation/train.py:104-110) -- and writes dv (count, lddv) and
+ * Lambda (count, K, ld).  The parameter cotangent is the SUM over the runs: operators with a deferred cotangent
+ * (bl_op_deferred_grad) send all count*K (lambda, q) pairs through one batched pass at the end, the others
+ * accumulate per step. */
 int bl_arnoldi_forward_batch(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_depth, int second_pass,
                              int64_t count, const void* v, int64_t ldv, void* Q, int64_t ld, void* H, void* r, void* c,
                              void* workspace, size_t workspace_bytes, void* stream);
 int bl_arnoldi_adjoint_batch(bl_operator_t* op, int dtype, int64_t n, int64_t krylov_depth, int reortho_full,
                              int64_t count, const void* Q, int64_t ld, const void* H, const void* r, const void* c,
-                             const void* dH, void* dv, int64_t lddv, void* Lambda, void* workspace,
-                             size_t workspace_bytes, void* stream);
+                             const void* dQ, const void* dH, const void* dr, const void* dc, void* dv, int64_t lddv,
+                             void* Lambda, void* workspace, size_t workspace_bytes, void* stream);
 /* 1 when the operator defers its parameter cotangent to one batched pass per adjoint sweep. */
 int bl_op_deferred_grad(bl_operator_t* op, int dtype, int* yes);
 

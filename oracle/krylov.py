@@ -63,7 +63,10 @@ def arnoldi_forward(op, krylov_depth, v, *params, reortho_fwd="match", symmetric
             h[: max(0, i - 1)] = 0.0  # BL_FWD_SYMMETRIC: q_j^H A q_i = O(eps |A|) for j < i-1
         v = v - Q @ h  # :88
         if reortho_fwd != "none":  # :91
-            v = v - Q @ (Q.T.conj() @ v)  # :92  -- h is NOT updated
+            h2 = Q.T.conj() @ v
+            v = v - Q @ h2  # :92  -- h is NOT updated
+            if symmetric:  # ... except (library only) for the entries the local first pass skipped: q_j^H v' there
+                h[: max(0, i - 1)] = h2[: max(0, i - 1)]  # IS q_j^H A q_i up to rounding, and completes column i of H
         length = np.sqrt(np.dot(v.conj(), v))  # :95
         if i + 1 < K:  # :98  out-of-bounds write at i+1 == K is dropped
             h[i + 1] = length
@@ -125,6 +128,103 @@ def arnoldi_adjoint(op, params, *, Q, H, r, c, dQ, dH, dr, dc, reortho, symmetri
         lam = xi - (alphas[idx] * lam - vecmat) - beta_pluses[idx] @ Lambda.T  # :218
         lam = lam / beta_minuses[idx]  # :219
     return lam * c, tuple(dp)  # :166-168
+
+
+# ---- the same two loops restricted to the columns that are non-zero at each step -------------------------------
+# `arnoldi_forward` / `arnoldi_adjoint` above are the literal restatement: every product runs over the full
+# (n, K) arrays like the reference's, including the columns that are still zero (forward) or masked (adjoint).
+# At the headline size (n = 1M, K = 100, float64: 0.8 GB per basis) that costs minutes and several GB of
+# temporaries, so the parity test at that size uses the two functions below: identical arithmetic with the
+# identically-zero terms left out, the basis held as K contiguous rows.  tests/test_oracle_golden.py checks them
+# against the literal loops.
+
+
+def arnoldi_forward_active(op, krylov_depth, v, *params, reortho_fwd="match"):
+    """`arnoldi.py:57-101` over the active columns only.  Returns `(Qt (K, n), H, r, c)`: `Qt = Q.T`."""
+    v = np.asarray(v)
+    n, K = len(v), krylov_depth
+    if K < 1 or K > n:
+        raise ValueError(f"Parameter depth {K} is outside the expected range")
+    Qt = np.zeros((K, n), dtype=v.dtype)
+    H = np.zeros((K, K), dtype=v.dtype)
+    length0 = np.sqrt(np.dot(v, v))
+    length = length0
+    for i in range(K):
+        v = v / length  # :80
+        Qt[i] = v  # :81
+        v = op.matvec(v, *params)  # :84
+        A = Qt[: i + 1]
+        h = A @ v  # :87  (the other entries of Q^T v are exact zeros)
+        v = v - h @ A  # :88
+        if reortho_fwd != "none":  # :91
+            v = v - (A @ v) @ A  # :92
+        length = np.sqrt(np.dot(v, v))  # :95
+        H[: i + 1, i] = h  # :99
+        if i + 1 < K:  # :98
+            H[i + 1, i] = length
+    return Qt, H, v, 1.0 / length0
+
+
+def arnoldi_adjoint_active(op, params, *, Qt, H, r, c, dQt, dH, dr, dc, reortho):
+    """`arnoldi.py:104-220` over the non-zero rows / columns only.  `Qt`, `dQt` are `(K, n)` (`dQt` may be None for
+    a zero cotangent, likewise `dr`).  Returns `(dv, dparams_tuple)`."""
+    K, n = Qt.shape
+    dt = Qt.dtype
+    dr_ = np.zeros(n, dtype=dt) if dr is None else dr
+    eta = dH[:, K - 1] - (Qt @ dr_ if dr is not None else 0.0)  # :119
+    lam = dr_ + eta @ Qt  # :120
+    Lt = np.zeros_like(Qt)  # Lambda^T
+    Gamma = np.zeros((K, K), dtype=dt)
+    dp = [np.zeros_like(np.asarray(p)) for p in params]
+    Pi_gamma = -dc * c * np.outer(np.eye(K, 1, dtype=dt), np.eye(K, 1, dtype=dt)) + H @ dH.T  # :127
+    if dQt is not None:
+        Pi_gamma = Pi_gamma - dQt @ Qt.T
+    beta_minuses = np.concatenate([np.ones(1, dtype=dt), np.diag(H, -1)])  # :136
+    alphas = np.diag(H)
+    for idx in range(K - 1, -1, -1):
+        if reortho == "full":  # :201-204, rows <= idx+1 of P = Q^T
+            m = min(idx + 2, K)
+            P = Qt[:m]
+            lam = lam - (P @ lam) @ P + dH[:m, idx] @ P
+        vecmat, dp_inc = op.vjp(Qt[idx], lam, *params)  # :207-208
+        dp = [g + h for g, h in zip(dp, dp_inc)]
+        g_row = Pi_gamma[idx, : idx + 1] - Qt[: idx + 1] @ vecmat  # :212-213 (lower mask: j <= idx, 1/2 on the diagonal)
+        g_row[idx] *= 0.5
+        Gamma[idx, : idx + 1] = g_row
+        Lt[idx] = lam  # :216
+        xi = (Gamma + Gamma.T)[idx, :] @ Qt + eta[idx] * r  # :217, Pi_xi[idx] = dQ[:, idx] + eta[idx] r
+        if dQt is not None:
+            xi = xi + dQt[idx]
+        lam = xi - (alphas[idx] * lam - vecmat)  # :218
+        if idx + 1 < K:  # beta_plus: row idx of H above the super... (diagonal and sub-diagonal removed)
+            lam = lam - H[idx, idx + 1 :] @ Lt[idx + 1 :]
+        lam = lam / beta_minuses[idx]  # :219
+    return lam * c, tuple(dp)
+
+
+def tridiag_full_active(op, krylov_depth, v, *params):
+    """`lanczos.tridiag(reortho="full")` (`lanczos.py:152-169`) on the active-column loops: returns
+    `(((Qt, (alpha, beta)), (r/||r||, ||r||)), pullback)` with `pullback(((dQt | None, (dalpha, dbeta)), (dq_rem | None,
+    dnorm)))`."""
+    Qt, H, r, c = arnoldi_forward_active(op, krylov_depth, v, *params)
+    T = 0.5 * (H + H.T)
+    norm = np.linalg.norm(r)
+    out = (Qt, (np.diag(T, 0), np.diag(T, 1))), (r / norm, norm)
+
+    def pullback(cot):
+        (dQt, (dalpha, dbeta)), (dq_rem, dnorm) = cot
+        K = H.shape[0]
+        dH = np.diag(np.asarray(dalpha, dtype=H.dtype))
+        if K > 1:
+            dH = dH + 0.5 * (np.diag(dbeta, 1) + np.diag(dbeta, -1))
+        dr = None
+        if dq_rem is not None or dnorm:
+            dq = np.zeros_like(r) if dq_rem is None else dq_rem
+            dr = dq / norm - r * (np.dot(r, dq) / norm**3) + (dnorm or 0.0) * r / norm
+        dv, dp = arnoldi_adjoint_active(op, params, Qt=Qt, H=H, r=r, c=c, dQt=dQt, dH=dH, dr=dr, dc=0.0, reortho="full")
+        return (dv, *dp)
+
+    return out, pullback
 
 
 class Hessenberg:

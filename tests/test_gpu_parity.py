@@ -268,7 +268,8 @@ def test_symmetric_adjoint_shortcuts_match_general_adjoint(dtype):
     assert np.abs(np.triu(Hs[1], 2)).max() < 100 * eps * np.abs(Hs[1]).max()
     # the symmetric forward (first Gram-Schmidt pass on rows i-1, i; BL_FWD_SYMMETRIC) against the general one
     t_val = F64 if dtype == np.float64 else F32_VAL
-    assert np.all(np.triu(Hs[7], 2) == 0)
+    # the local first pass skips rows j < i-1; the second pass's coefficients complete those entries of H (EPI_FWD_B)
+    assert np.abs(np.triu(Hs[7], 2)).max() < 100 * eps * np.abs(Hs[7]).max()
     assert rel_err(np.diag(Hs[7]), np.diag(Hs[1])) < t_val and rel_err(np.diag(Hs[7], 1), np.diag(Hs[1], 1)) < t_val
     assert rel_err(Qs[7], Qs[1]) < 10 * t_val
     gram = Qs[7].astype(np.float64).T @ Qs[7].astype(np.float64)
@@ -420,6 +421,107 @@ def test_full_size_properties(dtype):
     dv1_general, dp1_general = pull(((None, c1), (None, None)))
     assert rel_err(dv1.numpy(), dv1_general.numpy()) < 1e-4
     assert rel_err(dp1.numpy(), dp1_general.numpy()) < 1e-4
+
+
+@pytest.fixture(scope="module")
+def headline_oracle():
+    """ONE float64 oracle run at BASELINE config 2's full size (n = 1M, 11 entries per row, depth 100): forward,
+    the adjoint for the SLQ cotangent (on alpha / beta only) and the adjoint for a dense cotangent on every output
+    (the published benchmark recipe, benchmark.py:95-96).  About two minutes of host time; both dtypes of the test
+    below compare with it (the float32 inputs are exactly representable in float64)."""
+    n, K = 1_000_000, 100
+    row, col, data = banded_spd(n, 5, seed=0)
+    data = data.astype(np.float32).astype(np.float64)
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(n).astype(np.float32).astype(np.float64)
+    dalpha = rng.standard_normal(K).astype(np.float32).astype(np.float64)
+    dbeta = rng.standard_normal(K - 1).astype(np.float32).astype(np.float64)
+    dQt = rng.standard_normal((K, n)).astype(np.float32)
+    dq_rem = rng.standard_normal(n).astype(np.float32).astype(np.float64)
+    dnorm = float(np.float32(rng.standard_normal()))
+    op = operators.CsrFastOperator(row, col, (n, n))
+    ((Qt, (alpha, beta)), (q_rem, b_rem)), pull = krylov.tridiag_full_active(op, K, v, data)
+    ref = {"alpha": alpha, "beta": beta, "q_rem": q_rem, "b_rem": b_rem, "Q_last": Qt[K - 1].copy()}
+    ref["slq"] = pull(((None, (dalpha, dbeta)), (None, None)))
+    ref["dense"] = pull(((dQt.astype(np.float64), (dalpha, dbeta)), (dq_rem, dnorm)))
+    # SLQ log-determinant integrand of this probe (lanczos.py:48-59)
+    w, U = np.linalg.eigh(krylov.dense_tridiag(alpha, beta))
+    ref["logdet"] = float(np.dot(v, v) * np.dot(U[0], np.log(w) * U[0]))
+    return {"n": n, "K": K, "coo": (row, col, data), "v": v, "cot": (dalpha, dbeta, dQt, dq_rem, dnorm), "ref": ref}
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_headline_size_matches_oracle(headline_oracle, dtype):
+    """The tolerance contract of BASELINE.json at the size it is quoted on (n = 1M, depth 100), CUDA path against
+    the oracle: alpha, beta, SLQ log-det 1e-5 / 1e-10; gradients (dv, dtheta) 1e-4 / 1e-10 -- for the SLQ cotangent
+    and for the dense cotangent.  lanczos.py:152-169, arnoldi.py:201-219."""
+    h = headline_oracle
+    n, K, ref = h["n"], h["K"], h["ref"]
+    row, col, data = h["coo"]
+    dalpha, dbeta, dQt, dq_rem, dnorm = h["cot"]
+    t_val, t_grad = (F64, F64) if dtype == np.float64 else (F32_VAL, F32_GRAD)
+    op = bl.operators.SparseOperator(row, col, (n, n))
+    alg = bl.lanczos.tridiag(op, K, reortho="full")
+    ((Qt, (alpha, beta)), (q_rem, b_rem)), pull = bl.vjp(alg, h["v"].astype(dtype), data.astype(dtype))
+    assert rel_err(alpha, ref["alpha"]) < t_val
+    assert rel_err(beta, ref["beta"]) < t_val
+    assert np.max(np.abs(alpha - ref["alpha"]) / np.abs(ref["alpha"])) < 10 * t_val  # entry-wise too
+    assert np.max(np.abs(beta - ref["beta"]) / np.abs(ref["beta"])) < 10 * t_val
+    assert abs(float(b_rem) - ref["b_rem"]) < 10 * t_val * ref["b_rem"]
+    assert rel_err(q_rem.numpy(), ref["q_rem"]) < 10 * t_grad
+    assert rel_err(Qt.row(K - 1).numpy(), ref["Q_last"]) < 10 * t_grad  # last basis vector: 100 steps of rounding
+    integrand = bl.lanczos.integrand_spd(np.log, K, op)
+    value = integrand(h["v"].astype(dtype), data.astype(dtype))
+    assert abs(float(value) - ref["logdet"]) < t_val * abs(ref["logdet"])
+    dv, dp = pull(((None, (dalpha, dbeta)), (None, None)))
+    assert rel_err(dv.numpy(), ref["slq"][0]) < t_grad
+    assert rel_err(dp.numpy(), ref["slq"][1]) < t_grad
+    del dv, dp
+    dv, dp = pull(((dQt.astype(dtype), (dalpha, dbeta)), (dq_rem.astype(dtype), dnorm)))
+    assert rel_err(dv.numpy(), ref["dense"][0]) < t_grad
+    assert rel_err(dp.numpy(), ref["dense"][1]) < t_grad
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_tridiag_full_on_a_nonsymmetric_operand_matches_the_reference_loops(dtype):
+    """`tridiag(reortho="full")` runs the symmetric loops by default.  The reference runs general
+    Arnoldi and symmetrises (lanczos.py:152-169), whatever the operand: for `lambda s, p: p @ s` with a
+    non-symmetric `p` the library must notice (H is not tridiagonal) and return the gradient of the reference's
+    output -- the oracle's general loops -- with a warning."""
+    n, K = 257, 9
+    rng = np.random.default_rng(41)
+    A = np.diag(2.0 + np.arange(n) / n) + 0.3 * rng.standard_normal((n, n)) / np.sqrt(n)
+    v = rng.standard_normal(n)
+    op = bl.operators.DenseOperator(n, sym=False)
+    alg = bl.lanczos.tridiag(op, K, reortho="full")
+    ref = krylov.tridiag(operators.DenseOperator(), K, reortho="full")
+    ((Qt_r, (alpha_r, beta_r)), (q_r, b_r)), pull_r = ref.vjp(v, A)
+    t_val, t_grad = (F64, F64) if dtype == np.float64 else (F32_VAL, F32_GRAD)
+    with pytest.warns(UserWarning, match="not symmetric"):
+        ((Qt, (alpha, beta)), (q_rem, b_rem)), pull = bl.vjp(alg, v.astype(dtype), A.astype(dtype))
+    assert rel_err(alpha, alpha_r) < t_val and rel_err(beta, beta_r) < t_val
+    assert rel_err(Qt.numpy(), Qt_r) < 10 * t_val
+    cot = ((rng.standard_normal((K, n)), (rng.standard_normal(K), rng.standard_normal(K - 1))),
+           (rng.standard_normal(n), rng.standard_normal()))  # fmt: skip
+    dv, dp = pull(cot)
+    dv_r, dp_r = pull_r(cot)
+    assert rel_err(dv.numpy(), dv_r) < 10 * t_grad
+    assert rel_err(dp.numpy(), dp_r) < 10 * t_grad
+    slq_cot = ((None, cot[0][1]), (None, None))
+    dv, dp = pull(slq_cot)
+    z = np.zeros_like
+    dv_r, dp_r = pull_r(((z(Qt_r), cot[0][1]), (z(q_r), z(b_r))))
+    assert rel_err(dv.numpy(), dv_r) < 10 * t_grad
+    assert rel_err(dp.numpy(), dp_r) < 10 * t_grad
+    # a symmetric operand through the same factory stays on the symmetric loops, silently
+    import warnings as _w
+
+    S = 0.5 * (A + A.T)
+    with _w.catch_warnings():
+        _w.simplefilter("error")
+        (_, (alpha_s, _b)), _rem = alg(v.astype(dtype), S.astype(dtype))
+    (_, (alpha_sr, _b)), _ = ref(v, S)
+    assert rel_err(alpha_s, alpha_sr) < t_val
 
 
 def test_concurrent_plans_on_separate_streams_match_their_solo_runs():
