@@ -45,6 +45,7 @@ SIGNATURES = {
     "bl_event_create": (_i32, [_pvp]),
     "bl_event_destroy": (_i32, [_vp]),
     "bl_event_record": (_i32, [_vp, _vp]),
+    "bl_stream_wait_event": (_i32, [_vp, _vp]),
     "bl_event_sync": (_i32, [_vp]),
     "bl_event_elapsed_ms": (_i32, [_vp, _vp, C.POINTER(C.c_float)]),
     "bl_launch_count": (_i32, [C.POINTER(C.c_uint64)]),
@@ -70,6 +71,16 @@ SIGNATURES = {
     "bl_arnoldi_adjoint_batch": (_i32, [_vp, _i32, _i64, _i64, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
     "bl_op_deferred_grad": (_i32, [_vp, _i32, C.POINTER(C.c_int)]),
+    "bl_dist_nccl_available": (_i32, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bl_dist_nccl_unique_id": (_i32, [_vp]),
+    "bl_dist_nccl_init": (_i32, [_vp, _i32, _i32, _pvp]),
+    "bl_dist_nccl_allreduce": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "bl_dist_nccl_allgather": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "bl_dist_nccl_sendrecv": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i32, _vp]),
+    "bl_dist_nccl_reduce_hook": (_i32, [_vp]),
+    "bl_dist_nccl_destroy": (_i32, [_vp]),
+    "bl_step_trace_begin": (_i32, []),
+    "bl_step_trace_end": (_i32, [_vp, _i64, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "bl_precond_create": (_i32, [_i32, _i64, _i64, _vp, _i64, _vp, _pvp]),
     "bl_precond_set_shift": (_i32, [_vp, C.c_double, _vp]),
     "bl_precond_apply": (_i32, [_vp, _i32, _vp, _vp, _vp]),

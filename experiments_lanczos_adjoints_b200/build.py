@@ -103,7 +103,7 @@ def _build_locked(force: bool, verbose: bool) -> str:
             log = j.result()
             if verbose:
                 print(log, file=sys.stderr)
-    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs],
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"],
                          capture_output=True, text=True)  # fmt: skip
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)

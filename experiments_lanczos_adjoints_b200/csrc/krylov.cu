@@ -585,8 +585,8 @@ int launch_xdots(const Common& c, const XDotsSpec& f, cudaStream_t s, bool* done
 }
 
 // One launch for the three basis-streaming phases of a symmetric-loop step (k_step_tma, step_kernel.cuh).
-// BL_STEP=0 disables it (A/B measurements); BL_STEP_PDL=0 launches it without the programmatic-dependent-launch
-// attribute.  The kernel's blocks wait for one another, so the launch is cooperative (the driver starts the
+// BL_STEP=0 disables it, 1 (default) uses it for lockstep batches, 2 also for a single run; BL_STEP_PDL=0 launches
+// it without the programmatic-dependent-launch attribute.  The kernel's blocks wait for one another, so the launch is cooperative (the driver starts the
 // grid only when all of it is resident: kernels of other streams cannot wedge it) and the grid is capped at
 // what fits the device.
 int step_mode() {
@@ -604,18 +604,31 @@ bool step_pdl() {
   return on;
 }
 std::atomic<int> g_step_pdl_ok{1};  // cleared when the driver refuses cooperative + programmatic launch together
+bool step_coop() {  // BL_STEP_COOP=0: plain launch (measurements on ONE stream only: nothing else may hold SM slots)
+  static const bool on = [] {
+    const char* e = std::getenv("BL_STEP_COOP");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+std::atomic<int> g_step_trace_next{-1};  // bl_step_trace_begin arms it; every k_step_tma launch takes a slot
+
+struct StepItem {  // one run's share of a k_step_tma launch
+  const Common* c = nullptr;
+  StepArgs a;
+  double bytes = 0.0;  // algorithmic bytes of the three phases (profile classes)
+};
 
 template <typename T>
-size_t step_smem_bytes(int nrows1, int nrows2) {
+size_t step_smem_bytes(int count, int acc_stride, int coef_stride) {
   constexpr int TILE = kConsumerThreads * Vec<T>::N;
-  const int nacc = std::max(nrows1, kFewMax * kConsumerWarps);
-  return (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 2) * 8 + (size_t)nacc * 8 +
-         (size_t)std::max(nrows1, kFewMax) * 8 + (size_t)((nrows2 + kGroup - 1) / kGroup * kGroup) * sizeof(T) + 16;
+  return (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 2) * 8 +
+         (size_t)count * acc_stride * 8 + (size_t)count * coef_stride * sizeof(T) + 16;
 }
 
 // whether `blocks` blocks per SM of k_step_tma are co-resident on this device (cached per dtype and device)
 template <typename T>
-bool step_fits(size_t smem, int blocks) {
+bool step_fits(int blocks) {
   constexpr int TILE = kConsumerThreads * Vec<T>::N;
   static std::mutex mu;
   static std::set<std::pair<int, int>> ok, bad;  // (device, blocks per SM), for the 112 KB opt-in size
@@ -632,59 +645,102 @@ bool step_fits(size_t smem, int blocks) {
     ok.insert(key);
     return true;
   }
-  (void)smem;
   (void)cudaGetLastError();
   bad.insert(key);
   return false;
 }
 
+// The step of `count` runs (same n, same dtype) in ceil(count / kStepBatch) launches.  `*done` stays false -- nothing
+// launched -- when the kernel does not apply (switched off, row sharding, shape); the caller then runs the separate
+// kernels for every run.  min_batch: BL_STEP=1 (default) uses the kernel for batches of two or more runs only -- for
+// ONE run an in-kernel reduction costs what a kernel boundary with programmatic dependent launch costs (measured:
+// 24.3 vs 23.6 ms per forward + adjoint at n = 1M, depth 100) -- BL_STEP=2 for every run, BL_STEP=0 never.
 template <typename T>
-int launch_step(const Common& c, StepArgs a, double bytes, cudaStream_t s, bool* done) {
+int launch_step(std::vector<StepItem>& items, cudaStream_t s, bool* done) {
   *done = false;
   constexpr int TILE = kConsumerThreads * Vec<T>::N;
-  const size_t smem = step_smem_bytes<T>(a.nrows1, a.nrows2);
-  if (step_mode() == 0 || !xdots_enabled() || !use_tma(a.n) || stream_mode() == 2 || is_sharded() ||
-      a.nvec > kXTerms || a.few_n > kFewMax || a.nrows1 < 1 || a.nrows2 < 1 || smem > 112 * 1024)
+  const int total = (int)items.size();
+  const int mode = step_mode();
+  if (total < 1 || mode == 0 || (mode == 1 && total < 2) || !xdots_enabled() || stream_mode() == 2 || is_sharded())
     return BL_OK;
+  const long long n = items[0].a.n;
+  if (!use_tma(n)) return BL_OK;
+  int acc_stride = kFewSlots, coef_stride = kGroup;
+  for (const StepItem& it : items) {
+    const StepArgs& a = it.a;
+    if (a.n != n || a.nvec > kXTerms || a.few_n > kFewMax || a.nrows1 < 1 || a.nrows2 < 1) return BL_OK;
+    acc_stride = std::max(acc_stride, a.nrows1);
+    coef_stride = std::max(coef_stride, (a.nrows2 + kGroup - 1) / kGroup * kGroup);
+  }
+  // largest batch per launch whose per-run coefficient blocks still fit beside the ring (two blocks per SM)
+  int per_launch = std::min(total, kStepBatch);
+  while (per_launch > 1 && step_smem_bytes<T>(per_launch, acc_stride, coef_stride) > 112 * 1024) --per_launch;
+  if (step_smem_bytes<T>(per_launch, acc_stride, coef_stride) > 112 * 1024) return BL_OK;
+  if (mode == 1 && per_launch < 2) return BL_OK;
   BL_CHECK(set_smem(k_step_tma<T, TILE>, 112 * 1024));
-  const int bps = blocks_per_sm();
-  if (!step_fits<T>(smem, bps)) return BL_OK;
+  if (!step_fits<T>(blocks_per_sm())) return BL_OK;
   *done = true;
-  a.partials = c.partials_dots;
-  a.red_g = c.red;
-  a.partials_norm = c.partials_comb;
-  a.bar = c.counters + 8;
-  a.exit_counter = c.counters + 9;
-  for (Epi* e : {&a.epi0, &a.epi1, &a.epi2}) {
-    e->red = c.red;
-    e->scal = c.scal;
-  }
-  a.reverse = next_direction();
-  (void)next_direction();  // phase 2 walks the other way: the next streaming kernel starts where it ended
-  const int grid = tma_grid<T>(a.n, TILE);
-  ProfScope prof(BL_PROF_FUSED, bytes, s);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kStreamThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
+  const int grid = tma_grid<T>(n, TILE);
   const bool pdl = pdl_enabled() && step_pdl() && g_step_pdl_ok.load(std::memory_order_relaxed) != 0;
-  cfg.numAttrs = pdl ? 2 : 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, k_step_tma<T, TILE>, a);
-  if (err != cudaSuccess && pdl) {  // cooperative + programmatic launch refused together: cooperative alone
-    (void)cudaGetLastError();
-    g_step_pdl_ok.store(0, std::memory_order_relaxed);
-    cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, k_step_tma<T, TILE>, a);
+  for (int first = 0; first < total; first += per_launch) {
+    StepBatch B;
+    B.count = std::min(per_launch, total - first);
+    B.acc_stride = acc_stride;
+    B.coef_stride = coef_stride;
+    double bytes = 0.0;
+    for (int p = 0; p < B.count; ++p) {
+      StepItem& it = items[first + p];
+      StepArgs& a = it.a;
+      const Common& c = *it.c;
+      a.partials = c.partials_dots;
+      a.red_g = c.red;
+      a.partials_norm = c.partials_comb;
+      for (Epi* e : {&a.epi0, &a.epi1, &a.epi2}) {
+        e->red = c.red;
+        e->scal = c.scal;
+      }
+      B.a[p] = a;
+      bytes += it.bytes;
+    }
+    B.bar = items[first].c->counters + 8;
+    B.exit_counter = items[first].c->counters + 9;
+    B.reverse = next_direction();
+    (void)next_direction();  // phase 2 walks the other way: the next streaming kernel starts where it ended
+    if (g_step_trace_next.load(std::memory_order_relaxed) >= 0) {
+      const int slot = g_step_trace_next.fetch_add(1, std::memory_order_relaxed);
+      B.trace_slot = slot < kTraceLaunches ? slot : -1;
+    }
+    const size_t smem = step_smem_bytes<T>(B.count, acc_stride, coef_stride);
+    ProfScope prof(BL_PROF_FUSED, bytes, s);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kStreamThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (step_coop()) {
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, k_step_tma<T, TILE>, B);
+    if (err != cudaSuccess && pdl && step_coop()) {  // cooperative + programmatic refused together: cooperative alone
+      (void)cudaGetLastError();
+      g_step_pdl_ok.store(0, std::memory_order_relaxed);
+      cfg.numAttrs = 1;
+      err = cudaLaunchKernelEx(&cfg, k_step_tma<T, TILE>, B);
+    }
+    BL_CUDA(err);
+    BL_LAUNCHED();
   }
-  BL_CUDA(err);
-  BL_LAUNCHED();
   return BL_OK;
 }
 
@@ -834,8 +890,56 @@ struct FwdRun {
     BL_CHECK(launch_scale_copy<T>(n, r, 1.0, c.scal + S_LEN, qi, ld, s));
     return BL_OK;
   }
+  // symmetric loop, ONE launch: h = (q_{i-1}, q_i)^H v | v' = v - h_{i-1} q_{i-1} - h_i q_i, h2 = Q^H v' |
+  // v'' = v' - Q h2, ||v''||                                                     arnoldi.py:87-98
+  bool step_item(int i, StepItem& item) const {
+    if (!(second_pass && local_first)) return false;
+    const int m = i + 1, j0 = first_lo(i);
+    item.c = &c;
+    StepArgs& a = item.a;
+    a = StepArgs();
+    a.n = n;
+    a.few_n = m - j0;
+    for (int j = j0; j < m; ++j) a.few_row[j - j0] = q_row(j);
+    a.few_x = r;
+    a.epi0.mode = EPI_FWD_A;
+    a.epi0.i = i;
+    a.epi0.K = K;
+    a.epi0.j0 = j0;
+    a.epi0.m = m - j0;
+    a.epi0.H = H;
+    a.epi0.coef = c.coefA;
+    a.out1 = r;
+    a.vec[a.nvec++] = term(r);
+    for (int j = j0; j < m; ++j) a.vec[a.nvec++] = term(q_row(j), -1.0, c.coefA + j);
+    a.src1 = row_source(rows(Q, ld, 0, m), nullptr, sizeof(T));
+    a.nrows1 = m;
+    a.epi1 = pass_b_epi(i);
+    a.src2 = a.src1;
+    a.nrows2 = m;
+    a.coef2 = c.coefB;
+    a.sign2 = -1.0;
+    a.out2 = r;
+    a.norm = 1;
+    a.epi2.mode = EPI_FWD_NORM;  // length = sqrt(v . v); h[i+1] = length        arnoldi.py:95-98
+    a.epi2.i = i;
+    a.epi2.K = K;
+    a.epi2.H = H;
+    a.wait_row = i;  // row i is the operator kernel's output (fused normalise + matvec)
+    item.bytes = (double)((m - j0 + 1) + (m + a.nvec + 1) + (m + 2)) * n * sizeof(T);
+    return true;
+  }
+  bool skip_step = false;  // the batch driver already tried the step kernel for this step
   int post(int i) {
     const int m = i + 1;
+    if (!skip_step) {
+      std::vector<StepItem> items(1);
+      if (step_item(i, items[0])) {
+        bool stepped = false;
+        BL_CHECK(launch_step<T>(items, s, &stepped));
+        if (stepped) return BL_OK;
+      }
+    }
     {  // h = Q^H v (active columns only)                                       arnoldi.py:87
       Epi e;
       e.mode = EPI_FWD_A;
@@ -853,40 +957,6 @@ struct FwdRun {
     norm_epi.K = K;
     norm_epi.H = H;
     bool fused = false;
-    if (second_pass && local_first) {
-      // symmetric loop, ONE launch: h = (q_{i-1}, q_i)^H v | v' = v - h_{i-1} q_{i-1} - h_i q_i, h2 = Q^H v' |
-      // v'' = v' - Q h2, ||v''||                                                 arnoldi.py:87-98
-      const int j0 = first_lo(i);
-      StepArgs a;
-      a.n = n;
-      a.few_n = m - j0;
-      for (int j = j0; j < m; ++j) a.few_row[j - j0] = q_row(j);
-      a.few_x = r;
-      a.epi0.mode = EPI_FWD_A;
-      a.epi0.i = i;
-      a.epi0.K = K;
-      a.epi0.j0 = j0;
-      a.epi0.m = m - j0;
-      a.epi0.H = H;
-      a.epi0.coef = c.coefA;
-      a.out1 = r;
-      a.vec[a.nvec++] = term(r);
-      for (int j = j0; j < m; ++j) a.vec[a.nvec++] = term(q_row(j), -1.0, c.coefA + j);
-      a.src1 = row_source(rows(Q, ld, 0, m), nullptr, sizeof(T));
-      a.nrows1 = m;
-      a.epi1 = pass_b_epi(i);
-      a.src2 = a.src1;
-      a.nrows2 = m;
-      a.coef2 = c.coefB;
-      a.sign2 = -1.0;
-      a.out2 = r;
-      a.norm = 1;
-      a.epi2 = norm_epi;
-      a.wait_row = i;  // row i is the operator kernel's output (fused normalise + matvec)
-      bool stepped = false;
-      BL_CHECK(launch_step<T>(c, a, (double)((m - j0 + 1) + (m + a.nvec + 1) + (m + 2)) * n * sizeof(T), s, &stepped));
-      if (stepped) return BL_OK;
-    }
     if (second_pass && local_first) {
       // symmetric loop: v = v - h_{i-1} q_{i-1} - h_i q_i is a three-vector combination, and h2 = Q^H v streams
       // every active row once (no row is needed twice: nothing stays resident)   arnoldi.py:88,92
@@ -970,17 +1040,46 @@ int arnoldi_forward_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int 
     BL_CHECK(runs.back().begin());
     out[p] = runs[p].r;
   }
+  std::vector<const double*> lens(P);
+  std::vector<void*> qout(P);
   for (int i = 0; i < K; ++i) {
-    for (int p = 0; p < P; ++p) {
-      BL_CHECK(runs[p].pre(i));
-      in[p] = runs[p].q_row(i);
+    int rc = -1;
+    {  // q_i = v / length and v = A q_i of every run in one batched operator call     arnoldi.py:80-84
+      for (int p = 0; p < P; ++p) {
+        in[p] = runs[p].r;
+        lens[p] = runs[p].c.scal + S_LEN;
+        qout[p] = runs[p].q_row(i);
+        out[p] = runs[p].alt;
+      }
+      ProfScope prof(BL_PROF_MATVEC, op->matvec_batch_bytes(dtype, P) + 1.0 * P * n * sizeof(T), s);
+      rc = op->matvec_normalised_batch(dtype, P, in.data(), lens.data(), qout.data(), ld, out.data(), s);
     }
-    {
-      ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype) * P, s);
+    if (rc == BL_OK) {
+      for (int p = 0; p < P; ++p) std::swap(runs[p].r, runs[p].alt);
+    } else if (rc == -1) {
+      for (int p = 0; p < P; ++p) {
+        BL_CHECK(runs[p].pre(i));
+        in[p] = runs[p].q_row(i);
+        out[p] = runs[p].r;
+      }
+      ProfScope prof(BL_PROF_MATVEC, op->matvec_batch_bytes(dtype, P), s);
       BL_CHECK(op->matvec_batch(dtype, P, in.data(), out.data(), s));
+    } else {
+      return rc;
     }
-    for (int p = 0; p < P; ++p) BL_CHECK(runs[p].post(i));
+    {  // the Gram-Schmidt step of all runs in one launch per kStepBatch runs (k_step_tma)
+      std::vector<StepItem> items(P);
+      bool eligible = true, stepped = false;
+      for (int p = 0; p < P && eligible; ++p) eligible = runs[p].step_item(i, items[p]);
+      if (eligible) BL_CHECK(launch_step<T>(items, s, &stepped));
+      if (stepped) continue;
+    }
+    for (int p = 0; p < P; ++p) {
+      runs[p].skip_step = P > 1;  // the batch did not apply: neither does a batch of one under BL_STEP=1
+      BL_CHECK(runs[p].post(i));
+    }
   }
+  for (int p = 0; p < P; ++p) BL_CHECK(runs[p].finish());
   return BL_OK;
 }
 
@@ -1149,9 +1248,12 @@ struct AdjRun {
   }
   // banded Gamma, ONE launch: Gamma row from the dots of z with rows idx-2..idx | back-substitution and the
   // next step's re-projection dots | Lambda[idx-1] = lambda + Q (p - P lambda)   arnoldi.py:212-219, 201-204, 216
-  int post_step(int idx, bool* stepped) {
+  bool step_item(int idx, StepItem& item) const {
+    if (!(banded && idx > 0 && reortho_full)) return false;
     T* Lrow = Lambda + (int64_t)idx * ld;
-    StepArgs a;
+    item.c = &c;
+    StepArgs& a = item.a;
+    a = StepArgs();
     a.n = n;
     const int j0 = band_lo(idx);
     a.few_n = idx + 1 - j0;
@@ -1189,20 +1291,26 @@ struct AdjRun {
     a.sign2 = 1.0;
     a.out2 = Lambda + (int64_t)(idx - 1) * ld;
     a.norm = 0;
-    BL_CHECK(launch_step<T>(c, a, (double)((a.few_n + 1) + (idx + 1 + a.nvec + 1) + (idx + 1 + 2)) * n * sizeof(T), s,
-                            stepped));
-    if (*stepped) {
-      pre_done = idx - 1;
-      have_reproj = false;
-    }
-    return BL_OK;
+    item.bytes = (double)((a.few_n + 1) + (idx + 1 + a.nvec + 1) + (idx + 1 + 2)) * n * sizeof(T);
+    return true;
   }
+  void stepped(int idx) {  // the step kernel of idx also did pre(idx - 1)
+    pre_done = idx - 1;
+    have_reproj = false;
+  }
+  bool skip_step = false;  // the batch driver already tried the step kernel for this step
   int post(int idx) {
     T* Lrow = Lambda + (int64_t)idx * ld;
-    if (banded && idx > 0 && reortho_full) {
-      bool stepped = false;
-      BL_CHECK(post_step(idx, &stepped));
-      if (stepped) return BL_OK;
+    if (!skip_step) {
+      std::vector<StepItem> items(1);
+      if (step_item(idx, items[0])) {
+        bool done = false;
+        BL_CHECK(launch_step<T>(items, s, &done));
+        if (done) {
+          stepped(idx);
+          return BL_OK;
+        }
+      }
     }
     {  // Gamma[idx, :] and the coefficients of the back-substitution             arnoldi.py:212-218
       Epi e;
@@ -1363,17 +1471,30 @@ int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int 
       in[p] = runs[p].lam_row(idx);
     }
     {
-      ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype) * P, s);
+      ProfScope prof(BL_PROF_VJP, deferred ? op->matvec_batch_bytes(dtype, P) : op->vjp_bytes(dtype) * P, s);
       if (deferred) {
         BL_CHECK(op->apply_transpose_batch(dtype, P, in.data(), out.data(), s));
       } else {  // the parameter cotangent accumulates in the operator over steps and runs (a sum over the batch)
         for (int p = 0; p < P; ++p) BL_CHECK(op->vjp(dtype, runs[p].q_row(idx), in[p], out[p], s));
       }
     }
-    for (int p = 0; p < P; ++p) BL_CHECK(runs[p].post(idx));
+    {  // back-substitution, re-projection dots and the next Lambda row of all runs in one launch (k_step_tma)
+      std::vector<StepItem> items(P);
+      bool eligible = true, done = false;
+      for (int p = 0; p < P && eligible; ++p) eligible = runs[p].step_item(idx, items[p]);
+      if (eligible) BL_CHECK(launch_step<T>(items, s, &done));
+      if (done) {
+        for (int p = 0; p < P; ++p) runs[p].stepped(idx);
+        continue;
+      }
+    }
+    for (int p = 0; p < P; ++p) {
+      runs[p].skip_step = P > 1;
+      BL_CHECK(runs[p].post(idx));
+    }
   }
   if (deferred) {
-    ProfScope prof(BL_PROF_VJP, op->vjp_bytes(dtype), s);
+    ProfScope prof(BL_PROF_VJP, op->vjp_batch_bytes(dtype, P * K), s);
     BL_CHECK(op->vjp_batch(dtype, Q, ld, Lambda, ld, P * K, s));
   }
   for (int p = 0; p < P; ++p) BL_CHECK(runs[p].end());
@@ -1611,6 +1732,23 @@ int bl_arnoldi_adjoint_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K,
                                          (const double*)H, (const double*)r, (const double*)c, (const double*)dQ,
                                          (const double*)dH, (const double*)dr, (const double*)dc, (double*)dv, lddv,
                                          (double*)Lambda, workspace, workspace_bytes, s);
+}
+
+int bl_step_trace_begin(void) {
+  g_step_trace_next.store(0, std::memory_order_relaxed);
+  return BL_OK;
+}
+
+int bl_step_trace_end(unsigned long long* stamps_host, int64_t max_launches, int64_t* launches, int* pdl_accepted) {
+  BL_REQUIRE(stamps_host && launches, "NULL argument");
+  const int taken = g_step_trace_next.exchange(-1, std::memory_order_relaxed);
+  const int64_t count = std::max<int64_t>(0, std::min<int64_t>({(int64_t)taken, max_launches, (int64_t)kTraceLaunches}));
+  BL_CUDA(cudaDeviceSynchronize());
+  if (count > 0)
+    BL_CUDA(cudaMemcpyFromSymbol(stamps_host, g_step_trace, (size_t)count * kTraceStamps * sizeof(unsigned long long)));
+  *launches = count;
+  if (pdl_accepted) *pdl_accepted = g_step_pdl_ok.load(std::memory_order_relaxed);
+  return BL_OK;
 }
 
 int bl_set_blocks_per_sm(int blocks) {

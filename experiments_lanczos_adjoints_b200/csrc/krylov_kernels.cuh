@@ -80,19 +80,19 @@ struct BlockSync {
 };
 
 template <typename T, typename Sync>
-__device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync sync) {
+__device__ void run_epilogue_impl(const Epi& e, const double* red, const int t, const int nt, Sync sync) {
   const int K = e.K, i = e.i;
   switch (e.mode) {
     case EPI_NONE:
       break;
     case EPI_STORE: {
       T* o = static_cast<T*>(e.out_t);
-      for (int j = t; j < e.m; j += nt) o[j] = static_cast<T>(e.red[j]);
+      for (int j = t; j < e.m; j += nt) o[j] = static_cast<T>(red[j]);
     } break;
     case EPI_INIT_NORM: {
       if (t == 0) {
         // dtype-T arithmetic as the reference: sqrt(dot(v,v)), 1/len
-        T len = sqrt(static_cast<T>(e.red[0]));
+        T len = sqrt(static_cast<T>(red[0]));
         e.scal[S_LEN] = static_cast<double>(len);
         e.scal[S_INV_LEN] = static_cast<double>(T(1) / len);
         if (e.out_t) static_cast<T*>(e.out_t)[0] = T(1) / len;
@@ -101,22 +101,22 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
     case EPI_FWD_A: {
       T* H = static_cast<T*>(e.H);  // red[] holds the dots with rows j0..i; h[j < j0] = 0 (H starts as zeros)
       for (int j = t; j < e.j0 + e.m; j += nt) {
-        T h = j >= e.j0 ? static_cast<T>(e.red[j - e.j0]) : T(0);
+        T h = j >= e.j0 ? static_cast<T>(red[j - e.j0]) : T(0);
         if (j >= e.j0) H[(size_t)j * K + i] = h;
         e.coef[j] = static_cast<double>(h);
       }
     } break;
     case EPI_FWD_B: {
-      for (int j = t; j < e.m; j += nt) e.coef[j] = static_cast<double>(static_cast<T>(e.red[j]));
+      for (int j = t; j < e.m; j += nt) e.coef[j] = static_cast<double>(static_cast<T>(red[j]));
       // BL_FWD_SYMMETRIC: the first pass skipped rows j < j0, so the second pass's coefficient q_j . v' IS
       // q_j . (A q_i) up to rounding (v' differs from A q_i along q_{i-1}, q_i only): it completes column i of H.
       // O(eps |A|) for a symmetric operand; the host reads these entries to detect a non-symmetric one.
       if (e.H != nullptr)
-        for (int j = t; j < e.j0; j += nt) static_cast<T*>(e.H)[(size_t)j * K + i] = static_cast<T>(e.red[j]);
+        for (int j = t; j < e.j0; j += nt) static_cast<T*>(e.H)[(size_t)j * K + i] = static_cast<T>(red[j]);
     } break;
     case EPI_FWD_NORM: {
       if (t == 0) {
-        T len = sqrt(static_cast<T>(e.red[0]));
+        T len = sqrt(static_cast<T>(red[0]));
         e.scal[S_LEN] = static_cast<double>(len);
         e.scal[S_INV_LEN] = static_cast<double>(T(1) / len);
         if (i + 1 < K) static_cast<T*>(e.H)[(size_t)(i + 1) * K + i] = len;  // dropped at i+1 == K
@@ -125,7 +125,7 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
     case EPI_ADJ_ETA: {
       const T* dH = static_cast<const T*>(e.dH);
       for (int j = t; j < K; j += nt) {
-        double r = e.m > 0 ? e.red[j] : 0.0;
+        double r = e.m > 0 ? red[j] : 0.0;
         e.eta[j] = static_cast<double>(static_cast<T>(static_cast<double>(dH[(size_t)j * K + (K - 1)]) - r));
         e.coef[j] = e.eta[j];
       }
@@ -134,7 +134,7 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
       const T* dH = static_cast<const T*>(e.dH);
       // rows j <= idx+1 of P are active; p = mask * dH[:, idx]
       for (int j = t; j < e.m; j += nt)
-        e.coef[j] = static_cast<double>(static_cast<T>(static_cast<double>(dH[(size_t)j * K + i]) - e.red[j]));
+        e.coef[j] = static_cast<double>(static_cast<T>(static_cast<double>(dH[(size_t)j * K + i]) - red[j]));
     } break;
     case EPI_ADJ_GAMMA: {
       const T* H = static_cast<const T*>(e.Hc);
@@ -143,7 +143,7 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
       for (int j = t; j < K; j += nt) {
         double g = 0.0;
         if (j <= idx && j >= e.j0) {
-          g = e.PiGamma[(size_t)idx * K + j] - e.red[j - e.j0];
+          g = e.PiGamma[(size_t)idx * K + j] - red[j - e.j0];
           if (j == idx) g *= 0.5;
           g = static_cast<double>(static_cast<T>(g));
         }
@@ -166,7 +166,7 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
     } break;
     case EPI_L3_ALPHA: {
       if (t == 0) {
-        T a = static_cast<T>(e.red[0]);
+        T a = static_cast<T>(red[0]);
         static_cast<T*>(e.out_t)[i] = a;
         // residual = A x_i - a x_i - b_{i-1} x_{i-1}: coefficients for rows (i-1, i) or (i)
         if (i == 0) {
@@ -179,7 +179,7 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
     } break;
     case EPI_L3_BETA: {
       if (t == 0) {
-        T b = sqrt(static_cast<T>(e.red[0]));
+        T b = sqrt(static_cast<T>(red[0]));
         static_cast<T*>(e.out_t)[i] = b;
         e.scal[S_B] = static_cast<double>(b);
         e.scal[S_LEN] = static_cast<double>(b);
@@ -187,7 +187,7 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
       }
     } break;
     case EPI_L3_ADJ_DOT: {
-      if (t == 0) e.scal[e.slot] = e.red[0];
+      if (t == 0) e.scal[e.slot] = red[0];
     } break;
     case EPI_L3_ADJ_MUNU: {
       // red[0] = x_k . xi, red[1] = x_{k+1} . xi  (xi not yet divided by b_k);
@@ -199,8 +199,8 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
         double db = static_cast<double>(static_cast<const T*>(e.in_t2)[k]);
         double a = static_cast<double>(static_cast<const T*>(e.in_t3)[k]);
         double inv_b = 1.0 / b;
-        double mu = db - e.scal[S_DOT0] + e.red[1] * inv_b;
-        double nu = da + e.red[0] * inv_b;
+        double mu = db - e.scal[S_DOT0] + red[1] * inv_b;
+        double nu = da + red[0] * inv_b;
         mu = static_cast<double>(static_cast<T>(mu));
         nu = static_cast<double>(static_cast<T>(nu));
         e.scal[S_MU] = mu;
@@ -219,7 +219,7 @@ __device__ void run_epilogue_impl(const Epi& e, const int t, const int nt, Sync 
       // grad_initvec = ((xi . x_0) x_0 - xi) / ||v||
       if (t == 0) {
         double vn = static_cast<double>(static_cast<const T*>(e.in_t)[0]);
-        e.coef[0] = e.red[0] / vn;
+        e.coef[0] = red[0] / vn;
         e.scal[S_TMP0] = -1.0 / vn;
       }
     } break;
@@ -231,7 +231,7 @@ template <typename T>
 __device__ void run_epilogue(const Epi& e) {
   if (e.peer_mail != nullptr && e.peer_count > 0)
     dist::peer_allreduce_block(dist::view_from_mailbox(e.peer_mail, e.peer_seq), e.red, e.peer_count);
-  run_epilogue_impl<T>(e, (int)threadIdx.x, (int)blockDim.x, BlockSync());
+  run_epilogue_impl<T>(e, e.red, (int)threadIdx.x, (int)blockDim.x, BlockSync());
 }
 
 // ---- dots ---------------------------------------------------------------------------------

@@ -17,6 +17,8 @@ struct bl_operator {
   virtual int grad_export(int dtype, void* const* grads, int num, cudaStream_t s) = 0;
   // ALGORITHMIC bytes of one matvec / one vjp (roofline report); default: vectors only
   virtual double matvec_bytes(int dtype) const { return 2.0 * n * (dtype == BL_F32 ? 4 : 8); }
+  // ... of one batched call over `count` vectors (operators that read their own data once per batch override)
+  virtual double matvec_batch_bytes(int dtype, int count) const { return matvec_bytes(dtype) * count; }
   virtual double vjp_bytes(int dtype) const { return 3.0 * n * (dtype == BL_F32 ? 4 : 8); }
   // Forward step of the Krylov loops: q = v / *len (true division, arnoldi.py:80-81; the row is written up
   // to n_pad entries with zero padding) followed by y = A q.  Operators that can normalise on the fly
@@ -56,6 +58,12 @@ struct bl_operator {
       if (rc != BL_OK) return rc;
     }
     return BL_OK;
+  }
+  // matvec_normalised for `count` lockstep runs: q_out[p] = v[p] / *len[p], y[p] = A q_out[p].  -1: not supported
+  // (the caller normalises separately and calls matvec_batch).
+  virtual int matvec_normalised_batch(int /*dtype*/, int /*count*/, const void* const* /*v*/, const double* const* /*len*/,
+                                      void* const* /*q_out*/, int64_t /*n_pad*/, void* const* /*y*/, cudaStream_t) {
+    return -1;
   }
   virtual int apply_transpose_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) {
     for (int p = 0; p < count; ++p) {

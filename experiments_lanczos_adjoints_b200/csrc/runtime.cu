@@ -162,6 +162,10 @@ int bl_event_record(void* event, void* stream) {
   BL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), bl::as_stream(stream)));
   return BL_OK;
 }
+int bl_stream_wait_event(void* stream, void* event) {
+  BL_CUDA(cudaStreamWaitEvent(bl::as_stream(stream), static_cast<cudaEvent_t>(event), 0));
+  return BL_OK;
+}
 int bl_event_sync(void* event) {
   BL_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
   return BL_OK;

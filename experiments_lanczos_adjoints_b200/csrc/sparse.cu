@@ -177,6 +177,71 @@ k_sell_spmv_normalised(int64_t nrows, const int64_t* __restrict__ slice_ptr, con
   if (r < nrows) y[r] = acc0 + acc1;
 }
 
+// Up to kSpmvBatch vectors per launch (lockstep Krylov runs over probes / initial conditions): the slice's values
+// and column indices -- 8 of the ~9 bytes per non-zero a single-vector SpMV moves -- are read ONCE for all of them;
+// the gathers of the P vectors are independent loads in flight together.  NORM: the forward step's fused
+// normalisation, as k_sell_spmv_normalised, with one length per run.
+constexpr int kSpmvBatch = 4;
+struct MultiVec {
+  const void* x[kSpmvBatch];
+  void* y[kSpmvBatch];
+  const double* len[kSpmvBatch];
+  void* q[kSpmvBatch];
+};
+
+template <typename T, int P, bool NORM>
+__global__ void __launch_bounds__(256)
+k_sell_spmv_multi(int64_t nrows, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+                  const T* __restrict__ val, const MultiVec mv, int64_t n_pad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = slice * kSlice + lane;
+  if (slice * kSlice >= nrows) return;
+  const T* x[P];
+  T inv[P], acc0[P], acc1[P];
+#pragma unroll
+  for (int pp = 0; pp < P; ++pp) {
+    x[pp] = static_cast<const T*>(mv.x[pp]);
+    inv[pp] = T(1);
+    acc0[pp] = acc1[pp] = T(0);
+    if (NORM) {
+      const T d = static_cast<T>(*mv.len[pp]);
+      inv[pp] = T(1) / d;
+      if (r < n_pad) static_cast<T*>(mv.q[pp])[r] = r < nrows ? x[pp][r] * T(1) / d : T(0);
+    }
+  }
+  const int64_t s0 = slice_ptr[slice], s1 = slice_ptr[slice + 1];
+  int64_t p = s0 + lane;
+  for (; p + kSlice < s1; p += 2 * kSlice) {
+    const int c0 = ld_stream_i32(col + p), c1 = ld_stream_i32(col + p + kSlice);
+    const T v0 = ld_stream_t(val + p), v1 = ld_stream_t(val + p + kSlice);
+    T g0[P], g1[P];
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      g0[pp] = __ldg(x[pp] + c0);
+      g1[pp] = __ldg(x[pp] + c1);
+    }
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      acc0[pp] = fma(v0, NORM ? g0[pp] * inv[pp] : g0[pp], acc0[pp]);
+      acc1[pp] = fma(v1, NORM ? g1[pp] * inv[pp] : g1[pp], acc1[pp]);
+    }
+  }
+  if (p < s1) {
+    const int c0 = ld_stream_i32(col + p);
+    const T v0 = ld_stream_t(val + p);
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      const T g = __ldg(x[pp] + c0);
+      acc0[pp] = fma(v0, NORM ? g * inv[pp] : g, acc0[pp]);
+    }
+  }
+  if (r < nrows) {
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) static_cast<T*>(mv.y[pp])[r] = acc0[pp] + acc1[pp];
+  }
+}
+
 // Adjoint of the sparse matvec in one launch:
 //   z[r]       = sum_k valT[slot] * lam[colT[slot]]      (A^T lam, via SELL of A^T; optional)
 //   grad[slot] += lam[r] * q[col[slot]]                   (d<lam, A q>/dparams, SELL of A)
@@ -288,6 +353,11 @@ struct SparseOperator : bl_operator {
     const double w = dtype == BL_F32 ? 4 : 8;
     return nnz * (w + 4) + 4.0 * (n_rows + 1) + 2.0 * n_rows * w;
   }
+  double matvec_batch_bytes(int dtype, int count) const override {  // values + indices once per kSpmvBatch vectors
+    const double w = dtype == BL_F32 ? 4 : 8;
+    const int chunks = (count + kSpmvBatch - 1) / kSpmvBatch;
+    return chunks * (nnz * (w + 4) + 4.0 * (n_rows + 1)) + 2.0 * count * n_rows * w;
+  }
   double vjp_bytes(int dtype) const override {
     const double w = dtype == BL_F32 ? 4 : 8;
     return nnz * (3 * w + 4) + 4.0 * (n_rows + 1) + 3.0 * n_rows * w;
@@ -372,6 +442,57 @@ struct SparseOperator : bl_operator {
                                             static_cast<float*>(y), s)
                : matvec_normalised_t<double>(static_cast<const double*>(v), len, static_cast<double*>(q_out), n_pad,
                                              static_cast<double*>(y), s);
+  }
+
+  // ---- several vectors per launch (lockstep runs): the operand's values and indices are read once per chunk ----
+  template <typename T, bool NORM>
+  int spmv_multi_t(const SellDev& m, int64_t rows, int count, const void* const* in, const double* const* len,
+                   void* const* q_out, int64_t n_pad, void* const* out, cudaStream_t s) {
+    const int64_t threads = m.nslices * kSlice;
+    const int blocks = (int)((threads + 255) / 256);
+    if (blocks <= 0) return BL_OK;
+    for (int first = 0; first < count; first += kSpmvBatch) {
+      const int P = std::min(kSpmvBatch, count - first);
+      MultiVec mv = {};
+      for (int pp = 0; pp < P; ++pp) {
+        mv.x[pp] = in[first + pp];
+        mv.y[pp] = out[first + pp];
+        mv.len[pp] = NORM ? len[first + pp] : nullptr;
+        mv.q[pp] = NORM ? q_out[first + pp] : nullptr;
+      }
+      const int64_t* sp = m.slice_ptr.as<int64_t>();
+      const int32_t* cl = m.col.as<int32_t>();
+      const T* vl = m.val.as<T>();
+      switch (P) {
+        case 1: k_sell_spmv_multi<T, 1, NORM><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        case 2: k_sell_spmv_multi<T, 2, NORM><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        case 3: k_sell_spmv_multi<T, 3, NORM><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        default: k_sell_spmv_multi<T, 4, NORM><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+      }
+      BL_LAUNCHED();
+    }
+    return BL_OK;
+  }
+  int matvec_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) override {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    if (count == 1) return matvec(dtype, in[0], out[0], s);
+    return dtype == BL_F32 ? spmv_multi_t<float, false>(sell, n_rows, count, in, nullptr, nullptr, 0, out, s)
+                           : spmv_multi_t<double, false>(sell, n_rows, count, in, nullptr, nullptr, 0, out, s);
+  }
+  int apply_transpose_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) override {
+    BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
+    BL_REQUIRE(n_rows == n_cols, "A^T lam needs a square operator");
+    if (count == 1) return apply_transpose(dtype, in[0], out[0], s);
+    return dtype == BL_F32 ? spmv_multi_t<float, false>(sell_t, n_cols, count, in, nullptr, nullptr, 0, out, s)
+                           : spmv_multi_t<double, false>(sell_t, n_cols, count, in, nullptr, nullptr, 0, out, s);
+  }
+  int matvec_normalised_batch(int dtype, int count, const void* const* v, const double* const* len, void* const* q_out,
+                              int64_t n_pad, void* const* y, cudaStream_t s) override {
+    if (dtype != bound_dtype || n_rows != n_cols || n_pad > sell.nslices * kSlice || n_rows == 0) return -1;
+    for (int p = 0; p < count; ++p)
+      if (v[p] == y[p]) return -1;
+    return dtype == BL_F32 ? spmv_multi_t<float, true>(sell, n_rows, count, v, len, q_out, n_pad, y, s)
+                           : spmv_multi_t<double, true>(sell, n_rows, count, v, len, q_out, n_pad, y, s);
   }
 
   template <typename T>

@@ -64,6 +64,10 @@ class Stream:
     def synchronize(self):
         _lib.call("bl_stream_sync", self.ptr)
 
+    def wait_event(self, event):
+        """Work enqueued on this stream afterwards starts after `event` (recorded on another stream)."""
+        _lib.call("bl_stream_wait_event", self.ptr, event.ptr)
+
 
 def _destroy_stream(ptr):
     try:

@@ -5,8 +5,8 @@ Host-side mirror of `/root/reference/src/matfree_extensions/hutchinson.py` plus 
 (`/root/reference/src/matfree_extensions/util/gp_util.py:8,557`).  An estimator is
 `sample(key, *parameters)`; `sample_fun(key)` returns the `(num, n)` probe matrix.  Probe
 vectors are independent Lanczos runs: in lockstep batches on operators that share work between
-vectors (the Gram operator, `lanczos.probe_batch_sum`), four in flight on separate streams on a
-sparse operand (`lanczos.probe_pipelined_sum`), one after the other otherwise; sharded over GPUs
+vectors (the Gram operator, `lanczos.probe_batch_sum`; a sparse operand, `lanczos.probe_lockstep_sum`), one
+after the other otherwise; sharded over GPUs
 by `parallel.shard_probes`.
 
 PRNG note: JAX's threefry stream cannot be reproduced without JAX.  `sampler_rademacher` /
@@ -92,8 +92,10 @@ def probe_sum(integrand_fun, samples, parameters, *, with_grad=False):
     if isinstance(samples, np.ndarray) and samples.ndim == 2 and len(samples) > 1 and hasattr(integrand_fun, "alg"):
         from experiments_lanczos_adjoints_b200 import lanczos
 
-        if lanczos._pipeline_eligible(integrand_fun, samples):  # sparse operand: probes in flight on separate streams
-            return lanczos.probe_pipelined_sum(integrand_fun, samples, parameters, with_grad=with_grad)
+        if lanczos._pipeline_eligible(integrand_fun, samples):  # sparse operand: lockstep batches of probes
+            if lanczos._probe_mode() == "streams":  # ... or independent runs in flight on separate streams
+                return lanczos.probe_pipelined_sum(integrand_fun, samples, parameters, with_grad=with_grad)
+            return lanczos.probe_lockstep_sum(integrand_fun, samples, parameters, with_grad=with_grad)
         if samples.dtype in (np.float32, np.float64) and lanczos._batch_eligible(integrand_fun, samples.dtype):
             return lanczos.probe_batch_sum(integrand_fun, samples, parameters, with_grad=with_grad)
     total, grads, count = 0.0, None, 0

@@ -370,6 +370,98 @@ def probe_pipelined_sum(integrand, probes, parameters, *, with_grad, lanes=None)
     return _pipelined_finish(plans, used, dtype, total, P, with_grad)
 
 
+LOCKSTEP_BATCH = 4  # runs per lockstep batch (one k_step_tma launch serves up to four runs)
+LOCKSTEP_LANES = 2  # batches in flight: the host's K x K eigh of one batch runs under the other batch's kernels
+
+
+def probe_lockstep_sum(integrand, probes, parameters, *, with_grad, batch=None, lanes=None):
+    """Sum over the rows of `probes (P, n)` of the SLQ integrand (and of its parameter gradient) on a sparse
+    operand, the runs advancing in LOCKSTEP batches of `batch` probes (`plan.BatchedTridiagAdjointPlan`): per Krylov
+    step one multi-vector SpMV -- the operand's values and indices are read once for the whole batch -- and one
+    Gram-Schmidt step kernel whose grid-wide reductions serve all runs of the batch.  `lanes` batches are in flight
+    on separate streams, so the host's `eigh` of one batch (`lanczos.py:48-59`) overlaps the other's kernels.  Same
+    numbers as a loop of `integrand.value_and_grad` (`jax.vmap(integrand)`, hutchinson.py:14) up to summation
+    order."""
+    from experiments_lanczos_adjoints_b200 import plan as _plan
+
+    probes = np.asarray(probes)
+    P, n = probes.shape
+    dtype = probes.dtype
+    hess = integrand.alg.alg
+    K = hess.K
+    if not isinstance(K, (int, np.integer)) or K < 1 or K > n:
+        raise ValueError(f"Parameter depth {K} is outside the expected range")
+    B = max(1, min(batch or LOCKSTEP_BATCH, P))
+    groups = [probes[i : i + B] for i in range(0, P, B)]
+    L = max(1, min(lanes or LOCKSTEP_LANES, len(groups)))
+    cache = integrand.__dict__.setdefault("_lockstep_plans", {})
+    key = (L, B, dtype.str, n, K)
+    if key not in cache:
+        ops = [hess.op] + [hess.op.clone() for _ in range(L - 1)]
+        cache[key] = [_plan.BatchedTridiagAdjointPlan(o, K, dtype, B, stream=dev.Stream()) for o in ops]
+    plans = cache[key]
+    host_params = [p.numpy() if isinstance(p, dev.DeviceArray) else np.asarray(p) for p in parameters]
+    dev.synchronize()  # the lanes' streams start after whatever the caller enqueued
+    for pl in plans:
+        pl.set_params(*host_params)
+    total = 0.0
+    used = [False] * L
+    pending = [None] * L  # per lane: (scales, number of real probes) of the batch whose forward is enqueued
+
+    def complete(li):
+        nonlocal total
+        scales, real = pending[li]
+        pending[li] = None
+        pl = plans[li]
+        coefs, symmetric = pl.coefficients()  # synchronises this lane only
+        if not symmetric and integrand.alg.assume_symmetric is None:
+            warnings.warn("tridiag(reortho='full'): the operand is not symmetric on this Krylov space; the adjoint "
+                          "runs the general Arnoldi loops, as the reference does.", stacklevel=3)  # fmt: skip
+        dH = np.zeros((B, K, K), dtype)
+        for b in range(real):
+            diag, off = coefs[b]
+            g, dalpha, dbeta, _ = _quadform_and_cotangents(integrand.matfun, integrand.matfun_grad, diag, off, with_grad)
+            s2 = scales[b] ** 2
+            total += s2 * g
+            if with_grad:
+                dH[b] = np.diag(s2 * dalpha)
+                if K > 1:
+                    dH[b] += 0.5 * (np.diag(s2 * dbeta, 1) + np.diag(s2 * dbeta, -1))
+        if with_grad:
+            pl.set_cotangents(dH)  # padding runs of a short last batch carry a zero cotangent: no contribution
+            pl.adjoint(zero=not used[li], export=False,
+                       general=not symmetric and integrand.alg.assume_symmetric is None)
+            used[li] = True
+
+    try:
+        for gi, group in enumerate(groups):
+            li = gi % L
+            if pending[li] is not None:
+                complete(li)
+            real = len(group)
+            if real < B:  # short last batch: repeat its last probe (zero cotangent, value ignored)
+                group = np.concatenate([group, np.repeat(group[-1:], B - real, axis=0)])
+            scales = np.linalg.norm(group.astype(np.float64), axis=1)  # lanczos.py:25
+            plans[li].set_vectors((group / scales[:, None]).astype(dtype))
+            plans[li].forward()
+            pending[li] = (scales, real)
+        for li in range(L):
+            if pending[li] is not None:
+                complete(li)
+    finally:
+        for pl in plans:
+            pl.stream.synchronize()
+    return _pipelined_finish(plans, used, dtype, total, P, with_grad)
+
+
+def _probe_mode() -> str:
+    """BL_PROBE_MODE: `lockstep` (default; batched runs, `probe_lockstep_sum`) or `streams` (independent runs on
+    separate streams, `probe_pipelined_sum`) for the SLQ estimator on a sparse operand."""
+    import os
+
+    return os.environ.get("BL_PROBE_MODE", "lockstep")
+
+
 def _pipelined_groups(integrand, plans, probes, L, K, dtype, with_grad, used):
     total = 0.0
     P = len(probes)

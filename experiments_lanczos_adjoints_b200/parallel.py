@@ -1,20 +1,22 @@
-"""Multi-GPU layer: one process per GPU, `torch.distributed` for the plumbing.
+"""Multi-GPU layer: one process per GPU, NCCL from the library itself (no PyTorch).
 
 Probe sharding (BASELINE config 4): the Hutchinson / SLQ probe vectors are
 independent Lanczos runs, so each rank takes a contiguous block of the probes, runs forward +
 adjoint on its own GPU with a replicated operator, and the estimator ends with ONE all-reduce
-of `(sum of quadratic forms, probe count, parameter cotangents)` — NCCL over NVLink on GPUs,
-gloo in the CPU tests.  No collective sits on the data path of a probe.
+of `(sum of quadratic forms, probe count, parameter cotangents)` -- `ncclAllReduce` over NVLink
+through `bl_dist_nccl_allreduce` when the cotangents live on a GPU, the host communicator's sum in
+the CPU tests.  No collective sits on the data path of a probe.
 
-torch is imported lazily and only here: the single-GPU product path does not depend on it.
+`group` arguments are host communicators (`comm.Comm`: `comm.init_from_env()` builds one from the
+torchrun environment; `None` means the process-wide default); `comm` arguments are peer-memory
+communicators (`PeerComm`).
 """
 
 from __future__ import annotations
 
-import os
-
 import numpy as np
 
+from experiments_lanczos_adjoints_b200 import comm as _comm
 from experiments_lanczos_adjoints_b200 import device as dev
 from experiments_lanczos_adjoints_b200.hutchinson import _scale, probe_sum
 
@@ -29,69 +31,61 @@ def shard_bounds(num: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def init_from_env(backend: str | None = None):
-    """Initialise `torch.distributed` from the torchrun environment (RANK / WORLD_SIZE /
+def init_from_env():
+    """Build the process-wide host communicator from the torchrun environment (RANK / WORLD_SIZE /
     LOCAL_RANK / MASTER_ADDR / MASTER_PORT) and bind this process to its GPU.
     Returns `(rank, world, local_rank)`; a single-process run needs no initialisation."""
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-
-        if not dist.is_initialized():
-            if backend is None:
-                backend = "nccl" if torch.cuda.is_available() else "gloo"
-            kwargs = {}
-            if backend == "nccl":
-                torch.cuda.set_device(local_rank)
-                kwargs["device_id"] = torch.device("cuda", local_rank)
-            dist.init_process_group(backend, **kwargs)
-    if dev.device_count() > 0:
-        dev.set_device(local_rank)
-    return rank, world, local_rank
+    c = _comm.init_from_env()
+    return c.rank, c.world, c.local_rank
 
 
-def _dist():
-    import torch.distributed as dist
-
-    return dist if dist.is_available() and dist.is_initialized() else None
+def _group(group):
+    return group if group is not None else _comm.default()
 
 
 def all_reduce_sum(values, group=None):
-    """Sum a list of arrays over the ranks with ONE collective call.
-
-    Host arrays / scalars are packed into one buffer; `DeviceArray`s are reduced in place
-    through a zero-copy torch view (`__cuda_array_interface__`).  Returns the reduced list."""
-    dist = _dist()
-    if dist is None or dist.get_world_size(group) == 1:
-        return list(values)
-    import torch
-
-    backend = dist.get_backend(group)
-    host_idx = [i for i, v in enumerate(values) if not isinstance(v, dev.DeviceArray)]
+    """Sum a list of arrays over the ranks: ONE collective for everything that lives on the host (scalars and
+    host arrays are packed into one buffer) and ONE NCCL all-reduce for the device arrays (packed into one device
+    buffer when there are several).  Every rank must pass the same kinds and shapes in the same order.  Returns
+    the reduced list (device arrays are reduced in place)."""
+    g = _group(group)
     out = list(values)
+    if g.world == 1:
+        return out
+    host_idx = [i for i, v in enumerate(values) if not isinstance(v, dev.DeviceArray)]
+    dev_idx = [i for i, v in enumerate(values) if isinstance(v, dev.DeviceArray)]
     if host_idx:
         flat = np.concatenate([np.asarray(values[i], dtype=np.float64).reshape(-1) for i in host_idx])
-        t = torch.from_numpy(flat.copy())
-        if backend == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t, group=group)
-        flat = t.cpu().numpy()
+        flat = g.allreduce_host(flat)
         pos = 0
         for i in host_idx:
             shape = np.shape(values[i])
             size = int(np.prod(shape, dtype=np.int64)) if shape else 1
             out[i] = flat[pos : pos + size].reshape(shape)
             pos += size
-    for i, v in enumerate(values):
-        if isinstance(v, dev.DeviceArray):
-            dev.default_stream().synchronize()  # our kernels run on our own stream
-            t = torch.as_tensor(v, device="cuda")
-            dist.all_reduce(t, group=group)
-            torch.cuda.current_stream().synchronize()
-            out[i] = v
+    if dev_idx:
+        stream = dev.default_stream()
+        dtypes = {values[i].dtype for i in dev_idx}
+        contiguous = all(values[i].ld in (None, values[i]._shape[-1]) or values[i].ndim == 1 for i in dev_idx)
+        if len(dev_idx) == 1 or len(dtypes) > 1 or not contiguous:
+            for i in dev_idx:  # one array (the usual case: one parameter) or mixed dtypes: reduce in place
+                g.allreduce_device(values[i].ptr, values[i].size, values[i].dtype, stream)
+        else:  # several parameters: pack, one all-reduce, unpack
+            from experiments_lanczos_adjoints_b200 import _lib
+
+            dtype = dtypes.pop()
+            item = dtype.itemsize
+            pack = dev.DeviceArray((sum(values[i].size for i in dev_idx),), dtype)
+            pos = 0
+            for i in dev_idx:
+                _lib.call("bl_memcpy_d2d", pack.ptr + pos * item, values[i].ptr, values[i].size * item, stream.ptr)
+                pos += values[i].size
+            g.allreduce_device(pack.ptr, pack.size, dtype, stream)
+            pos = 0
+            for i in dev_idx:
+                _lib.call("bl_memcpy_d2d", values[i].ptr, pack.ptr + pos * item, values[i].size * item, stream.ptr)
+                pos += values[i].size
+        stream.synchronize()
     return out
 
 
@@ -102,12 +96,17 @@ class _ShardedEstimator:
         self.integrand_fun, self.sample_fun, self.group = integrand_fun, sample_fun, group
 
     def _local(self, key):
-        samples = self.sample_fun(key)  # same key on every rank -> same probe matrix
-        dist = _dist()
-        rank = dist.get_rank(self.group) if dist else 0
-        world = dist.get_world_size(self.group) if dist else 1
+        """This rank's block of the probes.  A sampler that can generate a slice (`sample_fun(key, lo, hi)`,
+        e.g. `parallel.sharded_sampler`) is asked for the local block only; a plain `sample_fun(key)` is called
+        as the reference calls it (same key on every rank -> same probe matrix) and sliced."""
+        g = _group(self.group)
+        slicer = getattr(self.sample_fun, "sample_slice", None)
+        if slicer is not None:
+            lo, hi = shard_bounds(self.sample_fun.num, g.rank, g.world)
+            return slicer(key, lo, hi)
+        samples = self.sample_fun(key)
         num = samples._shape[0] if isinstance(samples, dev.DeviceArray) else len(samples)
-        lo, hi = shard_bounds(num, rank, world)
+        lo, hi = shard_bounds(num, g.rank, g.world)
         if isinstance(samples, dev.DeviceArray):
             return [samples.row(i) for i in range(lo, hi)]
         return np.asarray(samples)[lo:hi]
@@ -118,13 +117,25 @@ class _ShardedEstimator:
         total, count = all_reduce_sum([np.asarray(total, np.float64), np.asarray(float(count))], self.group)
         return total / count
 
+    def _zero_grads(self, parameters):
+        """What a rank without probes contributes: zeros of the kind and shape the other ranks' gradients have
+        (device arrays in the operator's exported shapes when the integrand runs on the device), so that every
+        rank issues the same collectives with the same element counts."""
+        op = getattr(getattr(getattr(self.integrand_fun, "alg", None), "alg", None), "op", None)
+        if op is not None and hasattr(op, "param_shapes") and dev.device_count() > 0:
+            dtype = next((np.asarray(p).dtype for p in parameters if np.asarray(p).dtype.kind == "f"), np.dtype(np.float64))
+            if isinstance(parameters[0], dev.DeviceArray):
+                dtype = parameters[0].dtype
+            return [dev.zeros(tuple(s) or (1,), dtype) for s in op.param_shapes()]
+        return [np.zeros(np.shape(p)) for p in parameters]
+
     def value_and_grad(self, key, *parameters):
         local = self._local(key)
         if len(local):
             total, grads, count = probe_sum(self.integrand_fun, local, parameters, with_grad=True)
-        else:  # a rank without probes still takes part in the collective
+        else:  # a rank without probes still takes part in the collectives, with matching buffers
             total, count = 0.0, 0
-            grads = [np.zeros(np.shape(p)) for p in parameters]
+            grads = self._zero_grads(parameters)
         red = all_reduce_sum([np.asarray(total, np.float64), np.asarray(float(count)), *grads], self.group)
         total, count, grads = red[0], red[1], red[2:]
         return total / count, tuple(_scale(g, 1.0 / float(count)) for g in grads)
@@ -136,29 +147,35 @@ def hutchinson_sharded(integrand_fun, /, sample_fun, group=None):
     return _ShardedEstimator(integrand_fun, sample_fun, group)
 
 
+class sharded_sampler:
+    """Rademacher probes that every rank can generate BY SLICE: probe i is drawn from its own child stream of the
+    key, so rank r materialises only its block `[lo, hi)` (1024 x 1M fp32 probes are 4 GB: not on every rank)
+    and the union over ranks is the same `(num, n)` matrix whatever the number of ranks."""
+
+    def __init__(self, x_like, /, *, num: int):
+        self.n, self.dtype, self.num = int(np.size(x_like)), np.asarray(x_like).dtype, int(num)
+
+    def sample_slice(self, key, lo, hi):
+        from experiments_lanczos_adjoints_b200.hutchinson import split
+
+        keys = split(key, self.num)
+        out = np.empty((max(0, hi - lo), self.n), dtype=self.dtype)
+        for i in range(lo, hi):
+            out[i - lo] = np.random.default_rng(keys[i]).integers(0, 2, size=self.n) * 2 - 1
+        return out
+
+    def __call__(self, key):
+        return self.sample_slice(key, 0, self.num)
+
+
 # ---------------------------------------------------------------------------------------------
 # Row sharding: one large operator split by rows over the GPUs (SURVEY 8e, second half)
 # ---------------------------------------------------------------------------------------------
-class _RawDeviceBuffer:
-    """`__cuda_array_interface__` view of a raw device pointer (for torch.as_tensor)."""
-
-    def __init__(self, ptr, count, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 3, "strides": None}  # fmt: skip
-
-
-def _as_torch(ptr, count, dtype):
-    import torch
-
-    typestr = np.dtype(dtype).str
-    return torch.as_tensor(_RawDeviceBuffer(ptr, count, typestr), device="cuda")
-
-
 class PeerComm:
     """Peer-memory communicator (`bl_dist_comm_*`): every rank's mailbox is mapped into every other
     rank's address space (CUDA IPC over NVLink / NVSwitch); reductions and halo exchanges of the
     row-sharded path are then single-block kernels with no NCCL launch and no host callback.
-    `torch.distributed` is used once, to exchange the 64-byte IPC handles and for the barrier."""
+    The host communicator (`group`) is used once, to exchange the 64-byte IPC handles and for the barrier."""
 
     def __init__(self, group=None, *, rank=None, world=None):
         import ctypes as C
@@ -166,10 +183,10 @@ class PeerComm:
         from experiments_lanczos_adjoints_b200 import _lib
 
         self._lib = _lib
-        dist = _dist()
+        g = _group(group)
         self.group = group
-        self.rank = (dist.get_rank(group) if dist else 0) if rank is None else int(rank)
-        self.world = (dist.get_world_size(group) if dist else 1) if world is None else int(world)
+        self.rank = g.rank if rank is None else int(rank)
+        self.world = g.world if world is None else int(world)
         h = C.c_void_p()
         _lib.call("bl_dist_comm_create", self.rank, self.world, C.byref(h))
         self.handle = h.value
@@ -178,10 +195,9 @@ class PeerComm:
         if rank is None and self.world > 1:  # one process per rank: exchange IPC handles
             buf = C.create_string_buffer(64)
             _lib.call("bl_dist_comm_local", self.handle, None, buf)
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(buf.raw), group=group)
+            handles = g.allgather_bytes(bytes(buf.raw))
             _lib.call("bl_dist_comm_connect_ipc", self.handle, b"".join(handles))
-            dist.barrier(group=group)  # every mailbox is zeroed and mapped before the first store
+            g.barrier()  # every mailbox is zeroed and mapped before the first store
 
     @property
     def mailbox(self) -> int:
@@ -210,12 +226,11 @@ class PeerComm:
         buf = C.create_string_buffer(64)
         self._lib.call("bl_dist_comm_window_create", self.handle, int(slot_bytes), buf)
         self._window_bytes = int(slot_bytes)
-        dist = _dist()
         if self._multi_process and self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(buf.raw), group=self.group)
+            g = _group(self.group)
+            handles = g.allgather_bytes(bytes(buf.raw))
             self._lib.call("bl_dist_comm_window_connect_ipc", self.handle, b"".join(handles))
-            dist.barrier(group=self.group)
+            g.barrier()
 
     @property
     def window(self) -> int:
@@ -255,9 +270,10 @@ class row_sharded:
     summed over the ranks — the Arnoldi / Lanczos calls then operate on the LOCAL rows of every
     vector and produce the same `H`, coefficients and scalars on every rank.
 
-    `comm=PeerComm(...)`: native route, one single-block peer-memory kernel per reduction
-    (`bl_dist_comm_activate`).  Otherwise a hook (`bl_dist_set_reduce_hook`) enqueues an NCCL
-    all-reduce on the library's stream.  Neither synchronises the host."""
+    `comm=PeerComm(...)`: native route, the cross-rank sum rides in the streaming kernel's own last block over
+    peer memory (`bl_dist_comm_activate`).  Otherwise the library's NCCL hook (`bl_dist_nccl_reduce_hook`): an
+    `ncclAllReduce` of the reduced values enqueued on the library's stream between a kernel's local reduction and
+    its epilogue.  Neither synchronises the host or calls back into Python."""
 
     def __init__(self, group=None, comm=None):
         from experiments_lanczos_adjoints_b200 import _lib
@@ -265,39 +281,20 @@ class row_sharded:
         self.group = group
         self.comm = comm
         self._lib = _lib
-
-        def hook(_user, values, count, stream):
-            try:
-                import torch.distributed as dist
-
-                if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
-                    return 0  # one rank: the local sums are the global sums
-                import torch
-
-                with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
-                    dist.all_reduce(_as_torch(values, count, np.float64), group=self.group)
-                return 0
-            except Exception as exc:  # pragma: no cover - surfaced as BL_ECALLBACK
-                self.error = exc
-                return 1
-
         self.error = None
-        self._cb = _lib.ALLREDUCE_CB(hook)
 
     def __enter__(self):
         if self.comm is not None:
             self._lib.call("bl_dist_comm_activate", self.comm.handle)
         else:
-            self._lib.call("bl_dist_set_reduce_hook", self._cb, None)
+            _group(self.group).install_reduce_hook(True)
         return self
 
     def __exit__(self, *exc):
-        import ctypes as C
-
         if self.comm is not None:
             self._lib.call("bl_dist_comm_activate", None)
         else:
-            self._lib.call("bl_dist_set_reduce_hook", C.cast(None, self._lib.ALLREDUCE_CB), None)
+            _group(self.group).install_reduce_hook(False)
         return False
 
 
@@ -348,11 +345,11 @@ class RowShardedSparseOperator:
         order).  Without `comm`: NCCL all-gathers from a host callback."""
         from experiments_lanczos_adjoints_b200 import operators as ops
 
-        dist = _dist()
+        g = _group(group)
         self.group = group
         self.comm = comm
-        self.rank = comm.rank if comm is not None else (dist.get_rank(group) if dist else 0)
-        self.world = comm.world if comm is not None else (dist.get_world_size(group) if dist else 1)
+        self.rank = comm.rank if comm is not None else g.rank
+        self.world = comm.world if comm is not None else g.world
         self.n_global, self.nnz = int(n), len(row)
         (self.chunk, self.idx_a, row_a, col_a, self.idx_b, row_b, col_b) = shard_coo_rows(
             row, col, n, self.rank, self.world, align=32 if comm is not None else 1)  # fmt: skip
@@ -402,17 +399,8 @@ class RowShardedSparseOperator:
         if full is None:
             full = dev.empty((self.chunk * self.world,), x_loc.dtype)
             self._gathered[(slot, x_loc.dtype.str)] = full
-        if self.world == 1:
-            from experiments_lanczos_adjoints_b200 import _lib
-
-            _lib.call("bl_memcpy_d2d", full.ptr, x_loc.ptr, x_loc.size * x_loc.dtype.itemsize, dev.default_stream().ptr)
-            return full
-        import torch
-        import torch.distributed as dist
-
-        with torch.cuda.stream(torch.cuda.ExternalStream(dev.default_stream().ptr)):
-            dist.all_gather_into_tensor(torch.as_tensor(full, device="cuda"), torch.as_tensor(x_loc, device="cuda"),
-                                        group=self.group)  # fmt: skip
+        # one rank: a device copy; otherwise ncclAllGather on the library's stream
+        _group(self.group).allgather_device(x_loc.ptr, full.ptr, x_loc.size, x_loc.dtype, dev.default_stream())
         return full
 
     # operator protocol ----------------------------------------------------------------------
@@ -462,11 +450,11 @@ class RowShardedWaveOperator:
     def __init__(self, grid, stencil, group=None, comm=None):
         from experiments_lanczos_adjoints_b200 import operators as ops
 
-        dist = _dist()
+        hg = _group(group)
         self.group = group
         self.comm = comm
-        self.rank = comm.rank if comm is not None else (dist.get_rank(group) if dist else 0)
-        self.world = comm.world if comm is not None else (dist.get_world_size(group) if dist else 1)
+        self.rank = comm.rank if comm is not None else hg.rank
+        self.world = comm.world if comm is not None else hg.world
         self.g = int(grid)
         if self.g % self.world:
             raise ValueError(f"grid rows ({self.g}) must be divisible by the number of ranks ({self.world})")
@@ -500,23 +488,15 @@ class RowShardedWaveOperator:
         """Send my first / last row of `field` to the neighbours, receive theirs into the halo slots."""
         if self.world == 1:
             return
-        import torch
-        import torch.distributed as dist
-
         g, gs, item = self.g, self.gs, np.dtype(dtype).itemsize
-        ops_ = []
-        with torch.cuda.stream(torch.cuda.ExternalStream(dev.default_stream().ptr)):
-            if self.has_top:
-                ops_.append(dist.P2POp(dist.isend, _as_torch(field_ptr, g, dtype), self.rank - 1, self.group))
-                ops_.append(dist.P2POp(dist.irecv, _as_torch(self.local.halo_ptr(slot_top), g, dtype),
-                                       self.rank - 1, self.group))  # fmt: skip
-            if self.has_bot:
-                last = field_ptr + (gs - 1) * g * item
-                ops_.append(dist.P2POp(dist.isend, _as_torch(last, g, dtype), self.rank + 1, self.group))
-                ops_.append(dist.P2POp(dist.irecv, _as_torch(self.local.halo_ptr(slot_bot), g, dtype),
-                                       self.rank + 1, self.group))  # fmt: skip
-            for req in dist.batch_isend_irecv(ops_):
-                req.wait()
+        hg, s = _group(self.group), dev.default_stream()
+        up = self.rank - 1 if self.has_top else None
+        down = self.rank + 1 if self.has_bot else None
+        last = field_ptr + (gs - 1) * g * item
+        # two grouped ncclSend/ncclRecv pairs: first rows travel up while last rows arrive from above, then the
+        # other direction (every rank makes the same two calls, so the pairs match up along the chain)
+        hg.sendrecv_device(field_ptr, up, self.local.halo_ptr(slot_bot) if down is not None else None, down, g, dtype, s)
+        hg.sendrecv_device(last, down, self.local.halo_ptr(slot_top) if up is not None else None, up, g, dtype, s)
 
     def _bind(self, params, dtype, stream=None):
         from experiments_lanczos_adjoints_b200 import _lib

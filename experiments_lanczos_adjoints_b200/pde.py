@@ -137,6 +137,106 @@ class _SolverExpm:
         return self.expm.vjp(self.field, self.dt, flat, *p)
 
 
+class _BatchedSolverExpm:
+    """`jax.vmap(solve, in_axes=(0, None))(y0s, *p)` of the reference's training loss
+    (`/root/reference/experiments/applications/partial_differential_equation/train.py:104-110`): a stack of initial
+    conditions sharing one parameter set.  The B Arnoldi runs advance in lockstep
+    (`bl_arnoldi_forward_batch` / `bl_arnoldi_adjoint_batch`); the parameter cotangent returned by the pullback is
+    the SUM over the batch (what autodiff of a scalar loss of the stacked outputs gives), `dy0s` is per run."""
+
+    def __init__(self, solver):
+        if not isinstance(solver.expm, _ExpmArnoldi):
+            raise TypeError("vmap(solve) is implemented for expm_arnoldi")
+        self.solver = solver
+
+    def _forward(self, y0s, p, stream):
+        expm, op, dt = self.solver.expm, self.solver.field, float(self.solver.dt)
+        y0s = np.asarray(y0s)
+        B = y0s.shape[0]
+        flat = np.ascontiguousarray(y0s.reshape(B, -1))
+        n, dtype, K = flat.shape[1], flat.dtype, expm.K
+        if not isinstance(K, (int, np.integer)) or K < 1 or K > n:
+            raise ValueError(f"Parameter depth {K} is outside the expected range")
+        if n != op.n:
+            raise ValueError(f"operator acts on vectors of length {op.n}, got {n}")
+        alg = arnoldi.hessenberg(op, K, **expm.kwargs)  # validates reortho like the reference (arnoldi.py:16-19)
+        bound = op.bind(p, dtype, stream)
+        code, ld = dev.dtype_code(dtype), dev.basis_ld(n, dtype)
+        per = _lib.load().bl_arnoldi_workspace_bytes(n, K, code)
+        V = dev.asarray(flat)
+        Q = dev.DeviceArray((B * K, n), dtype, ld=ld)
+        H = dev.DeviceArray((B, K * K), dtype)
+        r = dev.DeviceArray((B, n), dtype, ld=ld)
+        c = dev.DeviceArray((B,), dtype)
+        ws = dev.DeviceArray(((per * B + 7) // 8,), np.float64)
+        arnoldi._run(op, "bl_arnoldi_forward_batch", op._handle, code, n, K, alg._forward_flags, B, V.ptr, n, Q.ptr, ld,
+                     H.ptr, r.ptr, c.ptr, ws.ptr, per * B, stream.ptr)  # fmt: skip
+        Hh = H.numpy(stream).reshape(B, K, K).astype(np.float64)
+        ch = c.numpy(stream).astype(np.float64)
+        out = dev.DeviceArray((B, n), dtype, ld=ld)
+        ys = np.zeros((B, K))
+        vws, vbytes = _vec_ws()
+        for b in range(B):
+            ys[b] = scipy.linalg.expm(dt * Hh[b])[:, 0]  # expm(dt H) e1                    pde_util.py:264-265
+            coef = np.ascontiguousarray(ys[b] / ch[b], dtype=np.float64)  # 1/c * Q @ expmat @ e1      :266
+            _lib.call("bl_rows_combine", code, n, K, Q.ptr + b * K * ld * dtype.itemsize, ld, coef.ctypes.data, 0,
+                      out.row(b).ptr, vws.ptr, vbytes, stream.ptr)  # fmt: skip
+            stream.synchronize()  # `coef` is a host temporary
+        return out, (alg, bound, B, n, K, dtype, code, ld, per, Q, H, r, c, ws, Hh, ch, ys)
+
+    def __call__(self, y0s, *p, stream=None):
+        stream = stream or dev.default_stream()
+        out, _ = self._forward(y0s, p, stream)
+        return out, {"num_matvecs": self.solver.expm.K}
+
+    def vjp(self, y0s, *p, stream=None):
+        stream = stream or dev.default_stream()
+        op, dt = self.solver.field, float(self.solver.dt)
+        out, (alg, bound, B, n, K, dtype, code, ld, per, Q, H, r, c, ws, Hh, ch, ys) = self._forward(y0s, p, stream)
+        if not alg.custom_vjp:
+            raise NotImplementedError("autodiff through the loop is not available; use custom_vjp=True")
+        item = dtype.itemsize
+
+        def pullback(cotangent):
+            u = cotangent[0] if isinstance(cotangent, tuple) else cotangent  # (outs, info): info carries none
+            U = dev.asarray(np.ascontiguousarray(np.asarray(u, dtype=dtype).reshape(B, n)))
+            dH = np.zeros((B, K, K), dtype)
+            dc = np.zeros(B, dtype)
+            dQ = dev.DeviceArray((B * K, n), dtype, ld=ld)  # rank one per run: row k = (y_k / c) u
+            qtu_d = dev.DeviceArray((K,), dtype)
+            vws, vbytes = _vec_ws()
+            e1 = np.zeros(K)
+            e1[0] = 1.0
+            for b in range(B):
+                ub = U.row(b)
+                _lib.call("bl_rows_dot", code, n, K, Q.ptr + b * K * ld * item, ld, ub.ptr, qtu_d.ptr, vws.ptr, vbytes,
+                          stream.ptr)  # fmt: skip
+                qtu = qtu_d.numpy(stream).astype(np.float64)  # Q^T u
+                dH[b] = dt * scipy.linalg.expm_frechet(dt * Hh[b].T, np.outer(qtu / ch[b], e1), compute_expm=False)
+                dc[b] = -float(qtu @ ys[b]) / ch[b] ** 2
+                for k in range(K):
+                    _lib.call("bl_vec_axpby", code, n, float(ys[b, k] / ch[b]), ub.ptr, 0.0, None,
+                              dQ.ptr + (b * K + k) * ld * item, stream.ptr)  # fmt: skip
+            dHd, dcd = dev.asarray(dH.reshape(B, K * K)), dev.asarray(dc)
+            op.bind(bound, dtype, stream)  # same parameter values as the forward pass
+            op.grad_zero(dtype, stream)
+            dv = dev.DeviceArray((B, n), dtype, ld=ld)
+            Lam = dev.DeviceArray((B * K, n), dtype, ld=ld)
+            arnoldi._run(op, "bl_arnoldi_adjoint_batch", op._handle, code, n, K, alg._adjoint_flags, B, Q.ptr, ld, H.ptr,
+                         r.ptr, c.ptr, dQ.ptr, dHd.ptr, None, dcd.ptr, dv.ptr, ld, Lam.ptr, ws.ptr, per * B,
+                         stream.ptr)  # fmt: skip
+            grads = op.grad_export(dtype, stream=stream)
+            return (dv, *grads)
+
+        return (out, {"num_matvecs": K}), pullback
+
+
+def vmap_solver(solve):
+    """`jax.vmap(solve, in_axes=(0, None))` for a `solver_expm` object: `vmap_solver(solve)(y0s, *p)` returns the
+    stacked outputs `(B, n)`; `bl.vjp(vmap_solver(solve), y0s, *p)` the pullback `(dy0s (B, n), *dparams)`."""
+    return _BatchedSolverExpm(solve)
+
+
 def solver_expm(t0, t1, vector_field, /, expm):
     """Drop-in for `pde_util.solver_expm` (`pde_util.py:240-254`) with an operator object as the
     vector field: `solve(y0, *p) -> (y1_flat, info)`; `bl.vjp(solve, y0, *p)` gives the pullback."""

@@ -145,6 +145,109 @@ class TridiagAdjointPlan:
         return np.diag(T, 0).copy(), np.diag(T, 1).copy()
 
 
+class BatchedTridiagAdjointPlan:
+    """`TridiagAdjointPlan` for P independent start vectors (Hutchinson probes) sharing one operand: the P runs
+    advance in LOCKSTEP through `bl_arnoldi_forward_batch` / `bl_arnoldi_adjoint_batch` -- per Krylov step one
+    batched operator call (a sparse operand's values and indices are read once for all runs) and one Gram-Schmidt
+    step kernel for every four runs (`k_step_tma`: the grid-wide reductions of a step are shared by the runs).  This
+    is the batched handler behind the reference's `jax.vmap(integrand)` (hutchinson.py:14,53).  The parameter
+    cotangent that comes out is the SUM over the P runs (what the Hutchinson mean needs, hutchinson.py:54)."""
+
+    def __init__(self, op, krylov_depth: int, dtype, count: int, stream: dev.Stream | None = None):
+        self.op, self.K, self.dtype, self.P = op, int(krylov_depth), np.dtype(dtype), int(count)
+        self.n = op.n
+        self.stream = stream or dev.default_stream()
+        n, K, P = self.n, self.K, self.P
+        if K < 1 or K > n:
+            raise ValueError(f"Parameter depth {K} is outside the expected range")
+        if P < 1:
+            raise ValueError("count must be positive")
+        self.code = dev.dtype_code(self.dtype)
+        self.forward_flags = forward_flags(True, True)
+        self.adjoint_flags = adjoint_flags(True, True, True)
+        self.ld = dev.basis_ld(n, self.dtype)
+        self.Q = dev.DeviceArray((P * K, n), self.dtype, ld=self.ld)
+        self.Lam = dev.DeviceArray((P * K, n), self.dtype, ld=self.ld)
+        self.H = dev.DeviceArray((P, K * K), self.dtype)
+        self.dH = dev.DeviceArray((P, K * K), self.dtype)
+        self.r = dev.DeviceArray((P, n), self.dtype, ld=self.ld)
+        self.c = dev.DeviceArray((P,), self.dtype)
+        self.v = dev.DeviceArray((P, n), self.dtype)
+        self.dv = dev.DeviceArray((P, n), self.dtype)
+        self.params = [dev.DeviceArray(tuple(s) or (1,), self.dtype) for s in op.param_shapes()]
+        self.grads = [dev.DeviceArray(tuple(s) or (1,), self.dtype) for s in op.param_shapes()]
+        self.ws_bytes = P * _lib.load().bl_arnoldi_workspace_bytes(n, K, self.code)
+        self.ws = dev.DeviceArray(((self.ws_bytes + 3) // 4,), np.float32)
+        self._pptr = (C.c_void_p * max(1, len(self.params)))(*[p.ptr for p in self.params])
+        self._gptr = (C.c_void_p * max(1, len(self.grads)))(*[g.ptr for g in self.grads])
+
+    def _h2d(self, dst: dev.DeviceArray, host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        _lib.call("bl_memcpy_h2d", dst.ptr, host.ctypes.data, host.nbytes, self.stream.ptr)
+        return host.nbytes
+
+    def set_vectors(self, v_host):  # (P, n)
+        return self._h2d(self.v, v_host)
+
+    def set_params(self, *params_host):
+        return sum(self._h2d(d, h) for d, h in zip(self.params, params_host))
+
+    def set_cotangents(self, dH_host):  # (P, K, K)
+        return self._h2d(self.dH, dH_host)
+
+    def forward(self):
+        s = self.stream.ptr
+        _lib.call("bl_op_set_params", self.op._handle, self.code, self._pptr, len(self.params), s)
+        _lib.call("bl_arnoldi_forward_batch", self.op._handle, self.code, self.n, self.K, self.forward_flags, self.P, self.v.ptr,
+                  self.n, self.Q.ptr, self.ld, self.H.ptr, self.r.ptr, self.c.ptr, self.ws.ptr, self.ws_bytes, s)  # fmt: skip
+
+    def adjoint(self, zero=True, export=True, general=False):
+        """`general=True`: the general Arnoldi adjoint loops (an operand that is not symmetric, see `coefficients`)."""
+        s = self.stream.ptr
+        if zero:
+            _lib.call("bl_op_grad_zero", self.op._handle, self.code, s)
+        flags = adjoint_flags(True, False, False) if general else self.adjoint_flags
+        _lib.call("bl_arnoldi_adjoint_batch", self.op._handle, self.code, self.n, self.K, flags, self.P, self.Q.ptr, self.ld,
+                  self.H.ptr, self.r.ptr, self.c.ptr, None, self.dH.ptr, None, None, self.dv.ptr, self.n, self.Lam.ptr,
+                  self.ws.ptr, self.ws_bytes, s)  # fmt: skip
+        if export:
+            self.export_grads()
+
+    def export_grads(self):
+        _lib.call("bl_op_grad_export", self.op._handle, self.code, self._gptr, len(self.grads), self.stream.ptr)
+
+    def run(self):
+        """Forward + adjoint of all P runs, enqueued back to back (no host sync)."""
+        self.forward()
+        self.adjoint()
+
+    def run_host(self, v_host, params_host, dH_host, out_H, out_dv, out_grads, sync=True):
+        """Host buffers in, host buffers out (see `TridiagAdjointPlan.run_host`); `v_host (P, n)`, `dH_host (P, K, K)`,
+        `out_H (P, K, K)`, `out_dv (P, n)`.  Returns (h2d_bytes, d2h_bytes)."""
+        h2d = self.set_vectors(v_host) + self.set_params(*params_host) + self.set_cotangents(dH_host)
+        self.run()
+        d2h = 0
+        for src, dst in [(self.H, out_H), (self.dv, out_dv), *zip(self.grads, out_grads)]:
+            _lib.call("bl_memcpy_d2h", dst.ctypes.data, src.ptr, dst.nbytes, self.stream.ptr)
+            d2h += dst.nbytes
+        if sync:
+            self.stream.synchronize()
+        return h2d, d2h
+
+    def coefficients(self):
+        """`[(alpha, beta)] * P` of the last forward (`lanczos.py:162-164`) and whether every `H` is tridiagonal up to
+        rounding (`lanczos.hessenberg_is_tridiagonal`: the operand behaved like a symmetric one); synchronises."""
+        from experiments_lanczos_adjoints_b200.lanczos import hessenberg_is_tridiagonal
+
+        H = self.H.numpy(self.stream).reshape(self.P, self.K, self.K)
+        out, symmetric = [], True
+        for Hp in H:
+            T = 0.5 * (Hp + Hp.T)
+            out.append((np.diag(T, 0).copy(), np.diag(T, 1).copy()))
+            symmetric = symmetric and hessenberg_is_tridiagonal(Hp)
+        return out, symmetric
+
+
 def profile(fn):
     """Run `fn()` with per-kernel-class event timing; returns
     `{class: {"launches", "ms", "algorithmic_bytes"}}` (see `bl_profile_begin` in the header)."""

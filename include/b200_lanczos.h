@@ -66,6 +66,7 @@ int bl_device_sync(void);
 int bl_event_create(void** event);
 int bl_event_destroy(void* event);
 int bl_event_record(void* event, void* stream);
+int bl_stream_wait_event(void* stream, void* event); /* work enqueued on `stream` afterwards waits for `event` */
 int bl_event_sync(void* event);
 int bl_event_elapsed_ms(void* start, void* stop, float* ms);
 /* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
@@ -85,6 +86,13 @@ enum { BL_PROF_DOTS = 0, BL_PROF_COMBINE = 1, BL_PROF_MATVEC = 2, BL_PROF_VJP = 
        BL_PROF_NCLASS = 6 };
 int bl_profile_begin(void);
 int bl_profile_end(uint64_t* counts, double* ms, double* bytes); /* arrays of BL_PROF_NCLASS */
+/* Time stamps inside the one-launch Gram-Schmidt step kernel (k_step_tma), taken by its block 0: per launch 8
+ * values -- [0] globaltimer (ns) at entry, [1..7] SM clock after the dependency wait, phase 0's loads, phase 0's
+ * grid-wide reduction, phase 1's stream, phase 1's reduction, phase 2's stream, exit.  begin() arms the next
+ * 2048 launches; end() synchronises the device, copies `launches` x 8 stamps out and says whether the driver
+ * accepted cooperative + programmatic launch together. */
+int bl_step_trace_begin(void);
+int bl_step_trace_end(unsigned long long* stamps_host, int64_t max_launches, int64_t* launches, int* pdl_accepted);
 
 /* ---- row sharding: one large operator split by rows over several GPUs (one process each) ----
  * Every rank owns the same row range of every Krylov vector (`n` in the Krylov calls is the LOCAL
@@ -96,6 +104,26 @@ int bl_profile_end(uint64_t* counts, double* ms, double* bytes); /* arrays of BL
  * belongs to the operator (bl_op_callback_create). */
 typedef int (*bl_allreduce_cb)(void* user, double* values_dev, int count, void* stream);
 int bl_dist_set_reduce_hook(bl_allreduce_cb hook, void* user);
+
+/* ---- NCCL from the library itself (csrc/nccl_comm.cu): one process per GPU, no PyTorch ------
+ * libnccl.so.2 is loaded with dlopen on first use (BL_NCCL_LIB overrides the name).  Rank 0 makes the
+ * 128-byte unique id, the caller's host channel (comm.py: a socket rendezvous from MASTER_ADDR / MASTER_PORT /
+ * RANK) hands it to the other ranks, every rank calls init on its own device.  Collectives are in place on the
+ * caller's stream: the ONE all-reduce that closes a probe-sharded Hutchinson estimate (hutchinson.py:54 summed
+ * over GPUs), the all-reduce of the per-step dot products and the all-gather of the Lanczos vector of a
+ * row-sharded operand.  op: 0 = sum, 1 = max.  reduce_hook(comm) installs the communicator as this host
+ * thread's bl_dist_set_reduce_hook (NULL removes it). */
+typedef struct bl_nccl bl_nccl_t;
+int bl_dist_nccl_available(int* yes, int* version);
+int bl_dist_nccl_unique_id(void* id_128);
+int bl_dist_nccl_init(const void* id_128, int rank, int world, bl_nccl_t** comm);
+int bl_dist_nccl_allreduce(bl_nccl_t* comm, void* buf, int64_t count, int dtype, int op, void* stream);
+int bl_dist_nccl_allgather(bl_nccl_t* comm, const void* send, void* recv, int64_t count_per_rank, int dtype,
+                           void* stream);
+int bl_dist_nccl_sendrecv(bl_nccl_t* comm, const void* send, int send_peer, void* recv, int recv_peer, int64_t count,
+                          int dtype, void* stream); /* a peer of -1 skips that half */
+int bl_dist_nccl_reduce_hook(bl_nccl_t* comm);
+int bl_dist_nccl_destroy(bl_nccl_t* comm);
 
 /* Peer-memory communicator (NVLink / NVSwitch, one process per GPU of one box; at most 8 ranks):
  * the native alternative to the hook.  Each rank allocates a mailbox in its own HBM, the ranks

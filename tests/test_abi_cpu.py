@@ -207,3 +207,36 @@ def test_probe_pipeline_eligibility_is_host_logic():
         assert not lanczos._pipeline_eligible(full, probes)
     finally:
         lanczos.PROBE_LANES = lanes
+
+
+def test_ffi_shim_handlers_match_their_bindings(tmp_path):
+    """`csrc/ffi_shim.cc` (the XLA-FFI layer north_star names) cannot be built here -- jaxlib's headers are absent --
+    but it is type-checked: `tests/stubs/xla/ffi/api/ffi.h` declares the part of the FFI API the shim uses and its
+    `Binding::To` static_asserts that every handler is invocable with exactly what its `.Ctx/.Arg/.Ret/.Attr` chain
+    describes; the C ABI calls inside are checked against include/b200_lanczos.h."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    cuda_inc = next((d for d in ("/usr/local/cuda/include", "/usr/include") if os.path.exists(os.path.join(d, "cuda_runtime_api.h"))), None)
+    if gxx is None or cuda_inc is None:
+        pytest.skip("g++ or cuda_runtime_api.h not available")
+    shim = os.path.join(ROOT, "experiments_lanczos_adjoints_b200", "csrc", "ffi_shim.cc")
+    base = [gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "stubs"),
+            "-I", os.path.join(ROOT, "include"), "-I", cuda_inc]  # fmt: skip
+    res = subprocess.run(base + [shim], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    text = open(shim).read()
+    handlers = re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((bl_ffi_[a-z0-9_]+)", text)
+    assert {"bl_ffi_matvec", "bl_ffi_matvec_vjp", "bl_ffi_arnoldi_forward", "bl_ffi_arnoldi_adjoint",
+            "bl_ffi_lanczos3_forward", "bl_ffi_lanczos3_adjoint", "bl_ffi_pcg_solve", "bl_ffi_precond_apply",
+            "bl_ffi_cholesky_partial"} <= set(handlers)  # fmt: skip
+    for entry in ("bl_arnoldi_forward_batch", "bl_arnoldi_adjoint_batch"):  # the batched handlers behind jax.vmap
+        assert entry in text
+    # the check has teeth: a handler whose parameters are out of order with its binding must not compile
+    bad = tmp_path / "bad_shim.cc"
+    good_sig = "ffi::Error PrecondApply(cudaStream_t stream, ffi::AnyBuffer v, ffi::Result<ffi::AnyBuffer> out, int64_t precond_handle)"
+    assert good_sig in text
+    bad.write_text(text.replace(good_sig, "ffi::Error PrecondApply(cudaStream_t stream, ffi::AnyBuffer v, int64_t precond_handle, ffi::Result<ffi::AnyBuffer> out)"))
+    res = subprocess.run(base + [str(bad)], capture_output=True, text=True)
+    assert res.returncode != 0 and "does not match" in res.stderr

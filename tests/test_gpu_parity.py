@@ -559,12 +559,17 @@ def test_concurrent_plans_on_separate_streams_match_their_solo_runs():
     assert rel_err(solo[0][0], solo[1][0]) > 1e-3  # different probes: the comparison above is not vacuous
 
 
+@pytest.mark.parametrize("mode", ["lockstep", "streams"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_slq_estimator_with_probes_in_flight_matches_the_sequential_loop(dtype):
-    """`hutchinson(integrand_spd(log, K, sparse_op), sampler)`: with >= 8 probes the estimator keeps four Lanczos
-    runs in flight (own operator handle, plan and stream per lane, `lanczos.probe_pipelined_sum`); value and gradient
-    must equal the one-probe-at-a-time loop (`jax.vmap(integrand)` + mean, hutchinson.py:14,54)."""
+def test_slq_estimator_with_probes_in_flight_matches_the_sequential_loop(dtype, mode, monkeypatch):
+    """`hutchinson(integrand_spd(log, K, sparse_op), sampler)`: with >= 8 probes the estimator runs the probes in
+    lockstep batches of four (`lanczos.probe_lockstep_sum`: multi-vector SpMV + one Gram-Schmidt step kernel per
+    batch; the default) or keeps four independent runs in flight on separate streams
+    (`lanczos.probe_pipelined_sum`, BL_PROBE_MODE=streams); value and gradient must equal the one-probe-at-a-time
+    loop (`jax.vmap(integrand)` + mean, hutchinson.py:14,54)."""
     from experiments_lanczos_adjoints_b200 import lanczos
+
+    monkeypatch.setattr(lanczos, "_probe_mode", lambda: mode)
 
     n, K, num = 20_000, 12, 9  # 9 = 4 + 4 + 1: the last group is ragged
     row, col, data = banded_spd(n, 4, seed=31)
