@@ -467,6 +467,7 @@ def main():
     if not args.no_extra:
         del plans[:], single
         bl.empty_cache()
+        bl.set_blocks_per_sm(0)  # the extras are single runs (or manage the setting themselves)
         import bench_extra
 
         extra = bench_extra.run_all(bl, group, row, col, data, N_ROWS, DEPTH, quick=bool(os.environ.get("BL_BENCH_EXTRA_QUICK")))

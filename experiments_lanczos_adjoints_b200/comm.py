@@ -171,20 +171,21 @@ class SocketComm(Comm):
         return parts
 
     def allreduce_host(self, array, op: str = "sum") -> np.ndarray:
-        arr = np.ascontiguousarray(array, dtype=np.float64)
+        shape = np.shape(array)
+        arr = np.array(array, dtype=np.float64, copy=True).reshape(-1)
         if self.world == 1:
-            return arr.copy()
+            return arr.reshape(shape)
         if self.rank == 0:
-            total = arr.copy()
+            total = arr
             for c in self._peers:  # rank order: the same result on every run
-                other = np.frombuffer(_recv_msg(c), dtype=np.float64).reshape(arr.shape)
+                other = np.frombuffer(_recv_msg(c), dtype=np.float64)
                 total = np.maximum(total, other) if op == "max" else total + other
             blob = total.tobytes()
             for c in self._peers:
                 _send_msg(c, blob)
-            return total
+            return total.reshape(shape)
         _send_msg(self._sock, arr.tobytes())
-        return np.frombuffer(_recv_msg(self._sock), dtype=np.float64).reshape(arr.shape).copy()
+        return np.frombuffer(_recv_msg(self._sock), dtype=np.float64).copy().reshape(shape)
 
     def barrier(self) -> None:
         self.allgather_bytes(b"")

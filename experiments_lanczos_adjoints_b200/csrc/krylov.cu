@@ -1198,12 +1198,16 @@ struct AdjRun {
   }
   // Pi_gamma = -dc c e1 e1^T + H dH^T - dQ^T Q                                arnoldi.py:127
   if (dQ) {
-    constexpr int TK = 16;
-    const size_t smem = 2 * (size_t)K * (TK + 1) * sizeof(T);
-    BL_REQUIRE(K <= 128, "dense dQ cotangent supported up to krylov depth 128");
-    BL_CUDA(cudaFuncSetAttribute(k_gram_partial<T, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gram_partial<T, TK><<<gram_parts, 256, smem, s>>>(K, n, dQ, Q, ld, gram_partial);
-    BL_LAUNCHED();
+    constexpr int TK = 16, KB = 128;  // blocks of at most 128 x 128 entries of dQ^T Q per launch: any Krylov depth
+    const size_t smem = 2 * (size_t)std::min(K, KB) * (TK + 1) * sizeof(T);
+    BL_CHECK(set_smem(k_gram_partial<T, TK>, 2 * (size_t)KB * (TK + 1) * sizeof(double)));
+    for (int a0 = 0; a0 < K; a0 += KB)
+      for (int b0 = 0; b0 < K; b0 += KB) {
+        k_gram_partial<T, TK><<<gram_parts, 256, smem, s>>>(std::min(KB, K - a0), std::min(KB, K - b0), K, n,
+                                                            dQ + (int64_t)a0 * ld, Q + (int64_t)b0 * ld, ld,
+                                                            gram_partial + (size_t)a0 * K + b0);
+        BL_LAUNCHED();
+      }
     k_gram_reduce<<<(K * K + 255) / 256, 256, 0, s>>>(K * K, gram_parts, gram_partial, Gmat);
     BL_LAUNCHED();
     BL_CHECK(sharded_sum(Gmat, (int)(K * K), s));

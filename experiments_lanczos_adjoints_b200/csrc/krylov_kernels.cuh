@@ -474,20 +474,24 @@ __global__ void k_pi_gamma(int K, const T* __restrict__ H, const T* __restrict__
 
 // G[a][b] += sum_col dQ[a][col] * Q[b][col] over a column tile; accumulated with double atomics
 // across tiles is avoided: each block owns a column slab and writes its own partial K x K.
+// One (Ka x Kb) block of the K x K result: rows a0.. of dQ against rows b0.. of Q (the host walks the blocks, at
+// most 128 x 128 each, so that a thread owns at most four 4x4 patches whatever the Krylov depth).
 template <typename T, int TK>
 __global__ void __launch_bounds__(256)
-k_gram_partial(int K, long long n, const T* __restrict__ dQ, const T* __restrict__ Q, long long ld,
-               double* __restrict__ partial /* [gridDim.x][K*K] */) {
-  // tile: TK columns at a time; thread (ta, tb) accumulates a 4x4 patch of the K x K result
+k_gram_partial(int Ka, int Kb, int ldp, long long n, const T* __restrict__ dQ, const T* __restrict__ Q, long long ld,
+               double* __restrict__ partial /* [gridDim.x][ldp*ldp], offset to (a0, b0) */) {
+  // tile: TK columns at a time; thread (ta, tb) accumulates a 4x4 patch of the block
   extern __shared__ unsigned char smem_raw[];
+  const int K = Ka > Kb ? Ka : Kb;
   T* sA = reinterpret_cast<T*>(smem_raw);  // [K][TK+1]
   T* sB = sA + (size_t)K * (TK + 1);       // [K][TK+1]
-  const int P = (K + 3) / 4;               // patches per dimension
+  const int P = (Kb + 3) / 4;              // patches per row of patches
+  const int PA = (Ka + 3) / 4;
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long c0 = per * blockIdx.x;
   long long c1 = c0 + per;
   if (c1 > n) c1 = n;
-  const int npatch = P * P;
+  const int npatch = PA * P;
   // each thread may own several patches
   constexpr int MAXP = 4;
   double acc[MAXP][16];
@@ -500,8 +504,8 @@ k_gram_partial(int K, long long n, const T* __restrict__ dQ, const T* __restrict
     __syncthreads();
     for (int e = threadIdx.x; e < K * TK; e += blockDim.x) {
       const int r = e / TK, k = e % TK;
-      sA[r * (TK + 1) + k] = k < w ? dQ[(long long)r * ld + c + k] : T(0);
-      sB[r * (TK + 1) + k] = k < w ? Q[(long long)r * ld + c + k] : T(0);
+      sA[r * (TK + 1) + k] = (k < w && r < Ka) ? dQ[(long long)r * ld + c + k] : T(0);
+      sB[r * (TK + 1) + k] = (k < w && r < Kb) ? Q[(long long)r * ld + c + k] : T(0);
     }
     __syncthreads();
 #pragma unroll
@@ -513,8 +517,8 @@ k_gram_partial(int K, long long n, const T* __restrict__ dQ, const T* __restrict
         T av[4], bv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          av[u] = pa + u < K ? sA[(pa + u) * (TK + 1) + k] : T(0);
-          bv[u] = pb + u < K ? sB[(pb + u) * (TK + 1) + k] : T(0);
+          av[u] = pa + u < Ka ? sA[(pa + u) * (TK + 1) + k] : T(0);
+          bv[u] = pb + u < Kb ? sB[(pb + u) * (TK + 1) + k] : T(0);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -523,7 +527,7 @@ k_gram_partial(int K, long long n, const T* __restrict__ dQ, const T* __restrict
       }
     }
   }
-  double* out = partial + (size_t)blockIdx.x * K * K;
+  double* out = partial + (size_t)blockIdx.x * ldp * ldp;
 #pragma unroll
   for (int p = 0; p < MAXP; ++p) {
     const int patch = threadIdx.x + p * blockDim.x;
@@ -533,7 +537,7 @@ k_gram_partial(int K, long long n, const T* __restrict__ dQ, const T* __restrict
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int v = 0; v < 4; ++v)
-        if (pa + u < K && pb + v < K) out[(size_t)(pa + u) * K + pb + v] = acc[p][u * 4 + v];
+        if (pa + u < Ka && pb + v < Kb) out[(size_t)(pa + u) * ldp + pb + v] = acc[p][u * 4 + v];
   }
 }
 

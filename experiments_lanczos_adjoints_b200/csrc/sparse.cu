@@ -189,7 +189,11 @@ struct MultiVec {
   void* q[kSpmvBatch];
 };
 
-template <typename T, int P, bool NORM>
+// W slots of the row are in flight per lane: their column indices and values are loaded first, then all W x P
+// gathers are issued before the first FMA.  (The two-slots-per-iteration loop of k_sell_spmv leaves a lane with two
+// dependent memory round trips per pair of entries: ~6 round trips for an 11-entry row, and the kernel runs at half
+// of the HBM rate for want of loads in flight.)
+template <typename T, int P, bool NORM, int W>
 __global__ void __launch_bounds__(256)
 k_sell_spmv_multi(int64_t nrows, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
                   const T* __restrict__ val, const MultiVec mv, int64_t n_pad) {
@@ -211,30 +215,32 @@ k_sell_spmv_multi(int64_t nrows, const int64_t* __restrict__ slice_ptr, const in
     }
   }
   const int64_t s0 = slice_ptr[slice], s1 = slice_ptr[slice + 1];
-  int64_t p = s0 + lane;
-  for (; p + kSlice < s1; p += 2 * kSlice) {
-    const int c0 = ld_stream_i32(col + p), c1 = ld_stream_i32(col + p + kSlice);
-    const T v0 = ld_stream_t(val + p), v1 = ld_stream_t(val + p + kSlice);
-    T g0[P], g1[P];
+  const int width = (int)((s1 - s0) / kSlice);
+  for (int k0 = 0; k0 < width; k0 += W) {
+    int c[W];
+    T v[W];
 #pragma unroll
-    for (int pp = 0; pp < P; ++pp) {
-      g0[pp] = __ldg(x[pp] + c0);
-      g1[pp] = __ldg(x[pp] + c1);
+    for (int j = 0; j < W; ++j) {
+      const bool ok = k0 + j < width;
+      const int64_t slot = s0 + (int64_t)(ok ? k0 + j : width - 1) * kSlice + lane;  // clamped: a valid column
+      c[j] = ld_stream_i32(col + slot);
+      v[j] = ok ? ld_stream_t(val + slot) : T(0);
     }
+    T g[W][P];
 #pragma unroll
-    for (int pp = 0; pp < P; ++pp) {
-      acc0[pp] = fma(v0, NORM ? g0[pp] * inv[pp] : g0[pp], acc0[pp]);
-      acc1[pp] = fma(v1, NORM ? g1[pp] * inv[pp] : g1[pp], acc1[pp]);
-    }
-  }
-  if (p < s1) {
-    const int c0 = ld_stream_i32(col + p);
-    const T v0 = ld_stream_t(val + p);
+    for (int j = 0; j < W; ++j)
 #pragma unroll
-    for (int pp = 0; pp < P; ++pp) {
-      const T g = __ldg(x[pp] + c0);
-      acc0[pp] = fma(v0, NORM ? g * inv[pp] : g, acc0[pp]);
-    }
+      for (int pp = 0; pp < P; ++pp) g[j][pp] = __ldg(x[pp] + c[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const T gv = NORM ? g[j][pp] * inv[pp] : g[j][pp];
+        if (j & 1)
+          acc1[pp] = fma(v[j], gv, acc1[pp]);
+        else
+          acc0[pp] = fma(v[j], gv, acc0[pp]);
+      }
   }
   if (r < nrows) {
 #pragma unroll
@@ -405,8 +411,20 @@ struct SparseOperator : bl_operator {
                            : set_params_t<double>(static_cast<const double*>(params[0]), s);
   }
 
+  static bool wide_spmv() {
+    static const bool on = [] {
+      const char* e = std::getenv("BL_SPMV_WIDE");
+      return !(e && e[0] == '0');
+    }();
+    return on;
+  }
   template <typename T>
   int matvec_t(const T* x, T* y, cudaStream_t s) {
+    if (wide_spmv()) {
+      const void* in[1] = {x};
+      void* out[1] = {y};
+      return spmv_multi_t<T, false>(sell, n_rows, 1, in, nullptr, nullptr, 0, out, s);
+    }
     const int64_t threads = sell.nslices * kSlice;
     const int blocks = (int)((threads + 255) / 256);
     if (blocks > 0) {
@@ -425,6 +443,13 @@ struct SparseOperator : bl_operator {
 
   template <typename T>
   int matvec_normalised_t(const T* v, const double* len, T* q_out, int64_t n_pad, T* y, cudaStream_t s) {
+    if (wide_spmv()) {
+      const void* in[1] = {v};
+      const double* lens[1] = {len};
+      void* q[1] = {q_out};
+      void* out[1] = {y};
+      return spmv_multi_t<T, true>(sell, n_rows, 1, in, lens, q, n_pad, out, s);
+    }
     const int64_t threads = sell.nslices * kSlice;
     const int blocks = (int)((threads + 255) / 256);
     k_sell_spmv_normalised<T><<<blocks, 256, 0, s>>>(n_rows, sell.slice_ptr.as<int64_t>(), sell.col.as<int32_t>(),
@@ -464,10 +489,10 @@ struct SparseOperator : bl_operator {
       const int32_t* cl = m.col.as<int32_t>();
       const T* vl = m.val.as<T>();
       switch (P) {
-        case 1: k_sell_spmv_multi<T, 1, NORM><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
-        case 2: k_sell_spmv_multi<T, 2, NORM><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
-        case 3: k_sell_spmv_multi<T, 3, NORM><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
-        default: k_sell_spmv_multi<T, 4, NORM><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        case 1: k_sell_spmv_multi<T, 1, NORM, 6><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        case 2: k_sell_spmv_multi<T, 2, NORM, 6><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        case 3: k_sell_spmv_multi<T, 3, NORM, 4><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        default: k_sell_spmv_multi<T, 4, NORM, 4><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
       }
       BL_LAUNCHED();
     }
@@ -475,14 +500,12 @@ struct SparseOperator : bl_operator {
   }
   int matvec_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) override {
     BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
-    if (count == 1) return matvec(dtype, in[0], out[0], s);
     return dtype == BL_F32 ? spmv_multi_t<float, false>(sell, n_rows, count, in, nullptr, nullptr, 0, out, s)
                            : spmv_multi_t<double, false>(sell, n_rows, count, in, nullptr, nullptr, 0, out, s);
   }
   int apply_transpose_batch(int dtype, int count, const void* const* in, void* const* out, cudaStream_t s) override {
     BL_REQUIRE(dtype == bound_dtype, "set_params must be called with the same dtype first");
     BL_REQUIRE(n_rows == n_cols, "A^T lam needs a square operator");
-    if (count == 1) return apply_transpose(dtype, in[0], out[0], s);
     return dtype == BL_F32 ? spmv_multi_t<float, false>(sell_t, n_cols, count, in, nullptr, nullptr, 0, out, s)
                            : spmv_multi_t<double, false>(sell_t, n_cols, count, in, nullptr, nullptr, 0, out, s);
   }
@@ -534,6 +557,11 @@ struct SparseOperator : bl_operator {
   }
   template <typename T>
   int apply_transpose_t(const T* lam, T* z, cudaStream_t s) {
+    if (wide_spmv()) {
+      const void* in[1] = {lam};
+      void* out[1] = {z};
+      return spmv_multi_t<T, false>(sell_t, n_cols, 1, in, nullptr, nullptr, 0, out, s);
+    }
     const int64_t threads = sell_t.nslices * kSlice;
     const int blocks = (int)((threads + 255) / 256);
     if (blocks > 0) {

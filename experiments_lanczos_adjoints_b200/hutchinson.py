@@ -89,16 +89,21 @@ def _resident(parameters, like):
 
 def probe_sum(integrand_fun, samples, parameters, *, with_grad=False):
     """Sum (not mean) of the integrand over probes; gradients stay on the device."""
-    if isinstance(samples, np.ndarray) and samples.ndim == 2 and len(samples) > 1 and hasattr(integrand_fun, "alg"):
+    lazy = type(samples).__name__ == "LazyProbes"  # rows drawn on demand (parallel.sharded_sampler)
+    if (isinstance(samples, np.ndarray) or lazy) and samples.ndim == 2 and len(samples) > 1 and hasattr(integrand_fun, "alg"):
         from experiments_lanczos_adjoints_b200 import lanczos
 
         if lanczos._pipeline_eligible(integrand_fun, samples):  # sparse operand: lockstep batches of probes
             if lanczos._probe_mode() == "streams":  # ... or independent runs in flight on separate streams
                 return lanczos.probe_pipelined_sum(integrand_fun, samples, parameters, with_grad=with_grad)
             return lanczos.probe_lockstep_sum(integrand_fun, samples, parameters, with_grad=with_grad)
+        if lazy:
+            samples = np.asarray(samples)
         if samples.dtype in (np.float32, np.float64) and lanczos._batch_eligible(integrand_fun, samples.dtype):
             return lanczos.probe_batch_sum(integrand_fun, samples, parameters, with_grad=with_grad)
     total, grads, count = 0.0, None, 0
+    if type(samples).__name__ == "LazyProbes":
+        samples = np.asarray(samples)
     rows = _probe_rows(samples)
     if len(rows):
         parameters = _resident(parameters, rows[0])

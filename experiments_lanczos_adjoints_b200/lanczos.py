@@ -384,16 +384,17 @@ def probe_lockstep_sum(integrand, probes, parameters, *, with_grad, batch=None, 
     order."""
     from experiments_lanczos_adjoints_b200 import plan as _plan
 
-    probes = np.asarray(probes)
+    if type(probes).__name__ != "LazyProbes":  # lazily drawn probes are materialised one batch at a time
+        probes = np.asarray(probes)
     P, n = probes.shape
-    dtype = probes.dtype
+    dtype = np.dtype(probes.dtype)
     hess = integrand.alg.alg
     K = hess.K
     if not isinstance(K, (int, np.integer)) or K < 1 or K > n:
         raise ValueError(f"Parameter depth {K} is outside the expected range")
     B = max(1, min(batch or LOCKSTEP_BATCH, P))
-    groups = [probes[i : i + B] for i in range(0, P, B)]
-    L = max(1, min(lanes or LOCKSTEP_LANES, len(groups)))
+    starts = list(range(0, P, B))
+    L = max(1, min(lanes or LOCKSTEP_LANES, len(starts)))
     cache = integrand.__dict__.setdefault("_lockstep_plans", {})
     key = (L, B, dtype.str, n, K)
     if key not in cache:
@@ -434,8 +435,9 @@ def probe_lockstep_sum(integrand, probes, parameters, *, with_grad, batch=None, 
             used[li] = True
 
     try:
-        for gi, group in enumerate(groups):
+        for gi, start in enumerate(starts):
             li = gi % L
+            group = np.asarray(probes[start : start + B])  # (drawn now, while the other lane's kernels run)
             if pending[li] is not None:
                 complete(li)
             real = len(group)

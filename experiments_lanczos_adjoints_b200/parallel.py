@@ -147,6 +147,37 @@ def hutchinson_sharded(integrand_fun, /, sample_fun, group=None):
     return _ShardedEstimator(integrand_fun, sample_fun, group)
 
 
+class LazyProbes:
+    """`(num, n)` probe matrix whose rows are drawn when they are sliced: the estimator takes four rows at a time,
+    so the host generates the next batch while the GPU runs the previous one, and no rank ever holds more than a
+    batch (1024 x 1M float32 probes would be 4 GB)."""
+
+    ndim = 2
+
+    def __init__(self, make_rows, lo, hi, n, dtype):
+        self._make, self._lo, self._hi = make_rows, int(lo), int(hi)
+        self.shape, self.dtype = (max(0, self._hi - self._lo), int(n)), np.dtype(dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            start, stop, step = idx.indices(len(self))
+            if step != 1:
+                raise IndexError("LazyProbes supports contiguous slices")
+            return self._make(self._lo + start, self._lo + max(start, stop))
+        if idx < 0:
+            idx += len(self)
+        if not 0 <= idx < len(self):
+            raise IndexError(idx)
+        return self._make(self._lo + idx, self._lo + idx + 1)[0]
+
+    def __array__(self, dtype=None, copy=None):
+        out = self._make(self._lo, self._hi)
+        return out if dtype is None else out.astype(dtype)
+
+
 class sharded_sampler:
     """Rademacher probes that every rank can generate BY SLICE: probe i is drawn from its own child stream of the
     key, so rank r materialises only its block `[lo, hi)` (1024 x 1M fp32 probes are 4 GB: not on every rank)
@@ -155,17 +186,21 @@ class sharded_sampler:
     def __init__(self, x_like, /, *, num: int):
         self.n, self.dtype, self.num = int(np.size(x_like)), np.asarray(x_like).dtype, int(num)
 
-    def sample_slice(self, key, lo, hi):
+    def _rows(self, key, lo, hi):
         from experiments_lanczos_adjoints_b200.hutchinson import split
 
         keys = split(key, self.num)
         out = np.empty((max(0, hi - lo), self.n), dtype=self.dtype)
         for i in range(lo, hi):
-            out[i - lo] = np.random.default_rng(keys[i]).integers(0, 2, size=self.n) * 2 - 1
+            out[i - lo] = np.random.default_rng(keys[i]).integers(0, 2, size=self.n, dtype=np.int8) * 2 - 1
         return out
 
+    def sample_slice(self, key, lo, hi):
+        """Rows `[lo, hi)` of the probe matrix, drawn lazily (`LazyProbes`)."""
+        return LazyProbes(lambda a, b: self._rows(key, a, b), lo, hi, self.n, self.dtype)
+
     def __call__(self, key):
-        return self.sample_slice(key, 0, self.num)
+        return self._rows(key, 0, self.num)
 
 
 # ---------------------------------------------------------------------------------------------

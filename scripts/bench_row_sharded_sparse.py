@@ -27,16 +27,14 @@ rng = np.random.default_rng(1)
 v = rng.standard_normal(n).astype(dtype)
 dalpha, dbeta = rng.standard_normal(K).astype(dtype), rng.standard_normal(K - 1).astype(dtype)
 
-dist = None
-if world > 1:
-    import torch
-    import torch.distributed as dist
+from experiments_lanczos_adjoints_b200 import comm as bl_comm
+
+group = bl_comm.default()  # the library's socket communicator (parallel.init_from_env); collectives are NCCL in the library
 
 
 def barrier():
     bl.synchronize()
-    if dist is not None:
-        dist.barrier()
+    group.barrier()
 
 
 comm = parallel.PeerComm()
@@ -64,10 +62,7 @@ e1.record()
 e1.synchronize()
 ms = e0.elapsed_ms(e1) / reps
 barrier()
-if dist is not None:
-    t = torch.tensor([ms], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+ms = float(group.allreduce_host(np.array(ms), op="max"))
 res = {"config": "sparse SPD operand, rows sharded (peer-memory route), Lanczos fwd+adjoint", "n": n, "nnz": len(data),
        "K": K, "dtype": np.dtype(dtype).name, "world": world, "sharded_ms": ms, "krylov_steps_per_s": K / (ms * 1e-3),
        "timed_out": bool(comm.timed_out())}
@@ -101,6 +96,5 @@ if rank == 0 and os.environ.get("SINGLE", "1") == "1":
                err_dparams=err(grad, dp0.numpy()))
 if rank == 0:
     print(json.dumps(res))
-if dist is not None:
-    dist.barrier()
-    dist.destroy_process_group()
+group.barrier()
+bl_comm.shutdown()

@@ -37,16 +37,14 @@ y0 = (y0 + rng.standard_normal((2, g, g))).astype(dtype)
 scale = (1.0 + 0.1 * np.sin(6 * xs)[:, None] * np.cos(4 * xs)[None, :]).astype(dtype)
 dH = np.eye(K, dtype=dtype) + 0.1 * rng.standard_normal((K, K)).astype(dtype)
 
-dist = None
-if world > 1:
-    import torch
-    import torch.distributed as dist
+from experiments_lanczos_adjoints_b200 import comm as bl_comm
+
+group = bl_comm.default()  # the library's socket communicator (parallel.init_from_env); collectives are NCCL in the library
 
 
 def barrier():
     bl.synchronize()
-    if dist is not None:
-        dist.barrier()
+    group.barrier()
 
 
 comm = parallel.PeerComm() if route == "peer" else None
@@ -74,10 +72,7 @@ e1.record()
 e1.synchronize()
 ms = e0.elapsed_ms(e1) / reps
 barrier()
-if dist is not None:
-    t = torch.tensor([ms], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+ms = float(group.allreduce_host(np.array(ms), op="max"))
 res = {"config": "C5 wave stencil Arnoldi fwd+adjoint", "grid": g, "n": 2 * g * g, "K": K,
        "dtype": np.dtype(dtype).name, "world": world, "route": route, "sharded_ms": ms,
        "timed_out": bool(comm.timed_out()) if comm else False}
@@ -112,6 +107,5 @@ if rank == 0 and os.environ.get("SINGLE", "1") == "1":
     res["err_dscale"] = err(ds_h, op.local_scale(ds_ref) if route == "peer" else ds_ref)
 if rank == 0:
     print(json.dumps(res))
-if dist is not None:
-    dist.barrier()
-    dist.destroy_process_group()
+group.barrier()
+bl_comm.shutdown()

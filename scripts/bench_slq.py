@@ -39,8 +39,7 @@ if rank == 0:
     print(json.dumps({"world": world, "n": n, "K": K, "probes": num, "seconds": dt, "probes_per_s": num / dt,
                       "krylov_steps_per_s": num * K / dt, "logdet_estimate": float(value),
                       "grad_norm": float(np.linalg.norm(g)), "grad_finite": bool(np.isfinite(g).all())}))
-if world > 1:
-    import torch.distributed as dist
+from experiments_lanczos_adjoints_b200 import comm as bl_comm
 
-    dist.barrier()
-    dist.destroy_process_group()
+bl_comm.default().barrier()
+bl_comm.shutdown()

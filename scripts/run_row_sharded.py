@@ -62,8 +62,7 @@ if rank == 0:
                err_dv_local=err(dv.numpy()[: min(chunk, n)], dv_ref.numpy()[:chunk]),
                err_dparams=err(dp, dp_ref.numpy()))
     print(json.dumps(res))
-if world > 1:
-    import torch.distributed as dist
+from experiments_lanczos_adjoints_b200 import comm as bl_comm
 
-    dist.barrier()
-    dist.destroy_process_group()
+bl_comm.default().barrier()
+bl_comm.shutdown()

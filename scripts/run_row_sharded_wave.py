@@ -80,8 +80,7 @@ if rank == 0:
     dv_ref_local = op.local_slice(dv0.numpy().reshape(2, g, g))
     res.update(err_H=err(H, H0.numpy()), err_dv_local=err(dv, dv_ref_local), err_dscale=err(ds, ds0.numpy()))
     print(json.dumps(res))
-if world > 1:
-    import torch.distributed as dist
+from experiments_lanczos_adjoints_b200 import comm as bl_comm
 
-    dist.barrier()
-    dist.destroy_process_group()
+bl_comm.default().barrier()
+bl_comm.shutdown()

@@ -239,6 +239,26 @@ def test_sparse_tridiag_and_adjoint_match_oracle(dtype, n, K):
     assert rel_err(dp.numpy(), dp_r) < 10 * t_grad
 
 
+def test_dense_basis_cotangent_beyond_depth_128():
+    """The published benchmark sweeps the Krylov depth to 250 with a dense cotangent on Q
+    (results/.../times_custom.npy[24], benchmark.py:95-96): `dQ^T Q` (arnoldi.py:127) is assembled in 128 x 128
+    blocks, any depth."""
+    n, K = 1500, 150
+    row, col, data = banded_spd(n, 3, seed=5, max_off=40)
+    rng = np.random.default_rng(6)
+    v = rng.standard_normal(n)
+    op = bl.operators.SparseOperator(row, col, (n, n))
+    alg = bl.arnoldi.hessenberg(op, K, reortho="full")
+    (Q, H, r, c), pull = bl.vjp(alg, v, data)
+    ref = krylov.Hessenberg(operators.CsrFastOperator(row, col, (n, n)), K, reortho="full")
+    (Q_r, H_r, r_r, c_r), pull_r = ref.vjp(v, data)
+    cot = (rng.standard_normal((n, K)), rng.standard_normal((K, K)), rng.standard_normal(n), rng.standard_normal())
+    dv, dp = pull(cot)
+    dv_r, dp_r = pull_r(cot)
+    assert rel_err(H.numpy(), H_r) < 1e-9
+    assert rel_err(dv.numpy(), dv_r) < 1e-8 and rel_err(dp.numpy(), dp_r) < 1e-8
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_symmetric_adjoint_shortcuts_match_general_adjoint(dtype):
     """What `tridiag(reortho="full")` passes to the adjoint -- `BL_ADJ_SYMMETRIC` (`Lambda beta_plus`, arnoldi.py:218,

@@ -171,3 +171,69 @@ def test_hutchinson_batch_averages_split_keys():
     expected = np.mean([est(k, A) for k in hutchinson.split(key, 4)])
     assert np.allclose(batched(key, A), expected)
     assert abs(batched(key, A) - np.log([1.0, 2.0, 3.0, 4.0]).sum()) < 0.5
+
+
+# ---- round-2 fixtures (oracle/make_golden_r2.py: the reference's own sources) ------------------------------------
+@pytest.mark.parametrize("name", ["suitesparse_1138_bus_k20_f64", "suitesparse_1138_bus_k20_f32"])
+def test_suitesparse_file_through_the_gpu_path(name):
+    """`exp_util.suite_sparse_load("1138_bus")` (exp_util.py:35-42) -> the benchmark's BCOO operand
+    (suite_sparse/benchmark.py:61-68) -> `tridiag(reortho="full")` and its VJP: here
+    `SparseOperator.from_matrix_market` on the same file -> the CUDA path.  SPD with cond ~ 8.6e6 (the only
+    ill-conditioned sparse fixture the reference ships); parameter gradient in the file's COO order."""
+    import os
+
+    from conftest import GOLDEN_DIR, golden, rel_err
+
+    g = golden(name)
+    x64 = bool(g["x64"])
+    dtype = np.float64 if x64 else np.float32
+    K, n = int(g["K"]), int(g["n"])
+    op, data = bl.operators.SparseOperator.from_matrix_market(os.path.join(GOLDEN_DIR, "1138_bus.mtx"))
+    assert np.array_equal(data, g["data"])
+    alg = bl.lanczos.tridiag(op, K, reortho="full")
+    ((Qt, (alpha, beta)), (q_rem, b_rem)), pull = bl.vjp(alg, g["v"].astype(dtype), data.astype(dtype))
+    t_val, t_grad = (1e-10, 1e-10) if x64 else (1e-5, 1e-4)
+    assert rel_err(alpha, g["alpha"]) < t_val and rel_err(beta, g["beta"]) < t_val
+    assert rel_err(Qt.numpy(), g["Qt"]) < 10 * t_val
+    assert rel_err(q_rem.numpy(), g["q_rem"]) < 10 * t_val and abs(float(b_rem) - float(g["b_rem"])) < 10 * t_val * float(g["b_rem"])
+    dv, dp = pull(((g["dQt"].astype(dtype), (g["dalpha"], g["dbeta"])), (g["dq_rem"].astype(dtype), float(g["db_rem"]))))
+    assert rel_err(dv.numpy(), g["dv"]) < 5 * t_grad and rel_err(dp.numpy(), g["dp"]) < 5 * t_grad
+    dv0, dp0 = pull(((None, (g["dalpha"], g["dbeta"])), (None, None)))  # SLQ-style cotangent
+    assert rel_err(dv0.numpy(), g["dv_slqcot"]) < 5 * t_grad and rel_err(dp0.numpy(), g["dp_slqcot"]) < 5 * t_grad
+    if not x64:  # and against the float64 run of the reference on the same file (different start vector: values only)
+        g64 = golden("suitesparse_1138_bus_k20_f64")
+        ((_, (a64, b64)), _), _ = bl.vjp(alg, g64["v"].astype(dtype), data.astype(dtype))
+        assert rel_err(a64, g64["alpha"]) < 1e-5 and rel_err(b64, g64["beta"]) < 1e-5
+
+
+def test_batched_initial_conditions_match_the_reference_vmap():
+    """`jax.vmap(solve, in_axes=(0, None))(y0s, scale)` of the PDE training loss
+    (/root/reference/experiments/applications/partial_differential_equation/train.py:104-110): three initial conditions,
+    one parameter field, lockstep Arnoldi runs (`pde.vmap_solver` -> bl_arnoldi_{forward,adjoint}_batch with per-run
+    dQ, dH, dc).  Outputs and dy0 per run, dscale summed over the batch, at the wave fixture's 1e-9."""
+    from conftest import golden, rel_err
+
+    from experiments_lanczos_adjoints_b200 import pde
+
+    g = golden("pde_wave_batch_g8_k6_f64")
+    gg, K, B, t1 = int(g["g"]), int(g["K"]), int(g["B"]), float(g["t1"])
+    field, _like = pde.pde_wave_anisotropic(g["scale"], stencil=g["stencil"])
+    solve = pde.solver_expm(0.0, t1, field, expm=pde.expm_arnoldi(K))
+    batched = pde.vmap_solver(solve)
+    y0s = g["y0s"].reshape(B, -1)
+    outs, info = batched(y0s, g["scale"])
+    assert info == {"num_matvecs": K}
+    assert rel_err(outs.numpy(), g["expm_out"].reshape(B, -1)) < 1e-10
+    (outs, _), pullback = bl.vjp(batched, y0s, g["scale"])
+    dy0s, dscale = pullback(g["u"].reshape(B, -1))
+    assert rel_err(outs.numpy(), g["expm_out"].reshape(B, -1)) < 1e-10
+    assert rel_err(dy0s.numpy(), g["loss_dy0s"].reshape(B, -1)) < 1e-9
+    assert rel_err(dscale.numpy(), g["loss_dscale"]) < 1e-9
+    # the batch equals the runs one at a time
+    total = 0.0
+    for b in range(B):
+        (y1, _), pull1 = bl.vjp(solve, g["y0s"][b], g["scale"])
+        d1, ds1 = pull1(g["u"][b])
+        assert rel_err(outs.numpy()[b], y1.numpy()) < 1e-12 and rel_err(dy0s.numpy()[b], d1.numpy()) < 1e-11
+        total = total + ds1.numpy()
+    assert rel_err(dscale.numpy(), total) < 1e-11

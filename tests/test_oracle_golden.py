@@ -2,6 +2,8 @@
 (`oracle/make_golden.py`).  Tolerances: fp64 1e-10 relative, fp32 goldens 1e-4/1e-5
 (BASELINE.json north_star)."""
 
+import os
+
 import numpy as np
 import pytest
 from conftest import golden, golden_names, rel_err
@@ -313,3 +315,53 @@ def test_symmetry_check_on_the_hessenberg_matrix():
         assert not hessenberg_is_tridiagonal(H)
     assert hessenberg_is_tridiagonal(np.ones((1, 1)))
     assert not hessenberg_is_tridiagonal(np.array([[1.0, np.nan], [0.5, 1.0]]))
+
+
+# ---- round-2 fixtures: SuiteSparse file through suite_sparse_load, batched initial conditions ---------------------
+@pytest.mark.parametrize("name", golden_names("suitesparse_"))
+def test_oracle_matches_the_suitesparse_fixture(name):
+    """`exp_util.suite_sparse_load("1138_bus")` -> BCOO operand -> `tridiag(reortho="full")` + VJP, made by the
+    reference's own sources (oracle/make_golden_r2.py).  The float32 fixture is compared at float32 tolerances (the
+    oracle runs in float64)."""
+    g = golden(name)
+    n, K = int(g["n"]), int(g["K"])
+    ref = krylov.tridiag(operators.CooOperator(g["row"], g["col"], (n, n)), K, reortho="full")
+    ((Qt, (alpha, beta)), (q_rem, b_rem)), pull = ref.vjp(g["v"], g["data"])
+    t_val, t_grad = (1e-12, 1e-12) if bool(g["x64"]) else (1e-5, 1e-4)
+    assert rel_err(alpha, g["alpha"]) < t_val and rel_err(beta, g["beta"]) < t_val and rel_err(Qt, g["Qt"]) < 10 * t_val
+    dv, dp = pull(((g["dQt"], (g["dalpha"], g["dbeta"])), (g["dq_rem"], g["db_rem"])))
+    assert rel_err(dv, g["dv"]) < t_grad and rel_err(dp, g["dp"]) < t_grad
+    z = np.zeros_like
+    dv0, dp0 = pull(((z(Qt), (g["dalpha"], g["dbeta"])), (z(q_rem), z(b_rem))))
+    assert rel_err(dv0, g["dv_slqcot"]) < t_grad and rel_err(dp0, g["dp_slqcot"]) < t_grad
+
+
+def test_matrix_market_loader_reproduces_suite_sparse_load_order():
+    """`SparseOperator.from_matrix_market` must hand out the COO entries -- and so the parameter vector and its
+    gradient -- in the order `scipy.io.mmread` gives `suite_sparse_load` (stored lower-triangular entries in file
+    order, then the mirrored strict upper triangle; exp_util.py:35-42): index work, bit-exact."""
+    from conftest import GOLDEN_DIR as GOLDEN
+
+    import experiments_lanczos_adjoints_b200 as bl
+
+    g = golden("suitesparse_1138_bus_k20_f64")
+    op, data = bl.operators.SparseOperator.from_matrix_market(os.path.join(GOLDEN, "1138_bus.mtx"))
+    assert op.shape == (1138, 1138) and len(data) == 4054
+    assert np.array_equal(op._coo[0], g["row"]) and np.array_equal(op._coo[1], g["col"])
+    assert np.array_equal(data, g["data"])
+
+
+def test_oracle_matches_the_batched_initial_conditions_fixture():
+    """`jax.vmap(solve, in_axes=(0, None))(y0s, scale)` (train.py:104-110): per-run outputs and `dy0`, the parameter
+    cotangent summed over the batch."""
+    g = golden("pde_wave_batch_g8_k6_f64")
+    gg, K, B, t1 = int(g["g"]), int(g["K"]), int(g["B"]), float(g["t1"])
+    op = operators.WaveStencilOperator(gg, g["stencil"])
+    dscale = 0.0
+    for b in range(B):
+        y0 = g["y0s"][b].ravel()
+        assert rel_err(krylov.expm_action(op, K, t1, y0, g["scale"]), g["expm_out"][b].ravel()) < 1e-12
+        dy0, ds = krylov.expm_action_vjp(op, K, t1, y0, (g["scale"],), g["u"][b].ravel())
+        assert rel_err(dy0, g["loss_dy0s"][b].ravel()) < 1e-11
+        dscale = dscale + ds
+    assert rel_err(dscale, g["loss_dscale"]) < 1e-11
