@@ -46,7 +46,11 @@ UNIT = "krylov_steps/s"
 
 # DRAM traffic of the dominant kernel from `ncu --set full` captures: dram__bytes_read.sum + dram__bytes_write.sum
 # of ONE launch, next to that launch's algorithmic bytes; each entry names the launch and the summary it comes from.
-NCU_TRAFFIC = {"k_xdots_tma": {"traffic": 396.5e6 + 11.7e6, "algorithmic": 100 * 4.0e6,
+NCU_TRAFFIC = {"k_step_tma": {"traffic": 3103.754e6 + 52.878e6, "algorithmic": 4 * (3 + 100 + 98) * 4.0e6,
+                              "launch": "forward step i=95 of a lockstep batch of 4 runs (per run: phase 0 three vectors, phase 1 "
+                                        "96 rows + 3 terms + out, phase 2 96 rows + v' + out), fp32, n=1M; 564.2 us = 5.60 TB/s",
+                              "source": "profiles/r2_prof_full.md"},
+               "k_xdots_tma": {"traffic": 396.5e6 + 11.7e6, "algorithmic": 100 * 4.0e6,
                                "launch": "forward pass B, i=95 (96 streamed rows + 3 terms + out), fp32, n=1M",
                                "source": "profiles/r1c_prof_xdots.md"},
                "k_fused_tma": {"traffic": 395.3e6 + 6.8e6, "algorithmic": 98 * 4.0e6,

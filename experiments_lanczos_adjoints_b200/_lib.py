@@ -50,6 +50,7 @@ SIGNATURES = {
     "bl_event_elapsed_ms": (_i32, [_vp, _vp, C.POINTER(C.c_float)]),
     "bl_launch_count": (_i32, [C.POINTER(C.c_uint64)]),
     "bl_set_blocks_per_sm": (_i32, [_i32]),
+    "bl_get_blocks_per_sm": (_i32, [C.POINTER(C.c_int)]),
     "bl_profile_begin": (_i32, []),
     "bl_profile_end": (_i32, [C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bl_dist_set_reduce_hook": (_i32, [ALLREDUCE_CB, _vp]),

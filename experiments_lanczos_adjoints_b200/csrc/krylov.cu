@@ -1761,6 +1761,12 @@ int bl_set_blocks_per_sm(int blocks) {
   return BL_OK;
 }
 
+int bl_get_blocks_per_sm(int* blocks) {
+  BL_REQUIRE(blocks != nullptr, "NULL argument");
+  *blocks = g_blocks_per_sm.load(std::memory_order_relaxed);
+  return BL_OK;
+}
+
 int bl_op_deferred_grad(bl_operator_t* op, int dtype, int* yes) {
   BL_REQUIRE(op && yes, "NULL argument");
   *yes = op->deferred_grad(dtype) ? 1 : 0;

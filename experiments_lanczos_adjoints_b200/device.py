@@ -48,6 +48,28 @@ def set_blocks_per_sm(blocks: int):
     _lib.call("bl_set_blocks_per_sm", int(blocks))
 
 
+def get_blocks_per_sm() -> int:
+    b = C.c_int(0)
+    _lib.call("bl_get_blocks_per_sm", C.byref(b))
+    return b.value
+
+
+class blocks_per_sm:
+    """`with blocks_per_sm(1): ...` -- set the process-wide value for a region and put the caller's value back."""
+
+    def __init__(self, blocks: int):
+        self.blocks = int(blocks)
+
+    def __enter__(self):
+        self.saved = get_blocks_per_sm()
+        set_blocks_per_sm(self.blocks)
+        return self
+
+    def __exit__(self, *exc):
+        set_blocks_per_sm(self.saved)
+        return False
+
+
 def launch_count() -> int:
     n = C.c_uint64(0)
     _lib.call("bl_launch_count", C.byref(n))
@@ -60,6 +82,7 @@ class Stream:
         _lib.call("bl_stream_create", C.byref(p))
         self.ptr = p.value
         self._fin = weakref.finalize(self, _destroy_stream, self.ptr)
+        _thread_streams().add(self)  # the streams THIS host thread enqueues on (see _Pool)
 
     def synchronize(self):
         _lib.call("bl_stream_sync", self.ptr)
@@ -77,6 +100,13 @@ def _destroy_stream(ptr):
 
 
 _tls = threading.local()
+
+
+def _thread_streams():
+    streams = getattr(_tls, "streams", None)
+    if streams is None:
+        streams = _tls.streams = weakref.WeakSet()
+    return streams
 
 
 def default_stream() -> Stream:
@@ -120,23 +150,39 @@ def _destroy_event(ptr):
 
 # --- a small caching allocator: cudaMalloc/cudaFree synchronise, the loops must not -----
 class _Pool:
-    """One pool per HOST THREAD: a returned buffer is reused without synchronisation, which is safe only
-    for work on the same stream (stream order) -- and every thread has its own default stream.  A buffer
-    finalised from another thread (garbage collection) still goes back to its owner's pool."""
+    """One pool per HOST THREAD: a returned buffer is reused without synchronisation, which is safe for work on
+    ONE stream (stream order) -- and every thread has its own default stream.  Once the thread has made further
+    streams (`stream=` arguments, plans, lanes), a buffer freed while work on stream A still uses it could be handed
+    to work on stream B: buffers returned since the last synchronisation are therefore marked, and reusing a marked
+    buffer synchronises the thread's streams first (only in programs that use several streams; the Krylov loops
+    themselves never allocate).  A buffer finalised from another thread (garbage collection) still goes back to
+    its owner's pool."""
 
     def __init__(self, max_cached_bytes=24 << 30):
         self.free = {}
         self.cached = 0
         self.max_cached = max_cached_bytes
         self.lock = threading.Lock()
+        self.in_doubt = set()  # returned since the last synchronisation
 
     def alloc(self, nbytes: int) -> tuple[int, int]:
         size = max(256, (int(nbytes) + 255) // 256 * 256)
+        ptr = None
+        streams = list(_thread_streams())
         with self.lock:
             bucket = self.free.get(size)
             if bucket:
                 self.cached -= size
-                return bucket.pop(), size
+                ptr = bucket.pop()
+                if ptr not in self.in_doubt or len(streams) <= 1:
+                    self.in_doubt.discard(ptr)
+                    return ptr, size
+        if ptr is not None:
+            for st in streams:  # this thread's streams are idle now: whatever used its returned buffers has finished
+                st.synchronize()
+            with self.lock:
+                self.in_doubt.clear()
+            return ptr, size
         p = C.c_void_p()
         try:
             _lib.call("bl_malloc", C.byref(p), size)
@@ -150,6 +196,7 @@ class _Pool:
             if self.cached + size <= self.max_cached:
                 self.free.setdefault(size, []).append(ptr)
                 self.cached += size
+                self.in_doubt.add(ptr)
                 return
         try:
             _lib.load().bl_free(ptr)
@@ -159,6 +206,7 @@ class _Pool:
     def release_all(self):
         with self.lock:
             buckets, self.free, self.cached = self.free, {}, 0
+            self.in_doubt.clear()
         for bucket in buckets.values():
             for ptr in bucket:
                 _lib.load().bl_free(ptr)

@@ -359,14 +359,14 @@ def probe_pipelined_sum(integrand, probes, parameters, *, with_grad, lanes=None)
         pl.set_params(*host_params)
     total = 0.0
     used = [False] * L
-    if L >= 3:  # kernels of different lanes share an SM (one block per SM and kernel), see bl_set_blocks_per_sm
-        dev.set_blocks_per_sm(1)
-    try:
-        total = _pipelined_groups(integrand, plans, probes, L, K, dtype, with_grad, used)
-    finally:
-        dev.set_blocks_per_sm(0)
-        for pl in plans:
-            pl.stream.synchronize()
+    # kernels of different lanes share an SM (one block per SM and kernel), see bl_set_blocks_per_sm; the caller's own
+    # setting comes back afterwards
+    with dev.blocks_per_sm(1 if L >= 3 else dev.get_blocks_per_sm()):
+        try:
+            total = _pipelined_groups(integrand, plans, probes, L, K, dtype, with_grad, used)
+        finally:
+            for pl in plans:
+                pl.stream.synchronize()
     return _pipelined_finish(plans, used, dtype, total, P, with_grad)
 
 
@@ -434,6 +434,10 @@ def probe_lockstep_sum(integrand, probes, parameters, *, with_grad, batch=None, 
                        general=not symmetric and integrand.alg.assume_symmetric is None)
             used[li] = True
 
+    # two batches in flight: one block per SM and kernel, so that a block of each lane is resident on every SM and one
+    # lane streams while the other sits in a grid-wide reduction (measured 4983 -> 5411 Krylov steps/s at n = 1M)
+    bps = dev.blocks_per_sm(1 if L >= 2 else dev.get_blocks_per_sm())
+    bps.__enter__()
     try:
         for gi, start in enumerate(starts):
             li = gi % L
@@ -453,6 +457,7 @@ def probe_lockstep_sum(integrand, probes, parameters, *, with_grad, batch=None, 
     finally:
         for pl in plans:
             pl.stream.synchronize()
+        bps.__exit__(None, None, None)
     return _pipelined_finish(plans, used, dtype, total, P, with_grad)
 
 

@@ -75,6 +75,7 @@ int bl_launch_count(uint64_t* count);
  * memory system), 1 (several independent runs in flight on separate streams: kernels of different runs share an
  * SM and fill each other's ramps and reduction tails), 0 = back to the default / BL_BLOCKS_PER_SM. */
 int bl_set_blocks_per_sm(int blocks);
+int bl_get_blocks_per_sm(int* blocks); /* what bl_set_blocks_per_sm last set (0 = environment / default) */
 
 /* Per-kernel-class device timing for the roofline report.  Between begin and end every
  * streaming launch of the Krylov loops is bracketed by CUDA events on its own stream; end
