@@ -157,10 +157,15 @@ class HessenbergEstimate:
         return (Q, H, r, c), (n, dtype, ld, nbytes, ws, bound)
 
     def __call__(self, v, *params, stream=None):
+        if np.iscomplexobj(v) or any(np.iscomplexobj(p) for p in params if not isinstance(p, dev.DeviceArray)):
+            return _forward_complex(self, v, params, stream or dev.default_stream())
         (Q, H, r, c), _ = self._forward(v, params, stream or dev.default_stream())
         return Q.T, H, r, c  # Q shown as (n, K) like the reference
 
     def vjp(self, v, *params, stream=None):
+        if np.iscomplexobj(v) or any(np.iscomplexobj(p) for p in params if not isinstance(p, dev.DeviceArray)):
+            raise NotImplementedError("complex inputs are supported in the forward only: the reference's adjoint "
+                                      "transposes without conjugation (arnoldi.py:130,202-204)")  # fmt: skip
         if not self.custom_vjp:
             raise NotImplementedError(
                 "custom_vjp=False asks for autodiff through the loop (arnoldi.py:51-53); this build "
@@ -187,6 +192,87 @@ class HessenbergEstimate:
             return (dv, *grads)
 
         return (Q.T, H, r, c), pullback
+
+
+class ComplexDeviceArray:
+    """A complex array held as two real device arrays (the library's kernels are real)."""
+
+    def __init__(self, re: dev.DeviceArray, im: dev.DeviceArray):
+        self.re, self.im = re, im
+        self.shape = re.shape
+        self.dtype = np.result_type(re.dtype, np.complex64)
+
+    @property
+    def T(self):
+        return ComplexDeviceArray(self.re.T, self.im.T)
+
+    def numpy(self, stream=None):
+        return self.re.numpy(stream) + 1j * self.im.numpy(stream)
+
+
+def _forward_complex(alg: "HessenbergEstimate", v, params, stream):
+    """`arnoldi._forward` for a COMPLEX start vector / operand (`arnoldi.py:57-101` with its `.conj()`s, `:66,87,92,95`;
+    the reference tests the forward with `dtype=complex`, `tests/test_arnoldi/test_hessenberg_forward.py:13`).  The
+    library's kernels are real, so the step is composed on the host from real device calls on the real and imaginary
+    parts -- four real matvecs per complex matvec, four blocks of row dots per `Q^H v`, four row combinations per
+    `Q h` -- through the same C ABI (`bl_op_matvec`, `bl_rows_dot`, `bl_rows_combine`, `bl_vec_axpby`).  Forward only,
+    one parameter array, sized for the reference's unit tests rather than for throughput."""
+    from experiments_lanczos_adjoints_b200.lanczos import device_axpby, device_dot
+    from experiments_lanczos_adjoints_b200.pde import _rows_combine, _rows_dot
+
+    op, K = alg.op, alg.K
+    v = np.asarray(v)
+    if v.ndim != 1:
+        raise ValueError("v must be a flat vector")
+    n = v.shape[0]
+    if not isinstance(K, (int, np.integer)) or K < 1 or K > n:  # arnoldi.py:58-60
+        raise ValueError(f"Parameter depth {K} is outside the expected range")
+    if len(params) != 1:
+        raise NotImplementedError("the complex forward takes one parameter array")
+    ctype = np.result_type(v.dtype, np.asarray(params[0]).dtype, np.complex64)
+    rtype = np.float32 if ctype == np.complex64 else np.float64
+    p = np.asarray(params[0], dtype=ctype)
+    p_re, p_im = np.ascontiguousarray(p.real, dtype=rtype), np.ascontiguousarray(p.imag, dtype=rtype)
+    v = v.astype(ctype)
+    vr, vi = dev.asarray(np.ascontiguousarray(v.real, dtype=rtype)), dev.asarray(np.ascontiguousarray(v.imag, dtype=rtype))
+    ld = dev.basis_ld(n, rtype)
+    Qr, Qi = dev.zeros((K, n), rtype, ld=ld, stream=stream), dev.zeros((K, n), rtype, ld=ld, stream=stream)
+    H = np.zeros((K, K), dtype=ctype)
+
+    def matvec(xr, xi):  # (Ar + i Ai)(xr + i xi)
+        a, b = op(xr, p_re), op(xi, p_im)
+        c, d = op(xi, p_re), op(xr, p_im)
+        return device_axpby(1.0, a, -1.0, b, stream), device_axpby(1.0, c, 1.0, d, stream)
+
+    def project(xr, xi):  # Q^H x: <q_j, x> with the conjugate on q (arnoldi.py:87)
+        return (_rows_dot(Qr, xr, stream) + _rows_dot(Qi, xi, stream)) + 1j * (_rows_dot(Qr, xi, stream) - _rows_dot(Qi, xr, stream))
+
+    def subtract(xr, xi, h):  # x - Q h
+        dr = device_axpby(1.0, _rows_combine(Qr, h.real, stream), -1.0, _rows_combine(Qi, h.imag, stream), stream)
+        di = device_axpby(1.0, _rows_combine(Qr, h.imag, stream), 1.0, _rows_combine(Qi, h.real, stream), stream)
+        return device_axpby(1.0, xr, -1.0, dr, stream), device_axpby(1.0, xi, -1.0, di, stream)
+
+    def norm(xr, xi):  # sqrt(v^H v), arnoldi.py:66,95
+        return float(np.sqrt(rtype(device_dot(xr, xr, stream) + device_dot(xi, xi, stream))))
+
+    length0 = length = norm(vr, vi)
+    for i in range(K):
+        vr = device_axpby(1.0 / length, vr, 0.0, None, stream)  # arnoldi.py:80
+        vi = device_axpby(1.0 / length, vi, 0.0, None, stream)
+        item = np.dtype(rtype).itemsize
+        for basis, part in ((Qr, vr), (Qi, vi)):  # Q[:, i] = v                   arnoldi.py:81
+            _lib.call("bl_memcpy_d2d", basis.ptr + i * ld * item, part.ptr, n * item, stream.ptr)
+        vr, vi = matvec(vr, vi)  # :84
+        h = project(vr, vi).astype(ctype)  # :87 (rows > i of Q are zero)
+        vr, vi = subtract(vr, vi, h)  # :88
+        if alg._second_pass:  # :91-92 -- h is NOT updated
+            vr, vi = subtract(vr, vi, project(vr, vi))
+        length = norm(vr, vi)  # :95
+        if i + 1 < K:  # :98 (the write at i+1 == K is dropped)
+            h[i + 1] = length
+        H[:, i] = h  # :99
+    Q = ComplexDeviceArray(Qr, Qi).T  # shown as (n, K) like the reference
+    return Q, H, ComplexDeviceArray(vr, vi), np.dtype(ctype).type(1.0 / length0)
 
 
 def hessenberg(matvec, krylov_depth, /, *, reortho: str, custom_vjp: bool = True, reortho_vjp: str = "match"):

@@ -216,21 +216,33 @@ k_sell_spmv_multi(int64_t nrows, const int64_t* __restrict__ slice_ptr, const in
   }
   const int64_t s0 = slice_ptr[slice], s1 = slice_ptr[slice + 1];
   const int width = (int)((s1 - s0) / kSlice);
-  for (int k0 = 0; k0 < width; k0 += W) {
-    int c[W];
-    T v[W];
+  const int32_t* colp = col + s0 + lane;
+  const T* valp = val + s0 + lane;
+  int c[W], cn[W];
+  T v[W], vn[W];
+  auto load_chunk = [&](int k0, int (&cc)[W], T (&vv)[W]) {  // indices and values of slots k0 .. k0+W-1 of this row
 #pragma unroll
     for (int j = 0; j < W; ++j) {
       const bool ok = k0 + j < width;
-      const int64_t slot = s0 + (int64_t)(ok ? k0 + j : width - 1) * kSlice + lane;  // clamped: a valid column
-      c[j] = ld_stream_i32(col + slot);
-      v[j] = ok ? ld_stream_t(val + slot) : T(0);
+      const int off = (ok ? k0 + j : width - 1) * kSlice;  // clamped: a valid column, value 0
+      cc[j] = ld_stream_i32(colp + off);
+      vv[j] = ok ? ld_stream_t(valp + off) : T(0);
+    }
+  };
+  if (width > 0) load_chunk(0, cn, vn);
+  for (int k0 = 0; k0 < width; k0 += W) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      c[j] = cn[j];
+      v[j] = vn[j];
     }
     T g[W][P];
 #pragma unroll
     for (int j = 0; j < W; ++j)
 #pragma unroll
       for (int pp = 0; pp < P; ++pp) g[j][pp] = __ldg(x[pp] + c[j]);
+    // the next chunk's indices and values travel with this chunk's gathers: one dependent round trip per chunk
+    if (k0 + W < width) load_chunk(k0 + W, cn, vn);
 #pragma unroll
     for (int j = 0; j < W; ++j)
 #pragma unroll
@@ -488,11 +500,24 @@ struct SparseOperator : bl_operator {
       const int64_t* sp = m.slice_ptr.as<int64_t>();
       const int32_t* cl = m.col.as<int32_t>();
       const T* vl = m.val.as<T>();
+      static const int wide = [] {  // BL_SPMV_W=12: the whole row of an 11-entry-per-row operand in one chunk (P <= 2)
+        const char* e = std::getenv("BL_SPMV_W");
+        return e ? std::atoi(e) : 0;
+      }();
       switch (P) {
-        case 1: k_sell_spmv_multi<T, 1, NORM, 6><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
-        case 2: k_sell_spmv_multi<T, 2, NORM, 6><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        case 1:
+          if (wide == 12) k_sell_spmv_multi<T, 1, NORM, 12><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad);
+          else k_sell_spmv_multi<T, 1, NORM, 6><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad);
+          break;
+        case 2:
+          if (wide == 12) k_sell_spmv_multi<T, 2, NORM, 12><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad);
+          else k_sell_spmv_multi<T, 2, NORM, 6><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad);
+          break;
         case 3: k_sell_spmv_multi<T, 3, NORM, 4><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
-        default: k_sell_spmv_multi<T, 4, NORM, 4><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad); break;
+        default:
+          if (wide == 6 || wide == 12) k_sell_spmv_multi<T, 4, NORM, 6><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad);
+          else k_sell_spmv_multi<T, 4, NORM, 4><<<blocks, 256, 0, s>>>(rows, sp, cl, vl, mv, n_pad);
+          break;
       }
       BL_LAUNCHED();
     }

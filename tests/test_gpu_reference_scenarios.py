@@ -237,3 +237,33 @@ def test_batched_initial_conditions_match_the_reference_vmap():
         assert rel_err(outs.numpy()[b], y1.numpy()) < 1e-12 and rel_err(dy0s.numpy()[b], d1.numpy()) < 1e-11
         total = total + ds1.numpy()
     assert rel_err(dscale.numpy(), total) < 1e-11
+
+
+@pytest.mark.parametrize("krylov_depth", [1, 5, 10])
+@pytest.mark.parametrize("reortho", ["none", "full"])
+@pytest.mark.parametrize("ctype", [np.complex64, np.complex128])
+def test_decomposition_is_satisfied_for_complex_inputs(krylov_depth, reortho, ctype, nrows=10):
+    # /root/reference/tests/test_arnoldi/test_hessenberg_forward.py:10-37 with dtype=complex
+    from oracle import krylov, operators
+
+    rng = np.random.default_rng(1)
+    A = (rng.standard_normal((nrows, nrows)) + 1j * rng.standard_normal((nrows, nrows))).astype(ctype)
+    v = (rng.standard_normal(nrows) + 1j * rng.standard_normal(nrows)).astype(ctype)
+    algorithm = arnoldi.hessenberg(bl.operators.DenseOperator(nrows), krylov_depth, reortho=reortho)
+    Q, H, r, c = algorithm(v, A)
+    assert Q.shape == (nrows, krylov_depth) and H.shape == (krylov_depth, krylov_depth)
+    assert r.shape == (nrows,) and np.shape(c) == ()
+    Qh, rh = Q.numpy(), r.numpy()
+    small_value = np.sqrt(np.finfo(H.dtype).eps)
+    tols = {"atol": small_value, "rtol": small_value}
+    e0, ek = np.eye(krylov_depth)[[0, -1], :]
+    assert np.allclose(A @ Qh - Qh @ H - np.outer(rh, ek), 0.0, **tols)
+    assert np.allclose(Qh.T.conj() @ Qh - np.eye(krylov_depth), 0.0, **tols)
+    assert np.allclose(Qh @ e0, c * v, **tols)
+    # and the oracle's complex restatement (arnoldi.py:66,87,92,95 keep their .conj())
+    Q_r, H_r, r_r, c_r = krylov.arnoldi_forward(operators.DenseOperator(), krylov_depth, v.astype(np.complex128),
+                                                A.astype(np.complex128))  # fmt: skip
+    t = 1e-4 if ctype == np.complex64 else 1e-10
+    assert np.abs(H - H_r).max() < t * np.abs(H_r).max() and np.abs(Qh - Q_r).max() < 10 * t
+    with pytest.raises(NotImplementedError):
+        bl.vjp(algorithm, v, A)
