@@ -617,7 +617,40 @@ struct StepItem {  // one run's share of a k_step_tma launch
   const Common* c = nullptr;
   StepArgs a;
   double bytes = 0.0;  // algorithmic bytes of the three phases (profile classes)
+  const StepOp* op = nullptr;  // the step's operator call rides in the launch (same for every run of a batch)
 };
+
+// BL_STEP_OP=0: the operator call stays its own launch (A/B measurements).
+bool step_op_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("BL_STEP_OP");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// The operator call of a Krylov step as phase S of k_step_tma: operands stored as SELL-32 only (SparseOperator).
+// norm: the forward's q = v / len on the way, rows written up to n_pad.
+bool make_step_op(bl_operator_t* op, int dtype, bool transpose, bool norm, int64_t n, int64_t n_pad, StepOp* so) {
+  if (!step_op_enabled() || step_mode() == 0) return false;
+  SellView v;
+  if (!op->sell_view(dtype, transpose, &v)) return false;
+  if (v.nrows != n || (norm && n_pad > v.nslices * 32)) return false;
+  *so = StepOp();
+  so->slice_ptr = v.slice_ptr;
+  so->col = v.col;
+  so->val = v.val;
+  so->nslices = v.nslices;
+  so->nrows = v.nrows;
+  so->n_pad = n_pad;
+  so->norm = norm ? 1 : 0;
+  static const int hints = [] {  // BL_STEP_L2: bit 0 basis rows evict_first, bit 1 operand evict_last
+    const char* e = std::getenv("BL_STEP_L2");
+    return e ? std::atoi(e) : 1;
+  }();
+  so->l2_hints = hints;
+  return true;
+}
 
 template <typename T>
 size_t step_smem_bytes(int count, int acc_stride, int coef_stride) {
@@ -661,6 +694,7 @@ int launch_step(std::vector<StepItem>& items, cudaStream_t s, bool* done) {
   constexpr int TILE = kConsumerThreads * Vec<T>::N;
   const int total = (int)items.size();
   const int mode = step_mode();
+  const StepOp* sop = total > 0 ? items[0].op : nullptr;
   if (total < 1 || mode == 0 || (mode == 1 && total < 2) || !xdots_enabled() || stream_mode() == 2 || is_sharded())
     return BL_OK;
   const long long n = items[0].a.n;
@@ -669,6 +703,7 @@ int launch_step(std::vector<StepItem>& items, cudaStream_t s, bool* done) {
   for (const StepItem& it : items) {
     const StepArgs& a = it.a;
     if (a.n != n || a.nvec > kXTerms || a.few_n > kFewMax || a.nrows1 < 1 || a.nrows2 < 1) return BL_OK;
+    if (it.op != sop || (sop && (a.few_n < 1 || a.op_x == nullptr || a.op_x == a.few_x))) return BL_OK;
     acc_stride = std::max(acc_stride, a.nrows1);
     coef_stride = std::max(coef_stride, (a.nrows2 + kGroup - 1) / kGroup * kGroup);
   }
@@ -706,6 +741,10 @@ int launch_step(std::vector<StepItem>& items, cudaStream_t s, bool* done) {
     B.exit_counter = items[first].c->counters + 9;
     B.reverse = next_direction();
     (void)next_direction();  // phase 2 walks the other way: the next streaming kernel starts where it ended
+    if (sop) {
+      B.op = *sop;
+      B.reverse = 0;  // old rows first: what the producer copies under phase S is older than the predecessor
+    }
     if (g_step_trace_next.load(std::memory_order_relaxed) >= 0) {
       const int slot = g_step_trace_next.fetch_add(1, std::memory_order_relaxed);
       B.trace_slot = slot < kTraceLaunches ? slot : -1;
@@ -929,6 +968,24 @@ struct FwdRun {
     item.bytes = (double)((m - j0 + 1) + (m + a.nvec + 1) + (m + 2)) * n * sizeof(T);
     return true;
   }
+  // The same with the operator call in the launch (phase S): q_i = v / length, v = A q_i, then the step.  The
+  // current vector moves to the spare buffer first (the gathers of phase S read the whole input while other blocks
+  // write the output); `unfuse` undoes that when the launch did not happen.               arnoldi.py:80-98
+  bool fused_item(int i, const StepOp* sop, StepItem& item) {
+    std::swap(r, alt);
+    if (!step_item(i, item)) {
+      std::swap(r, alt);
+      return false;
+    }
+    item.op = sop;
+    item.a.op_x = alt;
+    item.a.op_q = q_row(i);
+    item.a.op_len = c.scal + S_LEN;
+    item.a.wait_row = std::max(0, i - 1);  // rows i-1 (the predecessor's phase S) and i (this launch's)
+    item.bytes += op->matvec_bytes(dtype) + 1.0 * n * sizeof(T);
+    return true;
+  }
+  void unfuse() { std::swap(r, alt); }
   bool skip_step = false;  // the batch driver already tried the step kernel for this step
   int post(int i) {
     const int m = i + 1;
@@ -1015,7 +1072,19 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
   FwdRun<T> run{op, dtype, n, K, (flags & BL_FWD_SECOND_PASS) != 0, v, Q, ld, H, r, c_out, workspace, wbytes, s, {}, {}};
   run.local_first = symmetric_forward(flags);
   BL_CHECK(run.begin());
+  StepOp sop;
+  const bool fuse = run.second_pass && run.local_first && make_step_op(op, dtype, false, true, n, ld, &sop);
   for (int i = 0; i < K; ++i) {
+    if (fuse) {  // operator call + Gram-Schmidt step in one launch
+      std::vector<StepItem> items(1);
+      sop.wait_first = i == 0;
+      if (run.fused_item(i, &sop, items[0])) {
+        bool stepped = false;
+        BL_CHECK(launch_step<T>(items, s, &stepped));
+        if (stepped) continue;
+        run.unfuse();
+      }
+    }
     BL_CHECK(run.advance(i));
     BL_CHECK(run.post(i));
   }
@@ -1042,7 +1111,23 @@ int arnoldi_forward_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int 
   }
   std::vector<const double*> lens(P);
   std::vector<void*> qout(P);
+  StepOp sop;
+  const bool fuse = (flags & BL_FWD_SECOND_PASS) != 0 && symmetric_forward(flags) &&
+                    make_step_op(op, dtype, false, true, n, ld, &sop);
   for (int i = 0; i < K; ++i) {
+    if (fuse) {  // operator call + Gram-Schmidt step of all runs in one launch per kStepBatch runs
+      std::vector<StepItem> items(P);
+      sop.wait_first = i == 0;
+      int built = 0;
+      while (built < P && runs[built].fused_item(i, &sop, items[built])) ++built;
+      bool stepped = false;
+      if (built == P) {
+        for (StepItem& it : items) it.bytes += (op->matvec_batch_bytes(dtype, P) - P * op->matvec_bytes(dtype)) / P;
+        BL_CHECK(launch_step<T>(items, s, &stepped));
+      }
+      if (stepped) continue;
+      for (int p = 0; p < built; ++p) runs[p].unfuse();
+    }
     int rc = -1;
     {  // q_i = v / length and v = A q_i of every run in one batched operator call     arnoldi.py:80-84
       for (int p = 0; p < P; ++p) {
@@ -1298,6 +1383,14 @@ struct AdjRun {
     item.bytes = (double)((a.few_n + 1) + (idx + 1 + a.nvec + 1) + (idx + 1 + 2)) * n * sizeof(T);
     return true;
   }
+  // The same with z = A^T Lambda[idx] in the launch (phase S; deferred parameter cotangent only).
+  bool fused_item(int idx, const StepOp* sop, StepItem& item) const {
+    if (!defer_grad || !step_item(idx, item)) return false;
+    item.op = sop;
+    item.a.op_x = lam_row(idx);
+    item.bytes += op->apply_transpose_bytes(dtype);
+    return true;
+  }
   void stepped(int idx) {  // the step kernel of idx also did pre(idx - 1)
     pre_done = idx - 1;
     have_reproj = false;
@@ -1426,8 +1519,22 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
   run.symmetric = symmetric_shortcut(flags);
   run.tridiag_cot = (flags & BL_ADJ_TRIDIAG_COTANGENT) != 0;
   BL_CHECK(run.begin());
+  StepOp sop;
+  const bool fuse = run.banded && run.defer_grad && make_step_op(op, dtype, true, false, n, ld, &sop);
   for (int idx = K - 1; idx >= 0; --idx) {
     BL_CHECK(run.pre(idx));
+    if (fuse) {  // A^T lambda + back-substitution + the next re-projection in one launch
+      std::vector<StepItem> items(1);
+      sop.wait_first = idx == K - 1;
+      if (run.fused_item(idx, &sop, items[0])) {
+        bool done = false;
+        BL_CHECK(launch_step<T>(items, s, &done));
+        if (done) {
+          run.stepped(idx);
+          continue;
+        }
+      }
+    }
     // (A^T lambda, dparams += ...) = vjp of matvec at (q_idx, params)            arnoldi.py:207-209
     {
       ProfScope prof(BL_PROF_VJP, run.defer_grad ? op->apply_transpose_bytes(dtype) : op->vjp_bytes(dtype), s);
@@ -1469,10 +1576,27 @@ int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int 
     BL_CHECK(runs.back().begin());
     out[p] = runs[p].z;
   }
+  StepOp sop;
+  const bool fuse = deferred && runs[0].banded && make_step_op(op, dtype, true, false, n, ld, &sop);
   for (int idx = K - 1; idx >= 0; --idx) {
     for (int p = 0; p < P; ++p) {
       BL_CHECK(runs[p].pre(idx));
       in[p] = runs[p].lam_row(idx);
+    }
+    if (fuse) {  // A^T lambda + back-substitution + the next re-projection of all runs in one launch
+      std::vector<StepItem> items(P);
+      sop.wait_first = idx == K - 1;
+      int built = 0;
+      while (built < P && runs[built].fused_item(idx, &sop, items[built])) ++built;
+      bool done = false;
+      if (built == P) {
+        for (StepItem& it : items) it.bytes += (op->matvec_batch_bytes(dtype, P) - P * op->matvec_bytes(dtype)) / P;
+        BL_CHECK(launch_step<T>(items, s, &done));
+      }
+      if (done) {
+        for (int p = 0; p < P; ++p) runs[p].stepped(idx);
+        continue;
+      }
     }
     {
       ProfScope prof(BL_PROF_VJP, deferred ? op->matvec_batch_bytes(dtype, P) : op->vjp_bytes(dtype) * P, s);

@@ -4,6 +4,17 @@
 
 #include "common.cuh"
 
+namespace bl {
+// SELL-32 operand in device memory (layout: sparse.cu).  What the operator phase of k_step_tma reads when the
+// operator call of a Krylov step rides in the step kernel.
+struct SellView {
+  const int64_t* slice_ptr = nullptr;  // nslices + 1
+  const int32_t* col = nullptr;
+  const void* val = nullptr;           // T[nslots], T = the bound dtype
+  int64_t nslices = 0, nrows = 0;
+};
+}  // namespace bl
+
 struct bl_operator {
   int64_t n = 0;  // square operators: length of x and y
   virtual ~bl_operator() {}
@@ -72,6 +83,8 @@ struct bl_operator {
     }
     return BL_OK;
   }
+  // Operators stored as SELL-32 expose A (transpose = false) or A^T (true) to the step kernel; others return false.
+  virtual bool sell_view(int /*dtype*/, bool /*transpose*/, bl::SellView* /*out*/) const { return false; }
   // Lazily evaluated matrix elements (the `lazy_kernel(i, j)` of gp_util.py:257-258 / the
   // `matrix_element` callback of low_rank.py): diagonal and one column, for the partial Cholesky.
   // For the Gram operator these are the KERNEL entries (no noise term), as in the reference.

@@ -620,6 +620,18 @@ struct SparseOperator : bl_operator {
                            : vjp_batch_t<double>(static_cast<const double*>(Q), ldq, static_cast<const double*>(Lam), ldl, count, s);
   }
 
+  bool sell_view(int dtype, bool transpose, SellView* out) const override {
+    if (dtype != bound_dtype || n_rows != n_cols || n_rows == 0 || !uploaded) return false;
+    const SellDev& m = transpose ? sell_t : sell;
+    if (m.nslots == 0 || m.val.p == nullptr) return false;
+    out->slice_ptr = m.slice_ptr.as<int64_t>();
+    out->col = m.col.as<int32_t>();
+    out->val = m.val.p;
+    out->nslices = m.nslices;
+    out->nrows = n_rows;
+    return true;
+  }
+
   int grad_zero(int dtype, cudaStream_t s) override {
     BL_CHECK(grad.ensure(std::max<int64_t>(1, sell.nslots) * dtype_size(dtype)));
     BL_CUDA(cudaMemsetAsync(grad.p, 0, std::max<int64_t>(1, sell.nslots) * dtype_size(dtype), s));

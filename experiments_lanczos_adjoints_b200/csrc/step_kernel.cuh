@@ -24,6 +24,14 @@
 // Each block owns the same contiguous column range in all phases; thread t of the 256 consumers owns column
 // vector t of every tile, so phase 2 reads back what the same thread wrote in phase 1 (program order, no
 // fence), and phase 2 walks the tiles in the opposite direction (it starts on the rows phase 1 read last).
+//
+// Phase S (optional, StepOp): the OPERATOR CALL of the step rides in the same launch when the operand is stored as
+// SELL-32 (sparse.cu) -- x0 = A x (forward: q = x / len is written on the way, x0 = A q) for every run.  A block
+// computes the rows of its own column range: its slices' column indices are one contiguous range of `col`, which
+// the producer streams through the ring (bulk copies of 8 KB); the consumer warps read them from shared memory, gather
+// x from L2 and load the values alongside -- no dependent HBM round trip per slice, and the operand is read once for
+// all runs of the batch.  A step is then ONE launch with three grid-wide reductions instead of two launches
+// with four kernel boundaries.
 #pragma once
 
 #include "stream_kernels.cuh"
@@ -34,8 +42,23 @@ constexpr int kFewMax = 4;
 constexpr int kStepBatch = 4;
 constexpr int kFewSlots = kFewMax * kConsumerWarps + 8;  // per-run scratch of phase 0: warp partials, then block values
 
+struct StepOp {  // the step's operator call, shared by the runs of a launch (phase S)
+  const int64_t* slice_ptr = nullptr;  // nullptr: the operator ran as its own launch
+  const int32_t* col = nullptr;
+  const void* val = nullptr;
+  long long nslices = 0, nrows = 0;
+  long long n_pad = 0;  // norm: op_q is written up to n_pad entries (zero padding beyond nrows)
+  int norm = 0;         // forward step: q = op_x / *op_len (true division, arnoldi.py:80-81), few_x = A q
+  int wait_first = 0;   // the operand's values may be the predecessor's output: dependency wait before the first copy
+  int l2_hints = 0;     // bit 0: basis rows are copied with L2 evict_first, bit 1: the operand with evict_last
+};
+
 struct StepArgs {
   long long n = 0;
+  // ---- phase S (StepOp): few_x = A op_x ----
+  const void* op_x = nullptr;
+  void* op_q = nullptr;
+  const double* op_len = nullptr;
   // ---- phase 0 ----
   int few_n = 0;
   const void* few_row[kFewMax] = {nullptr, nullptr, nullptr, nullptr};
@@ -72,6 +95,7 @@ struct StepBatch {
   int acc_stride = 0, coef_stride = 0;  // per-run shared-memory strides (doubles / elements)
   unsigned int* bar = nullptr;          // arrival counter of the in-kernel barriers (0 between launches)
   unsigned int* exit_counter = nullptr;
+  StepOp op;
   StepArgs a[kStepBatch];
 };
 
@@ -185,6 +209,223 @@ __device__ __forceinline__ void grid_reduce(const StepBatch& B, double* acc_base
   tma::named_bar_sync(1, kConsumerThreads);
 }
 
+// ---- phase S: the operator call (SELL-32) ----
+// Phase S uses the ring's memory as kOpStages FINE stages with barriers of their own (they live in the x-tile buffer,
+// which phase 1 only needs later): a stage is held by a consumer warp for a gather round trip (~2 us), so what stays
+// in flight is (ring - held stages) -- with the three 32 KB stages of the basis stream that is one stage per block
+// and the operand arrives at a fraction of the HBM rate.  Only the COLUMN INDICES go through the ring (the gathers
+// depend on them); the values are plain coalesced loads issued together with the gathers, so they cost no round trip
+// of their own and the ring holds twice as many slices.
+constexpr int kOpStageBytes = 8192;
+constexpr int kOpStages = kStages * kGroup * kConsumerThreads * 16 / kOpStageBytes;  // the ring: 96 KB = 12 fine stages
+constexpr int kOpHold = kOpStages / 2 - 1;  // stages a warp may span with the slices it has in flight
+constexpr int kOpRing = kOpStages * kOpStageBytes / 4;  // slots in the ring
+// The head of the stage in ring slot 0 is copied a second time behind the ring's end (into the x-tile buffer), so a
+// chunk of up to kOpOverflow slots that starts in the last ring slot reads on linearly instead of wrapping.
+constexpr int kOpOverflow = 16 * 32;
+template <typename T>
+__host__ __device__ constexpr int op_stage_slots() {
+  return kOpStageBytes / 4;
+}
+
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p);
+template <>
+__device__ __forceinline__ float ld_stream<float>(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+template <>
+__device__ __forceinline__ double ld_stream<double>(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+struct OpRange {
+  long long s_lo = 0, s_hi = 0;  // slices of this block (rows of its column range)
+  long long a0 = 0, a1 = 0;      // their slots in col / val
+  int nstages = 0;
+};
+
+template <typename T>
+__device__ __forceinline__ OpRange op_range(const StepOp& op, const ColumnRange& cr, long long n) {
+  constexpr int VN = Vec<T>::N;
+  OpRange o;
+  if (op.slice_ptr == nullptr || cr.c0 >= cr.c1) return o;
+  const long long n_v = (n + VN - 1) / VN * VN;
+  o.s_lo = cr.c0 / 32;  // block ranges start on multiples of 32 columns
+  o.s_hi = cr.c1 >= n_v ? op.nslices : cr.c1 / 32;  // the last block also owns the padding rows
+  if (o.s_hi <= o.s_lo) return o;
+  o.a0 = __ldg(op.slice_ptr + o.s_lo);
+  o.a1 = __ldg(op.slice_ptr + o.s_hi);
+  o.nstages = (int)((o.a1 - o.a0 + op_stage_slots<T>() - 1) / op_stage_slots<T>());
+  return o;
+}
+
+// Consumer side: warp w takes the block's slices w, w + 8, ...; lane = row within the slice.  Summation order as in
+// k_sell_spmv_multi (entries k of even / odd position in two accumulators, added at the end): bit-identical results.
+// U slices of the warp are in flight together (their W x P gathers each are issued before the first FMA): with 16
+// consumer warps per SM the gathers' round trip, not the operand stream, bounds the phase.  A warp holds at most
+// kOpHold + 1 fine stages (lo .. hi): the slices of a group lie 8 slices apart; groups that span more fall back to one
+// slice at a time (whose chunks release the stages behind them as they go).
+template <typename T, int P, bool NORM, int W, int U>
+__device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, const unsigned char* stages_raw,
+                                         uint64_t* full, uint64_t* empty, int warp, int lane) {
+  constexpr int SLOTS = op_stage_slots<T>();
+  static_assert(W * 32 <= kOpOverflow && W * 32 <= SLOTS, "a chunk crosses at most one stage boundary");
+  const StepOp& op = B.op;
+  const T* x[P];
+  T inv[P], dlen[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    x[p] = static_cast<const T*>(B.a[p].op_x);
+    dlen[p] = NORM ? static_cast<T>(__ldcg(B.a[p].op_len)) : T(1);
+    inv[p] = T(1) / dlen[p];
+  }
+  const T* valp = static_cast<const T*>(op.val) + o.a0 + lane;  // this lane's values of the block's slots
+  const int* colp = reinterpret_cast<const int*>(stages_raw) + lane;
+  int lo = 0, hi = -1;  // stages [lo, hi] of the operand stream are held by this warp
+  int hi_ring = -1, lo_ring = 0;
+  auto need = [&](int st) {
+    while (hi < st) {
+      ++hi;
+      hi_ring = hi_ring + 1 == kOpStages ? 0 : hi_ring + 1;
+      tma::mbar_wait(full + hi_ring, (hi / kOpStages) & 1);
+    }
+  };
+  auto done_below = [&](int st) {
+    while (lo < st) {
+      if (hi < lo) need(lo);  // every warp passes every stage
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(empty + lo_ring);
+      ++lo;
+      lo_ring = lo_ring + 1 == kOpStages ? 0 : lo_ring + 1;
+    }
+  };
+  const long long first = o.s_lo + warp;
+  const int nmine = o.s_hi > first ? (int)((o.s_hi - first + kConsumerWarps - 1) / kConsumerWarps) : 0;
+  for (int base = 0; base < nmine; base += 32) {
+    // lane l fetches the slot range of the warp's (base + l)-th slice (relative to the block's first slot: 32 bits)
+    int sp0 = 0, sp1 = 0;
+    if (base + lane < nmine) {
+      const long long sl = first + (long long)(base + lane) * kConsumerWarps;
+      sp0 = (int)(__ldg(op.slice_ptr + sl) - o.a0);
+      sp1 = (int)(__ldg(op.slice_ptr + sl + 1) - o.a0);
+    }
+    const int cnt = nmine - base < 32 ? nmine - base : 32;
+    int i = 0;
+    while (i < cnt) {
+      // ---- a group of up to U slices whose slots span at most kOpHold + 1 stages ----
+      int rel[U], width[U];  // first slot of slice u (relative to the block's), entries per row
+      long long r[U];
+      int nu = 0, wmax = 0, head_st = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rel[u] = width[u] = 0;
+        r[u] = 0;
+        if (i + u < cnt) {
+          const int a = __shfl_sync(0xffffffffu, sp0, (i + u) & 31), b = __shfl_sync(0xffffffffu, sp1, (i + u) & 31);
+          const int last = b - 32 > a ? b - 32 : a;  // last slot row of the slice
+          if (u == 0) head_st = a / SLOTS;
+          if (u == 0 || (nu == u && last / SLOTS - head_st <= kOpHold)) {
+            rel[u] = a;
+            width[u] = (b - a) / 32;
+            r[u] = (first + (long long)(base + i + u) * kConsumerWarps) * 32 + lane;
+            wmax = width[u] > wmax ? width[u] : wmax;
+            nu = u + 1;
+          }
+        }
+      }
+      T xr[U][P], acc0[U][P], acc1[U][P];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          xr[u][p] = NORM && u < nu && r[u] < op.nrows ? x[p][r[u]] : T(0);
+          acc0[u][p] = acc1[u][p] = T(0);
+        }
+      for (int k0 = 0; k0 < wmax; k0 += W) {
+        int rows[U];
+        {  // stages below the first slot row that is still needed are finished with; wait for the last one of the round
+          int low = -1, last = -1;
+#pragma unroll
+          for (int u = U - 1; u >= 0; --u) {
+            rows[u] = width[u] - k0 < W ? width[u] - k0 : W;
+            if (rows[u] > 0) {
+              low = (rel[u] + k0 * 32) / SLOTS;
+              const int e = (rel[u] + (k0 + rows[u] - 1) * 32) / SLOTS;
+              last = e > last ? e : last;
+            }
+          }
+          if (low >= 0) done_below(low);
+          need(last);
+        }
+        int c[U][W];
+        T v[U][W];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int s = rel[u] + k0 * 32;          // first slot of the chunk
+          const int* cs = colp + s % kOpRing;      // linear in the ring (+ overflow copy behind its end)
+          const T* vs = valp + s;
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            c[u][j] = 0;  // padding gathers x[0] with value 0
+            v[u][j] = T(0);
+            if (j < rows[u]) {
+              c[u][j] = cs[j * 32];
+              v[u][j] = (op.l2_hints & 32) ? T(1) : ld_stream(vs + j * 32);
+            }
+          }
+        }
+        T g[U][W][P];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+#pragma unroll
+            for (int p = 0; p < P; ++p) g[u][j][p] = (op.l2_hints & 16) ? T(c[u][j]) : __ldg(x[p] + c[u][j]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              const T gv = NORM ? g[u][j][p] * inv[p] : g[u][j][p];
+              if (j & 1)
+                acc1[u][p] = fma(v[u][j], gv, acc1[u][p]);
+              else
+                acc0[u][p] = fma(v[u][j], gv, acc0[u][p]);
+            }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          if (u < nu && r[u] < op.nrows) static_cast<T*>(const_cast<void*>(B.a[p].few_x))[r[u]] = acc0[u][p] + acc1[u][p];
+          if (NORM && u < nu && r[u] < op.n_pad)
+            static_cast<T*>(B.a[p].op_q)[r[u]] = r[u] < op.nrows ? xr[u][p] * T(1) / dlen[p] : T(0);
+        }
+      i += nu;
+    }
+  }
+  done_below(o.nstages);  // every warp passes every stage of the operand stream
+}
+
+template <typename T, bool NORM>
+__device__ __forceinline__ void op_phase_dispatch(const StepBatch& B, const OpRange& o, const unsigned char* stages_raw,
+                                                  uint64_t* full, uint64_t* empty, int warp, int lane) {
+  // slots per chunk (W, even) and slices in flight (U) by run count: what the register budget of the kernel carries
+  constexpr bool F = sizeof(T) == 4;
+  switch (B.count) {
+    case 1: op_phase<T, 1, NORM, F ? 12 : 6, 2>(B, o, stages_raw, full, empty, warp, lane); break;
+    case 2: op_phase<T, 2, NORM, 6, F ? 2 : 1>(B, o, stages_raw, full, empty, warp, lane); break;
+    case 3: op_phase<T, 3, NORM, 4, F ? 2 : 1>(B, o, stages_raw, full, empty, warp, lane); break;
+    default: op_phase<T, 4, NORM, 4, F ? 2 : 1>(B, o, stages_raw, full, empty, warp, lane); break;
+  }
+}
+
 }  // namespace step
 
 template <typename T, int TILE>
@@ -199,11 +440,15 @@ k_step_tma(const __grid_constant__ StepBatch B) {
   T* xs = stages + (size_t)kStages * kGroup * TILE;                 // [2][TILE]
   uint64_t* full = reinterpret_cast<uint64_t*>(xs + 2 * TILE);
   uint64_t* empty = full + kStages;
+  uint64_t* gate = empty + kStages;  // phase S done in this block: the ring is free, its rows of the newest basis vector are written
+  uint64_t* op_full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xs) + step::kOpOverflow * 4);  // phase S's barriers
+  uint64_t* op_empty = op_full + step::kOpStages;
   double* acc_s = reinterpret_cast<double*>(empty + kStages + 2);   // [count][acc_stride]: dots of phase 1, in place reduced
   T* coef_s = reinterpret_cast<T*>(acc_s + (size_t)B.count * B.acc_stride);  // [count][coef_stride]
   __shared__ double red_smem[32];
 
   const int P = B.count;
+  const bool with_op = B.op.slice_ptr != nullptr;
   const int dir1 = B.reverse, dir2 = B.reverse ^ 1;
   const long long n = B.a[0].n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -212,18 +457,55 @@ k_step_tma(const __grid_constant__ StepBatch B) {
       tma::mbar_init(full + s, 1);
       tma::mbar_init(empty + s, kConsumerWarps);
     }
+    tma::mbar_init(gate, 1);
+    if (B.op.slice_ptr != nullptr)
+      for (int s = 0; s < step::kOpStages; ++s) {
+        tma::mbar_init(op_full + s, 1);
+        tma::mbar_init(op_empty + s, kConsumerWarps);
+      }
     tma::fence_barrier_init();
   }
   for (int j = threadIdx.x; j < P * B.acc_stride; j += blockDim.x) acc_s[j] = 0.0;
   __syncthreads();
-  tma::griddep_launch_dependents();
+  // With the operator in the launch the successor may only start once every block has finished phase S: its
+  // producer copies the basis rows written here before its own dependency wait (trigger after phase 0's barrier).
+  if (!with_op) tma::griddep_launch_dependents();
 
   const ColumnRange cr = block_columns<T>(n, TILE);
+  const step::OpRange orng = step::op_range<T>(B.op, cr, n);
 
   if (warp == kConsumerWarps) {
     if (lane == 0) {  // ---- producer: the rows of phase 1 of every run, then the rows of phase 2, one ring ----
+      const uint64_t pol_first = tma::policy_evict_first(), pol_last = tma::policy_evict_last();
+      const bool rows_first = (B.op.l2_hints & 1) != 0;
       bool waited = false;
+      bool gated = !with_op;  // with the operator in the launch the ring belongs to phase S first
       int it = 0;
+      if (orng.nstages > 0) {  // ---- phase S: this block's slots of the operand, indices and values side by side ----
+        constexpr int SLOTS = step::op_stage_slots<T>();
+        if (B.op.wait_first) {
+          tma::griddep_wait();
+          waited = true;
+        }
+        for (int k = 0; k < orng.nstages; ++k) {
+          const int s = k % step::kOpStages;
+          const long long pos = orng.a0 + (long long)k * SLOTS;
+          const uint32_t cnt = (uint32_t)((orng.a1 - pos) < SLOTS ? (orng.a1 - pos) : SLOTS);
+          tma::mbar_wait(op_empty + s, ((k / step::kOpStages) & 1) ^ 1);
+          const uint32_t over = s == 0 && k > 0 ? (cnt < (uint32_t)step::kOpOverflow ? cnt : (uint32_t)step::kOpOverflow) : 0u;
+          tma::mbar_arrive_expect_tx(op_full + s, (cnt + over) * 4u);
+          unsigned char* dst = smem_raw + (size_t)s * step::kOpStageBytes;
+          if (B.op.l2_hints & 2)
+            tma::bulk_g2s_hint(dst, B.op.col + pos, cnt * 4u, op_full + s, pol_last);
+          else
+            tma::bulk_g2s(dst, B.op.col + pos, cnt * 4u, op_full + s);
+          if (over) tma::bulk_g2s(xs, B.op.col + pos, over * 4u, op_full + s);  // the ring's end reads on linearly
+          if (!(B.op.l2_hints & 4))  // the values of these slots: on their way into L2 when the consumers load them
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const T*>(B.op.val) + pos),
+                         "r"(cnt * (uint32_t)sizeof(T))
+                         : "memory");
+        }
+      }
       for (int phase = 1; phase <= 2; ++phase) {
         const int dir = phase == 1 ? dir1 : dir2;
         for (int pp = 0; pp < P; ++pp) {
@@ -240,6 +522,10 @@ k_step_tma(const __grid_constant__ StepBatch B) {
             for (int gg = 0; gg < ngroups; ++gg, ++it) {
               const int g = dir ? ngroups - 1 - gg : gg;
               const int rows_here = nrows - g * kGroup < kGroup ? nrows - g * kGroup : kGroup;
+              if (!gated) {  // phase S is over in this block: the ring is free (and the newest row written)
+                tma::mbar_wait(gate, 0);
+                gated = true;
+              }
               if (!waited && (phase == 2 || g * kGroup + rows_here > a.wait_row)) {
                 tma::griddep_wait();
                 waited = true;
@@ -248,9 +534,15 @@ k_step_tma(const __grid_constant__ StepBatch B) {
               tma::mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
               tma::mbar_arrive_expect_tx(full + s, bytes * rows_here);
               T* dst = stages + (size_t)s * kGroup * TILE;
-              for (int r = 0; r < rows_here; ++r)
-                tma::bulk_g2s(dst + (size_t)r * TILE, src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes,
-                              full + s);
+              if (rows_first) {
+                for (int r = 0; r < rows_here; ++r)
+                  tma::bulk_g2s_hint(dst + (size_t)r * TILE, src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes,
+                                     full + s, pol_first);
+              } else {
+                for (int r = 0; r < rows_here; ++r)
+                  tma::bulk_g2s(dst + (size_t)r * TILE, src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes,
+                                full + s);
+              }
             }
           }
         }
@@ -262,6 +554,21 @@ k_step_tma(const __grid_constant__ StepBatch B) {
     tma::griddep_wait();          // everything below reads the predecessor's output
     step::ConsumerSync csync;
     step::stamp(B.trace_slot, 1, tid);
+
+    // ================= phase S: x0 = A x, every run (the operator call of the step) =================
+    int it0 = 0;
+    if (with_op) {
+      if (B.op.norm)
+        step::op_phase_dispatch<T, true>(B, orng, smem_raw, op_full, op_empty, warp, lane);
+      else
+        step::op_phase_dispatch<T, false>(B, orng, smem_raw, op_full, op_empty, warp, lane);
+      if (B.trace_slot >= 0 && (B.op.l2_hints & 8)) step::stamp(B.trace_slot, 2, tid);  // debugging: S alone
+      // the producer copies this block's columns of the rows written above (generic -> async proxy), the dots
+      // below read them back
+      asm volatile("fence.proxy.async;" ::: "memory");
+      csync();
+      if (tid == 0) tma::mbar_arrive(gate);
+    }
 
     // ================= phase 0: dots of a few rows with x0, every run =================
     bool any_few = false;
@@ -314,7 +621,7 @@ k_step_tma(const __grid_constant__ StepBatch B) {
         }
       }
       csync();
-      step::stamp(B.trace_slot, 2, tid);
+      if (!(with_op && (B.op.l2_hints & 8))) step::stamp(B.trace_slot, 2, tid);
       step::grid_reduce<0>(B, acc_s, kFewMax * kConsumerWarps, tid);
       for (int p = 0; p < P; ++p) {
         if (B.a[p].few_n <= 0) continue;
@@ -328,9 +635,10 @@ k_step_tma(const __grid_constant__ StepBatch B) {
       csync();
       step::stamp(B.trace_slot, 3, tid);
     }
+    if (with_op) tma::griddep_launch_dependents();  // every block is past phase S (phase 0's barrier)
 
     // ================= phase 1: out1 = (sum of terms) / div, red1[j] = <row_j, out1>, every run =================
-    int it = 0, xt = 0;
+    int it = it0, xt = 0;
     for (int p = 0; p < P; ++p) {
       const StepArgs& a = B.a[p];
       const int nrows1 = a.nrows1;
