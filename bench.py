@@ -9,9 +9,9 @@ coefficients (the SLQ case).  One forward + one adjoint sweep of one probe = 100
 metric is Krylov steps per second, `depth / (t_fwd + t_adj)`.
 
 One bench "step" = the forward + adjoint of `lanes x probes` independent probe vectors per GPU (default
-2 x 4): the probes of a lane advance in lockstep (`plan.BatchedTridiagAdjointPlan`: one multi-vector SpMV
-and one Gram-Schmidt step kernel per Krylov step for the whole batch), the lanes run on separate streams so
-that one batch's kernels fill the other's grid-wide reductions.  This is the product path of the SLQ /
+2 x 4): the probes of a lane advance in lockstep (`plan.BatchedTridiagAdjointPlan`: ONE launch per Krylov step
+for the whole batch -- the multi-vector operator call and the Gram-Schmidt step, `k_step_tma`), the lanes run on
+separate streams so that one batch's kernels fill the other's grid-wide reductions.  This is the product path of the SLQ /
 Hutchinson estimator (`lanczos.probe_lockstep_sum`).  `config.single_probe` is ONE run alone.
 
 N > 1 (launched by torchrun, one rank per GPU; the ranks meet over the library's own socket rendezvous and
@@ -46,10 +46,11 @@ UNIT = "krylov_steps/s"
 
 # DRAM traffic of the dominant kernel from `ncu --set full` captures: dram__bytes_read.sum + dram__bytes_write.sum
 # of ONE launch, next to that launch's algorithmic bytes; each entry names the launch and the summary it comes from.
-NCU_TRAFFIC = {"k_step_tma": {"traffic": 3103.754e6 + 52.878e6, "algorithmic": 4 * (3 + 100 + 98) * 4.0e6,
-                              "launch": "forward step i=95 of a lockstep batch of 4 runs (per run: phase 0 three vectors, phase 1 "
-                                        "96 rows + 3 terms + out, phase 2 96 rows + v' + out), fp32, n=1M; 564.2 us = 5.60 TB/s",
-                              "source": "profiles/r2_prof_full.md"},
+NCU_TRAFFIC = {"k_step_tma": {"traffic": 3099.842e6 + 22.251e6, "algorithmic": 4 * (3 + 100 + 98) * 4.0e6 + 82.6e6 + 48.0e6,
+                              "launch": "forward step i=95 of a lockstep batch of 4 runs, operator call inside the launch (phase S: "
+                                        "SELL operand 82.6 MB once + x, y, q per run; per run: phase 0 three vectors, phase 1 "
+                                        "96 rows + 3 terms + out, phase 2 96 rows + v' + out), fp32, n=1M; 605.2 us = 5.53 TB/s",
+                              "source": "profiles/r2b_prof_step.md"},
                "k_xdots_tma": {"traffic": 396.5e6 + 11.7e6, "algorithmic": 100 * 4.0e6,
                                "launch": "forward pass B, i=95 (96 streamed rows + 3 terms + out), fp32, n=1M",
                                "source": "profiles/r1c_prof_xdots.md"},
@@ -444,7 +445,7 @@ def main():
             "workload": f"sparse SPD COO operator n={N_ROWS} nnz={nnz} ({2 * BANDS + 1}/row), Lanczos full "
                         f"reortho depth {DEPTH}, forward + adjoint (cotangents on alpha/beta)",
             "per_gpu": (f"{probes_per_gpu} independent probe vectors per GPU per step: {L} lockstep batch(es) of {per_lane} "
-                        "(multi-vector SpMV + one k_step_tma launch per Krylov step and batch), one stream per batch"
+                        "(ONE k_step_tma launch per Krylov step and batch: operator call + Gram-Schmidt step), one stream per batch"
                         if lockstep else
                         f"{probes_per_gpu} independent probe vectors per GPU per step, each on its own stream") +
                        "; the parameter cotangent accumulates on the device over the steps and the timed region ends with "

@@ -272,8 +272,19 @@ bool few_rows_enabled() {
   return enabled;
 }
 
+// Basis rows are copied with the L2 evict_first policy by the separate streaming kernels too (the step kernel:
+// BL_STEP_L2): measured +4 % for one run alone; BL_ROWS_L2=0 switches it off.
+int rows_evict_first() {
+  static const int on = [] {
+    const char* e = std::getenv("BL_ROWS_L2");
+    return e ? std::atoi(e) : 1;
+  }();
+  return on;
+}
+
 RowSource row_source(const RowBlock& b0, const RowBlock* b1, size_t w) {
   RowSource r;
+  r.evict_first = rows_evict_first();
   r.base0 = static_cast<const char*>(b0.base) + (long long)b0.row0 * b0.ld * (long long)w;
   r.ldb0 = b0.ld * (long long)w;
   r.n0 = b0.nrows;
@@ -620,6 +631,7 @@ struct StepItem {  // one run's share of a k_step_tma launch
   const StepOp* op = nullptr;  // the step's operator call rides in the launch (same for every run of a batch)
 };
 
+constexpr int kOpStagesHost = step::kOpStages;
 // BL_STEP_OP=0: the operator call stays its own launch (A/B measurements).
 bool step_op_enabled() {
   static const bool on = [] {
@@ -649,6 +661,12 @@ bool make_step_op(bl_operator_t* op, int dtype, bool transpose, bool norm, int64
     return e ? std::atoi(e) : 1;
   }();
   so->l2_hints = hints;
+  static const int depth = [] {  // BL_STEP_DEPTH: fine stages of phase S's ring the producer keeps in flight (4..12)
+    const char* e = std::getenv("BL_STEP_DEPTH");
+    const int d = e ? std::atoi(e) : 8;
+    return d < 4 ? 4 : (d > kOpStagesHost ? kOpStagesHost : d);
+  }();
+  so->depth = depth;
   return true;
 }
 

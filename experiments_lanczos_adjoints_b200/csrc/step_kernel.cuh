@@ -51,6 +51,7 @@ struct StepOp {  // the step's operator call, shared by the runs of a launch (ph
   int norm = 0;         // forward step: q = op_x / *op_len (true division, arnoldi.py:80-81), few_x = A q
   int wait_first = 0;   // the operand's values may be the predecessor's output: dependency wait before the first copy
   int l2_hints = 0;     // bit 0: basis rows are copied with L2 evict_first, bit 1: the operand with evict_last
+  int depth = 8;        // fine stages of phase S's ring in use (<= kOpStages): what the producer keeps in flight
 };
 
 struct StepArgs {
@@ -286,13 +287,17 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
   }
   const T* valp = static_cast<const T*>(op.val) + o.a0 + lane;  // this lane's values of the block's slots
   const int* colp = reinterpret_cast<const int*>(stages_raw) + lane;
+  const int depth = op.depth, ring_slots = op.depth * SLOTS, hold = op.depth / 2 - 1;
   int lo = 0, hi = -1;  // stages [lo, hi] of the operand stream are held by this warp
-  int hi_ring = -1, lo_ring = 0;
+  int hi_ring = -1, lo_ring = 0, hi_par = 0;
   auto need = [&](int st) {
     while (hi < st) {
       ++hi;
-      hi_ring = hi_ring + 1 == kOpStages ? 0 : hi_ring + 1;
-      tma::mbar_wait(full + hi_ring, (hi / kOpStages) & 1);
+      if (++hi_ring == depth) {
+        hi_ring = 0;
+        hi_par ^= hi > 0;
+      }
+      tma::mbar_wait(full + hi_ring, hi_par);
     }
   };
   auto done_below = [&](int st) {
@@ -301,7 +306,7 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
       __syncwarp();
       if (lane == 0) tma::mbar_arrive(empty + lo_ring);
       ++lo;
-      lo_ring = lo_ring + 1 == kOpStages ? 0 : lo_ring + 1;
+      lo_ring = lo_ring + 1 == depth ? 0 : lo_ring + 1;
     }
   };
   const long long first = o.s_lo + warp;
@@ -329,7 +334,7 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
           const int a = __shfl_sync(0xffffffffu, sp0, (i + u) & 31), b = __shfl_sync(0xffffffffu, sp1, (i + u) & 31);
           const int last = b - 32 > a ? b - 32 : a;  // last slot row of the slice
           if (u == 0) head_st = a / SLOTS;
-          if (u == 0 || (nu == u && last / SLOTS - head_st <= kOpHold)) {
+          if (u == 0 || (nu == u && last / SLOTS - head_st <= hold)) {
             rel[u] = a;
             width[u] = (b - a) / 32;
             r[u] = (first + (long long)(base + i + u) * kConsumerWarps) * 32 + lane;
@@ -367,7 +372,7 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int s = rel[u] + k0 * 32;          // first slot of the chunk
-          const int* cs = colp + s % kOpRing;      // linear in the ring (+ overflow copy behind its end)
+          const int* cs = colp + s % ring_slots;   // linear in the ring (+ overflow copy behind its end)
           const T* vs = valp + s;
 #pragma unroll
           for (int j = 0; j < W; ++j) {
@@ -487,11 +492,11 @@ k_step_tma(const __grid_constant__ StepBatch B) {
           tma::griddep_wait();
           waited = true;
         }
-        for (int k = 0; k < orng.nstages; ++k) {
-          const int s = k % step::kOpStages;
+        const int depth = B.op.depth;
+        for (int k = 0, s = 0, par = 1; k < orng.nstages; ++k) {
           const long long pos = orng.a0 + (long long)k * SLOTS;
           const uint32_t cnt = (uint32_t)((orng.a1 - pos) < SLOTS ? (orng.a1 - pos) : SLOTS);
-          tma::mbar_wait(op_empty + s, ((k / step::kOpStages) & 1) ^ 1);
+          tma::mbar_wait(op_empty + s, par);
           const uint32_t over = s == 0 && k > 0 ? (cnt < (uint32_t)step::kOpOverflow ? cnt : (uint32_t)step::kOpOverflow) : 0u;
           tma::mbar_arrive_expect_tx(op_full + s, (cnt + over) * 4u);
           unsigned char* dst = smem_raw + (size_t)s * step::kOpStageBytes;
@@ -499,11 +504,16 @@ k_step_tma(const __grid_constant__ StepBatch B) {
             tma::bulk_g2s_hint(dst, B.op.col + pos, cnt * 4u, op_full + s, pol_last);
           else
             tma::bulk_g2s(dst, B.op.col + pos, cnt * 4u, op_full + s);
-          if (over) tma::bulk_g2s(xs, B.op.col + pos, over * 4u, op_full + s);  // the ring's end reads on linearly
-          if (!(B.op.l2_hints & 4))  // the values of these slots: on their way into L2 when the consumers load them
+          if (over)  // the ring's end reads on linearly
+            tma::bulk_g2s(smem_raw + (size_t)depth * step::kOpStageBytes, B.op.col + pos, over * 4u, op_full + s);
+          if (B.op.l2_hints & 4)  // the values of these slots: on their way into L2 when the consumers load them
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const T*>(B.op.val) + pos),
                          "r"(cnt * (uint32_t)sizeof(T))
                          : "memory");
+          if (++s == depth) {
+            s = 0;
+            par ^= 1;
+          }
         }
       }
       for (int phase = 1; phase <= 2; ++phase) {

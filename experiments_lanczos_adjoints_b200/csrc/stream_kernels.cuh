@@ -35,6 +35,8 @@ struct RowSource {  // rows [0, n0) from block 0, [n0, n0 + n1) from block 1
   const char* base1 = nullptr;
   long long ldb1 = 0;
   int n1 = 0;
+  int evict_first = 0;  // copy the rows with the L2 evict_first policy: a stream that is larger than L2 does not push the
+                        // vectors (and the operand) out, which every step reads again
   __device__ __forceinline__ const char* row(int j) const {
     return j < n0 ? base0 + (long long)j * ldb0 : base1 + (long long)(j - n0) * ldb1;
   }
@@ -180,7 +182,8 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
         tma::mbar_arrive_expect_tx(full + s, bytes * rows_here);
         T* dst = stages + (size_t)s * kGroup * TILE;
         for (int r = 0; r < rows_here; ++r)
-          tma::bulk_g2s(dst + (size_t)r * TILE, src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes, full + s);
+          tma::bulk_g2s_opt(dst + (size_t)r * TILE, src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes, full + s,
+                            src.evict_first);
       }
       if (!waited && total > 0) {
         tma::griddep_wait();
@@ -330,7 +333,8 @@ k_xdots_tma(const __grid_constant__ XDotsArgs a) {
         tma::mbar_arrive_expect_tx(full + s, bytes * rows_here);
         T* dst = stages + (size_t)s * kGroup * TILE;
         for (int r = 0; r < rows_here; ++r)
-          tma::bulk_g2s(dst + (size_t)r * TILE, a.src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes, full + s);
+          tma::bulk_g2s_opt(dst + (size_t)r * TILE, a.src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes, full + s,
+                            a.src.evict_first);
       }
     }
   } else {
@@ -530,8 +534,8 @@ k_combine_tma(CombineTmaArgs a) {
             const int rows_here = nbasis - g * kGroup < kGroup ? nbasis - g * kGroup : kGroup;
             tma::mbar_arrive_expect_tx(full + s, bytes * rows_here);
             for (int r = 0; r < rows_here; ++r)
-              tma::bulk_g2s(dst + (size_t)r * TILE, a.src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes,
-                            full + s);
+              tma::bulk_g2s_opt(dst + (size_t)r * TILE, a.src.row(g * kGroup + r) + tc0 * (long long)sizeof(T), bytes,
+                                full + s, a.src.evict_first);
           }
         }
       }

@@ -13,11 +13,20 @@ import bench
 
 row, col, data, dalpha, dbeta = bench.build_workload()
 n, K, dtype = bench.N_ROWS, bench.DEPTH, np.float32
+import os
+
+P = int(os.environ.get("TRACE_PROBES", 1))  # > 1: a lockstep batch (BatchedTridiagAdjointPlan)
 op = bl.operators.SparseOperator(row, col, (n, n))
-pl = bl_plan.TridiagAdjointPlan(op, K, dtype)
-pl.set_vector(np.random.default_rng(0).standard_normal(n).astype(dtype))
-pl.set_params(data.astype(dtype))
-pl.set_cotangent(synthetic.slq_cotangent_dH(dalpha, dbeta, dtype))
+if P > 1:
+    pl = bl_plan.BatchedTridiagAdjointPlan(op, K, dtype, P)
+    pl.set_vectors(np.random.default_rng(0).standard_normal((P, n)).astype(dtype))
+    pl.set_params(data.astype(dtype))
+    pl.set_cotangents(np.stack([synthetic.slq_cotangent_dH(dalpha, dbeta, dtype)] * P))
+else:
+    pl = bl_plan.TridiagAdjointPlan(op, K, dtype)
+    pl.set_vector(np.random.default_rng(0).standard_normal(n).astype(dtype))
+    pl.set_params(data.astype(dtype))
+    pl.set_cotangent(synthetic.slq_cotangent_dH(dalpha, dbeta, dtype))
 for _ in range(3):
     pl.run()
 bl.synchronize()
@@ -33,7 +42,7 @@ d = np.diff(st[:, 1:], axis=1) / clk_ghz / 1e3  # us
 names = ["phase0 loads", "phase0 reduce+epilogue", "phase1 stream", "phase1 reduce+epilogue", "phase2 stream", "exit sum"]
 gap = np.diff(st[:, 0]) / 1e3  # us between consecutive kernel entries
 total = (st[:, 7] - st[:, 1]) / clk_ghz / 1e3
-out = {"launches": int(count.value), "pdl_accepted": int(pdl.value), "sm_clock_ghz_assumed": clk_ghz,
+out = {"probes": P, "launches": int(count.value), "pdl_accepted": int(pdl.value), "sm_clock_ghz_assumed": clk_ghz,
        "phases_us_mean": {nm: float(d[:, i].mean()) for i, nm in enumerate(names)},
        "phases_us_first_step": {nm: float(d[0, i]) for i, nm in enumerate(names)},
        "phases_us_step_50": {nm: float(d[50, i]) for i, nm in enumerate(names)},
