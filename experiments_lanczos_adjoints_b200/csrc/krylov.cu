@@ -69,8 +69,10 @@ struct Common {
   double* coefC;
   double* partials_dots;
   double* partials_comb;
+  double* partials_few;  // [kFewMaxHost][kMaxDotsGrid]: per-block shares of the neighbouring-row dots (k_op_dots)
   long long partials_dots_count = 0;  // doubles behind partials_dots
 };
+constexpr int kFewMaxHost = 4;
 
 size_t common_bytes(int64_t n, int64_t K) {
   size_t b = 0;
@@ -79,8 +81,9 @@ size_t common_bytes(int64_t n, int64_t K) {
   b += 4 * align_up((K + 2) * 8, 256);        // red, coefA, coefB, coefC
   b += align_up((size_t)(K + 2) * kMaxDotsGrid * 8, 256);  // partials_dots
   b += align_up((size_t)kMaxCombineGrid * 8, 256);         // partials_comb
+  b += align_up((size_t)kFewMaxHost * kMaxDotsGrid * 8, 256);  // partials_few
   (void)n;
-  return b + 8 * 256;
+  return b + 9 * 256;
 }
 
 void carve_common(Workspace& w, int64_t K, Common& c) {
@@ -93,6 +96,7 @@ void carve_common(Workspace& w, int64_t K, Common& c) {
   c.partials_dots = static_cast<double*>(w.take((size_t)(K + 2) * kMaxDotsGrid * 8));
   c.partials_dots_count = (long long)(K + 2) * kMaxDotsGrid;
   c.partials_comb = static_cast<double*>(w.take((size_t)kMaxCombineGrid * 8));
+  c.partials_few = static_cast<double*>(w.take((size_t)kFewMaxHost * kMaxDotsGrid * 8));
 }
 
 // BL_STREAM=0 forces the register-staged (LDG) kernels; default: TMA-staged kernels for n >= 8192.
@@ -545,6 +549,10 @@ struct XDotsSpec {
   RowBlock rows;
   const double* out_div_ptr = nullptr;
   Epi epi;
+  // the neighbouring-row dots arrive as per-block shares (k_op_dots): the kernel adds them up and runs pre_epi first
+  const double* pre_partials = nullptr;
+  int pre_count = 0, pre_grid = 0;
+  Epi pre_epi;
 };
 
 bool xdots_enabled() {
@@ -578,6 +586,12 @@ int launch_xdots(const Common& c, const XDotsSpec& f, cudaStream_t s, bool* done
   a.epi = f.epi;
   a.epi.red = c.red;
   a.epi.scal = c.scal;
+  a.pre_partials = f.pre_partials;
+  a.pre_count = f.pre_count;
+  a.pre_grid = f.pre_grid;
+  a.pre_epi = f.pre_epi;
+  a.pre_epi.red = c.red;
+  a.pre_epi.scal = c.scal;
   const Epi full_epi = a.epi;
   int prc = BL_OK;
   const bool peer = arm_peer_epilogue(a.epi, f.rows.nrows, &prc);
@@ -801,6 +815,58 @@ int launch_step(std::vector<StepItem>& items, cudaStream_t s, bool* done) {
   return BL_OK;
 }
 
+// BL_OP_DOTS=1: one run alone takes its operator call and the block-local part of the neighbouring-row dots from ONE
+// plain launch (k_op_dots; 611 launches per run instead of 811).  Off by default: measured 23.8 vs 22.9 ms per forward +
+// adjoint at n = 1M -- inside a kernel whose blocks carry the 96 KB ring the operator call has 16 warps per SM instead
+// of the stand-alone SpMV's 40, and what the k_dots_few launch cost comes back as the longer operator kernel.
+bool op_dots_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("BL_OP_DOTS");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+// Operator call + block-local neighbouring-row dots of `items.size()` runs in one PLAIN launch (k_op_dots); the shares
+// land in each run's c.partials_few and the run's next k_xdots_tma launch finishes the reduction (XDotsSpec::pre_*).
+// `*done` stays false when the kernel does not apply.  `*grid_out`: blocks that wrote shares.
+template <typename T>
+int launch_op_dots(std::vector<StepItem>& items, double op_bytes, cudaStream_t s, bool* done, int* grid_out) {
+  *done = false;
+  constexpr int TILE = kConsumerThreads * Vec<T>::N;
+  const int total = (int)items.size();
+  if (total < 1 || total > kStepBatch || !op_dots_enabled() || !xdots_enabled() || stream_mode() != 1 || is_sharded())
+    return BL_OK;
+  const StepOp* sop = items[0].op;
+  const long long n = items[0].a.n;
+  if (sop == nullptr || !use_tma(n)) return BL_OK;
+  for (const StepItem& it : items)
+    if (it.op != sop || it.a.n != n || it.a.few_n < 1 || it.a.few_n > kFewMax || it.a.op_x == nullptr || it.a.op_x == it.a.few_x)
+      return BL_OK;
+  const size_t smem = step_smem_bytes<T>(total, kFewSlots, kGroup);
+  if (smem > 112 * 1024) return BL_OK;
+  BL_CHECK(set_smem(k_op_dots<T, TILE>, 112 * 1024));
+  const int grid = tma_grid<T>(n, TILE);
+  if (grid > kMaxDotsGrid) return BL_OK;
+  *done = true;
+  *grid_out = grid;
+  StepBatch B;
+  B.count = total;
+  B.acc_stride = kFewSlots;
+  B.coef_stride = kGroup;
+  B.op = *sop;
+  double bytes = op_bytes;  // + the rows of the dots (the operand's output is still on the chip)
+  for (int p = 0; p < total; ++p) {
+    B.a[p] = items[p].a;
+    B.a[p].partials = items[p].c->partials_few;
+    bytes += (double)items[p].a.few_n * n * sizeof(T);
+  }
+  ProfScope prof(BL_PROF_MATVEC, bytes, s);
+  k_op_dots<T, TILE><<<grid, kStreamThreads, smem, s>>>(B);
+  BL_LAUNCHED();
+  return BL_OK;
+}
+
 template <typename T>
 int launch_scale_copy(int64_t n, const T* x, double mul, const double* div_ptr, T* out, int64_t n_pad, cudaStream_t s) {
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(16 * sm_count(), (n_pad + 255) / 256));
@@ -1005,9 +1071,10 @@ struct FwdRun {
   }
   void unfuse() { std::swap(r, alt); }
   bool skip_step = false;  // the batch driver already tried the step kernel for this step
-  int post(int i) {
+  // pre_grid > 0: the operator call came from k_op_dots, which left the first pass's dots as per-block shares
+  int post(int i, int pre_grid = 0) {
     const int m = i + 1;
-    if (!skip_step) {
+    if (!skip_step && pre_grid == 0) {
       std::vector<StepItem> items(1);
       if (step_item(i, items[0])) {
         bool stepped = false;
@@ -1015,24 +1082,21 @@ struct FwdRun {
         if (stepped) return BL_OK;
       }
     }
-    {  // h = Q^H v (active columns only)                                       arnoldi.py:87
-      Epi e;
-      e.mode = EPI_FWD_A;
-      e.i = i;
-      e.K = K;
-      e.j0 = first_lo(i);
-      e.m = m - e.j0;
-      e.H = H;
-      e.coef = c.coefA;
-      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, e.j0, e.m), r, n, e, s));
-    }
+    Epi epi_a;  // h = Q^H v (active columns only)                              arnoldi.py:87
+    epi_a.mode = EPI_FWD_A;
+    epi_a.i = i;
+    epi_a.K = K;
+    epi_a.j0 = first_lo(i);
+    epi_a.m = m - epi_a.j0;
+    epi_a.H = H;
+    epi_a.coef = c.coefA;
     Epi norm_epi;  // length = sqrt(v . v); h[i+1] = length                      arnoldi.py:95-98
     norm_epi.mode = EPI_FWD_NORM;
     norm_epi.i = i;
     norm_epi.K = K;
     norm_epi.H = H;
     bool fused = false;
-    if (second_pass && local_first) {
+    auto pass_b_xdots = [&](bool with_pre) {
       // symmetric loop: v = v - h_{i-1} q_{i-1} - h_i q_i is a three-vector combination, and h2 = Q^H v streams
       // every active row once (no row is needed twice: nothing stays resident)   arnoldi.py:88,92
       XDotsSpec f;
@@ -1042,7 +1106,18 @@ struct FwdRun {
       for (int j = first_lo(i); j < m; ++j) f.vec[f.nvec++] = term(q_row(j), -1.0, c.coefA + j);
       f.rows = rows(Q, ld, 0, m);
       f.epi = pass_b_epi(i);
-      BL_CHECK(launch_xdots<T>(c, f, s, &fused));
+      if (with_pre) {
+        f.pre_partials = c.partials_few;
+        f.pre_count = epi_a.m;
+        f.pre_grid = pre_grid;
+        f.pre_epi = epi_a;
+      }
+      return launch_xdots<T>(c, f, s, &fused);
+    };
+    if (pre_grid > 0 && second_pass && local_first) BL_CHECK(pass_b_xdots(true));
+    if (!fused) {
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, epi_a.j0, epi_a.m), r, n, epi_a, s));
+      if (second_pass && local_first) BL_CHECK(pass_b_xdots(false));
     }
     if (second_pass && !fused) {
       // v = v - Q h and, from the same read of Q, h2 = Q^H v (the second pass's coefficients;
@@ -1100,6 +1175,14 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
         bool stepped = false;
         BL_CHECK(launch_step<T>(items, s, &stepped));
         if (stepped) continue;
+        // one run alone: operator call + block-local dots as one plain launch, reduction finished by k_xdots_tma
+        bool done = false;
+        int pre_grid = 0;
+        BL_CHECK(launch_op_dots<T>(items, op->matvec_bytes(dtype) + 1.0 * n * sizeof(T), s, &done, &pre_grid));
+        if (done) {
+          BL_CHECK(run.post(i, pre_grid));
+          continue;
+        }
         run.unfuse();
       }
     }
@@ -1414,9 +1497,10 @@ struct AdjRun {
     have_reproj = false;
   }
   bool skip_step = false;  // the batch driver already tried the step kernel for this step
-  int post(int idx) {
+  // pre_grid > 0: A^T lambda came from k_op_dots, which left the dots with rows idx-2..idx as per-block shares
+  int post(int idx, int pre_grid = 0) {
     T* Lrow = Lambda + (int64_t)idx * ld;
-    if (!skip_step) {
+    if (!skip_step && pre_grid == 0) {
       std::vector<StepItem> items(1);
       if (step_item(idx, items[0])) {
         bool done = false;
@@ -1427,24 +1511,21 @@ struct AdjRun {
         }
       }
     }
-    {  // Gamma[idx, :] and the coefficients of the back-substitution             arnoldi.py:212-218
-      Epi e;
-      e.mode = EPI_ADJ_GAMMA;
-      e.i = idx;
-      e.K = K;
-      e.j0 = band_lo(idx);
-      e.m = idx + 1 - e.j0;
-      e.Hc = H;
-      e.Gamma = Gamma;
-      e.PiGamma = PiGamma;
-      e.eta = eta;
-      e.coef = c.coefB;
-      e.coef2 = c.coefC;
-      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, e.j0, e.m), z, n, e, s));
-    }
+    Epi epi_g;  // Gamma[idx, :] and the coefficients of the back-substitution      arnoldi.py:212-218
+    epi_g.mode = EPI_ADJ_GAMMA;
+    epi_g.i = idx;
+    epi_g.K = K;
+    epi_g.j0 = band_lo(idx);
+    epi_g.m = idx + 1 - epi_g.j0;
+    epi_g.Hc = H;
+    epi_g.Gamma = Gamma;
+    epi_g.PiGamma = PiGamma;
+    epi_g.eta = eta;
+    epi_g.coef = c.coefB;
+    epi_g.coef2 = c.coefC;
     // lambda = (Pi_xi[idx] + Q gamma_row - alpha lambda + A^T lambda - Lambda beta_plus) / beta_minus
     have_reproj = false;
-    if (banded && idx > 0) {
+    auto back_substitution_xdots = [&](bool with_pre) {
       // banded Gamma: the back-substitution combines nine vectors at most, and the NEXT step's re-projection dots
       // t = P lambda stream rows 0..idx once                                    arnoldi.py:202,217-219
       XDotsSpec f;
@@ -1463,7 +1544,18 @@ struct AdjRun {
       f.epi.m = idx + 1;
       f.epi.dH = dH;
       f.epi.coef = c.coefA;
-      BL_CHECK(launch_xdots<T>(c, f, s, &have_reproj));
+      if (with_pre) {
+        f.pre_partials = c.partials_few;
+        f.pre_count = epi_g.m;
+        f.pre_grid = pre_grid;
+        f.pre_epi = epi_g;
+      }
+      return launch_xdots<T>(c, f, s, &have_reproj);
+    };
+    if (pre_grid > 0 && banded && idx > 0) BL_CHECK(back_substitution_xdots(true));
+    if (!have_reproj) {
+      BL_CHECK(launch_dots<T>(g, c, rows(Q, ld, epi_g.j0, epi_g.m), z, n, epi_g, s));
+      if (banded && idx > 0) BL_CHECK(back_substitution_xdots(false));
     }
     if (!have_reproj && reortho_full && idx > 0) {
       // ... fused with the NEXT step's re-projection dots t = P lambda (rows 0..idx of Q are the
@@ -1549,6 +1641,12 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
         BL_CHECK(launch_step<T>(items, s, &done));
         if (done) {
           run.stepped(idx);
+          continue;
+        }
+        int pre_grid = 0;  // one run alone: A^T lambda + block-local dots as one plain launch
+        BL_CHECK(launch_op_dots<T>(items, op->apply_transpose_bytes(dtype), s, &done, &pre_grid));
+        if (done) {
+          BL_CHECK(run.post(idx, pre_grid));
           continue;
         }
       }

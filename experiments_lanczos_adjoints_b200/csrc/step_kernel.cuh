@@ -146,27 +146,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, int tid) {
   tma::named_bar_sync(1, kConsumerThreads);
 }
 
-// fixed-order sum of one row of per-block partials by one warp; all loads of a lane are issued before the adds
-__device__ __forceinline__ double row_sum(const double* __restrict__ p, int G, int lane) {
-  double s = 0.0;
-  if ((G & 1) == 0 && G <= 320) {
-    const double2* p2 = reinterpret_cast<const double2*>(p);
-    const int nv = G >> 1;
-    double2 v[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int i = lane + 32 * k;
-      v[k] = __ldcg(p2 + (i < nv ? i : 0));
-      if (i >= nv) v[k] = make_double2(0.0, 0.0);
-    }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) s += v[k].x + v[k].y;
-  } else {
-    for (int k = lane; k < G; k += 32) s += __ldcg(p + k);
-  }
-  return warp_sum(s);
-}
-
 // Sum over blocks of the per-block values of every run: run p has nvals(p) values at vals(p)[0..), reduced in
 // place -- bit-identical in every block (fixed order).  Few values in total: one barrier, every block reduces all of
 // them.  Many: block j reduces value j (j, j+G, ... over the runs' values laid end to end), a second barrier,
@@ -431,6 +410,63 @@ __device__ __forceinline__ void op_phase_dispatch(const StepBatch& B, const OpRa
   }
 }
 
+// Phase 0, block-local part: this block's share of <few_j, x0> for every run, left in the run's scratch area
+// (acc_s + p * acc_stride + kFewMax * kConsumerWarps + j).
+template <typename T, int TILE, typename Sync>
+__device__ __forceinline__ void few_dots_local(const StepBatch& B, const ColumnRange& cr, long long n, double* acc_s,
+                                         int tid, int warp, int lane, Sync csync) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  const int P = B.count;
+  for (int p = 0; p < P; ++p) {
+    const StepArgs& a = B.a[p];
+    if (a.few_n <= 0) continue;
+    T facc[kFewMax];
+#pragma unroll
+    for (int r = 0; r < kFewMax; ++r) facc[r] = T(0);
+    const T* x0 = static_cast<const T*>(a.few_x);
+    for (int tt = 0; tt < cr.ntiles; ++tt) {
+      const long long c = cr.c0 + (long long)tt * TILE + (long long)tid * VN;
+      if (c >= cr.c1 || c >= n) continue;
+      T xx[VN];
+      if (c + VN <= n) {
+        vec_unpack(*reinterpret_cast<const V*>(x0 + c), xx);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VN; ++k) xx[k] = c + k < n ? x0[c + k] : T(0);
+      }
+#pragma unroll
+      for (int r = 0; r < kFewMax; ++r) {
+        if (r < a.few_n) {
+          T q[VN];  // basis rows are zero-padded up to ld: the straddling vector is readable
+          vec_unpack(*reinterpret_cast<const V*>(static_cast<const T*>(a.few_row[r]) + c), q);
+#pragma unroll
+          for (int k = 0; k < VN; ++k) facc[r] = fma(q[k], xx[k], facc[r]);
+        }
+      }
+    }
+    double* scratch = acc_s + (size_t)p * B.acc_stride;
+#pragma unroll
+    for (int r = 0; r < kFewMax; ++r) {
+      if (r < a.few_n) {
+        const double w = warp_sum(static_cast<double>(facc[r]));
+        if (lane == 0) scratch[r * kConsumerWarps + warp] = w;
+      }
+    }
+  }
+  csync();
+  for (int p = 0; p < P; ++p) {
+    double* scratch = acc_s + (size_t)p * B.acc_stride;
+    if (tid < B.a[p].few_n) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kConsumerWarps; ++w) s += scratch[tid * kConsumerWarps + w];
+      scratch[kFewMax * kConsumerWarps + tid] = s;  // this block's value of row tid
+    }
+  }
+  csync();
+}
+
 }  // namespace step
 
 template <typename T, int TILE>
@@ -584,53 +620,7 @@ k_step_tma(const __grid_constant__ StepBatch B) {
     bool any_few = false;
     for (int p = 0; p < P; ++p) any_few = any_few || B.a[p].few_n > 0;
     if (any_few) {
-      for (int p = 0; p < P; ++p) {
-        const StepArgs& a = B.a[p];
-        if (a.few_n <= 0) continue;
-        T facc[kFewMax];
-#pragma unroll
-        for (int r = 0; r < kFewMax; ++r) facc[r] = T(0);
-        const T* x0 = static_cast<const T*>(a.few_x);
-        for (int tt = 0; tt < cr.ntiles; ++tt) {
-          const long long c = cr.c0 + (long long)tt * TILE + (long long)tid * VN;
-          if (c >= cr.c1 || c >= n) continue;
-          T xx[VN];
-          if (c + VN <= n) {
-            vec_unpack(*reinterpret_cast<const V*>(x0 + c), xx);
-          } else {
-#pragma unroll
-            for (int k = 0; k < VN; ++k) xx[k] = c + k < n ? x0[c + k] : T(0);
-          }
-#pragma unroll
-          for (int r = 0; r < kFewMax; ++r) {
-            if (r < a.few_n) {
-              T q[VN];  // basis rows are zero-padded up to ld: the straddling vector is readable
-              vec_unpack(*reinterpret_cast<const V*>(static_cast<const T*>(a.few_row[r]) + c), q);
-#pragma unroll
-              for (int k = 0; k < VN; ++k) facc[r] = fma(q[k], xx[k], facc[r]);
-            }
-          }
-        }
-        double* scratch = acc_s + (size_t)p * B.acc_stride;
-#pragma unroll
-        for (int r = 0; r < kFewMax; ++r) {
-          if (r < a.few_n) {
-            const double w = warp_sum(static_cast<double>(facc[r]));
-            if (lane == 0) scratch[r * kConsumerWarps + warp] = w;
-          }
-        }
-      }
-      csync();
-      for (int p = 0; p < P; ++p) {
-        double* scratch = acc_s + (size_t)p * B.acc_stride;
-        if (tid < B.a[p].few_n) {
-          double s = 0.0;
-#pragma unroll
-          for (int w = 0; w < kConsumerWarps; ++w) s += scratch[tid * kConsumerWarps + w];
-          scratch[kFewMax * kConsumerWarps + tid] = s;  // this block's value of row tid
-        }
-      }
-      csync();
+      step::few_dots_local<T, TILE>(B, cr, n, acc_s, tid, warp, lane, csync);
       if (!(with_op && (B.op.l2_hints & 8))) step::stamp(B.trace_slot, 2, tid);
       step::grid_reduce<0>(B, acc_s, kFewMax * kConsumerWarps, tid);
       for (int p = 0; p < P; ++p) {
@@ -884,6 +874,67 @@ k_step_tma(const __grid_constant__ StepBatch B) {
     run_epilogue<T>(B.a[p].epi2);
     __syncthreads();
   }
+}
+
+// The operator call of ONE run's step together with the block-local part of the neighbouring-row dots, as a PLAIN
+// launch (the separate streaming kernels that follow prefetch basis rows before their dependency wait: the newest row
+// must be complete when they are scheduled).  Phase S as in k_step_tma; the block's shares of <few_j, A x> go to
+// partials[j * gridDim.x + block] and the NEXT kernel (k_xdots_tma, XDotsArgs::pre_*) adds them up in every block and
+// runs the epilogue itself -- no k_dots_few launch, no last-block pass, no grid barrier.
+template <typename T, int TILE>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+k_op_dots(const __grid_constant__ StepBatch B) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* stages = reinterpret_cast<T*>(smem_raw);
+  T* xs = stages + (size_t)kStages * kGroup * TILE;
+  uint64_t* op_full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xs) + step::kOpOverflow * 4);
+  uint64_t* op_empty = op_full + step::kOpStages;
+  double* acc_s = reinterpret_cast<double*>(reinterpret_cast<uint64_t*>(xs + 2 * TILE) + 2 * kStages + 2);
+  const long long n = B.a[0].n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < step::kOpStages; ++s) {
+      tma::mbar_init(op_full + s, 1);
+      tma::mbar_init(op_empty + s, kConsumerWarps);
+    }
+    tma::fence_barrier_init();
+  }
+  for (int j = threadIdx.x; j < B.count * B.acc_stride; j += blockDim.x) acc_s[j] = 0.0;
+  __syncthreads();
+  const ColumnRange cr = block_columns<T>(n, TILE);
+  const step::OpRange orng = step::op_range<T>(B.op, cr, n);
+  if (warp == kConsumerWarps) {
+    if (lane == 0 && orng.nstages > 0) {
+      constexpr int SLOTS = step::op_stage_slots<T>();
+      const int depth = B.op.depth;
+      for (int k = 0, s = 0, par = 1; k < orng.nstages; ++k) {
+        const long long pos = orng.a0 + (long long)k * SLOTS;
+        const uint32_t cnt = (uint32_t)((orng.a1 - pos) < SLOTS ? (orng.a1 - pos) : SLOTS);
+        tma::mbar_wait(op_empty + s, par);
+        const uint32_t over = s == 0 && k > 0 ? (cnt < (uint32_t)step::kOpOverflow ? cnt : (uint32_t)step::kOpOverflow) : 0u;
+        tma::mbar_arrive_expect_tx(op_full + s, (cnt + over) * 4u);
+        tma::bulk_g2s(smem_raw + (size_t)s * step::kOpStageBytes, B.op.col + pos, cnt * 4u, op_full + s);
+        if (over) tma::bulk_g2s(smem_raw + (size_t)depth * step::kOpStageBytes, B.op.col + pos, over * 4u, op_full + s);
+        if (++s == depth) {
+          s = 0;
+          par ^= 1;
+        }
+      }
+    }
+    return;
+  }
+  const int tid = threadIdx.x;
+  step::ConsumerSync csync;
+  if (B.op.norm)
+    step::op_phase_dispatch<T, true>(B, orng, smem_raw, op_full, op_empty, warp, lane);
+  else
+    step::op_phase_dispatch<T, false>(B, orng, smem_raw, op_full, op_empty, warp, lane);
+  csync();  // the rows written above are read back below (same block)
+  step::few_dots_local<T, TILE>(B, cr, n, acc_s, tid, warp, lane, csync);
+  for (int p = 0; p < B.count; ++p)
+    if (tid < B.a[p].few_n)
+      __stcg(B.a[p].partials + (size_t)tid * gridDim.x + blockIdx.x,
+             acc_s[(size_t)p * B.acc_stride + kFewMax * kConsumerWarps + tid]);
 }
 
 }  // namespace bl

@@ -270,6 +270,30 @@ k_dots_tma(RowSource src, int nrows, const T* __restrict__ x, long long n, doubl
 // in k_dots_tma.  Thread t of the 256 consumers owns one 16-byte column vector of the tile: it holds that vector
 // of every term in registers (loaded one tile ahead: only tile 0's loads are exposed, and they depend on the
 // predecessor anyway), writes the combined vector to `out` and to the shared x tile.
+namespace step {
+// fixed-order sum of one row of per-block partials by one warp; all loads of a lane are issued before the adds
+__device__ __forceinline__ double row_sum(const double* __restrict__ p, int G, int lane) {
+  double s = 0.0;
+  if ((G & 1) == 0 && G <= 320) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+    const int nv = G >> 1;
+    double2 v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int i = lane + 32 * k;
+      v[k] = __ldcg(p2 + (i < nv ? i : 0));
+      if (i >= nv) v[k] = make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s += v[k].x + v[k].y;
+  } else {
+    for (int k = lane; k < G; k += 32) s += __ldcg(p + k);
+  }
+  return warp_sum(s);
+}
+
+}  // namespace step
+
 constexpr int kXTerms = 10;
 
 struct XDotsArgs {
@@ -284,6 +308,12 @@ struct XDotsArgs {
   unsigned int* counter = nullptr;
   Epi epi;
   int reverse = 0;
+  // Optional: the predecessor (k_op_dots) left per-block shares of `pre_count` dot products in
+  // pre_partials[j * pre_grid + block]; every block adds them up in a fixed order and runs `pre_epi` on the sums
+  // (identical numbers, idempotent writes) before it reads the coefficients that epilogue produces.
+  const double* pre_partials = nullptr;
+  int pre_count = 0, pre_grid = 0;
+  Epi pre_epi;
 };
 
 template <typename T, int TILE>
@@ -340,6 +370,20 @@ k_xdots_tma(const __grid_constant__ XDotsArgs a) {
   } else {
     const int tid = threadIdx.x;  // 0..255: column vector tid of every tile
     tma::griddep_wait();          // the terms and their coefficients are the predecessor's output
+    if (a.pre_count > 0) {
+      __shared__ double pre_s[8];
+      if (warp < a.pre_count) {
+        const double sum = step::row_sum(a.pre_partials + (size_t)warp * a.pre_grid, a.pre_grid, lane);
+        if (lane == 0) pre_s[warp] = sum;
+      }
+      tma::named_bar_sync(1, kConsumerThreads);
+      struct PreSync {
+        __device__ __forceinline__ void operator()() const { tma::named_bar_sync(1, kConsumerThreads); }
+      };
+      run_epilogue_impl<T>(a.pre_epi, pre_s, tid, kConsumerThreads, PreSync());
+      __threadfence();  // the coefficients go through global memory (every block writes the same values)
+      tma::named_bar_sync(1, kConsumerThreads);
+    }
     T cv[kXTerms];
 #pragma unroll
     for (int v = 0; v < kXTerms; ++v)
