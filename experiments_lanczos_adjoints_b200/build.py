@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
 ]  # fmt: skip
+NVCC_FLAGS += os.environ.get("BL_NVCC_EXTRA", "").split()  # e.g. -DBL_STEP_DEBUG (debug builds; part of the stamp)
 
 
 def sources():

@@ -659,6 +659,11 @@ bool step_op_enabled() {
 // norm: the forward's q = v / len on the way, rows written up to n_pad.
 bool make_step_op(bl_operator_t* op, int dtype, bool transpose, bool norm, int64_t n, int64_t n_pad, StepOp* so) {
   if (!step_op_enabled() || step_mode() == 0) return false;
+  static const int sides = [] {  // BL_STEP_OP_SIDES: bit 0 forward sweeps, bit 1 adjoint sweeps (debugging)
+    const char* e = std::getenv("BL_STEP_OP_SIDES");
+    return e ? std::atoi(e) : 3;
+  }();
+  if (!(sides & (transpose ? 2 : 1))) return false;
   SellView v;
   if (!op->sell_view(dtype, transpose, &v)) return false;
   if (v.nrows != n || (norm && n_pad > v.nslices * 32)) return false;
@@ -687,7 +692,7 @@ bool make_step_op(bl_operator_t* op, int dtype, bool transpose, bool norm, int64
 template <typename T>
 size_t step_smem_bytes(int count, int acc_stride, int coef_stride) {
   constexpr int TILE = kConsumerThreads * Vec<T>::N;
-  return (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 2) * 8 +
+  return (size_t)(kStages * kGroup + 2) * TILE * sizeof(T) + (2 * kStages + 2 + 2 * kOpStagesHost) * 8 +
          (size_t)count * acc_stride * 8 + (size_t)count * coef_stride * sizeof(T) + 16;
 }
 
@@ -760,6 +765,7 @@ int launch_step(std::vector<StepItem>& items, cudaStream_t s, bool* done) {
       StepArgs& a = it.a;
       const Common& c = *it.c;
       a.partials = c.partials_dots;
+      a.partials0 = c.partials_few;
       a.red_g = c.red;
       a.partials_norm = c.partials_comb;
       for (Epi* e : {&a.epi0, &a.epi1, &a.epi2}) {
@@ -1977,6 +1983,18 @@ int bl_arnoldi_adjoint_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K,
                                          (const double*)dH, (const double*)dr, (const double*)dc, (double*)dv, lddv,
                                          (double*)Lambda, workspace, workspace_bytes, s);
 }
+
+#ifdef BL_STEP_DEBUG
+extern "C" int bl_step_debug_read(unsigned long long* out16, int reset) {
+  BL_CUDA(cudaDeviceSynchronize());
+  BL_CUDA(cudaMemcpyFromSymbol(out16, bl::g_step_dbg, 16 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    BL_CUDA(cudaMemcpyToSymbol(bl::g_step_dbg, z, sizeof(z)));
+  }
+  return BL_OK;
+}
+#endif
 
 int bl_step_trace_begin(void) {
   g_step_trace_next.store(0, std::memory_order_relaxed);

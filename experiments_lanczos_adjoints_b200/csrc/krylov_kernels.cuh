@@ -122,11 +122,13 @@ __device__ void run_epilogue_impl(const Epi& e, const double* red, const int t, 
         if (i + 1 < K) static_cast<T*>(e.H)[(size_t)(i + 1) * K + i] = len;  // dropped at i+1 == K
       }
     } break;
+    // The adjoint's epilogues read what EARLIER kernels of the sweep wrote (Gamma rows, eta) and run redundantly in
+    // every block of k_step_tma: through L2 (`ld.global.cg` / `st.global.cg`), like everything else that crosses blocks.
     case EPI_ADJ_ETA: {
       const T* dH = static_cast<const T*>(e.dH);
       for (int j = t; j < K; j += nt) {
         double r = e.m > 0 ? red[j] : 0.0;
-        e.eta[j] = static_cast<double>(static_cast<T>(static_cast<double>(dH[(size_t)j * K + (K - 1)]) - r));
+        e.eta[j] = static_cast<double>(static_cast<T>(static_cast<double>(__ldcg(dH + (size_t)j * K + (K - 1))) - r));
         e.coef[j] = e.eta[j];
       }
     } break;
@@ -134,7 +136,7 @@ __device__ void run_epilogue_impl(const Epi& e, const double* red, const int t, 
       const T* dH = static_cast<const T*>(e.dH);
       // rows j <= idx+1 of P are active; p = mask * dH[:, idx]
       for (int j = t; j < e.m; j += nt)
-        e.coef[j] = static_cast<double>(static_cast<T>(static_cast<double>(dH[(size_t)j * K + i]) - red[j]));
+        e.coef[j] = static_cast<double>(static_cast<T>(static_cast<double>(__ldcg(dH + (size_t)j * K + i)) - red[j]));
     } break;
     case EPI_ADJ_GAMMA: {
       const T* H = static_cast<const T*>(e.Hc);
@@ -143,25 +145,26 @@ __device__ void run_epilogue_impl(const Epi& e, const double* red, const int t, 
       for (int j = t; j < K; j += nt) {
         double g = 0.0;
         if (j <= idx && j >= e.j0) {
-          g = e.PiGamma[(size_t)idx * K + j] - red[j - e.j0];
+          g = __ldcg(e.PiGamma + (size_t)idx * K + j) - red[j - e.j0];
           if (j == idx) g *= 0.5;
           g = static_cast<double>(static_cast<T>(g));
         }
-        e.Gamma[(size_t)idx * K + j] = g;
+        __stcg(e.Gamma + (size_t)idx * K + j, g);
       }
+      __threadfence();
       sync();
       for (int j = t; j < K; j += nt) {
         // (Gamma + Gamma^T)[idx, j]
         e.coef[j] = static_cast<double>(
-            static_cast<T>(e.Gamma[(size_t)idx * K + j] + e.Gamma[(size_t)j * K + idx]));
+            static_cast<T>(__ldcg(e.Gamma + (size_t)idx * K + j) + __ldcg(e.Gamma + (size_t)j * K + idx)));
         // -beta_plus[j] = -H[idx, j] for j > idx (diagonal and sub-diagonal removed)
-        e.coef2[j] = j > idx ? -static_cast<double>(H[(size_t)idx * K + j]) : 0.0;
+        e.coef2[j] = j > idx ? -static_cast<double>(__ldcg(H + (size_t)idx * K + j)) : 0.0;
       }
       if (t == 0) {
-        e.scal[S_NEG_ALPHA] = -static_cast<double>(H[(size_t)idx * K + idx]);
-        double bm = idx == 0 ? 1.0 : static_cast<double>(H[(size_t)idx * K + idx - 1]);
+        e.scal[S_NEG_ALPHA] = -static_cast<double>(__ldcg(H + (size_t)idx * K + idx));
+        double bm = idx == 0 ? 1.0 : static_cast<double>(__ldcg(H + (size_t)idx * K + idx - 1));
         e.scal[S_BETA_MINUS] = bm;  // combine divides by it (lambda_k /= beta_minus)
-        e.scal[S_ETA_IDX] = e.eta[idx];
+        e.scal[S_ETA_IDX] = __ldcg(e.eta + idx);
       }
     } break;
     case EPI_L3_ALPHA: {

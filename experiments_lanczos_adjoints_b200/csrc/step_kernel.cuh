@@ -82,7 +82,9 @@ struct StepArgs {
   int norm = 0;  // ||out2||^2 -> epi2 (run by the last block to leave)
   Epi epi2;
   // ---- reductions (per run) ----
-  double* partials = nullptr;       // [rows][gridDim.x]
+  double* partials = nullptr;       // [rows][gridDim.x]: phase 1
+  double* partials0 = nullptr;      // [kFewMax][gridDim.x]: phase 0 -- an area of its own: a block that is fast through a
+                                    // short phase 1 must not overwrite shares a slow block is still adding up
   double* red_g = nullptr;          // [rows] reduced values of the distributed path
   double* partials_norm = nullptr;  // [gridDim.x]
   int wait_row = 1 << 30;  // rows >= wait_row of src1 are the predecessor kernel's output: the producer
@@ -105,6 +107,36 @@ struct StepBatch {
 constexpr int kTraceStamps = 8;
 constexpr int kTraceLaunches = 2048;
 __device__ unsigned long long g_step_trace[kTraceStamps * kTraceLaunches];
+
+#ifdef BL_STEP_DEBUG
+// Debugging (-DBL_STEP_DEBUG): the FIRST non-finite value a k_step_tma launch meets, where it met it.
+__device__ unsigned long long g_step_dbg[16];
+__device__ __forceinline__ void dbg_record(int code, int p, int step_i, long long a, double v0, double v1) {
+  if (atomicCAS(&g_step_dbg[0], 0ull, (unsigned long long)code) == 0ull) {
+    g_step_dbg[1] = blockIdx.x;
+    g_step_dbg[2] = threadIdx.x;
+    g_step_dbg[3] = (unsigned long long)p;
+    g_step_dbg[4] = (unsigned long long)step_i;
+    g_step_dbg[5] = (unsigned long long)a;
+    g_step_dbg[6] = (unsigned long long)__double_as_longlong(v0);
+    g_step_dbg[7] = (unsigned long long)__double_as_longlong(v1);
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_step_dbg[8] = smid;
+    __threadfence();
+  }
+}
+#define BL_DBG(cond, code, p, i, a, v0, v1) \
+  do {                                      \
+    if (cond) dbg_record(code, p, i, a, v0, v1); \
+  } while (0)
+template <typename X>
+__device__ __forceinline__ bool dbg_bad(X v) { return !(fabs((double)v) < 1e30); }
+#else
+#define BL_DBG(cond, code, p, i, a, v0, v1) \
+  do {                                      \
+  } while (0)
+#endif
 
 namespace step {
 
@@ -163,7 +195,8 @@ __device__ __forceinline__ void grid_reduce(const StepBatch& B, double* acc_base
   for (int p = 0; p < B.count; ++p) {
     const int nv = nvals_of<PHASE>(B.a[p]);
     const double* src = acc_base + (size_t)p * B.acc_stride + val_off;
-    for (int j = tid; j < nv; j += kConsumerThreads) __stcg(B.a[p].partials + (size_t)j * G + b, src[j]);
+    double* part = PHASE == 0 ? B.a[p].partials0 : B.a[p].partials;
+    for (int j = tid; j < nv; j += kConsumerThreads) __stcg(part + (size_t)j * G + b, src[j]);
     total += nv;
   }
   grid_barrier(B.bar, tid);
@@ -171,7 +204,7 @@ __device__ __forceinline__ void grid_reduce(const StepBatch& B, double* acc_base
   for (int v = everyone ? warp : b + warp * G; v < total; v += everyone ? kConsumerWarps : kConsumerWarps * G) {
     int p = 0, j = v;
     while (j >= nvals_of<PHASE>(B.a[p])) j -= nvals_of<PHASE>(B.a[p++]);
-    const double s = row_sum(B.a[p].partials + (size_t)j * G, G, lane);
+    const double s = row_sum((PHASE == 0 ? B.a[p].partials0 : B.a[p].partials) + (size_t)j * G, G, lane);
     if (lane == 0) {
       if (everyone)
         acc_base[(size_t)p * B.acc_stride + val_off + j] = s;
@@ -190,8 +223,7 @@ __device__ __forceinline__ void grid_reduce(const StepBatch& B, double* acc_base
 }
 
 // ---- phase S: the operator call (SELL-32) ----
-// Phase S uses the ring's memory as kOpStages FINE stages with barriers of their own (they live in the x-tile buffer,
-// which phase 1 only needs later): a stage is held by a consumer warp for a gather round trip (~2 us), so what stays
+// Phase S uses the ring's memory as kOpStages FINE stages with barriers of their own: a stage is held by a consumer warp for a gather round trip (~2 us), so what stays
 // in flight is (ring - held stages) -- with the three 32 KB stages of the basis stream that is one stage per block
 // and the operand arrives at a fraction of the HBM rate.  Only the COLUMN INDICES go through the ring (the gathers
 // depend on them); the values are plain coalesced loads issued together with the gathers, so they cost no round trip
@@ -244,6 +276,10 @@ __device__ __forceinline__ OpRange op_range(const StepOp& op, const ColumnRange&
   return o;
 }
 
+// Loads of what a PREDECESSOR kernel wrote (x here, the vectors of phase 0) go through L2 (`ld.global.cg`): in a chain of
+// programmatic dependent launches this kernel's lifetime overlaps the predecessor's, which is outside what `ld.global.nc`
+// promises, and L1 buys nothing measurable here (BL_STEP_L2 bit 6 switches the gathers back to `ld.global.nc`: 5558 vs
+// 5532 Krylov steps/s, within the noise).
 // Consumer side: warp w takes the block's slices w, w + 8, ...; lane = row within the slice.  Summation order as in
 // k_sell_spmv_multi (entries k of even / odd position in two accumulators, added at the end): bit-identical results.
 // U slices of the warp are in flight together (their W x P gathers each are issued before the first FMA): with 16
@@ -327,7 +363,7 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-          xr[u][p] = NORM && u < nu && r[u] < op.nrows ? x[p][r[u]] : T(0);
+          xr[u][p] = NORM && u < nu && r[u] < op.nrows ? __ldcg(x[p] + r[u]) : T(0);
           acc0[u][p] = acc1[u][p] = T(0);
         }
       for (int k0 = 0; k0 < wmax; k0 += W) {
@@ -364,12 +400,25 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
           }
         }
         T g[U][W][P];
+#ifdef BL_STEP_DEBUG
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            BL_DBG(c[u][j] < 0 || c[u][j] >= op.nrows, 1, u, B.a[0].epi0.i, c[u][j], (double)(rel[u] + k0 * 32), (double)j);
+            if (c[u][j] < 0 || c[u][j] >= op.nrows) c[u][j] = 0;
+            BL_DBG(dbg_bad(v[u][j]), 3, u, B.a[0].epi0.i, rel[u] + k0 * 32 + j * 32, (double)v[u][j], 0.0);
+          }
+#endif
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int j = 0; j < W; ++j)
 #pragma unroll
-            for (int p = 0; p < P; ++p) g[u][j][p] = (op.l2_hints & 16) ? T(c[u][j]) : __ldg(x[p] + c[u][j]);
+            for (int p = 0; p < P; ++p) {  // through L2 (see the note above)
+              g[u][j][p] = (op.l2_hints & 16) ? T(c[u][j]) : ((op.l2_hints & 64) ? __ldg(x[p] + c[u][j]) : __ldcg(x[p] + c[u][j]));
+              BL_DBG(dbg_bad(g[u][j][p]), 2, p, B.a[p].epi0.i, c[u][j], (double)g[u][j][p], (double)inv[p]);
+            }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -387,6 +436,7 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int p = 0; p < P; ++p) {
+          BL_DBG(u < nu && r[u] < op.nrows && dbg_bad(acc0[u][p] + acc1[u][p]), 4, p, B.a[p].epi0.i, r[u], (double)acc0[u][p], (double)inv[p]);
           if (u < nu && r[u] < op.nrows) static_cast<T*>(const_cast<void*>(B.a[p].few_x))[r[u]] = acc0[u][p] + acc1[u][p];
           if (NORM && u < nu && r[u] < op.n_pad)
             static_cast<T*>(B.a[p].op_q)[r[u]] = r[u] < op.nrows ? xr[u][p] * T(1) / dlen[p] : T(0);
@@ -430,16 +480,16 @@ __device__ __forceinline__ void few_dots_local(const StepBatch& B, const ColumnR
       if (c >= cr.c1 || c >= n) continue;
       T xx[VN];
       if (c + VN <= n) {
-        vec_unpack(*reinterpret_cast<const V*>(x0 + c), xx);
+        vec_unpack(__ldcg(reinterpret_cast<const V*>(x0 + c)), xx);  // through L2 (op_phase's note)
       } else {
 #pragma unroll
-        for (int k = 0; k < VN; ++k) xx[k] = c + k < n ? x0[c + k] : T(0);
+        for (int k = 0; k < VN; ++k) xx[k] = c + k < n ? __ldcg(x0 + c + k) : T(0);
       }
 #pragma unroll
       for (int r = 0; r < kFewMax; ++r) {
         if (r < a.few_n) {
           T q[VN];  // basis rows are zero-padded up to ld: the straddling vector is readable
-          vec_unpack(*reinterpret_cast<const V*>(static_cast<const T*>(a.few_row[r]) + c), q);
+          vec_unpack(__ldcg(reinterpret_cast<const V*>(static_cast<const T*>(a.few_row[r]) + c)), q);
 #pragma unroll
           for (int k = 0; k < VN; ++k) facc[r] = fma(q[k], xx[k], facc[r]);
         }
@@ -461,6 +511,7 @@ __device__ __forceinline__ void few_dots_local(const StepBatch& B, const ColumnR
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < kConsumerWarps; ++w) s += scratch[tid * kConsumerWarps + w];
+      BL_DBG(dbg_bad(s), 5, p, B.a[p].epi0.i, tid, s, 0.0);
       scratch[kFewMax * kConsumerWarps + tid] = s;  // this block's value of row tid
     }
   }
@@ -482,9 +533,13 @@ k_step_tma(const __grid_constant__ StepBatch B) {
   uint64_t* full = reinterpret_cast<uint64_t*>(xs + 2 * TILE);
   uint64_t* empty = full + kStages;
   uint64_t* gate = empty + kStages;  // phase S done in this block: the ring is free, its rows of the newest basis vector are written
-  uint64_t* op_full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xs) + step::kOpOverflow * 4);  // phase S's barriers
+  // Phase S's barriers have memory of their OWN.  (They used to live in the x-tile buffer, which phase 1 overwrites
+  // long after the last arrival -- with a block of another lane's kernel on the same SM the x tile then came back with
+  // barrier words in it: 12 vectors of NaN exactly where the 24 barriers had been.  PTX wants mbarrier.inval before
+  // an mbarrier's memory is put to another use; here the memory simply is not reused.)
+  uint64_t* op_full = empty + kStages + 2;
   uint64_t* op_empty = op_full + step::kOpStages;
-  double* acc_s = reinterpret_cast<double*>(empty + kStages + 2);   // [count][acc_stride]: dots of phase 1, in place reduced
+  double* acc_s = reinterpret_cast<double*>(op_empty + step::kOpStages);   // [count][acc_stride]: dots of phase 1, in place reduced
   T* coef_s = reinterpret_cast<T*>(acc_s + (size_t)B.count * B.acc_stride);  // [count][coef_stride]
   __shared__ double red_smem[32];
 
@@ -625,6 +680,8 @@ k_step_tma(const __grid_constant__ StepBatch B) {
       step::grid_reduce<0>(B, acc_s, kFewMax * kConsumerWarps, tid);
       for (int p = 0; p < P; ++p) {
         if (B.a[p].few_n <= 0) continue;
+        BL_DBG(tid < B.a[p].few_n && dbg_bad(acc_s[(size_t)p * B.acc_stride + kFewMax * kConsumerWarps + tid]), 6, p,
+               B.a[p].epi0.i, tid, acc_s[(size_t)p * B.acc_stride + kFewMax * kConsumerWarps + tid], 0.0);
         run_epilogue_impl<T>(B.a[p].epi0, acc_s + (size_t)p * B.acc_stride + kFewMax * kConsumerWarps, tid,
                              kConsumerThreads, csync);
       }
@@ -635,7 +692,8 @@ k_step_tma(const __grid_constant__ StepBatch B) {
       csync();
       step::stamp(B.trace_slot, 3, tid);
     }
-    if (with_op) tma::griddep_launch_dependents();  // every block is past phase S (phase 0's barrier)
+    // every block is past phase S (phase 0's barrier); BL_STEP_L2 bit 7: no early trigger (debugging)
+    if (with_op && !(B.op.l2_hints & 128)) tma::griddep_launch_dependents();
 
     // ================= phase 1: out1 = (sum of terms) / div, red1[j] = <row_j, out1>, every run =================
     int it = it0, xt = 0;
@@ -649,6 +707,11 @@ k_step_tma(const __grid_constant__ StepBatch B) {
       for (int v = 0; v < kXTerms; ++v)
         cv[v] = v < a.nvec ? static_cast<T>(a.vec[v].coef_imm * (a.vec[v].coef_ptr ? __ldcg(a.vec[v].coef_ptr) : 1.0)) : T(0);
       const T oscale = a.out_div_ptr ? static_cast<T>(__ldcg(a.out_div_ptr)) : T(1);
+#ifdef BL_STEP_DEBUG
+#pragma unroll
+      for (int v = 0; v < kXTerms; ++v) BL_DBG(tid == 0 && dbg_bad(cv[v]), 7, p, a.epi0.i, v, (double)cv[v], (double)oscale);
+      BL_DBG(tid == 0 && (dbg_bad(oscale) || oscale == T(0)), 7, p, a.epi0.i, 99, (double)oscale, 0.0);
+#endif
       V term[kXTerms];
       auto load_terms = [&](int tt) {  // this thread's vector of every term, tile tt (columns past n read as zero)
         const int t = dir1 ? cr.ntiles - 1 - tt : tt;
@@ -689,7 +752,10 @@ k_step_tma(const __grid_constant__ StepBatch B) {
               T e[VN];
               vec_unpack(term[v], e);
 #pragma unroll
-              for (int k = 0; k < VN; ++k) acc[k] = fma(cv[v], e[k], acc[k]);
+              for (int k = 0; k < VN; ++k) {
+                BL_DBG(dbg_bad(e[k]), 8, p, a.epi0.i, v * 100000000ll + tc0 + tid * VN + k, (double)e[k], (double)cv[v]);
+                acc[k] = fma(cv[v], e[k], acc[k]);
+              }
             }
           }
           const long long c = tc0 + (long long)tid * VN;
@@ -728,6 +794,13 @@ k_step_tma(const __grid_constant__ StepBatch B) {
                 T q[VN], xx[VN];
                 vec_unpack(row[lane + 32 * u], q);
                 vec_unpack(xr[u], xx);
+#ifdef BL_STEP_DEBUG
+#pragma unroll
+                for (int k = 0; k < VN; ++k) {
+                  BL_DBG(dbg_bad(q[k]), 9, p, a.epi0.i, j * 100000000ll + tc0 + (lane + 32 * u) * VN + k, (double)q[k], (double)s);
+                  BL_DBG(dbg_bad(xx[k]), 10, p, a.epi0.i, j * 100000000ll + tc0 + (lane + 32 * u) * VN + k, (double)xx[k], 0.0);
+                }
+#endif
 #pragma unroll
                 for (int k = 0; k < VN; ++k) {
                   if (u & 1)
@@ -751,8 +824,11 @@ k_step_tma(const __grid_constant__ StepBatch B) {
     csync();
     step::stamp(B.trace_slot, 4, tid);
     step::grid_reduce<1>(B, acc_s, 0, tid);
-    for (int p = 0; p < P; ++p)
+    for (int p = 0; p < P; ++p) {
+      BL_DBG(tid < B.a[p].nrows1 && dbg_bad(acc_s[(size_t)p * B.acc_stride + tid]), 11, p, B.a[p].epi0.i, tid,
+             acc_s[(size_t)p * B.acc_stride + tid], 0.0);
       run_epilogue_impl<T>(B.a[p].epi1, acc_s + (size_t)p * B.acc_stride, tid, kConsumerThreads, csync);
+    }
     __threadfence();
     csync();
 
@@ -887,9 +963,9 @@ k_op_dots(const __grid_constant__ StepBatch B) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* stages = reinterpret_cast<T*>(smem_raw);
   T* xs = stages + (size_t)kStages * kGroup * TILE;
-  uint64_t* op_full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xs) + step::kOpOverflow * 4);
+  uint64_t* op_full = reinterpret_cast<uint64_t*>(xs + 2 * TILE) + 2 * kStages + 2;  // the layout of k_step_tma
   uint64_t* op_empty = op_full + step::kOpStages;
-  double* acc_s = reinterpret_cast<double*>(reinterpret_cast<uint64_t*>(xs + 2 * TILE) + 2 * kStages + 2);
+  double* acc_s = reinterpret_cast<double*>(op_empty + step::kOpStages);
   const long long n = B.a[0].n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {

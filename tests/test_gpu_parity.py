@@ -579,6 +579,54 @@ def test_concurrent_plans_on_separate_streams_match_their_solo_runs():
     assert rel_err(solo[0][0], solo[1][0]) > 1e-3  # different probes: the comparison above is not vacuous
 
 
+def test_two_lockstep_lanes_in_flight_reproduce_their_solo_runs_bit_for_bit():
+    """The bench configuration: two lockstep batches of four runs on two streams, one block per SM and kernel, so a
+    block of each lane's step kernel shares every SM -- at the headline size (the failure this test pins needs both
+    lanes' blocks resident together: phase S's mbarriers once lived in the x-tile buffer, and with another kernel's
+    block on the SM the tile came back with barrier words in it; NaN rows in Q / Lambda a few steps later)."""
+    from experiments_lanczos_adjoints_b200 import device as dev
+    from experiments_lanczos_adjoints_b200 import plan as bl_plan
+    from experiments_lanczos_adjoints_b200 import synthetic
+
+    n, K, P, lanes, dtype = 1_000_000, 16, 4, 2, np.float32
+    row, col, data = synthetic.banded_spd_coo(n, 5, seed=0)
+    rng = np.random.default_rng(1)
+    ops = [bl.operators.SparseOperator(row, col, (n, n))]
+    ops += [ops[0].clone() for _ in range(lanes - 1)]
+    plans = [bl_plan.BatchedTridiagAdjointPlan(o, K, dtype, P, stream=dev.Stream()) for o in ops]
+    dH = np.stack([synthetic.slq_cotangent_dH(rng.standard_normal(K), rng.standard_normal(K - 1), dtype) for _ in range(P)])
+    vs = [(rng.integers(0, 2, size=(P, n)) * 2 - 1).astype(dtype) / np.sqrt(n) for _ in range(lanes)]
+
+    def load():
+        for pl, v in zip(plans, vs):
+            pl.set_vectors(v)
+            pl.set_params(data.astype(dtype))
+            pl.set_cotangents(dH)
+        bl.synchronize()
+
+    def results(pl):
+        return [a.numpy(pl.stream).copy() for a in (pl.H, pl.dv, pl.grads[0])]
+
+    with dev.blocks_per_sm(1):
+        load()
+        solo = []
+        for pl in plans:  # one lane at a time
+            pl.run()
+            bl.synchronize()
+            solo.append(results(pl))
+        assert all(np.isfinite(a).all() for res in solo for a in res)
+        for rep in range(4):  # both lanes in flight
+            load()
+            for pl in plans:
+                pl.forward()
+            for pl in plans:
+                pl.adjoint()
+            bl.synchronize()
+            for li, pl in enumerate(plans):
+                for name, got, want in zip(("H", "dv", "dparams"), results(pl), solo[li]):
+                    assert np.array_equal(got, want), f"rep {rep} lane {li}: {name} differs from the solo run"
+
+
 @pytest.mark.parametrize("mode", ["lockstep", "streams"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_slq_estimator_with_probes_in_flight_matches_the_sequential_loop(dtype, mode, monkeypatch):
