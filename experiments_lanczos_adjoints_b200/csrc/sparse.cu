@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "operators.cuh"
+#include "tma_pipeline.cuh"
 
 namespace bl {
 
@@ -336,6 +337,147 @@ k_sell_grad_batch(int64_t nrows, const int64_t* __restrict__ slice_ptr, const in
   }
 }
 
+// The same pass with the (lambda, q) pairs STAGED by the TMA engine.  k_sell_grad_batch keeps two pairs in flight per
+// warp and is bound by the round trip of its loads (3.96 ms for the 400 pairs of a lockstep batch at n = 1M, where the
+// bytes take 0.5 ms).  Here a block owns kGradRows consecutive rows (8 slices); its rows of Lam[m] are one contiguous
+// segment, and so is the WINDOW of columns its entries touch when the operand is banded or locally clustered: a
+// producer thread streams both segments of pair m = count-1 .. 0 through a ring of shared-memory stages (bulk copies,
+// mbarrier completion), the consumer warps read lambda and gather q from the stage -- no registers and no warp slots
+// are spent on loads in flight, and a block keeps the whole ring outstanding.  Same summation order, same arithmetic:
+// bit-identical to k_sell_grad_batch.  A block whose window does not fit (kGradWinMax columns) gathers from global
+// memory as before.
+constexpr int kGradRows = 256;    // rows of a block: 8 slices, one consumer warp each
+constexpr int kGradWarps = kGradRows / kSlice;
+constexpr int kGradWinMax = 512;  // columns of the q window a stage can hold
+constexpr int kGradStageBytes = 48 * 1024;
+
+template <typename T>
+constexpr int grad_stages() {
+  return kGradStageBytes / ((kGradRows + kGradWinMax) * (int)sizeof(T));
+}
+
+template <typename T, int W>
+__global__ void __launch_bounds__((kGradWarps + 1) * 32)
+k_sell_grad_tma(int64_t nrows, int64_t nslices, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+                T* __restrict__ grad, const T* __restrict__ Q, int64_t ldq, const T* __restrict__ Lam, int64_t ldl,
+                int count) {
+  constexpr int STAGES = grad_stages<T>();
+  constexpr int STAGE_ELEMS = kGradRows + kGradWinMax;
+  constexpr int ALIGN = 16 / (int)sizeof(T);  // elements per 16 bytes (bulk copies)
+  extern __shared__ __align__(128) unsigned char grad_smem[];
+  T* stages = reinterpret_cast<T*>(grad_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)STAGES * STAGE_ELEMS);
+  uint64_t* empty = full + STAGES;
+  __shared__ int win_s[3];  // min column, max column, max width over the block's slices
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kGradRows;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tma::mbar_init(full + s, 1);
+      tma::mbar_init(empty + s, kGradWarps);
+    }
+    tma::fence_barrier_init();
+    win_s[0] = 0x7fffffff;
+    win_s[1] = -1;
+    win_s[2] = 0;
+  }
+  __syncthreads();
+  const int64_t slice = (int64_t)blockIdx.x * kGradWarps + warp;
+  const bool consumer = warp < kGradWarps;
+  const bool active = consumer && slice < nslices;
+  const int64_t r = slice * kSlice + lane;
+  int64_t s0 = 0;
+  int width = 0;
+  if (active) {
+    s0 = slice_ptr[slice];
+    width = (int)((slice_ptr[slice + 1] - s0) / kSlice);
+    int cmin = 0x7fffffff, cmax = -1;
+    if (r < nrows)
+      for (int k = 0; k < width; ++k) {
+        const int c = ld_stream_i32(col + s0 + (int64_t)k * kSlice + lane);
+        cmin = c < cmin ? c : cmin;
+        cmax = c > cmax ? c : cmax;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int a = __shfl_xor_sync(0xffffffffu, cmin, o), b = __shfl_xor_sync(0xffffffffu, cmax, o);
+      cmin = a < cmin ? a : cmin;
+      cmax = b > cmax ? b : cmax;
+    }
+    if (lane == 0) {
+      atomicMin(&win_s[0], cmin);
+      atomicMax(&win_s[1], cmax);
+      atomicMax(&win_s[2], width);
+    }
+  }
+  __syncthreads();
+  const int cmin = win_s[0], cmax = win_s[1], wmax = win_s[2];
+  if (cmax < cmin || wmax == 0) return;  // nothing stored in these rows
+  const int w0 = cmin / ALIGN * ALIGN;
+  const int wlen = (cmax + 1 - w0 + ALIGN - 1) / ALIGN * ALIGN;
+  const bool staged = wlen <= kGradWinMax;
+  const int npass = (wmax + W - 1) / W;
+  if (!consumer) {
+    if (lane == 0 && staged) {  // ---- producer ----
+      const int64_t lrows = ldl - row0 < kGradRows ? ldl - row0 : kGradRows;  // ld is a multiple of 16 bytes
+      const uint32_t bytes_l = (uint32_t)(lrows * (int64_t)sizeof(T)), bytes_q = (uint32_t)wlen * (uint32_t)sizeof(T);
+      int it = 0;
+      for (int pass = 0; pass < npass; ++pass)
+        for (int m = count - 1; m >= 0; --m, ++it) {
+          const int s = it % STAGES;
+          tma::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
+          tma::mbar_arrive_expect_tx(full + s, bytes_l + bytes_q);
+          T* dst = stages + (size_t)s * STAGE_ELEMS;
+          tma::bulk_g2s(dst, Lam + (int64_t)m * ldl + row0, bytes_l, full + s);
+          tma::bulk_g2s(dst + kGradRows, Q + (int64_t)m * ldq + w0, bytes_q, full + s);
+        }
+    }
+    return;
+  }
+  const bool live = active && r < nrows;
+  int it = 0;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int k0 = pass * W;
+    int c[W];
+    T acc[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const int k = k0 + j < width ? k0 + j : width - 1;
+      c[j] = active && width > 0 ? ld_stream_i32(col + s0 + (int64_t)k * kSlice + lane) : w0;
+      if (staged) c[j] = live ? c[j] - w0 : 0;  // padded lanes hold a lambda of zero: any column of the window does
+      acc[j] = T(0);
+    }
+    if (staged) {
+      for (int m = count - 1; m >= 0; --m, ++it) {
+        const int s = it % STAGES;
+        tma::mbar_wait(full + s, (it / STAGES) & 1);
+        const T* st = stages + (size_t)s * STAGE_ELEMS;
+        const T lr = live ? st[warp * kSlice + lane] : T(0);
+        const T* qs = st + kGradRows;
+        if (k0 < width) {
+#pragma unroll
+          for (int j = 0; j < W; ++j) acc[j] = fma(lr, qs[c[j]], acc[j]);
+        }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(empty + s);
+      }
+    } else if (active && k0 < width) {
+      const int64_t rr = r < nrows ? r : nrows - 1;
+#pragma unroll 2
+      for (int m = count - 1; m >= 0; --m) {
+        const T lr = r < nrows ? __ldg(Lam + (int64_t)m * ldl + rr) : T(0);
+        const T* qm = Q + (int64_t)m * ldq;
+#pragma unroll
+        for (int j = 0; j < W; ++j) acc[j] = fma(lr, __ldg(qm + c[j]), acc[j]);
+      }
+    }
+    if (active)
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (k0 + j < width) grad[s0 + (int64_t)(k0 + j) * kSlice + lane] += acc[j];
+  }
+}
+
 struct SellDev {
   DevBuf slice_ptr, col, src, val;
   int64_t nslots = 0, nslices = 0;
@@ -386,8 +528,21 @@ struct SparseOperator : bl_operator {
     sell_h = csr_to_sell(n_rows, csr);
     CsrHost csr_t = coo_to_csr(n_cols, nnz, col, row);
     sell_t_h = csr_to_sell(n_cols, csr_t);
+    // how many blocks of kGradRows rows keep their columns inside one window k_sell_grad_tma can stage
+    int64_t blocks = 0, fit = 0;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += kGradRows, ++blocks) {
+      const int64_t r1 = std::min<int64_t>(n_rows, r0 + kGradRows);
+      int32_t lo = INT32_MAX, hi = -1;
+      for (int64_t k = csr.row_ptr[r0]; k < csr.row_ptr[r1]; ++k) {
+        lo = std::min(lo, csr.col_idx[k]);
+        hi = std::max(hi, csr.col_idx[k]);
+      }
+      if (hi < lo || hi - lo + 8 <= kGradWinMax) ++fit;
+    }
+    grad_windows_fit = blocks > 0 && 4 * fit >= 3 * blocks;
     return BL_OK;  // pure host index work: testable without a GPU; upload happens on first bind
   }
+  bool grad_windows_fit = false;  // banded / locally clustered rows: the deferred cotangent pass stages its pairs (TMA)
 
   bool uploaded = false;
   int ensure_uploaded() {
@@ -604,6 +759,27 @@ struct SparseOperator : bl_operator {
   }
   template <typename T>
   int vjp_batch_t(const T* Q, int64_t ldq, const T* Lam, int64_t ldl, int count, cudaStream_t s) {
+    static const bool staged = [] {  // BL_GRAD_TMA=0: the register-staged pass everywhere (A/B measurements)
+      const char* e = std::getenv("BL_GRAD_TMA");
+      return !(e && e[0] == '0');
+    }();
+    // bulk copies: 16-byte aligned rows of Q and Lam (basis buffers of the drivers are)
+    const bool aligned = (reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Lam)) % 16 == 0 &&
+                         (ldq * sizeof(T)) % 16 == 0 && (ldl * sizeof(T)) % 16 == 0 && ldl >= n_rows && ldq >= n_cols;
+    if (staged && grad_windows_fit && aligned && sell.nslices > 0 && count > 0) {
+      constexpr size_t smem = (size_t)grad_stages<T>() * (kGradRows + kGradWinMax) * sizeof(T) + 2 * grad_stages<T>() * 8;
+      static bool attr_set = false;  // per instantiation (T)
+      if (!attr_set) {
+        BL_CUDA(cudaFuncSetAttribute(k_sell_grad_tma<T, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      const int blocks = (int)((sell.nslices + kGradWarps - 1) / kGradWarps);
+      k_sell_grad_tma<T, 12><<<blocks, (kGradWarps + 1) * 32, smem, s>>>(n_rows, sell.nslices, sell.slice_ptr.as<int64_t>(),
+                                                                       sell.col.as<int32_t>(), grad.as<T>(), Q, ldq, Lam,
+                                                                       ldl, count);
+      BL_LAUNCHED();
+      return BL_OK;
+    }
     const int64_t threads = sell.nslices * kSlice;
     const int blocks = (int)((threads + 255) / 256);
     if (blocks > 0 && count > 0) {
