@@ -279,12 +279,26 @@ def main():
     main_stream = bl_dev.default_stream()
     grad_total = bl_dev.DeviceArray((nnz,), dtype)
 
+    # Lanes half a cycle apart: every second lane runs [adjoint of its previous forward, next forward] while its
+    # neighbour runs [forward, adjoint] -- one sweep with many active rows (bandwidth-bound) is then always in flight
+    # beside one with few (bound by its grid-wide reductions), instead of both lanes being short of rows together.
+    # Every step still is one forward + one adjoint of every probe batch (BL_BENCH_STAGGER=0: all lanes in phase).
+    stagger = lockstep and L >= 2 and os.environ.get("BL_BENCH_STAGGER", "1") != "0"
+    behind = [stagger and li % 2 == 1 for li in range(L)]
+    for pl, late in zip(plans, behind):
+        if late:
+            pl.forward()  # primes the pipeline: the lane's first step starts with this forward's adjoint
+
     def step_device(active=None, first=False):
         """Forward + adjoint of every probe.  The parameter cotangent ACCUMULATES inside each lane's operator
         (zeroed on the first step only), as it does over the probes of an estimate (`lanczos.probe_lockstep_sum`)."""
         for pl in active or plans:
-            pl.forward()
-            pl.adjoint(zero=first, export=False)
+            if behind[plans.index(pl)]:
+                pl.adjoint(zero=first, export=False)
+                pl.forward()
+            else:
+                pl.forward()
+                pl.adjoint(zero=first, export=False)
 
     def finish_estimate(active=None):
         """Close the estimate: export each lane's accumulated cotangent, add the lanes up, and -- probe sharding --
@@ -350,7 +364,7 @@ def main():
 
     if args.quick:
         emit({"value": value, "ms_per_step": ms_per_step, "gpu_launches": launches, "probes_per_gpu": probes_per_gpu,
-              "mode": args.mode, "lanes": L, "quick": True})  # fmt: skip
+              "mode": args.mode, "lanes": L, "stagger": bool(stagger), "quick": True})  # fmt: skip
         bl_comm.shutdown()
         return
 
@@ -359,8 +373,11 @@ def main():
 
     def step_host(_first):
         h2d = d2h = 0
-        for pl, v_host, (out_H, out_dv, out_g) in zip(plans, v_hosts, outs):
-            a, b = pl.run_host(v_host, [p_host], dH_host, out_H, out_dv, out_g, sync=False)
+        for pl, late, v_host, (out_H, out_dv, out_g) in zip(plans, behind, v_hosts, outs):
+            if late:
+                a, b = pl.run_host(v_host, [p_host], dH_host, out_H, out_dv, out_g, sync=False, adjoint_first=True)
+            else:
+                a, b = pl.run_host(v_host, [p_host], dH_host, out_H, out_dv, out_g, sync=False)
             h2d, d2h = h2d + a, d2h + b
         for pl in plans:
             pl.stream.synchronize()  # the step's results (H, dv, dparams of every probe) are on the host
@@ -448,9 +465,10 @@ def main():
                         "(ONE k_step_tma launch per Krylov step and batch: operator call + Gram-Schmidt step), one stream per batch"
                         if lockstep else
                         f"{probes_per_gpu} independent probe vectors per GPU per step, each on its own stream") +
+                       ("; every second batch runs half a cycle behind (its adjoint beside its neighbour's forward)" if stagger else "") +
                        "; the parameter cotangent accumulates on the device over the steps and the timed region ends with "
                        "one export + sum" + (" + ONE ncclAllReduce over the ranks" if world > 1 else ""),
-            "mode": args.mode, "lanes": L, "probes_per_lane": per_lane, "probes_per_gpu": probes_per_gpu,
+            "mode": args.mode, "lanes": L, "probes_per_lane": per_lane, "probes_per_gpu": probes_per_gpu, "stagger": bool(stagger),
             "blocks_per_sm": {"timed_region": blocks_in_flight or 2, "single_probe_and_kernel_profile": 2},
             "single_probe": {"ms_per_forward_adjoint": ms_single, "krylov_steps_per_s": DEPTH / (ms_single * 1e-3),
                              "launches_per_run": int(launches_single)},

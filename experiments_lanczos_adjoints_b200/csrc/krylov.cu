@@ -18,6 +18,7 @@
 #include "krylov_kernels.cuh"
 #include "stream_kernels.cuh"
 #include "step_kernel.cuh"
+#include "spmv_dots.cuh"
 #include "operators.cuh"
 
 namespace bl {
@@ -69,10 +70,16 @@ struct Common {
   double* coefC;
   double* partials_dots;
   double* partials_comb;
-  double* partials_few;  // [kFewMaxHost][kMaxDotsGrid]: per-block shares of the neighbouring-row dots (k_op_dots)
+  double* partials_few;  // [kFewMaxHost][few_capacity]: per-block shares of the neighbouring-row dots (k_op_dots, k_sell_spmv_dots)
   long long partials_dots_count = 0;  // doubles behind partials_dots
+  long long few_capacity = 0;         // blocks per value behind partials_few
 };
 constexpr int kFewMaxHost = 4;
+constexpr int kSpmvDotsMinThreads = 256;
+// shares per value the workspace holds: the grid of the streaming kernels or of k_sell_spmv_dots (one block per 8+ slices)
+long long few_capacity_for(int64_t n) {
+  return std::max<long long>(kMaxDotsGrid, (n + kSpmvDotsMinThreads - 1) / kSpmvDotsMinThreads + 1);
+}
 
 size_t common_bytes(int64_t n, int64_t K) {
   size_t b = 0;
@@ -81,12 +88,11 @@ size_t common_bytes(int64_t n, int64_t K) {
   b += 4 * align_up((K + 2) * 8, 256);        // red, coefA, coefB, coefC
   b += align_up((size_t)(K + 2) * kMaxDotsGrid * 8, 256);  // partials_dots
   b += align_up((size_t)kMaxCombineGrid * 8, 256);         // partials_comb
-  b += align_up((size_t)kFewMaxHost * kMaxDotsGrid * 8, 256);  // partials_few
-  (void)n;
+  b += align_up((size_t)kFewMaxHost * few_capacity_for(n) * 8, 256);  // partials_few
   return b + 9 * 256;
 }
 
-void carve_common(Workspace& w, int64_t K, Common& c) {
+void carve_common(Workspace& w, int64_t K, Common& c, int64_t n = 0) {
   c.counters = static_cast<unsigned int*>(w.take(256));
   c.scal = static_cast<double*>(w.take(S_COUNT * 8));
   c.red = static_cast<double*>(w.take((K + 2) * 8));
@@ -96,7 +102,8 @@ void carve_common(Workspace& w, int64_t K, Common& c) {
   c.partials_dots = static_cast<double*>(w.take((size_t)(K + 2) * kMaxDotsGrid * 8));
   c.partials_dots_count = (long long)(K + 2) * kMaxDotsGrid;
   c.partials_comb = static_cast<double*>(w.take((size_t)kMaxCombineGrid * 8));
-  c.partials_few = static_cast<double*>(w.take((size_t)kFewMaxHost * kMaxDotsGrid * 8));
+  c.few_capacity = few_capacity_for(n);
+  c.partials_few = static_cast<double*>(w.take((size_t)kFewMaxHost * c.few_capacity * 8));
 }
 
 // BL_STREAM=0 forces the register-staged (LDG) kernels; default: TMA-staged kernels for n >= 8192.
@@ -873,6 +880,63 @@ int launch_op_dots(std::vector<StepItem>& items, double op_bytes, cudaStream_t s
   return BL_OK;
 }
 
+// BL_SPMV_DOTS=0: one run alone keeps k_dots_few for its neighbouring-row dots (A/B measurements).
+// BL_SPMV_DOTS_THREADS: threads per block of k_sell_spmv_dots (256..1024; shares per value = slices / warps per block).
+int spmv_dots_threads() {
+  static const int t = [] {
+    const char* off = std::getenv("BL_SPMV_DOTS");
+    if (off && off[0] == '0') return 0;
+    const char* e = std::getenv("BL_SPMV_DOTS_THREADS");
+    int v = e ? std::atoi(e) : 512;
+    v = std::max(kSpmvDotsMinThreads, std::min(kSpmvDotsMaxWarps * 32, v));
+    return v / 32 * 32;
+  }();
+  return t;
+}
+
+// Operator call of one run (SELL-32 operand) + per-block shares of <few_j, y> in c.partials_few, one PLAIN launch
+// (k_sell_spmv_dots).  `*grid_out` stays 0 -- nothing launched -- when the kernel does not apply.
+template <typename T>
+int launch_spmv_dots(bl_operator_t* op, int dtype, bool transpose, int64_t n, int64_t n_pad, const T* x, const double* len,
+                     T* q, T* y, int few_n, const void* const* few_rows, int self, const Common& c, double op_bytes,
+                     cudaStream_t s, int* grid_out) {
+  *grid_out = 0;
+  const int threads = spmv_dots_threads();
+  if (threads == 0 || !xdots_enabled() || stream_mode() != 1 || is_sharded() || !use_tma(n) || few_n < 1 || few_n > kFewMax ||
+      x == y)
+    return BL_OK;
+  SellView v;
+  if (!op->sell_view(dtype, transpose, &v)) return BL_OK;
+  const bool norm = len != nullptr;
+  if (v.nrows != n || (norm && n_pad > v.nslices * 32)) return BL_OK;
+  const int wpb = threads / 32;
+  const long long grid = (v.nslices + wpb - 1) / wpb;
+  if (grid < 1 || grid > c.few_capacity) return BL_OK;
+  SpmvDotsArgs a;
+  a.slice_ptr = v.slice_ptr;
+  a.col = v.col;
+  a.val = v.val;
+  a.nslices = v.nslices;
+  a.nrows = v.nrows;
+  a.n_pad = n_pad;
+  a.x = x;
+  a.y = y;
+  a.len = len;
+  a.q = q;
+  a.few_n = few_n;
+  for (int j = 0; j < few_n; ++j) a.few_row[j] = few_rows[j];
+  a.self = self;
+  a.partials = c.partials_few;
+  ProfScope prof(BL_PROF_MATVEC, op_bytes + (double)few_n * n * sizeof(T), s);
+  if (norm)
+    k_sell_spmv_dots<T, true, 6><<<(int)grid, threads, 0, s>>>(a);
+  else
+    k_sell_spmv_dots<T, false, 6><<<(int)grid, threads, 0, s>>>(a);
+  BL_LAUNCHED();
+  *grid_out = (int)grid;
+  return BL_OK;
+}
+
 template <typename T>
 int launch_scale_copy(int64_t n, const T* x, double mul, const double* div_ptr, T* out, int64_t n_pad, cudaStream_t s) {
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(16 * sm_count(), (n_pad + 255) / 256));
@@ -972,6 +1036,19 @@ struct FwdRun {
     ProfScope prof(BL_PROF_MATVEC, op->matvec_bytes(dtype), s);
     return op->matvec(dtype, q_row(i), r, s);
   }
+  // the same as ONE launch that also leaves the first pass's dots <q_j, A q_i>, j = first_lo(i)..i, as per-block shares
+  // (k_sell_spmv_dots; symmetric loops of one run alone).  `*pre_grid` stays 0 when it does not apply.
+  int advance_dots(int i, int* pre_grid) {
+    *pre_grid = 0;
+    if (!(second_pass && local_first)) return BL_OK;
+    const int j0 = first_lo(i);
+    const void* few[kFewMax];
+    for (int j = j0; j <= i; ++j) few[j - j0] = q_row(j);
+    BL_CHECK(launch_spmv_dots<T>(op, dtype, false, n, ld, r, c.scal + S_LEN, q_row(i), alt, i + 1 - j0, few, i - j0, c,
+                                 op->matvec_bytes(dtype) + 1.0 * n * sizeof(T), s, pre_grid));
+    if (*pre_grid > 0) std::swap(r, alt);
+    return BL_OK;
+  }
   int finish() {
     if (r != r_out) {
       BL_CUDA(cudaMemcpyAsync(r_out, r, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
@@ -982,7 +1059,7 @@ struct FwdRun {
 
   int begin() {
   Workspace w(workspace, wbytes);
-  carve_common(w, K, c);
+  carve_common(w, K, c, n);
   alt = static_cast<T*>(w.take((size_t)ld * sizeof(T)));
   r_out = r;
   BL_REQUIRE(w.ok(), "workspace too small (bl_arnoldi_workspace_bytes)");
@@ -1192,6 +1269,14 @@ int arnoldi_forward_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
         run.unfuse();
       }
     }
+    {  // one run alone: operator call + shares of the neighbouring-row dots in one plain launch, finished by k_xdots_tma
+      int pre_grid = 0;
+      BL_CHECK(run.advance_dots(i, &pre_grid));
+      if (pre_grid > 0) {
+        BL_CHECK(run.post(i, pre_grid));
+        continue;
+      }
+    }
     BL_CHECK(run.advance(i));
     BL_CHECK(run.post(i));
   }
@@ -1341,7 +1426,7 @@ struct AdjRun {
 
   int begin() {
   Workspace w(workspace, wbytes);
-  carve_common(w, K, c);
+  carve_common(w, K, c, n);
   eta = static_cast<double*>(w.take((size_t)K * 8));
   Gamma = static_cast<double*>(w.take((size_t)K * K * 8));
   PiGamma = static_cast<double*>(w.take((size_t)K * K * 8));
@@ -1497,6 +1582,17 @@ struct AdjRun {
     item.a.op_x = lam_row(idx);
     item.bytes += op->apply_transpose_bytes(dtype);
     return true;
+  }
+  // z = A^T Lambda[idx] and the shares of its dots with rows band_lo(idx)..idx in one plain launch (k_sell_spmv_dots;
+  // banded Gamma, deferred parameter cotangent, one run alone).  `*pre_grid` stays 0 when it does not apply.
+  int apply_transpose_dots(int idx, int* pre_grid) {
+    *pre_grid = 0;
+    if (!(banded && defer_grad && reortho_full && idx > 0)) return BL_OK;
+    const int j0 = band_lo(idx);
+    const void* few[kFewMax];
+    for (int j = j0; j <= idx; ++j) few[j - j0] = q_row(j);
+    return launch_spmv_dots<T>(op, dtype, true, n, ld, lam_row(idx), nullptr, nullptr, z, idx + 1 - j0, few, -1, c,
+                               op->apply_transpose_bytes(dtype), s, pre_grid);
   }
   void stepped(int idx) {  // the step kernel of idx also did pre(idx - 1)
     pre_done = idx - 1;
@@ -1655,6 +1751,14 @@ int arnoldi_adjoint_t(bl_operator_t* op, int dtype, int64_t n, int K, int flags,
           BL_CHECK(run.post(idx, pre_grid));
           continue;
         }
+      }
+    }
+    {  // one run alone: A^T lambda + shares of its dots with rows idx-2..idx in one plain launch
+      int pre_grid = 0;
+      BL_CHECK(run.apply_transpose_dots(idx, &pre_grid));
+      if (pre_grid > 0) {
+        BL_CHECK(run.post(idx, pre_grid));
+        continue;
       }
     }
     // (A^T lambda, dparams += ...) = vjp of matvec at (q_idx, params)            arnoldi.py:207-209

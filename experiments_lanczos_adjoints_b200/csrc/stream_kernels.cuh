@@ -372,9 +372,38 @@ k_xdots_tma(const __grid_constant__ XDotsArgs a) {
     tma::griddep_wait();          // the terms and their coefficients are the predecessor's output
     if (a.pre_count > 0) {
       __shared__ double pre_s[8];
-      if (warp < a.pre_count) {
-        const double sum = step::row_sum(a.pre_partials + (size_t)warp * a.pre_grid, a.pre_grid, lane);
-        if (lane == 0) pre_s[warp] = sum;
+      if (a.pre_grid <= 320) {
+        if (warp < a.pre_count) {
+          const double sum = step::row_sum(a.pre_partials + (size_t)warp * a.pre_grid, a.pre_grid, lane);
+          if (lane == 0) pre_s[warp] = sum;
+        }
+      } else {
+        // thousands of shares per value (k_sell_spmv_dots: one per SpMV block): all consumer threads add them up,
+        // thread t the shares t, t + 256, ... (eight loads in flight), then lanes, then warps -- a fixed order
+        __shared__ double pre_w[8][kConsumerWarps];
+        for (int j = 0; j < a.pre_count; ++j) {
+          const double* p = a.pre_partials + (size_t)j * a.pre_grid;
+          double s = 0.0;
+          for (int k0 = tid; k0 < a.pre_grid; k0 += 8 * kConsumerThreads) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int k = k0 + u * kConsumerThreads;
+              v[u] = k < a.pre_grid ? __ldcg(p + k) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+          }
+          s = warp_sum(s);
+          if (lane == 0) pre_w[j][warp] = s;
+        }
+        tma::named_bar_sync(1, kConsumerThreads);
+        if (tid < a.pre_count) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < kConsumerWarps; ++w) s += pre_w[tid][w];
+          pre_s[tid] = s;
+        }
       }
       tma::named_bar_sync(1, kConsumerThreads);
       struct PreSync {

@@ -221,15 +221,30 @@ class BatchedTridiagAdjointPlan:
         self.forward()
         self.adjoint()
 
-    def run_host(self, v_host, params_host, dH_host, out_H, out_dv, out_grads, sync=True):
+    def run_host(self, v_host, params_host, dH_host, out_H, out_dv, out_grads, sync=True, adjoint_first=False):
         """Host buffers in, host buffers out (see `TridiagAdjointPlan.run_host`); `v_host (P, n)`, `dH_host (P, K, K)`,
-        `out_H (P, K, K)`, `out_dv (P, n)`.  Returns (h2d_bytes, d2h_bytes)."""
-        h2d = self.set_vectors(v_host) + self.set_params(*params_host) + self.set_cotangents(dH_host)
-        self.run()
+        `out_H (P, K, K)`, `out_dv (P, n)`.  Returns (h2d_bytes, d2h_bytes).
+
+        `adjoint_first`: the software-pipelined order of a lane that runs half a cycle behind its neighbour (see
+        `bench.py`): adjoint of the PREVIOUS call's forward, its results to the host, then this call's inputs to the device
+        and their forward.  Same copies, same kernels per call; the outputs are those of the previous call's inputs."""
         d2h = 0
-        for src, dst in [(self.H, out_H), (self.dv, out_dv), *zip(self.grads, out_grads)]:
-            _lib.call("bl_memcpy_d2h", dst.ctypes.data, src.ptr, dst.nbytes, self.stream.ptr)
-            d2h += dst.nbytes
+
+        def results():
+            nonlocal d2h
+            for src, dst in [(self.H, out_H), (self.dv, out_dv), *zip(self.grads, out_grads)]:
+                _lib.call("bl_memcpy_d2h", dst.ctypes.data, src.ptr, dst.nbytes, self.stream.ptr)
+                d2h += dst.nbytes
+
+        if adjoint_first:
+            self.adjoint()
+            results()
+            h2d = self.set_vectors(v_host) + self.set_params(*params_host) + self.set_cotangents(dH_host)
+            self.forward()
+        else:
+            h2d = self.set_vectors(v_host) + self.set_params(*params_host) + self.set_cotangents(dH_host)
+            self.run()
+            results()
         if sync:
             self.stream.synchronize()
         return h2d, d2h
