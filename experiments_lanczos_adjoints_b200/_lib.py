@@ -93,6 +93,7 @@ SIGNATURES = {
     "bl_cholesky_partial": (_i32, [_vp, _i32, _i64, _i64, _i32, _vp, _i64, C.POINTER(C.c_int), C.POINTER(C.c_int64),
                                    _vp, C.c_size_t, _vp]),
     "bl_op_sparse_create": (_i32, [_i64, _i64, _i64, _vp, _vp, _pvp]),
+    "bl_op_sparse_clone": (_i32, [_vp, _pvp]),
     "bl_op_sparse_export_csr": (_i32, [_vp, _vp, _vp, _vp]),
     "bl_op_sparse_export_sell": (_i32, [_vp, _i32, _vp, _vp]),
     "bl_op_dense_create": (_i32, [_i64, _i32, _pvp]),

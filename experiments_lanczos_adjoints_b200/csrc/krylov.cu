@@ -880,12 +880,16 @@ int launch_op_dots(std::vector<StepItem>& items, double op_bytes, cudaStream_t s
   return BL_OK;
 }
 
-// BL_SPMV_DOTS=0: one run alone keeps k_dots_few for its neighbouring-row dots (A/B measurements).
+// BL_SPMV_DOTS=1: one run alone takes its operator call and the shares of its neighbouring-row dots from ONE launch
+// (k_sell_spmv_dots; 611 launches per run instead of 811).  Off by default: measured 23.8 (256 threads per block) / 23.9
+// (512) / 24.3 ms (1024) against 23.0 ms per forward + adjoint at n = 1M -- under programmatic dependent launch the 200
+// k_dots_few launches it removes were mostly hidden already, and adding up thousands of shares in every block of the
+// next kernel costs more than what was left of them.
 // BL_SPMV_DOTS_THREADS: threads per block of k_sell_spmv_dots (256..1024; shares per value = slices / warps per block).
 int spmv_dots_threads() {
   static const int t = [] {
-    const char* off = std::getenv("BL_SPMV_DOTS");
-    if (off && off[0] == '0') return 0;
+    const char* on = std::getenv("BL_SPMV_DOTS");
+    if (!(on && on[0] == '1')) return 0;
     const char* e = std::getenv("BL_SPMV_DOTS_THREADS");
     int v = e ? std::atoi(e) : 512;
     v = std::max(kSpmvDotsMinThreads, std::min(kSpmvDotsMaxWarps * 32, v));

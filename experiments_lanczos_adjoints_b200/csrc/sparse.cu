@@ -855,6 +855,22 @@ int bl_op_sparse_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32
   return BL_OK;
 }
 
+int bl_op_sparse_clone(const bl_operator_t* op, bl_operator_t** clone) {
+  auto* src = dynamic_cast<const bl::SparseOperator*>(op);
+  BL_REQUIRE(src != nullptr && clone != nullptr, "not a sparse operator");
+  auto* o = new bl::SparseOperator();
+  o->n = src->n;
+  o->n_rows = src->n_rows;
+  o->n_cols = src->n_cols;
+  o->nnz = src->nnz;
+  o->csr = src->csr;
+  o->sell_h = src->sell_h;
+  o->sell_t_h = src->sell_t_h;
+  o->grad_windows_fit = src->grad_windows_fit;
+  *clone = o;  // device buffers are uploaded on the clone's first bind
+  return BL_OK;
+}
+
 int bl_op_sparse_export_csr(const bl_operator_t* op, int32_t* row_ptr_host, int32_t* col_idx_host,
                             int32_t* perm_host) {
   auto* o = dynamic_cast<const bl::SparseOperator*>(op);

@@ -399,8 +399,9 @@ def probe_lockstep_sum(integrand, probes, parameters, *, with_grad, batch=None, 
     key = (L, B, dtype.str, n, K)
     if key not in cache:
         ops = [hess.op] + [hess.op.clone() for _ in range(L - 1)]
-        cache[key] = [_plan.BatchedTridiagAdjointPlan(o, K, dtype, B, stream=dev.Stream()) for o in ops]
-    plans = cache[key]
+        cache[key] = ([_plan.BatchedTridiagAdjointPlan(o, K, dtype, B, stream=dev.Stream()) for o in ops],
+                      [_plan.pinned_empty((B, n), dtype) for _ in ops])  # fmt: skip
+    plans, staging = cache[key]  # per lane: the plan and a pinned buffer its normalised probes are copied from
     host_params = [p.numpy() if isinstance(p, dev.DeviceArray) else np.asarray(p) for p in parameters]
     dev.synchronize()  # the lanes' streams start after whatever the caller enqueued
     for pl in plans:
@@ -447,8 +448,11 @@ def probe_lockstep_sum(integrand, probes, parameters, *, with_grad, batch=None, 
             real = len(group)
             if real < B:  # short last batch: repeat its last probe (zero cotangent, value ignored)
                 group = np.concatenate([group, np.repeat(group[-1:], B - real, axis=0)])
-            scales = np.linalg.norm(group.astype(np.float64), axis=1)  # lanczos.py:25
-            plans[li].set_vectors((group / scales[:, None]).astype(dtype))
+            # lanczos.py:25: the norm accumulated in float64, the division in the working precision (as the reference's);
+            # the lane's previous copy out of `staging[li]` finished before its coefficients were read (complete)
+            scales = np.sqrt(np.einsum("ij,ij->i", group, group, dtype=np.float64))
+            np.divide(group, scales.astype(dtype)[:, None], out=staging[li])
+            plans[li].set_vectors(staging[li])
             plans[li].forward()
             pending[li] = (scales, real)
         for li in range(L):

@@ -139,7 +139,12 @@ class SparseOperator(Operator):
     def clone(self):
         """A second handle on the same sparsity pattern with its own values and cotangent accumulator: independent
         Krylov runs (probes) on different streams need one operator each."""
-        return SparseOperator(self._coo[0], self._coo[1], self.shape)
+        twin = object.__new__(SparseOperator)
+        twin.shape, twin.nnz, twin._coo = self.shape, self.nnz, self._coo
+        h = C.c_void_p()
+        _lib.call("bl_op_sparse_clone", self._handle, C.byref(h))  # the finished index work is copied, not redone
+        Operator.__init__(twin, h.value, self.shape[0])
+        return twin
 
     @classmethod
     def from_matrix_market(cls, path):

@@ -187,12 +187,20 @@ class sharded_sampler:
         self.n, self.dtype, self.num = int(np.size(x_like)), np.asarray(x_like).dtype, int(num)
 
     def _rows(self, key, lo, hi):
-        from experiments_lanczos_adjoints_b200.hutchinson import split
-
-        keys = split(key, self.num)
+        # child stream i of the key, as `hutchinson.split(key, num)[i]` derives it (only the children that are needed:
+        # the estimator asks for four rows at a time); one random BIT per entry -- the host draws a batch in a few
+        # milliseconds, under the other lane's kernels
+        if not isinstance(key, np.random.SeedSequence):
+            key = np.random.SeedSequence(int(np.asarray(key).sum()))
         out = np.empty((max(0, hi - lo), self.n), dtype=self.dtype)
+        nbytes = (self.n + 7) // 8
         for i in range(lo, hi):
-            out[i - lo] = np.random.default_rng(keys[i]).integers(0, 2, size=self.n, dtype=np.int8) * 2 - 1
+            child = np.random.SeedSequence(entropy=key.entropy, spawn_key=tuple(key.spawn_key) + (i,))
+            bits = np.unpackbits(np.frombuffer(np.random.default_rng(child).bytes(nbytes), np.uint8))[: self.n]
+            row = out[i - lo]
+            row[:] = bits
+            row *= 2
+            row -= 1
         return out
 
     def sample_slice(self, key, lo, hi):

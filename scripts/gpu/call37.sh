@@ -8,4 +8,4 @@ for cfg in "BL_SPMV_DOTS=0" "BL_SPMV_DOTS_THREADS=512"; do
   env $cfg timeout 300 python bench.py --quick --mode streams --probes 4 --steps 5 --warmup 3 > $O/q.json 2>$O/q.err; echo "$cfg 4 streams: $(cat $O/q.json)"; tail -2 $O/q.err
   env $cfg timeout 300 python bench.py --quick --mode streams --probes 1 --dtype f64 --steps 5 --warmup 3 > $O/q.json 2>$O/q.err; echo "$cfg single f64: $(cat $O/q.json)"; tail -2 $O/q.err
 done
-timeout 900 python -m pytest tests -m gpu -x -q -k "parity or suite or slq or oracle or golden" > $O/tests.log 2>&1; echo "exit=$?" >> $O/tests.log; tail -3 $O/tests.log
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/tests.log 2>&1; echo "exit=$?" >> $O/tests.log; tail -3 $O/tests.log

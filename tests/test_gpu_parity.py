@@ -5,6 +5,8 @@
 Tolerances (BASELINE.json north_star): fp32 1e-5 on tridiagonal coefficients / log-dets and
 1e-4 on gradients; fp64 1e-10 on all three; integer index work bit-exact."""
 
+import os
+
 import numpy as np
 import pytest
 from conftest import golden, golden_names, rel_err
@@ -577,6 +579,31 @@ def test_concurrent_plans_on_separate_streams_match_their_solo_runs():
         assert rel_err(a, a0) < F32_VAL and rel_err(b, b0) < F32_VAL
         assert rel_err(pl.dv.numpy(pl.stream), dv0) < F32_GRAD and rel_err(pl.grads[0].numpy(pl.stream), g0) < F32_GRAD
     assert rel_err(solo[0][0], solo[1][0]) > 1e-3  # different probes: the comparison above is not vacuous
+
+
+def _run_check_script(name):
+    """A/B checks whose two sides are selected by an environment variable the library reads once per process."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", name)], cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    return res.stdout
+
+
+def test_staged_cotangent_pass_is_bit_identical_to_the_gather_pass():
+    """`k_sell_grad_tma` (pairs staged by TMA; banded operands) against `k_sell_grad_batch` (BL_GRAD_TMA=0): the same
+    summation order, so the exported parameter cotangent must agree bit for bit -- banded (all blocks staged), random
+    sparse (none) and banded with a few far entries (mixed), fp32 and fp64."""
+    out = _run_check_script("check_grad_tma.py")
+    assert out.count("bit-identical True") == 4, out
+
+
+def test_operator_call_with_neighbouring_row_dots_matches_the_separate_launches():
+    """`k_sell_spmv_dots` + shares finished by `k_xdots_tma` (one run alone) against `k_dots_few` (BL_SPMV_DOTS=0): fewer
+    launches, H / dv / dparams equal to rounding (fp32 2e-5, fp64 1e-11; the dots are added up in another order)."""
+    _run_check_script("check_spmv_dots.py")
 
 
 def test_two_lockstep_lanes_in_flight_reproduce_their_solo_runs_bit_for_bit():
