@@ -15,6 +15,7 @@
 //   grad[slot] (T) accumulates lam[r]*q[col] in the same layout; grad_export scatters to COO order.
 #include <algorithm>
 #include <cstdlib>
+#include <memory>
 #include <numeric>
 #include <vector>
 
@@ -500,8 +501,11 @@ struct SellDev {
 
 struct SparseOperator : bl_operator {
   int64_t n_rows = 0, n_cols = 0, nnz = 0;
-  CsrHost csr;                 // kept for the bit-exact export
-  SellHost sell_h, sell_t_h;   // idem
+  struct HostIndex {  // the finished index work, shared by the clones of an operator
+    CsrHost csr;                 // kept for the bit-exact export
+    SellHost sell_h, sell_t_h;   // idem
+  };
+  std::shared_ptr<HostIndex> host = std::make_shared<HostIndex>();
   SellDev sell, sell_t;
   DevBuf grad;
   int bound_dtype = -1;
@@ -524,10 +528,11 @@ struct SparseOperator : bl_operator {
   }
 
   int build(const int32_t* row, const int32_t* col) {
+    CsrHost& csr = host->csr;
     csr = coo_to_csr(n_rows, nnz, row, col);
-    sell_h = csr_to_sell(n_rows, csr);
+    host->sell_h = csr_to_sell(n_rows, csr);
     CsrHost csr_t = coo_to_csr(n_cols, nnz, col, row);
-    sell_t_h = csr_to_sell(n_cols, csr_t);
+    host->sell_t_h = csr_to_sell(n_cols, csr_t);
     // how many blocks of kGradRows rows keep their columns inside one window k_sell_grad_tma can stage
     int64_t blocks = 0, fit = 0;
     for (int64_t r0 = 0; r0 < n_rows; r0 += kGradRows, ++blocks) {
@@ -547,8 +552,8 @@ struct SparseOperator : bl_operator {
   bool uploaded = false;
   int ensure_uploaded() {
     if (uploaded) return BL_OK;
-    BL_CHECK(sell.upload(sell_h));
-    BL_CHECK(sell_t.upload(sell_t_h));
+    BL_CHECK(sell.upload(host->sell_h));
+    BL_CHECK(sell_t.upload(host->sell_t_h));
     uploaded = true;
     return BL_OK;
   }
@@ -863,9 +868,7 @@ int bl_op_sparse_clone(const bl_operator_t* op, bl_operator_t** clone) {
   o->n_rows = src->n_rows;
   o->n_cols = src->n_cols;
   o->nnz = src->nnz;
-  o->csr = src->csr;
-  o->sell_h = src->sell_h;
-  o->sell_t_h = src->sell_t_h;
+  o->host = src->host;  // shared, read-only after build()
   o->grad_windows_fit = src->grad_windows_fit;
   *clone = o;  // device buffers are uploaded on the clone's first bind
   return BL_OK;
@@ -875,9 +878,9 @@ int bl_op_sparse_export_csr(const bl_operator_t* op, int32_t* row_ptr_host, int3
                             int32_t* perm_host) {
   auto* o = dynamic_cast<const bl::SparseOperator*>(op);
   BL_REQUIRE(o != nullptr, "not a sparse operator");
-  if (row_ptr_host) std::copy(o->csr.row_ptr.begin(), o->csr.row_ptr.end(), row_ptr_host);
-  if (col_idx_host) std::copy(o->csr.col_idx.begin(), o->csr.col_idx.end(), col_idx_host);
-  if (perm_host) std::copy(o->csr.perm.begin(), o->csr.perm.end(), perm_host);
+  if (row_ptr_host) std::copy(o->host->csr.row_ptr.begin(), o->host->csr.row_ptr.end(), row_ptr_host);
+  if (col_idx_host) std::copy(o->host->csr.col_idx.begin(), o->host->csr.col_idx.end(), col_idx_host);
+  if (perm_host) std::copy(o->host->csr.perm.begin(), o->host->csr.perm.end(), perm_host);
   return BL_OK;
 }
 
@@ -885,7 +888,7 @@ int bl_op_sparse_export_sell(const bl_operator_t* op, int transpose, int64_t* sl
                              int64_t* slot_of_csr_host) {
   auto* o = dynamic_cast<const bl::SparseOperator*>(op);
   BL_REQUIRE(o != nullptr, "not a sparse operator");
-  const auto& h = transpose ? o->sell_t_h : o->sell_h;
+  const auto& h = transpose ? o->host->sell_t_h : o->host->sell_h;
   if (slice_ptr_host) std::copy(h.slice_ptr.begin(), h.slice_ptr.end(), slice_ptr_host);
   if (slot_of_csr_host) std::copy(h.slot_of_csr.begin(), h.slot_of_csr.end(), slot_of_csr_host);
   return BL_OK;

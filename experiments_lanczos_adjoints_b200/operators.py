@@ -142,7 +142,7 @@ class SparseOperator(Operator):
         twin = object.__new__(SparseOperator)
         twin.shape, twin.nnz, twin._coo = self.shape, self.nnz, self._coo
         h = C.c_void_p()
-        _lib.call("bl_op_sparse_clone", self._handle, C.byref(h))  # the finished index work is copied, not redone
+        _lib.call("bl_op_sparse_clone", self._handle, C.byref(h))  # the finished index work is shared, not redone
         Operator.__init__(twin, h.value, self.shape[0])
         return twin
 

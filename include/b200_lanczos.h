@@ -175,7 +175,7 @@ typedef struct bl_operator bl_operator_t;
 int bl_op_sparse_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* coo_row_host,
                         const int32_t* coo_col_host, bl_operator_t** op);
 /* A second handle on the same sparsity pattern with values and cotangent accumulator of its own (independent Krylov
- * runs on different streams need one operator each): the finished index work is copied, not redone. */
+ * runs on different streams need one operator each): the finished index work is shared, not redone. */
 int bl_op_sparse_clone(const bl_operator_t* op, bl_operator_t** clone);
 /* CSR view of the index work, for the bit-exact tests: row_ptr[n_rows+1], col_idx[nnz],
  * perm[nnz] (perm[k] = COO position of CSR slot k).  Any pointer may be NULL. */
