@@ -304,8 +304,40 @@ k_sell_vjp(int64_t nrows, const int64_t* __restrict__ slice_ptr, const int32_t* 
 // W entries of the row are accumulated in registers while m runs over the K (lambda, q) pairs: `Lam[m][r]` is one
 // coalesced load per m, `Q[m][col]` a gather that is coalesced for banded rows and mostly served by L2 (neighbouring
 // slices read the same lines).  Same summation order as the per-step kernel (m = count-1 .. 0).
-template <typename T, int W>
-__global__ void __launch_bounds__(256)
+// acc[j] += sum_m Lam[m][rr] * Q[m][c[j]], m = count-1 .. 0.  U pairs per round: their U lambdas and U x W gathers are
+// ISSUED before the first FMA.  (Left to the compiler, the loop kept two or three loads in flight per warp -- ncu: 24
+// warps per issue on the long scoreboard, DRAM 17 %, L2 -> L1 4.7 TB/s -- and the pass was bound by the round trip of
+// its gathers: 3.95 ms for the 400 pairs of a lockstep batch at C2, 1.80 ms with the loads batched.)
+template <typename T, int W, int U>
+__device__ __forceinline__ void grad_accumulate(T (&acc)[W], const int (&c)[W], const T* __restrict__ Lam, int64_t ldl,
+                                                int64_t rr, bool live, const T* __restrict__ Q, int64_t ldq, int count) {
+  int m = count - 1;
+  for (; m >= U - 1; m -= U) {
+    T lr[U], g[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      lr[u] = __ldg(Lam + (int64_t)(m - u) * ldl + rr);
+      const T* qm = Q + (int64_t)(m - u) * ldq;
+#pragma unroll
+      for (int j = 0; j < W; ++j) g[u][j] = __ldg(qm + c[j]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const T l = live ? lr[u] : T(0);
+#pragma unroll
+      for (int j = 0; j < W; ++j) acc[j] = fma(l, g[u][j], acc[j]);
+    }
+  }
+  for (; m >= 0; --m) {
+    const T l = live ? __ldg(Lam + (int64_t)m * ldl + rr) : T(0);
+    const T* qm = Q + (int64_t)m * ldq;
+#pragma unroll
+    for (int j = 0; j < W; ++j) acc[j] = fma(l, __ldg(qm + c[j]), acc[j]);
+  }
+}
+
+template <typename T, int W, int U>
+__global__ void __launch_bounds__(256, U >= 4 ? 2 : 3)
 k_sell_grad_batch(int64_t nrows, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
                   T* __restrict__ grad, const T* __restrict__ Q, int64_t ldq, const T* __restrict__ Lam, int64_t ldl,
                   int count) {
@@ -316,6 +348,7 @@ k_sell_grad_batch(int64_t nrows, const int64_t* __restrict__ slice_ptr, const in
   const int64_t rr = r < nrows ? r : nrows - 1;  // padded lanes read a valid row, their lambda counts as zero
   const int64_t s0 = slice_ptr[slice], s1 = slice_ptr[slice + 1];
   const int width = (int)((s1 - s0) / kSlice);
+  const bool live = r < nrows;
   for (int k0 = 0; k0 < width; k0 += W) {
     int c[W];
     T acc[W];
@@ -325,13 +358,7 @@ k_sell_grad_batch(int64_t nrows, const int64_t* __restrict__ slice_ptr, const in
       c[j] = ld_stream_i32(col + s0 + (int64_t)k * kSlice + lane);
       acc[j] = T(0);
     }
-#pragma unroll 2
-    for (int m = count - 1; m >= 0; --m) {
-      const T lr = r < nrows ? __ldg(Lam + (int64_t)m * ldl + rr) : T(0);
-      const T* qm = Q + (int64_t)m * ldq;
-#pragma unroll
-      for (int j = 0; j < W; ++j) acc[j] = fma(lr, __ldg(qm + c[j]), acc[j]);
-    }
+    grad_accumulate<T, W, U>(acc, c, Lam, ldl, rr, live, Q, ldq, count);
 #pragma unroll
     for (int j = 0; j < W; ++j)
       if (k0 + j < width) grad[s0 + (int64_t)(k0 + j) * kSlice + lane] += acc[j];
@@ -463,14 +490,7 @@ k_sell_grad_tma(int64_t nrows, int64_t nslices, const int64_t* __restrict__ slic
         if (lane == 0) tma::mbar_arrive(empty + s);
       }
     } else if (active && k0 < width) {
-      const int64_t rr = r < nrows ? r : nrows - 1;
-#pragma unroll 2
-      for (int m = count - 1; m >= 0; --m) {
-        const T lr = r < nrows ? __ldg(Lam + (int64_t)m * ldl + rr) : T(0);
-        const T* qm = Q + (int64_t)m * ldq;
-#pragma unroll
-        for (int j = 0; j < W; ++j) acc[j] = fma(lr, __ldg(qm + c[j]), acc[j]);
-      }
+      grad_accumulate<T, W, 2>(acc, c, Lam, ldl, r < nrows ? r : nrows - 1, r < nrows, Q, ldq, count);
     }
     if (active)
 #pragma unroll
@@ -788,8 +808,20 @@ struct SparseOperator : bl_operator {
     const int64_t threads = sell.nslices * kSlice;
     const int blocks = (int)((threads + 255) / 256);
     if (blocks > 0 && count > 0) {
-      k_sell_grad_batch<T, 12><<<blocks, 256, 0, s>>>(n_rows, sell.slice_ptr.as<int64_t>(), sell.col.as<int32_t>(),
-                                                      grad.as<T>(), Q, ldq, Lam, ldl, count);
+      static const int rounds = [] {  // BL_GRAD_U: pairs per round of k_sell_grad_batch (1, 2 or 4)
+        const char* e = std::getenv("BL_GRAD_U");
+        return e ? std::atoi(e) : (sizeof(T) == 8 ? 4 : 2);  // fp64: 6.57 -> 4.0 (2) -> 2.63 ms (4) for 400 pairs at C2
+      }();
+      auto launch = [&](auto kern) {
+        kern<<<blocks, 256, 0, s>>>(n_rows, sell.slice_ptr.as<int64_t>(), sell.col.as<int32_t>(), grad.as<T>(), Q, ldq, Lam,
+                                    ldl, count);
+      };
+      if (rounds >= 4)
+        launch(k_sell_grad_batch<T, 12, 4>);
+      else if (rounds == 2)
+        launch(k_sell_grad_batch<T, 12, 2>);
+      else
+        launch(k_sell_grad_batch<T, 12, 1>);
       BL_LAUNCHED();
     }
     return BL_OK;
