@@ -2092,7 +2092,7 @@ int bl_arnoldi_adjoint_batch(bl_operator_t* op, int dtype, int64_t n, int64_t K,
                                          (double*)Lambda, workspace, workspace_bytes, s);
 }
 
-#ifdef BL_STEP_DEBUG
+#if defined(BL_STEP_DEBUG) || defined(BL_STEP_CYCLES)
 extern "C" int bl_step_debug_read(unsigned long long* out16, int reset) {
   BL_CUDA(cudaDeviceSynchronize());
   BL_CUDA(cudaMemcpyFromSymbol(out16, bl::g_step_dbg, 16 * sizeof(unsigned long long)));

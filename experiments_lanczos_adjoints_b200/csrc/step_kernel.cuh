@@ -108,7 +108,7 @@ constexpr int kTraceStamps = 8;
 constexpr int kTraceLaunches = 2048;
 __device__ unsigned long long g_step_trace[kTraceStamps * kTraceLaunches];
 
-#ifdef BL_STEP_DEBUG
+#if defined(BL_STEP_DEBUG) || defined(BL_STEP_CYCLES)
 // Debugging (-DBL_STEP_DEBUG): the FIRST non-finite value a k_step_tma launch meets, where it met it.
 __device__ unsigned long long g_step_dbg[16];
 __device__ __forceinline__ void dbg_record(int code, int p, int step_i, long long a, double v0, double v1) {
@@ -126,13 +126,39 @@ __device__ __forceinline__ void dbg_record(int code, int p, int step_i, long lon
     __threadfence();
   }
 }
+#ifdef BL_STEP_DEBUG
 #define BL_DBG(cond, code, p, i, a, v0, v1) \
   do {                                      \
     if (cond) dbg_record(code, p, i, a, v0, v1); \
   } while (0)
+#else
+#define BL_DBG(cond, code, p, i, a, v0, v1) \
+  do {                                      \
+  } while (0)
+#endif
 template <typename X>
 __device__ __forceinline__ bool dbg_bad(X v) { return !(fabs((double)v) < 1e30); }
+// cycle counters of block 0 / warp 0 / lane 0 inside phase S: g_step_dbg[9 + k] accumulates section k
+#define BL_CYC_DECL long long cyc_t0 = clock64(), cyc_acc[6] = {0, 0, 0, 0, 0, 0};
+#define BL_CYC(k)                          \
+  do {                                     \
+    const long long cyc_t1 = clock64();    \
+    cyc_acc[k] += cyc_t1 - cyc_t0;         \
+    cyc_t0 = cyc_t1;                       \
+  } while (0)
+#define BL_CYC_FLUSH                                                                    \
+  do {                                                                                  \
+    if (blockIdx.x == 0 && warp == 0 && lane == 0)                                      \
+      for (int k = 0; k < 6; ++k) atomicAdd(&g_step_dbg[9 + k], (unsigned long long)cyc_acc[k]); \
+  } while (0)
 #else
+#define BL_CYC_DECL
+#define BL_CYC(k) \
+  do {            \
+  } while (0)
+#define BL_CYC_FLUSH \
+  do {               \
+  } while (0)
 #define BL_DBG(cond, code, p, i, a, v0, v1) \
   do {                                      \
   } while (0)
@@ -325,7 +351,9 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
     }
   };
   const long long first = o.s_lo + warp;
-  const int nmine = o.s_hi > first ? (int)((o.s_hi - first + kConsumerWarps - 1) / kConsumerWarps) : 0;
+  int nmine = o.s_hi > first ? (int)((o.s_hi - first + kConsumerWarps - 1) / kConsumerWarps) : 0;
+  if (op.l2_hints & 256) nmine = 0;  // timing experiment: the ring's protocol alone (every warp passes every stage)
+  BL_CYC_DECL
   for (int base = 0; base < nmine; base += 32) {
     // lane l fetches the slot range of the warp's (base + l)-th slice (relative to the block's first slot: 32 bits)
     int sp0 = 0, sp1 = 0;
@@ -366,6 +394,7 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
           xr[u][p] = NORM && u < nu && r[u] < op.nrows ? __ldcg(x[p] + r[u]) : T(0);
           acc0[u][p] = acc1[u][p] = T(0);
         }
+      BL_CYC(0);  // group set-up (shuffles, row loads issued)
       for (int k0 = 0; k0 < wmax; k0 += W) {
         int rows[U];
         {  // stages below the first slot row that is still needed are finished with; wait for the last one of the round
@@ -382,6 +411,7 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
           if (low >= 0) done_below(low);
           need(last);
         }
+        BL_CYC(1);  // ring: release + wait
         int c[U][W];
         T v[U][W];
 #pragma unroll
@@ -431,6 +461,7 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
               else
                 acc0[u][p] = fma(v[u][j], gv, acc0[u][p]);
             }
+        BL_CYC(2);  // loads + FMAs of the round
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -442,9 +473,12 @@ __device__ __forceinline__ void op_phase(const StepBatch& B, const OpRange& o, c
             static_cast<T*>(B.a[p].op_q)[r[u]] = r[u] < op.nrows ? xr[u][p] * T(1) / dlen[p] : T(0);
         }
       i += nu;
+      BL_CYC(3);  // stores of the group
     }
   }
   done_below(o.nstages);  // every warp passes every stage of the operand stream
+  BL_CYC(4);
+  BL_CYC_FLUSH;
 }
 
 template <typename T, bool NORM>
@@ -460,13 +494,58 @@ __device__ __forceinline__ void op_phase_dispatch(const StepBatch& B, const OpRa
   }
 }
 
+// One run's lane sums of <few_j, x0> over the block's tiles, TU tiles per round: the TU x (FN + 1) vector loads of a round
+// are issued before the first FMA.  (One tile per round left a block with 4 runs x 13 tiles = 52 dependent L2 round trips
+// in phase 0: 20-29 us of a launch whose phase 0 moves 64 MB.)
+template <typename T, int TILE, int FN, int TU>
+__device__ __forceinline__ void few_dots_run(const StepArgs& a, const ColumnRange& cr, long long n, int tid, T (&facc)[kFewMax]) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  const T* x0 = static_cast<const T*>(a.few_x);
+  for (int t0 = 0; t0 < cr.ntiles; t0 += TU) {
+    V xv[TU], qv[TU][FN];
+    bool ok[TU];
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      const long long c = cr.c0 + (long long)(t0 + u) * TILE + (long long)tid * VN;
+      // whole vectors only (basis rows are zero-padded up to ld, x0 is not: the vector that straddles n goes below)
+      ok[u] = t0 + u < cr.ntiles && c < cr.c1 && c + VN <= n;
+      const long long cc = ok[u] ? c : cr.c0;
+      xv[u] = __ldcg(reinterpret_cast<const V*>(x0 + cc));  // through L2 (op_phase's note)
+#pragma unroll
+      for (int r = 0; r < FN; ++r) qv[u][r] = __ldcg(reinterpret_cast<const V*>(static_cast<const T*>(a.few_row[r]) + cc));
+    }
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      if (ok[u]) {
+        T xx[VN];
+        vec_unpack(xv[u], xx);
+#pragma unroll
+        for (int r = 0; r < FN; ++r) {
+          T q[VN];
+          vec_unpack(qv[u][r], q);
+#pragma unroll
+          for (int k = 0; k < VN; ++k) facc[r] = fma(q[k], xx[k], facc[r]);
+        }
+      }
+    }
+  }
+  // the vector that straddles n (at most one thread of one block)
+  for (int tt = 0; tt < cr.ntiles; ++tt) {
+    const long long c = cr.c0 + (long long)tt * TILE + (long long)tid * VN;
+    if (c < cr.c1 && c < n && c + VN > n) {
+#pragma unroll
+      for (int r = 0; r < FN; ++r)
+        for (int k = 0; c + k < n; ++k) facc[r] = fma(static_cast<const T*>(a.few_row[r])[c + k], __ldcg(x0 + c + k), facc[r]);
+    }
+  }
+}
+
 // Phase 0, block-local part: this block's share of <few_j, x0> for every run, left in the run's scratch area
 // (acc_s + p * acc_stride + kFewMax * kConsumerWarps + j).
 template <typename T, int TILE, typename Sync>
 __device__ __forceinline__ void few_dots_local(const StepBatch& B, const ColumnRange& cr, long long n, double* acc_s,
                                          int tid, int warp, int lane, Sync csync) {
-  using V = typename Vec<T>::type;
-  constexpr int VN = Vec<T>::N;
   const int P = B.count;
   for (int p = 0; p < P; ++p) {
     const StepArgs& a = B.a[p];
@@ -474,26 +553,11 @@ __device__ __forceinline__ void few_dots_local(const StepBatch& B, const ColumnR
     T facc[kFewMax];
 #pragma unroll
     for (int r = 0; r < kFewMax; ++r) facc[r] = T(0);
-    const T* x0 = static_cast<const T*>(a.few_x);
-    for (int tt = 0; tt < cr.ntiles; ++tt) {
-      const long long c = cr.c0 + (long long)tt * TILE + (long long)tid * VN;
-      if (c >= cr.c1 || c >= n) continue;
-      T xx[VN];
-      if (c + VN <= n) {
-        vec_unpack(__ldcg(reinterpret_cast<const V*>(x0 + c)), xx);  // through L2 (op_phase's note)
-      } else {
-#pragma unroll
-        for (int k = 0; k < VN; ++k) xx[k] = c + k < n ? __ldcg(x0 + c + k) : T(0);
-      }
-#pragma unroll
-      for (int r = 0; r < kFewMax; ++r) {
-        if (r < a.few_n) {
-          T q[VN];  // basis rows are zero-padded up to ld: the straddling vector is readable
-          vec_unpack(__ldcg(reinterpret_cast<const V*>(static_cast<const T*>(a.few_row[r]) + c)), q);
-#pragma unroll
-          for (int k = 0; k < VN; ++k) facc[r] = fma(q[k], xx[k], facc[r]);
-        }
-      }
+    switch (a.few_n) {
+      case 1: few_dots_run<T, TILE, 1, 4>(a, cr, n, tid, facc); break;
+      case 2: few_dots_run<T, TILE, 2, 4>(a, cr, n, tid, facc); break;
+      case 3: few_dots_run<T, TILE, 3, 3>(a, cr, n, tid, facc); break;
+      default: few_dots_run<T, TILE, 4, 2>(a, cr, n, tid, facc); break;
     }
     double* scratch = acc_s + (size_t)p * B.acc_stride;
 #pragma unroll
