@@ -1855,7 +1855,15 @@ int arnoldi_adjoint_batch_t(bl_operator_t* op, int dtype, int64_t n, int K, int 
     ProfScope prof(BL_PROF_VJP, op->vjp_batch_bytes(dtype, P * K), s);
     BL_CHECK(op->vjp_batch(dtype, Q, ld, Lambda, ld, P * K, s));
   }
-  for (int p = 0; p < P; ++p) BL_CHECK(runs[p].end());
+  for (int p = 0; p < P; ++p) {
+    // dv = lambda * c is written with 16-byte stores: a row of the caller's (count, lddv) array that is not aligned
+    // (lddv = n, n odd) goes through the run's scratch vector
+    T* dst = runs[p].dv;
+    const bool misaligned = reinterpret_cast<uintptr_t>(dst) % 16 != 0;
+    if (misaligned) runs[p].dv = runs[p].z;
+    BL_CHECK(runs[p].end());
+    if (misaligned) BL_CUDA(cudaMemcpyAsync(dst, runs[p].z, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  }
   return BL_OK;
 }
 

@@ -666,7 +666,7 @@ def test_slq_estimator_with_probes_in_flight_matches_the_sequential_loop(dtype, 
 
     monkeypatch.setattr(lanczos, "_probe_mode", lambda: mode)
 
-    n, K, num = 20_000, 12, 9  # 9 = 4 + 4 + 1: the last group is ragged
+    n, K, num = 20_003, 12, 9  # 9 = 4 + 4 + 1: the last group is ragged; n odd: rows 1..3 of a batch's (4, n) arrays are not 16-byte aligned
     row, col, data = banded_spd(n, 4, seed=31)
     probes = (np.random.default_rng(32).integers(0, 2, size=(num, n)) * 2 - 1).astype(dtype)
     results = {}
