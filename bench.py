@@ -46,11 +46,11 @@ UNIT = "krylov_steps/s"
 
 # DRAM traffic of the dominant kernel from `ncu --set full` captures: dram__bytes_read.sum + dram__bytes_write.sum
 # of ONE launch, next to that launch's algorithmic bytes; each entry names the launch and the summary it comes from.
-NCU_TRAFFIC = {"k_step_tma": {"traffic": 3100.131e6 + 24.838e6, "algorithmic": 4 * (3 + 100 + 98) * 4.0e6 + 82.6e6 + 48.0e6,
+NCU_TRAFFIC = {"k_step_tma": {"traffic": 3103.660e6 + 26.833e6, "algorithmic": 4 * (3 + 100 + 98) * 4.0e6 + 82.6e6 + 48.0e6,
                               "launch": "forward step i=95 of a lockstep batch of 4 runs, operator call inside the launch (phase S: "
                                         "SELL operand 82.6 MB once + x, y, q per run; per run: phase 0 three vectors, phase 1 "
-                                        "96 rows + 3 terms + out, phase 2 96 rows + v' + out), fp32, n=1M; 613.7 us = 5.45 TB/s",
-                              "source": "profiles/r2c_lockstep_prof_step.md"},
+                                        "96 rows + 3 terms + out, phase 2 96 rows + v' + out), fp32, n=1M; 608.3 us = 5.50 TB/s",
+                              "source": "profiles/r2d_lockstep_prof_step.md"},
                "k_xdots_tma": {"traffic": 396.5e6 + 11.7e6, "algorithmic": 100 * 4.0e6,
                                "launch": "forward pass B, i=95 (96 streamed rows + 3 terms + out), fp32, n=1M",
                                "source": "profiles/r1c_prof_xdots.md"},
