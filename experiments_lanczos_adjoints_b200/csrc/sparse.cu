@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
 #include <numeric>
+#include <set>
 #include <vector>
 
 #include "operators.cuh"
@@ -793,10 +795,16 @@ struct SparseOperator : bl_operator {
                          (ldq * sizeof(T)) % 16 == 0 && (ldl * sizeof(T)) % 16 == 0 && ldl >= n_rows && ldq >= n_cols;
     if (staged && grad_windows_fit && aligned && sell.nslices > 0 && count > 0) {
       constexpr size_t smem = (size_t)grad_stages<T>() * (kGradRows + kGradWinMax) * sizeof(T) + 2 * grad_stages<T>() * 8;
-      static bool attr_set = false;  // per instantiation (T)
-      if (!attr_set) {
-        BL_CUDA(cudaFuncSetAttribute(k_sell_grad_tma<T, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+      {  // the opt-in is per device: one process may drive several GPUs from different host threads
+        static std::mutex mu;
+        static std::set<int> done;  // per instantiation (T)
+        int dev = 0;
+        BL_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (!done.count(dev)) {
+          BL_CUDA(cudaFuncSetAttribute(k_sell_grad_tma<T, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          done.insert(dev);
+        }
       }
       const int blocks = (int)((sell.nslices + kGradWarps - 1) / kGradWarps);
       k_sell_grad_tma<T, 12><<<blocks, (kGradWarps + 1) * 32, smem, s>>>(n_rows, sell.nslices, sell.slice_ptr.as<int64_t>(),

@@ -400,7 +400,7 @@ def probe_lockstep_sum(integrand, probes, parameters, *, with_grad, batch=None, 
     if key not in cache:
         ops = [hess.op] + [hess.op.clone() for _ in range(L - 1)]
         cache[key] = ([_plan.BatchedTridiagAdjointPlan(o, K, dtype, B, stream=dev.Stream()) for o in ops],
-                      [_plan.pinned_empty((B, n), dtype) for _ in ops])  # fmt: skip
+                      _plan.PinnedBuffers([(B, n)] * len(ops), dtype))  # fmt: skip
     plans, staging = cache[key]  # per lane: the plan and a pinned buffer its normalised probes are copied from
     host_params = [p.numpy() if isinstance(p, dev.DeviceArray) else np.asarray(p) for p in parameters]
     dev.synchronize()  # the lanes' streams start after whatever the caller enqueued

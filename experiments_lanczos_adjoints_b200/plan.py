@@ -34,6 +34,32 @@ def pinned_empty(shape, dtype) -> np.ndarray:
 _PINNED = {}
 
 
+def pinned_free(arr: np.ndarray) -> None:
+    """Give back a buffer of `pinned_empty` (the caller guarantees that no copy from or to it is in flight)."""
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p is not None:
+        _lib.call("bl_host_free", p)
+
+
+class PinnedBuffers:
+    """Pinned arrays that live as long as their owner (a cache entry of an estimator): freed with it."""
+
+    def __init__(self, shapes, dtype):
+        self.arrays = [pinned_empty(shape, dtype) for shape in shapes]
+
+    def __getitem__(self, i):
+        return self.arrays[i]
+
+    def __del__(self):
+        try:
+            dev.synchronize()  # copies out of the buffers may still be enqueued
+            for a in self.arrays:
+                pinned_free(a)
+        except Exception:  # interpreter shutdown: the CUDA context takes the memory with it
+            pass
+        self.arrays = []
+
+
 class TridiagAdjointPlan:
     """`(Q^T, alpha, beta), r = tridiag(op, K, reortho="full")(v, params)` followed by the adjoint
     for cotangents on `(alpha, beta)` (the SLQ case) or on every output."""
