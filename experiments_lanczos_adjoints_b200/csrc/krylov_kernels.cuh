@@ -559,9 +559,21 @@ __global__ void k_scale_copy(long long n, const T* __restrict__ x, double mul_im
                              T* __restrict__ out, long long n_pad) {
   const T m = static_cast<T>(mul_imm);
   const T d = div_ptr ? static_cast<T>(*div_ptr) : T(1);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad;
-       i += (long long)gridDim.x * blockDim.x)
-    out[i] = i < n ? (div_ptr ? x[i] * m / d : x[i] * m) : T(0);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 8;  // grid strides per round: their loads are issued before the first store
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_pad; i0 += U * stride) {
+    T v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      v[u] = i < n ? x[i] : T(0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n_pad) out[i] = i < n ? (div_ptr ? v[u] * m / d : v[u] * m) : T(0);
+    }
+  }
 }
 
 template <typename T>
