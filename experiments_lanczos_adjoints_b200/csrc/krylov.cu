@@ -1479,12 +1479,12 @@ struct AdjRun {
   }
   // Pi_gamma = -dc c e1 e1^T + H dH^T - dQ^T Q                                arnoldi.py:127
   if (dQ) {
-    constexpr int TK = 16, KB = 128;  // blocks of at most 128 x 128 entries of dQ^T Q per launch: any Krylov depth
-    const size_t smem = 2 * (size_t)std::min(K, KB) * (TK + 1) * sizeof(T);
-    BL_CHECK(set_smem(k_gram_partial<T, TK>, 2 * (size_t)KB * (TK + 1) * sizeof(double)));
+    constexpr int TK = 32, KB = 128;  // blocks of at most 128 x 128 entries of dQ^T Q per launch: any Krylov depth
+    const size_t smem = 2 * (size_t)TK * kGramKP * sizeof(T);
+    BL_CHECK(set_smem(k_gram_partial<T, TK>, smem));
     for (int a0 = 0; a0 < K; a0 += KB)
       for (int b0 = 0; b0 < K; b0 += KB) {
-        k_gram_partial<T, TK><<<gram_parts, 256, smem, s>>>(std::min(KB, K - a0), std::min(KB, K - b0), K, n,
+        k_gram_partial<T, TK><<<gram_parts, kGramThreads, smem, s>>>(std::min(KB, K - a0), std::min(KB, K - b0), K, n,
                                                             dQ + (int64_t)a0 * ld, Q + (int64_t)b0 * ld, ld,
                                                             gram_partial + (size_t)a0 * K + b0);
         BL_LAUNCHED();

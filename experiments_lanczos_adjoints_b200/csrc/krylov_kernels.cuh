@@ -475,19 +475,42 @@ __global__ void k_pi_gamma(int K, const T* __restrict__ H, const T* __restrict__
   out[(size_t)a * K + b] = s;
 }
 
-// G[a][b] += sum_col dQ[a][col] * Q[b][col] over a column tile; accumulated with double atomics
-// across tiles is avoided: each block owns a column slab and writes its own partial K x K.
-// One (Ka x Kb) block of the K x K result: rows a0.. of dQ against rows b0.. of Q (the host walks the blocks, at
-// most 128 x 128 each, so that a thread owns at most four 4x4 patches whatever the Krylov depth).
+// G[a][b] = sum_col dQ[a][col] * Q[b][col]: each block owns a column slab and writes its own partial K x K (summed in a
+// fixed order by k_gram_reduce).  One (Ka x Kb) block of the result per launch: rows a0.. of dQ against rows b0.. of Q
+// (the host walks the blocks, at most 128 x 128 each, so that a thread owns at most two 4x4 patches whatever the depth).
+// A tile is TK = 32 columns, staged TRANSPOSED in shared memory ([column][row], row stride kGramKP = 132): a warp loads 32
+// consecutive columns of a row (one coalesced 128-byte request; the loads of a tile are issued before the first store),
+// and a thread reads the four rows of its patch as ONE 16-byte word per operand and column -- 2 shared loads for 16 FMAs.
+// The 32 products of a tile are summed in T, the tile sums in double (a conversion and an fp64 add per product made the
+// F2D pipe the bound: 5.4 ms at K = 100, n = 1M, where the bytes take 0.15 ms).
+constexpr int kGramKP = 132;
+constexpr int kGramThreads = 512;
+
+template <typename T>
+__device__ __forceinline__ void ld4_shared(const T* p, T (&o)[4]);
+template <>
+__device__ __forceinline__ void ld4_shared<float>(const float* p, float (&o)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void ld4_shared<double>(const double* p, double (&o)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y;
+}
+
 template <typename T, int TK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kGramThreads)
 k_gram_partial(int Ka, int Kb, int ldp, long long n, const T* __restrict__ dQ, const T* __restrict__ Q, long long ld,
                double* __restrict__ partial /* [gridDim.x][ldp*ldp], offset to (a0, b0) */) {
-  // tile: TK columns at a time; thread (ta, tb) accumulates a 4x4 patch of the block
-  extern __shared__ unsigned char smem_raw[];
+  static_assert(TK == 32, "a warp loads one row of a tile");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sA = reinterpret_cast<T*>(smem_raw);  // [TK][kGramKP]
+  T* sB = sA + (size_t)TK * kGramKP;       // [TK][kGramKP]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kGramThreads / 32;
   const int K = Ka > Kb ? Ka : Kb;
-  T* sA = reinterpret_cast<T*>(smem_raw);  // [K][TK+1]
-  T* sB = sA + (size_t)K * (TK + 1);       // [K][TK+1]
+  const int K4 = (K + 3) / 4 * 4;          // rows K .. K4-1 are staged as zeros (the patches read whole 4-row words)
   const int P = (Kb + 3) / 4;              // patches per row of patches
   const int PA = (Ka + 3) / 4;
   const long long per = (n + gridDim.x - 1) / gridDim.x;
@@ -495,8 +518,8 @@ k_gram_partial(int Ka, int Kb, int ldp, long long n, const T* __restrict__ dQ, c
   long long c1 = c0 + per;
   if (c1 > n) c1 = n;
   const int npatch = PA * P;
-  // each thread may own several patches
-  constexpr int MAXP = 4;
+  constexpr int MAXP = 2;  // 32 x 32 patches of a 128 x 128 block over 512 threads
+  constexpr int RMAX = 128 / NW;  // rows a warp stages per tile
   double acc[MAXP][16];
 #pragma unroll
   for (int p = 0; p < MAXP; ++p)
@@ -504,36 +527,49 @@ k_gram_partial(int Ka, int Kb, int ldp, long long n, const T* __restrict__ dQ, c
     for (int k = 0; k < 16; ++k) acc[p][k] = 0.0;
   for (long long c = c0; c < c1; c += TK) {
     const int w = (int)((c1 - c) < TK ? (c1 - c) : TK);
-    __syncthreads();
-    for (int e = threadIdx.x; e < K * TK; e += blockDim.x) {
-      const int r = e / TK, k = e % TK;
-      sA[r * (TK + 1) + k] = (k < w && r < Ka) ? dQ[(long long)r * ld + c + k] : T(0);
-      sB[r * (TK + 1) + k] = (k < w && r < Kb) ? Q[(long long)r * ld + c + k] : T(0);
+    T ra[RMAX], rb[RMAX];
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+      const int r = warp + i * NW;
+      ra[i] = (lane < w && r < Ka) ? dQ[(long long)r * ld + c + lane] : T(0);
+      rb[i] = (lane < w && r < Kb) ? Q[(long long)r * ld + c + lane] : T(0);
+    }
+    __syncthreads();  // the previous tile has been consumed
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+      const int r = warp + i * NW;
+      if (r < K4) {
+        sA[lane * kGramKP + r] = ra[i];
+        sB[lane * kGramKP + r] = rb[i];
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int p = 0; p < MAXP; ++p) {
-      const int patch = threadIdx.x + p * blockDim.x;
+      const int patch = threadIdx.x + p * kGramThreads;
       if (patch >= npatch) break;
       const int pa = (patch / P) * 4, pb = (patch % P) * 4;
+      T tile[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tile[k] = T(0);
+#pragma unroll 8
       for (int k = 0; k < TK; ++k) {
         T av[4], bv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          av[u] = pa + u < Ka ? sA[(pa + u) * (TK + 1) + k] : T(0);
-          bv[u] = pb + u < Kb ? sB[(pb + u) * (TK + 1) + k] : T(0);
-        }
+        ld4_shared<T>(sA + k * kGramKP + pa, av);
+        ld4_shared<T>(sB + k * kGramKP + pb, bv);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int v = 0; v < 4; ++v) acc[p][u * 4 + v] += static_cast<double>(av[u] * bv[v]);
+          for (int v = 0; v < 4; ++v) tile[u * 4 + v] = fma(av[u], bv[v], tile[u * 4 + v]);
       }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[p][k] += static_cast<double>(tile[k]);
     }
   }
   double* out = partial + (size_t)blockIdx.x * ldp * ldp;
 #pragma unroll
   for (int p = 0; p < MAXP; ++p) {
-    const int patch = threadIdx.x + p * blockDim.x;
+    const int patch = threadIdx.x + p * kGramThreads;
     if (patch >= npatch) break;
     const int pa = (patch / P) * 4, pb = (patch % P) * 4;
 #pragma unroll
